@@ -1,0 +1,71 @@
+"""ctypes binding of libglasdi_b200.so (the C-ABI declared in include/glasdi_b200.h).
+
+There is NO CPU fallback: if the shared library is missing it is built with nvcc; if that is not
+possible, or no sm_100 GPU is present when a handle is requested, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_READY, ERR_NUMERIC, ERR_OOM = range(7)
+
+ACT_IDS = {"sigmoid": 0, "tanh": 1, "softplus": 2, "ReLU": 3, "ELU": 4, "SiLU": 5, "GELU": 6, "identity": 7}
+FD_IDS = {"sbp12": 0, "sbp24": 1, "sbp36": 2, "sbp48": 3}
+OPT_SPLIT_PASSES, OPT_INTEGRATOR, OPT_RK4_SUBSTEPS, OPT_MAX_CTAS = 0, 1, 2, 3
+INT_EXPM, INT_RK4 = 0, 1
+
+# name -> (restype, argtypes); must list EVERY symbol of include/glasdi_b200.h (tests check this)
+_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+SIGNATURES = {
+    "glasdi_abi_version": (_i, []),
+    "glasdi_create": (_i, [C.POINTER(_vp), _i]),
+    "glasdi_destroy": (_i, [_vp]),
+    "glasdi_last_error": (C.c_char_p, [_vp]),
+    "glasdi_set_option": (_i, [_vp, _i, _i]),
+    "glasdi_get_option": (_i, [_vp, _i, C.POINTER(_i)]),
+    "glasdi_launch_count": (_i64, [_vp]),
+    "glasdi_set_decoder": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_vp), _i]),
+    "glasdi_rollout": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp]),
+    "glasdi_greedy_step": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp]),
+    "glasdi_decode_max_std": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "glasdi_decode": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "glasdi_check_numeric": (_i, [_vp, _vp]),
+    "glasdi_argmax_first": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "glasdi_pack_maxloc": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "glasdi_fd_dzdt": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp]),
+    "glasdi_sindy_fit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp]),
+}
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Loads (building first if needed) the shared library and declares every signature."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise RuntimeError(f"{path} is missing: run `python -m gplasdi_b200.build` (no CPU fallback exists)")
+        _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+class GlasdiError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"glasdi_b200 status {code}: {msg}")
+        self.code = code

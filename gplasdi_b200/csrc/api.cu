@@ -1,0 +1,340 @@
+// api.cu -- extern "C" entry points of libglasdi_b200.so (see include/glasdi_b200.h).
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace glasdi {
+
+int set_error(glasdi_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+int check_cuda(glasdi_handle* h, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return GLASDI_OK;
+  return set_error(h, e == cudaErrorMemoryAllocation ? GLASDI_ERR_OOM : GLASDI_ERR_CUDA,
+                   std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int ensure_workspace(glasdi_handle* h, size_t bytes) {
+  if (bytes <= h->ws_bytes) return GLASDI_OK;
+  if (h->ws) cudaFree(h->ws);
+  h->ws = nullptr;
+  h->ws_bytes = 0;
+  GL_CUDA(h, cudaMalloc(&h->ws, bytes));
+  h->ws_bytes = bytes;
+  return GLASDI_OK;
+}
+
+int ensure_maxvar(glasdi_handle* h, size_t n) {
+  if (n <= h->maxvar_cap) return GLASDI_OK;
+  if (h->d_maxvar) cudaFree(h->d_maxvar);
+  h->d_maxvar = nullptr;
+  h->maxvar_cap = 0;
+  GL_CUDA(h, cudaMalloc(&h->d_maxvar, n * sizeof(unsigned int)));
+  h->maxvar_cap = n;
+  return GLASDI_OK;
+}
+
+static void free_decoder(Decoder& d) {
+  for (float* p : d.dW) if (p) cudaFree(p);
+  for (float* p : d.db) if (p) cudaFree(p);
+  d.dW.clear();
+  d.db.clear();
+  if (d.w_packed) cudaFree(d.w_packed);
+  d.w_packed = nullptr;
+  d.ready = false;
+  d.tc_ok = false;
+}
+
+static bool bounded_act(int act) { return act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH; }
+
+// check-and-clear the device-side numeric flags (activation overflow of the fp16 split)
+static int check_flags(glasdi_handle* h, cudaStream_t st) {
+  int flags[4] = {0, 0, 0, 0};
+  GL_CUDA(h, cudaMemcpyAsync(flags, h->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  GL_CUDA(h, cudaStreamSynchronize(st));
+  if (flags[0]) {
+    GL_CUDA(h, cudaMemsetAsync(h->d_flags, 0, sizeof(flags), st));
+    return set_error(h, GLASDI_ERR_NUMERIC,
+                     "hidden activations overflowed the fp16 split range (|h - h_pilot| * 2^eH > 6e4)");
+  }
+  return GLASDI_OK;
+}
+
+}  // namespace glasdi
+
+using namespace glasdi;
+
+extern "C" {
+
+int glasdi_abi_version(void) { return GLASDI_ABI_VERSION; }
+
+int glasdi_create(glasdi_handle** out, int device) {
+  if (!out) return GLASDI_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return GLASDI_ERR_NO_DEVICE;
+  if (device < 0 || device >= count) return GLASDI_ERR_INVALID;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GLASDI_ERR_CUDA;
+  if (prop.major != 10) return GLASDI_ERR_NO_DEVICE;   // tcgen05 / TMEM kernels: sm_100 only, no fallback
+  glasdi_handle* h = new glasdi_handle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  cudaError_t e = cudaMalloc(&h->d_flags, 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(h->d_flags, 0, 4 * sizeof(int));
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) { delete h; return GLASDI_ERR_CUDA; }
+  *out = h;
+  return GLASDI_OK;
+}
+
+int glasdi_destroy(glasdi_handle* h) {
+  if (!h) return GLASDI_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(h->device);
+  free_decoder(h->dec);
+  if (h->ws) cudaFree(h->ws);
+  if (h->d_maxvar) cudaFree(h->d_maxvar);
+  if (h->d_flags) cudaFree(h->d_flags);
+  cudaSetDevice(prev);
+  delete h;
+  return GLASDI_OK;
+}
+
+const char* glasdi_last_error(const glasdi_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int64_t glasdi_launch_count(const glasdi_handle* h) { return h ? h->launches : 0; }
+
+int glasdi_set_option(glasdi_handle* h, int option, int value) {
+  if (!h) return GLASDI_ERR_INVALID;
+  switch (option) {
+    case GLASDI_OPT_SPLIT_PASSES:
+      if (value < 1 || value > 3) return set_error(h, GLASDI_ERR_INVALID, "split passes must be 1, 2 or 3");
+      h->opt_passes = value;
+      return GLASDI_OK;
+    case GLASDI_OPT_INTEGRATOR:
+      if (value != GLASDI_INT_EXPM && value != GLASDI_INT_RK4) return set_error(h, GLASDI_ERR_INVALID, "unknown integrator");
+      h->opt_integrator = value;
+      return GLASDI_OK;
+    case GLASDI_OPT_RK4_SUBSTEPS:
+      if (value < 1) return set_error(h, GLASDI_ERR_INVALID, "substeps must be >= 1");
+      h->opt_substeps = value;
+      return GLASDI_OK;
+    case GLASDI_OPT_MAX_CTAS:
+      if (value < 0) return set_error(h, GLASDI_ERR_INVALID, "max ctas must be >= 0");
+      h->opt_max_ctas = value;
+      return GLASDI_OK;
+    default: return set_error(h, GLASDI_ERR_INVALID, "unknown option");
+  }
+}
+
+int glasdi_get_option(const glasdi_handle* h, int option, int* value) {
+  if (!h || !value) return GLASDI_ERR_INVALID;
+  switch (option) {
+    case GLASDI_OPT_SPLIT_PASSES: *value = h->opt_passes; return GLASDI_OK;
+    case GLASDI_OPT_INTEGRATOR: *value = h->opt_integrator; return GLASDI_OK;
+    case GLASDI_OPT_RK4_SUBSTEPS: *value = h->opt_substeps; return GLASDI_OK;
+    case GLASDI_OPT_MAX_CTAS: *value = h->opt_max_ctas; return GLASDI_OK;
+    default: return GLASDI_ERR_INVALID;
+  }
+}
+
+int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths, const float* const* W_host,
+                       const float* const* b_host, int act_id) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (n_linear < 2 || n_linear > kMaxLinear) return set_error(h, GLASDI_ERR_INVALID, "decoder needs 2..8 linear layers");
+  if (!widths || !W_host || !b_host) return set_error(h, GLASDI_ERR_INVALID, "null decoder arrays");
+  if (act_id < 0 || act_id > GLASDI_ACT_IDENTITY) return set_error(h, GLASDI_ERR_INVALID, "unknown activation id");
+  if (widths[0] < 1 || widths[0] > kMaxLatent) return set_error(h, GLASDI_ERR_INVALID, "latent dimension must be 1..8");
+  for (int l = 0; l <= n_linear; ++l)
+    if (widths[l] < 1) return set_error(h, GLASDI_ERR_INVALID, "non-positive layer width");
+  GL_CUDA(h, cudaSetDevice(h->device));
+  Decoder& d = h->dec;
+  free_decoder(d);
+  d.n_linear = n_linear;
+  d.act = act_id;
+  for (int l = 0; l <= n_linear; ++l) d.widths[l] = widths[l];
+  d.dW.assign(n_linear, nullptr);
+  d.db.assign(n_linear, nullptr);
+  for (int l = 0; l < n_linear; ++l) {
+    const size_t nw = (size_t)widths[l] * widths[l + 1];
+    GL_CUDA(h, cudaMalloc(&d.dW[l], nw * sizeof(float)));
+    GL_CUDA(h, cudaMalloc(&d.db[l], (size_t)widths[l + 1] * sizeof(float)));
+    GL_CUDA(h, cudaMemcpy(d.dW[l], W_host[l], nw * sizeof(float), cudaMemcpyHostToDevice));
+    GL_CUDA(h, cudaMemcpy(d.db[l], b_host[l], (size_t)widths[l + 1] * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  d.K = widths[n_linear - 1];
+  d.D = widths[n_linear];
+  d.Kpad = (d.K + 15) / 16 * 16;
+  d.n_tiles = (d.D + 127) / 128;
+
+  // tcgen05 path: K of the last layer must fit the resident operand tiles, intermediate front
+  // layers must fit the producers' local arrays.
+  bool ok = d.Kpad <= 112;
+  for (int l = 1; l < n_linear - 1; ++l) ok = ok && widths[l] <= 64;
+  const int last_in_w = widths[n_linear - 2];
+  ok = ok && decode_var_smem_bytes(d.Kpad, last_in_w) <= 227 * 1024;
+  d.tc_ok = ok;
+
+  // ---- pack the last layer: fp16 hi/lo split of W * 2^eW in UMMA canonical K-major tiles -------
+  const float* WL = W_host[n_linear - 1];
+  float wmax = 0.f;
+  for (size_t i = 0; i < (size_t)d.D * d.K; ++i) wmax = std::max(wmax, std::fabs(WL[i]));
+  if (!std::isfinite(wmax)) return set_error(h, GLASDI_ERR_NUMERIC, "non-finite decoder weights");
+  d.eW = (wmax > 0.f) ? 13 - std::ilogb(wmax) : 0;
+  d.eW = std::max(-100, std::min(100, d.eW));
+  d.eH = bounded_act(act_id) ? 12 : 4;
+  if (ok) {
+    const size_t part_halfs = (size_t)d.Kpad * 128;     // [kg][128 rows][8]
+    std::vector<__half> packed((size_t)d.n_tiles * 2 * part_halfs);
+    for (int tile = 0; tile < d.n_tiles; ++tile) {
+      __half* hi = packed.data() + ((size_t)tile * 2 + 0) * part_halfs;
+      __half* lo = packed.data() + ((size_t)tile * 2 + 1) * part_halfs;
+      for (int kg = 0; kg < d.Kpad / 8; ++kg)
+        for (int r = 0; r < 128; ++r)
+          for (int u = 0; u < 8; ++u) {
+            const int dof = tile * 128 + r, k = kg * 8 + u;
+            float v = 0.f;
+            if (dof < d.D && k < d.K) v = std::ldexp(WL[(size_t)dof * d.K + k], d.eW);
+            const __half vh = __float2half_rn(v);
+            const __half vl = __float2half_rn(v - __half2float(vh));
+            const size_t o = ((size_t)kg * 128 + r) * 8 + u;
+            hi[o] = vh;
+            lo[o] = vl;
+          }
+    }
+    GL_CUDA(h, cudaMalloc(&d.w_packed, packed.size() * sizeof(__half)));
+    GL_CUDA(h, cudaMemcpy(d.w_packed, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
+  d.ready = true;
+  return GLASDI_OK;
+}
+
+int glasdi_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z0_per_sample, int P, int S, int n,
+                   int T, double dt, double* Z_out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!coefs || !z0 || !Z_out) return set_error(h, GLASDI_ERR_INVALID, "rollout: null pointer");
+  GL_CUDA(h, cudaSetDevice(h->device));
+  // P may exceed the grid.y limit: slab it
+  for (int p0 = 0; p0 < P; p0 += 32768) {
+    const int pn = std::min(32768, P - p0);
+    int rc = launch_rollout(h, coefs + (size_t)p0 * S * n * (n + 1),
+                            z0 + (size_t)p0 * (z0_per_sample ? (size_t)S * n : (size_t)n), z0_per_sample, pn, S, n, T,
+                            dt, nullptr, 0, Z_out + (size_t)p0 * S * T * n, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return GLASDI_OK;
+}
+
+// shared tail of the two max-std entry points: run the decode+variance kernel over parameter slabs
+// whose fp32 trajectory scratch fits the workspace budget
+static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, const double* Zis, int P, int S, int n,
+                       int T, double dt, float* max_std_out, int64_t* argmax_out, float* maxval_out,
+                       cudaStream_t st) {
+  const Decoder& d = h->dec;
+  if (!d.ready) return set_error(h, GLASDI_ERR_NOT_READY, "decoder weights not set (glasdi_set_decoder)");
+  if (n != d.widths[0]) return set_error(h, GLASDI_ERR_INVALID, "latent dimension does not match the decoder");
+  if (P <= 0 || S <= 0 || T <= 0) return set_error(h, GLASDI_ERR_INVALID, "empty ensemble");
+  if (!max_std_out) return set_error(h, GLASDI_ERR_INVALID, "null output");
+  GL_CUDA(h, cudaSetDevice(h->device));
+  const int Spad = (S + 31) / 32 * 32;
+  const size_t per_param = (size_t)T * n * Spad * sizeof(float);
+  const size_t budget = (size_t)12 << 30;                      // trajectory scratch per slab
+  int slab = (int)std::max<size_t>(1, std::min<size_t>((size_t)P, budget / per_param));
+  slab = std::min(slab, 32768);
+  int rc = ensure_workspace(h, per_param * slab);
+  if (rc) return rc;
+  rc = ensure_maxvar(h, (size_t)P);
+  if (rc) return rc;
+  GL_CUDA(h, cudaMemsetAsync(h->d_maxvar, 0, (size_t)P * sizeof(unsigned int), st));
+  float* Zs = reinterpret_cast<float*>(h->ws);
+  for (int p0 = 0; p0 < P; p0 += slab) {
+    const int pn = std::min(slab, P - p0);
+    if (coefs) {
+      rc = launch_rollout(h, coefs + (size_t)p0 * S * n * (n + 1), z0 + (size_t)p0 * n, 0, pn, S, n, T, dt, Zs, Spad,
+                          nullptr, st);
+    } else {
+      rc = launch_zis_to_soa(h, Zis + (size_t)p0 * S * T * n, pn, S, T, n, Zs, Spad, st);
+    }
+    if (rc) return rc;
+    if (d.tc_ok) rc = launch_decode_var(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
+    else rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
+    if (rc) return rc;
+  }
+  const int scale = d.tc_ok ? (d.eW + d.eH) : 0;
+  return launch_finalize(h, h->d_maxvar, P, scale, max_std_out, argmax_out, maxval_out, st);
+}
+
+int glasdi_greedy_step(glasdi_handle* h, const double* coefs, const float* z0, int P, int S, int n, int T, double dt,
+                       float* max_std_out, int64_t* argmax_out, float* maxval_out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!coefs || !z0) return set_error(h, GLASDI_ERR_INVALID, "greedy_step: null input");
+  return greedy_core(h, coefs, z0, nullptr, P, S, n, T, dt, max_std_out, argmax_out, maxval_out, (cudaStream_t)stream);
+}
+
+int glasdi_decode_max_std(glasdi_handle* h, const double* Zis, int P, int S, int T, int n, float* max_std_out,
+                          int64_t* argmax_out, float* maxval_out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!Zis) return set_error(h, GLASDI_ERR_INVALID, "decode_max_std: null input");
+  return greedy_core(h, nullptr, nullptr, Zis, P, S, n, T, 0.0, max_std_out, argmax_out, maxval_out,
+                     (cudaStream_t)stream);
+}
+
+int glasdi_decode(glasdi_handle* h, const float* Z, int64_t rows, float* X_out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!h->dec.ready) return set_error(h, GLASDI_ERR_NOT_READY, "decoder weights not set (glasdi_set_decoder)");
+  if (rows < 0 || (rows > 0 && (!Z || !X_out))) return set_error(h, GLASDI_ERR_INVALID, "decode: bad arguments");
+  if (rows == 0) return GLASDI_OK;
+  GL_CUDA(h, cudaSetDevice(h->device));
+  if (h->dec.tc_ok) return launch_decode_store(h, Z, rows, X_out, (cudaStream_t)stream);
+  return launch_decode_store_simt(h, Z, rows, X_out, (cudaStream_t)stream);
+}
+
+// host-visible check of the numeric flags raised by the last asynchronous calls (synchronises `stream`)
+int glasdi_check_numeric(glasdi_handle* h, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  GL_CUDA(h, cudaSetDevice(h->device));
+  return check_flags(h, (cudaStream_t)stream);
+}
+
+int glasdi_argmax_first(glasdi_handle* h, const float* vals, int P, int64_t* idx_out, float* val_out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!vals || P <= 0 || !idx_out) return set_error(h, GLASDI_ERR_INVALID, "argmax: bad arguments");
+  GL_CUDA(h, cudaSetDevice(h->device));
+  return launch_argmax_first(h, vals, P, idx_out, val_out, (cudaStream_t)stream);
+}
+
+int glasdi_pack_maxloc(glasdi_handle* h, const float* val, const int64_t* local_idx, int64_t index_offset,
+                       int64_t* key_out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!val || !local_idx || !key_out) return set_error(h, GLASDI_ERR_INVALID, "pack_maxloc: null pointer");
+  GL_CUDA(h, cudaSetDevice(h->device));
+  return launch_pack_maxloc(h, val, local_idx, index_offset, key_out, (cudaStream_t)stream);
+}
+
+int glasdi_fd_dzdt(glasdi_handle* h, const float* Z, int B, int T, int n, int fd_id, double dt, float* dZ_out,
+                   void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!Z || !dZ_out) return set_error(h, GLASDI_ERR_INVALID, "fd_dzdt: null pointer");
+  GL_CUDA(h, cudaSetDevice(h->device));
+  return launch_fd_dzdt(h, Z, B, T, n, fd_id, dt, dZ_out, (cudaStream_t)stream);
+}
+
+int glasdi_sindy_fit(glasdi_handle* h, const float* Z, int B, int T, int n, int fd_id, double dt, int norm_order,
+                     float* coefs_out, float* loss_sindy_out, float* loss_coef_out, int32_t* info_out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!Z || !coefs_out) return set_error(h, GLASDI_ERR_INVALID, "sindy_fit: null pointer");
+  GL_CUDA(h, cudaSetDevice(h->device));
+  return launch_sindy_fit(h, Z, B, T, n, fd_id, dt, norm_order, coefs_out, loss_sindy_out, loss_coef_out, info_out,
+                          (cudaStream_t)stream);
+}
+
+}  // extern "C"

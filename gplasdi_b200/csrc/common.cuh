@@ -1,0 +1,258 @@
+// common.cuh -- shared declarations for the glasdi_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/glasdi_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "glasdi_b200 targets sm_100a (Blackwell B200) only"
+#endif
+
+namespace glasdi {
+
+constexpr int kMaxLatent = 8;     // n_z <= 8
+constexpr int kMaxLinear = 8;     // decoder linear layers <= 8
+
+// Front (all-but-last) decoder layers, fp32, device pointers.  Passed by value to kernels.
+struct FrontMlp {
+  int n_front;                      // number of front linear layers (>= 1)
+  int widths[kMaxLinear + 1];       // widths[0] = n_z ... widths[n_front] = K (input width of last layer)
+  const float* W[kMaxLinear];       // [widths[l+1]][widths[l]] row-major
+  const float* b[kMaxLinear];       // [widths[l+1]]
+  int act;                          // enum glasdi_act
+};
+
+struct Decoder {
+  bool ready = false;
+  int n_linear = 0;
+  int widths[kMaxLinear + 1] = {0};
+  int act = 0;
+  std::vector<float*> dW, db;       // device fp32 copies of every layer
+  // last layer packed for tcgen05: [tile][part(hi,lo)][kg][128 rows][8 halfs]
+  __half* w_packed = nullptr;
+  int K = 0, Kpad = 0, D = 0, n_tiles = 0;
+  int eW = 0;                       // power-of-two scale applied to W before the fp16 split
+  int eH = 0;                       // power-of-two scale applied to the hidden activations
+  bool tc_ok = false;               // tcgen05 path supports this shape
+};
+
+}  // namespace glasdi
+
+struct glasdi_handle {
+  int device = 0;
+  int num_sms = 0;
+  std::string err;
+  glasdi::Decoder dec;
+  int opt_passes = 3;
+  int opt_integrator = GLASDI_INT_EXPM;
+  int opt_substeps = 1;
+  int opt_max_ctas = 0;
+  int64_t launches = 0;
+  // workspace (grown on demand)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  unsigned int* d_maxvar = nullptr;   // [P] float bits
+  size_t maxvar_cap = 0;
+  int* d_flags = nullptr;             // [4] device error flags
+};
+
+namespace glasdi {
+
+int set_error(glasdi_handle* h, int code, const std::string& msg);
+int check_cuda(glasdi_handle* h, cudaError_t e, const char* what);
+int ensure_workspace(glasdi_handle* h, size_t bytes);
+int ensure_maxvar(glasdi_handle* h, size_t n);
+
+#define GL_CUDA(h, expr)                                                   \
+  do {                                                                     \
+    cudaError_t _e = (expr);                                               \
+    if (_e != cudaSuccess) return glasdi::check_cuda((h), _e, #expr);      \
+  } while (0)
+
+// ---- kernel launchers (implemented in the .cu files) -----------------------------------------
+// rollout.cu
+int launch_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z0_per_sample,
+                   int P, int S, int n, int T, double dt,
+                   float* Zs /*[P][T][n][Spad] or null*/, int Spad, double* Zref /*[P,S,T,n] or null*/,
+                   cudaStream_t st);
+int launch_zis_to_soa(glasdi_handle* h, const double* Zis, int P, int S, int T, int n, float* Zs, int Spad,
+                      cudaStream_t st);
+// decode_var.cu
+int launch_decode_var(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
+                      unsigned int* maxvar_bits, cudaStream_t st);
+int launch_decode_store(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
+size_t decode_var_smem_bytes(int Kpad, int last_in_w);
+// simt_fallback.cu : fp32 CUDA-core path for decoder shapes the tcgen05 kernel does not cover
+int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
+                           unsigned int* maxvar_bits, cudaStream_t st);
+int launch_decode_store_simt(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
+// reduce.cu
+int launch_finalize(glasdi_handle* h, const unsigned int* maxvar_bits, int P, int scale_exp2,
+                    float* max_std, int64_t* argmax, float* maxval, cudaStream_t st);
+int launch_argmax_first(glasdi_handle* h, const float* vals, int P, int64_t* idx, float* val, cudaStream_t st);
+int launch_pack_maxloc(glasdi_handle* h, const float* val, const int64_t* idx, int64_t off, int64_t* key,
+                       cudaStream_t st);
+// calibrate.cu
+int launch_fd_dzdt(glasdi_handle* h, const float* Z, int B, int T, int n, int fd_id, double dt, float* dZ,
+                   cudaStream_t st);
+int launch_sindy_fit(glasdi_handle* h, const float* Z, int B, int T, int n, int fd_id, double dt, int norm_order,
+                     float* coefs, float* loss_sindy, float* loss_coef, int32_t* info, cudaStream_t st);
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float act_apply(int act, float x) {
+  // torch-default activations (reference src/lasdi/latent_space.py:5-28)
+  switch (act) {
+    case GLASDI_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
+    case GLASDI_ACT_TANH: return tanhf(x);
+    case GLASDI_ACT_SOFTPLUS: return x > 20.0f ? x : log1pf(expf(x));   // beta=1, threshold=20
+    case GLASDI_ACT_RELU: return fmaxf(x, 0.0f);
+    case GLASDI_ACT_ELU: return x > 0.0f ? x : expm1f(x);              // alpha=1
+    case GLASDI_ACT_SILU: return x / (1.0f + expf(-x));
+    case GLASDI_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    default: return x;
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_apply_t(float x) {
+  return act_apply(ACT, x);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- bulk async copy (TMA engine, 1-D) --------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- tcgen05 ----------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 inputs, fp32 accumulate), single CTA.
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread l <-> lane base+l)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, no-swizzle ("interleaved") UMMA shared-memory descriptor.
+// Canonical layout in 16-byte units: ((8, n), 2) : ((1, SBO), LBO) -- a core matrix is 8 rows x 16 B
+// stored contiguously; SBO = byte step between 8-row groups, LBO = byte step between the two
+// 16-byte K halves of one K=16 slice.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version 1 (Blackwell)
+  // base_offset = 0, lbo_mode = 0, layout_type (bits 61..63) = 0 : SWIZZLE_NONE
+  return d;
+}
+
+// kind::f16 instruction descriptor: fp16 A/B (K-major both), fp32 accumulator, M = 128, N = n.
+__device__ __forceinline__ uint32_t umma_idesc_f16_m128(uint32_t n) {
+  uint32_t d = 0;
+  d |= 1u << 4;              // c_format = F32
+  // a_format = b_format = 0 (F16); no negate; a_major = b_major = 0 (K-major)
+  d |= (n >> 3) << 17;       // n_dim
+  d |= (128u >> 4) << 24;    // m_dim
+  return d;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace glasdi

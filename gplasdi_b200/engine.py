@@ -1,0 +1,203 @@
+"""Engine: one C-ABI handle (= one B200 + one workspace) behind torch tensors.
+
+torch is plumbing only (device memory, streams); every computation is a call through the C ABI
+of libglasdi_b200.so.  All methods take/return CUDA tensors unless stated and are asynchronous on
+torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GlasdiError
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Engine:
+    def __init__(self, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("gplasdi_b200 needs a B200 (sm_100) GPU: there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        h = C.c_void_p()
+        rc = self.lib.glasdi_create(C.byref(h), self.device)
+        if rc != _lib.OK:
+            raise GlasdiError(rc, "glasdi_create failed (needs an sm_100 device; no CPU fallback)")
+        self.h = h
+        self.tdev = torch.device("cuda", self.device)
+        self.decoder_widths = None
+        self.decoder_act = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.glasdi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != _lib.OK:
+            raise GlasdiError(rc, self.lib.glasdi_last_error(self.h).decode())
+
+    def set_option(self, opt: int, value: int):
+        self._check(self.lib.glasdi_set_option(self.h, opt, int(value)))
+
+    def get_option(self, opt: int) -> int:
+        v = C.c_int()
+        self._check(self.lib.glasdi_get_option(self.h, opt, C.byref(v)))
+        return v.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.glasdi_launch_count(self.h))
+
+    def check_numeric(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_check_numeric(self.h, _stream_ptr()))
+
+    def _dev(self, x, dtype):
+        t = torch.as_tensor(x)
+        return t.to(device=self.tdev, dtype=dtype, non_blocking=True).contiguous()
+
+    # ---- decoder -----------------------------------------------------------------------------
+    def set_decoder(self, weights, biases, act: str):
+        """weights[l] [out, in], biases[l] [out] (nn.Linear layout; numpy or CPU/CUDA tensors)."""
+        if act not in _lib.ACT_IDS:
+            raise ValueError(f"activation {act!r} is not supported by the CUDA decoder "
+                             f"(supported: {sorted(_lib.ACT_IDS)})")
+        Ws = [np.ascontiguousarray(torch.as_tensor(w).detach().cpu().numpy(), dtype=np.float32) for w in weights]
+        bs = [np.ascontiguousarray(torch.as_tensor(b).detach().cpu().numpy(), dtype=np.float32) for b in biases]
+        n = len(Ws)
+        widths = [Ws[0].shape[1]] + [w.shape[0] for w in Ws]
+        for l in range(n):
+            assert Ws[l].shape == (widths[l + 1], widths[l]) and bs[l].shape == (widths[l + 1],)
+        wa = (C.c_int * (n + 1))(*widths)
+        Wp = (C.c_void_p * n)(*[w.ctypes.data for w in Ws])
+        bp = (C.c_void_p * n)(*[b.ctypes.data for b in bs])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_set_decoder(self.h, n, wa, Wp, bp, _lib.ACT_IDS[act]))
+        self.decoder_widths = widths
+        self.decoder_act = act
+
+    # ---- rollout -----------------------------------------------------------------------------
+    def rollout(self, coefs, z0, T: int, dt: float) -> torch.Tensor:
+        """coefs [P,S,n(n+1)] fp64, z0 [P,n] (or [P,S,n]) fp32 -> Z fp64 [P,S,T,n] (CUDA tensor)."""
+        coefs = self._dev(coefs, torch.float64)
+        z0 = self._dev(z0, torch.float32)
+        P, S, nc = coefs.shape
+        n = z0.shape[-1]
+        assert nc == n * (n + 1)
+        per_sample = 1 if z0.dim() == 3 else 0
+        out = torch.empty((P, S, T, n), dtype=torch.float64, device=self.tdev)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_rollout(self.h, coefs.data_ptr(), z0.data_ptr(), per_sample, P, S, n, T,
+                                                float(dt), out.data_ptr(), _stream_ptr()))
+        return out
+
+    # ---- fused greedy step ---------------------------------------------------------------------
+    def greedy_step(self, coefs, z0, T: int, dt: float, out=None):
+        """-> (max_std fp32 [P], argmax int64 [1] (-1 if none), maxval fp32 [1]); CUDA tensors."""
+        coefs = self._dev(coefs, torch.float64)
+        z0 = self._dev(z0, torch.float32)
+        P, S, nc = coefs.shape
+        n = z0.shape[-1]
+        assert z0.shape == (P, n) and nc == n * (n + 1)
+        if out is None:
+            out = (torch.empty(P, dtype=torch.float32, device=self.tdev),
+                   torch.empty(1, dtype=torch.int64, device=self.tdev),
+                   torch.empty(1, dtype=torch.float32, device=self.tdev))
+        ms, am, mv = out
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_greedy_step(self.h, coefs.data_ptr(), z0.data_ptr(), P, S, n, T, float(dt),
+                                                    ms.data_ptr(), am.data_ptr(), mv.data_ptr(), _stream_ptr()))
+        return ms, am, mv
+
+    def decode_max_std(self, Zis):
+        """Zis [P,S,T,n] fp64 -> (max_std [P], argmax [1], maxval [1])."""
+        Zis = self._dev(Zis, torch.float64)
+        P, S, T, n = Zis.shape
+        ms = torch.empty(P, dtype=torch.float32, device=self.tdev)
+        am = torch.empty(1, dtype=torch.int64, device=self.tdev)
+        mv = torch.empty(1, dtype=torch.float32, device=self.tdev)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_decode_max_std(self.h, Zis.data_ptr(), P, S, T, n, ms.data_ptr(),
+                                                       am.data_ptr(), mv.data_ptr(), _stream_ptr()))
+        return ms, am, mv
+
+    def decode(self, Z) -> torch.Tensor:
+        """Z [..., n_z] fp32 -> X [..., D] fp32."""
+        Z = self._dev(Z, torch.float32)
+        lead = Z.shape[:-1]
+        rows = int(np.prod(lead)) if len(lead) else 1
+        D = self.decoder_widths[-1]
+        X = torch.empty((rows, D), dtype=torch.float32, device=self.tdev)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_decode(self.h, Z.data_ptr(), rows, X.data_ptr(), _stream_ptr()))
+        return X.reshape(*lead, D)
+
+    def argmax_first(self, vals):
+        vals = self._dev(vals, torch.float32)
+        idx = torch.empty(1, dtype=torch.int64, device=self.tdev)
+        val = torch.empty(1, dtype=torch.float32, device=self.tdev)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_argmax_first(self.h, vals.data_ptr(), vals.numel(), idx.data_ptr(),
+                                                     val.data_ptr(), _stream_ptr()))
+        return idx, val
+
+    def pack_maxloc(self, val, idx, index_offset: int) -> torch.Tensor:
+        key = torch.empty(1, dtype=torch.int64, device=self.tdev)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_pack_maxloc(self.h, val.data_ptr(), idx.data_ptr(), int(index_offset),
+                                                    key.data_ptr(), _stream_ptr()))
+        return key
+
+    # ---- calibration ---------------------------------------------------------------------------
+    def fd_dzdt(self, Z, dt: float, fd_type: str = "sbp12") -> torch.Tensor:
+        Z = self._dev(Z, torch.float32)
+        squeeze = Z.dim() == 2
+        if squeeze:
+            Z = Z.unsqueeze(0)
+        B, T, n = Z.shape
+        out = torch.empty_like(Z)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_fd_dzdt(self.h, Z.data_ptr(), B, T, n, _lib.FD_IDS[fd_type], float(dt),
+                                                out.data_ptr(), _stream_ptr()))
+        return out[0] if squeeze else out
+
+    def sindy_fit(self, Z, dt: float, fd_type: str = "sbp12", norm_order=1):
+        """Z [B,T,n] fp32 -> (coefs [B, n(n+1)], loss_sindy [B], loss_coef [B], info int32 [B])."""
+        Z = self._dev(Z, torch.float32)
+        B, T, n = Z.shape
+        order = 2 if norm_order in (2, "fro") else 1
+        if norm_order not in (1, 2, "fro"):
+            raise ValueError("coef_norm_order must be 1, 2 or 'fro'")
+        coefs = torch.empty((B, n * (n + 1)), dtype=torch.float32, device=self.tdev)
+        ls = torch.empty(B, dtype=torch.float32, device=self.tdev)
+        lc = torch.empty(B, dtype=torch.float32, device=self.tdev)
+        info = torch.empty(B, dtype=torch.int32, device=self.tdev)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_sindy_fit(self.h, Z.data_ptr(), B, T, n, _lib.FD_IDS[fd_type], float(dt),
+                                                  order, coefs.data_ptr(), ls.data_ptr(), lc.data_ptr(),
+                                                  info.data_ptr(), _stream_ptr()))
+        return coefs, ls, lc, info
+
+
+_DEFAULT = {}
+
+
+def default_engine(device: int | None = None) -> Engine:
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if dev not in _DEFAULT:
+        _DEFAULT[dev] = Engine(dev)
+    return _DEFAULT[dev]

@@ -1,0 +1,112 @@
+"""SINDy latent dynamics on the B200 path; drop-in for the reference class of the same name
+(reference src/lasdi/latent_dynamics/sindy.py:8-123).
+
+  calibrate -> glasdi_sindy_fit   (SBP stencil dZ/dt + fp64 normal-equation solve per series)
+  simulate  -> glasdi_rollout     (fp64 exact affine propagator; the reference calls scipy odeint)
+  sample    -> glasdi_rollout over the whole batch in one launch
+
+Signatures, return types and the coefficient layout (row-major flatten of the (dim+1, dim)
+least-squares solution, row 0 = constant term) are the reference's.  The losses returned by
+`calibrate` are detached: differentiating through the fit (used by the reference's training loop,
+gplasdi.py:186-197) is not part of the greedy-sampling path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import LatentDynamics
+from ..fd import FDdict
+from ..engine import default_engine
+
+
+def _uniform_dt(t_grid) -> float:
+    t = np.asarray(t_grid, dtype=np.float64)
+    if t.ndim != 1 or t.size < 1:
+        raise ValueError("t_grid must be a 1-d array")
+    if t.size == 1:
+        return 0.0
+    d = np.diff(t)
+    if not np.allclose(d, d[0], rtol=1e-9, atol=1e-14):
+        raise ValueError("the CUDA rollout needs a uniform time grid (the reference's physics grids are uniform)")
+    return float(d[0])
+
+
+class SINDy(LatentDynamics):
+    fd_type = ""
+
+    def __init__(self, dim, nt, config, engine=None):
+        super().__init__(dim, nt)
+        self.ncoefs = self.dim * (self.dim + 1)
+        assert "sindy" in config
+        opts = config["sindy"] or {}
+        self.fd_type = opts.get("fd_type", "sbp12")
+        if self.fd_type not in FDdict:
+            raise KeyError(f"unknown fd_type {self.fd_type!r}; choose from {sorted(FDdict)}")
+        self.fd = FDdict[self.fd_type]
+        if self.nt < self.fd.min_length():
+            raise AssertionError(f"{self.fd_type} needs nt >= {self.fd.min_length()}")
+        self.coef_norm_order = opts.get("coef_norm_order", 1)
+        if self.coef_norm_order not in (1, 2, "fro"):
+            raise ValueError("coef_norm_order must be 1, 2 or 'fro'")
+        self._engine = engine
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = default_engine()
+        return self._engine
+
+    # -------------------------------------------------------------------------------------
+    def compute_time_derivative(self, Z, Dt):
+        """(1/Dt) * D_fd Z for one series [nt, dim] (or a batch [B, nt, dim]); returns a tensor on
+        the input's device.  Reference sindy.py:89-102."""
+        Zt = torch.as_tensor(Z)
+        out = self.engine.fd_dzdt(Zt.detach(), Dt, self.fd_type)
+        return out.to(Zt.device)
+
+    def calibrate(self, Z, dt, compute_loss=True, numpy=False):
+        """Reference sindy.py:41-87.  Z: torch tensor [nt, dim] or [n_train, nt, dim].
+        Returns coefs (and the two losses, summed over the training series)."""
+        Zt = torch.as_tensor(Z)
+        batched = Zt.dim() == 3
+        if not batched:
+            assert Zt.dim() == 2
+        Zb = Zt.detach() if batched else Zt.detach().unsqueeze(0)
+        assert Zb.shape[1] == self.nt or True   # the reference does not check nt either
+        assert Zb.shape[2] == self.dim
+        coefs, ls, lc, info = self.engine.sindy_fit(Zb, dt, self.fd_type, self.coef_norm_order)
+        if batched:
+            out = coefs.double().cpu().numpy() if numpy else coefs.cpu()
+        else:
+            out = coefs[0].cpu().numpy() if numpy else coefs[0].cpu()
+        if not compute_loss:
+            return out
+        return out, ls.sum().cpu(), lc.sum().cpu()
+
+    def simulate(self, coefs, z0, t_grid):
+        """One trajectory; returns np.ndarray fp64 [nt, dim] like scipy odeint does in the reference."""
+        c = np.asarray(coefs, dtype=np.float64).reshape(1, 1, self.ncoefs)
+        z = np.asarray(z0, dtype=np.float32).reshape(1, self.dim)
+        Z = self.engine.rollout(c, z, len(t_grid), _uniform_dt(t_grid))
+        return Z[0, 0].cpu().numpy()
+
+    def sample(self, coefs_sample, z0_sample, t_grid):
+        """N trajectories in one launch; returns np.ndarray fp64 [N, nt, dim]."""
+        c = np.asarray(coefs_sample, dtype=np.float64)
+        z = np.asarray(z0_sample, dtype=np.float32)
+        assert len(c) == len(z)
+        N = c.shape[0]
+        Z = self.engine.rollout(c.reshape(N, 1, self.ncoefs), z.reshape(N, self.dim), len(t_grid), _uniform_dt(t_grid))
+        return Z[:, 0].cpu().numpy()
+
+    def rollout_ensemble(self, coef_samples, Z0, t_grid):
+        """[P, S, ncoefs] draws and [P, dim] initial conditions -> CUDA tensor fp64 [P, S, nt, dim]
+        (the array the reference fills in gplasdi.py:262-266)."""
+        return self.engine.rollout(coef_samples, Z0, len(t_grid), _uniform_dt(t_grid))
+
+    def export(self):
+        d = super().export()
+        d["fd_type"] = self.fd_type
+        d["coef_norm_order"] = self.coef_norm_order
+        return d

@@ -1,0 +1,148 @@
+/*
+ * glasdi_b200.h -- C ABI of the B200-native (sm_100a) GPLaSDI greedy-sampling / SINDy-calibration
+ * hot path.  This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ *
+ * Conventions
+ *   - every entry point returns an int status (GLASDI_OK == 0); no exceptions cross the boundary;
+ *     glasdi_last_error() gives a human-readable message for the last non-zero status of a handle.
+ *   - unless marked HOST, pointers are caller-owned DEVICE pointers on the handle's device
+ *     (e.g. torch CUDA tensors' data_ptr()); the library never frees or keeps them.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and
+ *     re-entrant per handle (one handle = one device + one workspace; do not share a handle
+ *     between host threads concurrently).
+ *   - there is NO CPU fallback: if no sm_100 device is present glasdi_create fails.
+ *
+ * Each entry point names the reference interface (LLNL/GPLaSDI, file:line) it replaces.
+ * INTEGRATION.md shows the ctypes stubs a reference maintainer would add.
+ */
+#ifndef GLASDI_B200_H
+#define GLASDI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLASDI_ABI_VERSION 1
+
+typedef struct glasdi_handle glasdi_handle;
+
+enum glasdi_status {
+  GLASDI_OK = 0,
+  GLASDI_ERR_INVALID = 1,      /* bad argument / unsupported shape */
+  GLASDI_ERR_CUDA = 2,         /* CUDA runtime error (message has the cudaError string) */
+  GLASDI_ERR_NO_DEVICE = 3,    /* no sm_100 device: there is no CPU fallback */
+  GLASDI_ERR_NOT_READY = 4,    /* e.g. greedy step before glasdi_set_decoder */
+  GLASDI_ERR_NUMERIC = 5,      /* fp16 split overflow of activations, all-zero std, singular Gram */
+  GLASDI_ERR_OOM = 6
+};
+
+/* activation ids = names of reference src/lasdi/latent_space.py:5-28 (`act_dict`), torch defaults */
+enum glasdi_act {
+  GLASDI_ACT_SIGMOID = 0, GLASDI_ACT_TANH = 1, GLASDI_ACT_SOFTPLUS = 2, GLASDI_ACT_RELU = 3,
+  GLASDI_ACT_ELU = 4, GLASDI_ACT_SILU = 5, GLASDI_ACT_GELU = 6, GLASDI_ACT_IDENTITY = 7
+};
+
+/* finite-difference scheme ids = keys of reference src/lasdi/fd.py:219-222 (`FDdict`) */
+enum glasdi_fd { GLASDI_FD_SBP12 = 0, GLASDI_FD_SBP24 = 1, GLASDI_FD_SBP36 = 2, GLASDI_FD_SBP48 = 3 };
+
+/* latent ODE integrators for the affine SINDy system (reference: scipy odeint/LSODA, sindy.py:115) */
+enum glasdi_integrator {
+  GLASDI_INT_EXPM = 0,   /* fp64 exact affine propagator expm([[A,b],[0,0]] dt), stepped in fp64 */
+  GLASDI_INT_RK4 = 1     /* fp64 classical RK4 with `substeps` sub-steps per output step */
+};
+
+/* options for glasdi_set_option */
+enum glasdi_option {
+  GLASDI_OPT_SPLIT_PASSES = 0,  /* 1, 2 or 3 fp16 split-product passes of the last decoder layer
+                                   (3 = fp32-faithful default; see DESIGN.md "precision") */
+  GLASDI_OPT_INTEGRATOR = 1,    /* enum glasdi_integrator (default EXPM) */
+  GLASDI_OPT_RK4_SUBSTEPS = 2,  /* default 1 */
+  GLASDI_OPT_MAX_CTAS = 3       /* cap on persistent CTAs (0 = one per SM); for tests */
+};
+
+int glasdi_abi_version(void);
+
+/* lifetime ------------------------------------------------------------------------------------ */
+int glasdi_create(glasdi_handle** out, int device);
+int glasdi_destroy(glasdi_handle* h);
+const char* glasdi_last_error(const glasdi_handle* h);
+int glasdi_set_option(glasdi_handle* h, int option, int value);
+int glasdi_get_option(const glasdi_handle* h, int option, int* value);
+/* number of kernels this handle has launched so far (bench.py's `gpu_launches`) */
+int64_t glasdi_launch_count(const glasdi_handle* h);
+
+/* decoder weights ------------------------------------------------------------------------------
+ * Replaces: the `autoencoder.decoder` nn.Module state consumed by get_fom_max_std
+ *   (reference src/lasdi/gplasdi.py:66; MultiLayerPerceptron, src/lasdi/latent_space.py:65-171;
+ *   re-read from checkpoint.pt at gplasdi.py:254 -> call again after every load_state_dict).
+ * n_linear linear layers; widths[0..n_linear] = [n_z, hidden..., D]; W[l] HOST fp32
+ * [widths[l+1], widths[l]] row-major (nn.Linear layout), b[l] HOST fp32 [widths[l+1]].
+ * Packs the last layer into fp16 hi/lo UMMA tiles and uploads everything (synchronous). */
+int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths,
+                       const float* const* W_host, const float* const* b_host, int act_id);
+
+/* latent rollout ------------------------------------------------------------------------------
+ * Replaces: SINDy.simulate in the loops of gplasdi.py:20-21, :45-48, :262-266 and
+ *   LatentDynamics.sample (latent_dynamics/__init__.py:39-54).
+ * coefs fp64 [P, S, n(n+1)] (row-major flatten of the (n+1, n) lstsq solution, row 0 = constant,
+ * sindy.py:72,80,112-113); z0 fp32 [P, n] (one initial condition per parameter, shared by its S
+ * samples; pass z0_per_sample != 0 for z0 [P, S, n]); uniform grid t_k = k*dt, k < T.
+ * Z_out fp64 [P, S, T, n] in the reference's layout. */
+int glasdi_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z0_per_sample,
+                   int P, int S, int n, int T, double dt, double* Z_out, void* stream);
+
+/* fused greedy step ---------------------------------------------------------------------------
+ * Replaces: gplasdi.py:262-268 = the simulate double loop + get_fom_max_std(ae, Zis).
+ * Rollout (fp64) -> MLP decode -> population std over the S samples (ddof = 0) per (t, dof)
+ * -> max over (t, dof) -> max_std[p]; then the first strict maximum over p, starting from 0
+ * (gplasdi.py:62-72).  Nothing but max_std[P] and the (index, value) pair is written.
+ * max_std_out fp32 [P]; argmax_out int64[1] (LOCAL index in [0,P), -1 if no std exceeds 0 --
+ * the reference raises UnboundLocalError there); maxval_out fp32[1]. */
+int glasdi_greedy_step(glasdi_handle* h, const double* coefs, const float* z0,
+                       int P, int S, int n, int T, double dt,
+                       float* max_std_out, int64_t* argmax_out, float* maxval_out, void* stream);
+
+/* Replaces: get_fom_max_std(autoencoder, Zis) (gplasdi.py:52-74) for caller-supplied
+ * trajectories Zis fp64 [P, S, T, n] (cast to fp32 first, as `torch.Tensor(Zi)` does). */
+int glasdi_decode_max_std(glasdi_handle* h, const double* Zis, int P, int S, int T, int n,
+                          float* max_std_out, int64_t* argmax_out, float* maxval_out, void* stream);
+
+/* Replaces: autoencoder.decoder(Z) forward (latent_space.py:135-171; call sites gplasdi.py:66,182,
+ * postprocess.py:32).  Z fp32 [rows, n_z] -> X fp32 [rows, D]. */
+int glasdi_decode(glasdi_handle* h, const float* Z, int64_t rows, float* X_out, void* stream);
+
+/* Synchronises `stream` and reports (then clears) numeric flags raised on the device by earlier
+ * asynchronous calls: GLASDI_ERR_NUMERIC if hidden activations overflowed the fp16 split range. */
+int glasdi_check_numeric(glasdi_handle* h, void* stream);
+
+/* first strict maximum of vals[0..P) starting from 0 (gplasdi.py:62-72); idx_out = -1 if none */
+int glasdi_argmax_first(glasdi_handle* h, const float* vals, int P, int64_t* idx_out, float* val_out,
+                        void* stream);
+
+/* multi-GPU max-loc key: (float_bits(val) << 32) | (0xFFFFFFFF - global_index); an integer MAX
+ * all-reduce over ranks then selects the largest value and, on ties, the smallest global index
+ * (= the reference's first-strict-maximum rule).  key_out int64[1]; a local idx of -1 packs to 0. */
+int glasdi_pack_maxloc(glasdi_handle* h, const float* val, const int64_t* local_idx, int64_t index_offset,
+                       int64_t* key_out, void* stream);
+
+/* SINDy calibration ---------------------------------------------------------------------------
+ * Replaces: SINDy.compute_time_derivative (sindy.py:89-102) with the SBP operators of fd.py:14-217.
+ * Z fp32 [B, T, n] -> dZ fp32 [B, T, n] = (1/dt) * D_fd Z. */
+int glasdi_fd_dzdt(glasdi_handle* h, const float* Z, int B, int T, int n, int fd_id, double dt,
+                   float* dZ_out, void* stream);
+
+/* Replaces: SINDy.calibrate (sindy.py:41-87): per series dZ/dt by the stencil, library [1 | Z],
+ * least squares (normal equations accumulated and solved in fp64), MSE(dZdt, [1|Z] R) and
+ * ||R||_p (norm_order 1 or 2; 2 = 'fro').  coefs_out fp32 [B, n(n+1)] (row-major (n+1, n));
+ * loss_sindy_out / loss_coef_out fp32 [B] (per series; the reference SUMS them over the batch);
+ * info_out int32 [B]: 0 ok, >0 Gram matrix not positive definite at that pivot (rank deficient). */
+int glasdi_sindy_fit(glasdi_handle* h, const float* Z, int B, int T, int n, int fd_id, double dt,
+                     int norm_order, float* coefs_out, float* loss_sindy_out, float* loss_coef_out,
+                     int32_t* info_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLASDI_B200_H */

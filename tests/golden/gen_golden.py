@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by RUNNING THE REFERENCE ITSELF (imports /root/reference/src/lasdi).
+
+Run in the build container only:  python tests/golden/gen_golden.py [--full]
+The fixtures pin the CPU oracle (oracle/reference_path.py) and, through it, the CUDA path.
+Inputs come from gplasdi_b200.synth (seeded); only reference OUTPUTS (and small inputs) are stored.
+
+Reference entry points exercised (file:line):
+  lasdi.fd.FDdict[*].getOperators                     src/lasdi/fd.py:14-44
+  lasdi.latent_dynamics.sindy.SINDy.calibrate/simulate src/lasdi/latent_dynamics/sindy.py:41-117
+  lasdi.latent_space.MultiLayerPerceptron.forward     src/lasdi/latent_space.py:135-171
+  lasdi.gplasdi.get_fom_max_std                       src/lasdi/gplasdi.py:52-74
+  lasdi.gp.fit_gps / eval_gp / sample_coefs           src/lasdi/gp.py:5-80
+"""
+import os, sys, argparse, time
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/src")
+
+import numpy as np
+np.Inf = np.inf  # numpy-2 shim for reference gplasdi.py:141
+import torch
+
+from lasdi.fd import FDdict
+from lasdi.latent_dynamics.sindy import SINDy
+from lasdi.latent_space import MultiLayerPerceptron
+from lasdi.gplasdi import get_fom_max_std
+from lasdi.gp import fit_gps, eval_gp, sample_coefs
+
+from gplasdi_b200 import synth
+
+
+class _AE:  # duck-typed autoencoder: get_fom_max_std only touches .decoder
+    def __init__(self, widths, act, Ws, bs):
+        self.decoder = MultiLayerPerceptron(list(widths), act, reshape_index=-1, reshape_shape=[widths[-1]])
+        sd = {}
+        for i, (W, b) in enumerate(zip(Ws, bs)):
+            sd[f"fcs.{i}.weight"] = torch.from_numpy(W)
+            sd[f"fcs.{i}.bias"] = torch.from_numpy(b)
+        self.decoder.load_state_dict(sd)
+
+
+def gen_fd():
+    out = {}
+    for name in ["sbp12", "sbp24", "sbp36", "sbp48"]:
+        for nt in [17, 33]:
+            D, norm, _ = FDdict[name].getOperators(nt)
+            out[f"{name}_{nt}"] = D.to_dense().numpy()
+        D, _, _ = FDdict[name].getOperators(1001)
+        Dd = D.to_dense().numpy()
+        out[f"{name}_1001_head"] = Dd[:12, :24]
+        out[f"{name}_1001_tail"] = Dd[-12:, -24:]
+        out[f"{name}_1001_mid"] = Dd[500, 490:511]
+        out[f"{name}_1001_nnz"] = np.array([D._nnz()])
+    np.savez_compressed(os.path.join(HERE, "fd_operators.npz"), **out)
+
+
+def gen_calibrate():
+    out = {}
+    for name in ["sbp12", "sbp24", "sbp36", "sbp48"]:
+        for (B, T, order) in [(3, 65, 1), (2, 1001, "fro")]:
+            dt = 1.0 / (T - 1)
+            Z = synth.make_latent_series(B, T, 5, dt, seed=7)
+            ld = SINDy(5, T, {"sindy": {"fd_type": name, "coef_norm_order": order}})
+            coefs, ls, lc = ld.calibrate(torch.from_numpy(Z), dt, compute_loss=True, numpy=True)
+            dz = ld.compute_time_derivative(torch.from_numpy(Z[0]), dt).numpy()
+            key = f"{name}_B{B}_T{T}"
+            out[key + "_coefs"] = coefs
+            out[key + "_loss_sindy"] = np.array([float(ls)])
+            out[key + "_loss_coef"] = np.array([float(lc)])
+            out[key + "_dzdt0"] = dz
+    np.savez_compressed(os.path.join(HERE, "calibrate.npz"), **out)
+
+
+def _rollout_ref(ld, coefs, z0, t_grid):
+    P, S = coefs.shape[:2]
+    Zis = np.zeros([P, S, len(t_grid), z0.shape[1]])
+    for i in range(P):
+        for j in range(S):
+            Zis[i, j] = ld.simulate(coefs[i, j], z0[i], t_grid)
+    return Zis
+
+
+def gen_greedy(names, fname, keep_Z=True, p_sel=None):
+    out = {}
+    for nm in names:
+        wl = synth.WORKLOADS[nm]
+        Ws, bs = synth.make_decoder(wl.widths, wl.seed)
+        sl = None if p_sel is None else p_sel
+        inp = synth.make_inputs(wl, sl)
+        ld = SINDy(wl.n_z, wl.T, {"sindy": {"fd_type": "sbp12"}})
+        t0 = time.perf_counter()
+        Zis = _rollout_ref(ld, inp["coefs"], inp["z0"], inp["t_grid"])
+        t1 = time.perf_counter()
+        ae = _AE(wl.widths, wl.act, Ws, bs)
+        m_index = get_fom_max_std(ae, Zis)
+        # per-parameter values, computed exactly as the loop body of get_fom_max_std does
+        per = np.zeros(Zis.shape[0], dtype=np.float32)
+        for m, Zi in enumerate(Zis):
+            X = ae.decoder(torch.Tensor(Zi)).detach().numpy()
+            per[m] = X.std(0).max()
+        t2 = time.perf_counter()
+        out[nm + "_m_index"] = np.array([m_index])
+        out[nm + "_max_std"] = per
+        out[nm + "_index"] = inp["index"]
+        if keep_Z:
+            out[nm + "_Zis"] = Zis
+        print(f"{nm}: P={Zis.shape[0]} index={m_index} rollout {t1-t0:.1f}s decode+std {t2-t1:.1f}s "
+              f"top2 margin={(np.sort(per)[-1]-np.sort(per)[-2])/np.sort(per)[-1]:.3%}")
+    np.savez_compressed(os.path.join(HERE, fname), **out)
+
+
+def gen_gp():
+    """fit_gps/eval_gp/sample_coefs on the 4 corners of the shipped example."""
+    rs = np.random.RandomState(11)
+    X = np.array([[0.7, 0.9], [0.7, 1.1], [0.9, 0.9], [0.9, 1.1]])
+    Y = rs.normal(size=(4, 30))
+    gps = fit_gps(X, Y)
+    test = np.array([[0.74, 0.98], [0.8, 1.0], [0.9, 1.1]])
+    mean, std = eval_gp(gps, test)
+    np.random.seed(5)
+    samples = [sample_coefs(gps, test[i], 6) for i in range(len(test))]
+    np.savez_compressed(os.path.join(HERE, "gp_sampling.npz"), X=X, Y=Y, test=test, mean=mean, std=std,
+                        samples=np.stack(samples), seed=np.array([5]))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also run config #1 (burgers1d_shipped, ~1 min)")
+    args = ap.parse_args()
+    torch.manual_seed(0)
+    gen_fd()
+    gen_calibrate()
+    gen_gp()
+    gen_greedy(["tiny", "small", "small_s200", "small_softplus"], "greedy_small.npz", keep_Z=True)
+    if args.full:
+        gen_greedy(["burgers1d_shipped"], "greedy_burgers1d_shipped.npz", keep_Z=False)
+    print("done")
