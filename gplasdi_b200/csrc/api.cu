@@ -104,6 +104,7 @@ int glasdi_destroy(glasdi_handle* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->d_maxvar) cudaFree(h->d_maxvar);
   if (h->d_flags) cudaFree(h->d_flags);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   cudaSetDevice(prev);
   delete h;
   return GLASDI_OK;
@@ -132,6 +133,9 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
       if (value < 0) return set_error(h, GLASDI_ERR_INVALID, "max ctas must be >= 0");
       h->opt_max_ctas = value;
       return GLASDI_OK;
+    case GLASDI_OPT_STAGE_TIMING:
+      h->opt_timing = value ? 1 : 0;
+      return GLASDI_OK;
     default: return set_error(h, GLASDI_ERR_INVALID, "unknown option");
   }
 }
@@ -143,6 +147,7 @@ int glasdi_get_option(const glasdi_handle* h, int option, int* value) {
     case GLASDI_OPT_INTEGRATOR: *value = h->opt_integrator; return GLASDI_OK;
     case GLASDI_OPT_RK4_SUBSTEPS: *value = h->opt_substeps; return GLASDI_OK;
     case GLASDI_OPT_MAX_CTAS: *value = h->opt_max_ctas; return GLASDI_OK;
+    case GLASDI_OPT_STAGE_TIMING: *value = h->opt_timing; return GLASDI_OK;
     default: return GLASDI_ERR_INVALID;
   }
 }
@@ -234,6 +239,24 @@ int glasdi_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z
   return GLASDI_OK;
 }
 
+// event pair helpers for GLASDI_OPT_STAGE_TIMING
+static int ev_get(glasdi_handle* h, size_t idx, cudaEvent_t* out) {
+  while (h->ev_pool.size() <= idx) {
+    cudaEvent_t e;
+    GL_CUDA(h, cudaEventCreate(&e));
+    h->ev_pool.push_back(e);
+  }
+  *out = h->ev_pool[idx];
+  return GLASDI_OK;
+}
+struct StageTimer {
+  glasdi_handle* h; cudaStream_t st; std::vector<int>* list; bool on; size_t base;
+  StageTimer(glasdi_handle* h_, cudaStream_t st_, std::vector<int>* l, size_t& next)
+      : h(h_), st(st_), list(l), on(h_->opt_timing != 0), base(next) { if (on) next += 2; }
+  int start() { if (!on) return 0; cudaEvent_t e; int rc = ev_get(h, base, &e); if (rc) return rc; return check_cuda(h, cudaEventRecord(e, st), "event record"); }
+  int stop() { if (!on) return 0; cudaEvent_t e; int rc = ev_get(h, base + 1, &e); if (rc) return rc; list->push_back((int)base); return check_cuda(h, cudaEventRecord(e, st), "event record"); }
+};
+
 // shared tail of the two max-std entry points: run the decode+variance kernel over parameter slabs
 // whose fp32 trajectory scratch fits the workspace budget
 static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, const double* Zis, int P, int S, int n,
@@ -256,8 +279,13 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
   if (rc) return rc;
   GL_CUDA(h, cudaMemsetAsync(h->d_maxvar, 0, (size_t)P * sizeof(unsigned int), st));
   float* Zs = reinterpret_cast<float*>(h->ws);
+  h->ev_rollout.clear();
+  h->ev_decode.clear();
+  size_t ev_next = 0;
   for (int p0 = 0; p0 < P; p0 += slab) {
     const int pn = std::min(slab, P - p0);
+    StageTimer t_roll(h, st, &h->ev_rollout, ev_next), t_dec(h, st, &h->ev_decode, ev_next);
+    if ((rc = t_roll.start())) return rc;
     if (coefs) {
       rc = launch_rollout(h, coefs + (size_t)p0 * S * n * (n + 1), z0 + (size_t)p0 * n, 0, pn, S, n, T, dt, Zs, Spad,
                           nullptr, st);
@@ -265,9 +293,12 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
       rc = launch_zis_to_soa(h, Zis + (size_t)p0 * S * T * n, pn, S, T, n, Zs, Spad, st);
     }
     if (rc) return rc;
+    if ((rc = t_roll.stop())) return rc;
+    if ((rc = t_dec.start())) return rc;
     if (d.tc_ok) rc = launch_decode_var(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
     else rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
     if (rc) return rc;
+    if ((rc = t_dec.stop())) return rc;
   }
   const int scale = d.tc_ok ? (d.eW + d.eH) : 0;
   return launch_finalize(h, h->d_maxvar, P, scale, max_std_out, argmax_out, maxval_out, st);
@@ -296,6 +327,24 @@ int glasdi_decode(glasdi_handle* h, const float* Z, int64_t rows, float* X_out, 
   GL_CUDA(h, cudaSetDevice(h->device));
   if (h->dec.tc_ok) return launch_decode_store(h, Z, rows, X_out, (cudaStream_t)stream);
   return launch_decode_store_simt(h, Z, rows, X_out, (cudaStream_t)stream);
+}
+
+int glasdi_stage_times(glasdi_handle* h, double* rollout_ms, double* decode_ms, int* decode_launches) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!h->opt_timing) return set_error(h, GLASDI_ERR_NOT_READY, "stage timing is off (GLASDI_OPT_STAGE_TIMING)");
+  double acc[2] = {0.0, 0.0};
+  const std::vector<int>* lists[2] = {&h->ev_rollout, &h->ev_decode};
+  for (int k = 0; k < 2; ++k)
+    for (int base : *lists[k]) {
+      GL_CUDA(h, cudaEventSynchronize(h->ev_pool[base + 1]));
+      float ms = 0.f;
+      GL_CUDA(h, cudaEventElapsedTime(&ms, h->ev_pool[base], h->ev_pool[base + 1]));
+      acc[k] += ms;
+    }
+  if (rollout_ms) *rollout_ms = acc[0];
+  if (decode_ms) *decode_ms = acc[1];
+  if (decode_launches) *decode_launches = (int)h->ev_decode.size();
+  return GLASDI_OK;
 }
 
 // host-visible check of the numeric flags raised by the last asynchronous calls (synchronises `stream`)

@@ -52,7 +52,11 @@ struct glasdi_handle {
   int opt_integrator = GLASDI_INT_EXPM;
   int opt_substeps = 1;
   int opt_max_ctas = 0;
+  int opt_timing = 0;
   int64_t launches = 0;
+  // stage timing (GLASDI_OPT_STAGE_TIMING): event pairs of the last greedy call
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_rollout, ev_decode;   // indices of (start, stop) pairs into ev_pool
   // workspace (grown on demand)
   void* ws = nullptr;
   size_t ws_bytes = 0;

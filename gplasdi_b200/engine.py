@@ -33,6 +33,7 @@ class Engine:
         self.tdev = torch.device("cuda", self.device)
         self.decoder_widths = None
         self.decoder_act = None
+        self.decoder_owner = None   # module whose weights are currently packed in the handle
 
     def close(self):
         if getattr(self, "h", None):
@@ -61,6 +62,12 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.glasdi_launch_count(self.h))
+
+    def stage_times(self):
+        """(rollout_ms, decode_ms, decode_launches) of the last greedy call (OPT_STAGE_TIMING must be on)."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int()
+        self._check(self.lib.glasdi_stage_times(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
 
     def check_numeric(self):
         with torch.cuda.device(self.device):
@@ -197,6 +204,8 @@ _DEFAULT = {}
 
 
 def default_engine(device: int | None = None) -> Engine:
+    if not torch.cuda.is_available():
+        raise RuntimeError("gplasdi_b200 needs a B200 (sm_100) GPU: there is no CPU fallback")
     dev = torch.cuda.current_device() if device is None else int(device)
     if dev not in _DEFAULT:
         _DEFAULT[dev] = Engine(dev)

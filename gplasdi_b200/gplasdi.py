@@ -1,0 +1,152 @@
+"""Greedy-sampling trainer front end on the B200 path; drop-in for the sampler functions of the
+reference trainer module (reference src/lasdi/gplasdi.py:9-74, :241-274).
+
+`BayesianGLaSDI.get_new_sample_point` keeps its signature and return value (np.ndarray
+[1, n_param]) but hands the whole ensemble to ONE fused call (rollout -> decode -> variance ->
+max -> argmax) instead of the reference's python loops; `get_fom_max_std`, `sample_roms` and
+`average_rom` are the literal drop-ins for callers that pass their own arrays.
+
+Out of scope in this round: the autoencoder training loop (`train`), which is
+where gradients flow through `calibrate`; use the reference trainer for training and this class
+for the greedy step -- checkpoints and `best_coefs` are interchangeable.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .gp import eval_gp, fit_gps, sample_coefs, sample_coefs_all
+from .latent_space import initial_condition_latent
+from .engine import default_engine
+from . import sharding
+
+
+def _engine_for(autoencoder):
+    dec = autoencoder.decoder
+    if hasattr(dec, "_engine_with_weights"):
+        dec._require_cuda_decoder()
+        return dec._engine_with_weights()
+    # foreign (e.g. the reference's own) MultiLayerPerceptron: read its nn.Linear stack
+    eng = default_engine()
+    eng.set_decoder([fc.weight for fc in dec.fcs], [fc.bias for fc in dec.fcs], dec.act_type)
+    eng.decoder_owner = dec
+    return eng
+
+
+def average_rom(autoencoder, physics, latent_dynamics, gp_dictionary, param_grid):
+    """Mean-coefficient rollout per test parameter, [n_test, nt, n_z] (reference gplasdi.py:9-23)."""
+    param_grid = np.asarray(param_grid)
+    if param_grid.ndim == 1:
+        param_grid = param_grid.reshape(1, -1)
+    Z0 = np.stack(initial_condition_latent(param_grid, physics, autoencoder))
+    pred_mean, _ = eval_gp(gp_dictionary, param_grid)
+    return latent_dynamics.sample(pred_mean, Z0, physics.t_grid)
+
+
+def sample_roms(autoencoder, physics, latent_dynamics, gp_dictionary, param_grid, n_samples):
+    """[n_test, n_samples, nt, n_z] ROM trajectories (reference gplasdi.py:25-50), one rollout launch."""
+    param_grid = np.asarray(param_grid)
+    if param_grid.ndim == 1:
+        param_grid = param_grid.reshape(1, -1)
+    Z0 = np.stack(initial_condition_latent(param_grid, physics, autoencoder))
+    coef_samples = np.stack([sample_coefs(gp_dictionary, param_grid[i], n_samples)
+                             for i in range(param_grid.shape[0])])
+    Z = latent_dynamics.rollout_ensemble(coef_samples, Z0, physics.t_grid)
+    return Z.cpu().numpy()
+
+
+def fom_max_std(autoencoder, Zis):
+    """(m_index, max_std[P]) for caller-supplied trajectories Zis [P, S, nt, n_z]."""
+    eng = _engine_for(autoencoder)
+    ms, am, _ = eng.decode_max_std(torch.as_tensor(np.ascontiguousarray(Zis)))
+    eng.check_numeric()
+    return int(am.item()), ms.cpu().numpy()
+
+
+def get_fom_max_std(autoencoder, Zis):
+    """Index of the test parameter with the largest decoded sample std (reference gplasdi.py:52-74)."""
+    m_index, _ = fom_max_std(autoencoder, Zis)
+    if m_index < 0:
+        # the reference leaves m_index unbound here and raises UnboundLocalError
+        raise RuntimeError("no test parameter has a positive standard deviation")
+    return m_index
+
+
+class BayesianGLaSDI:
+    """Sampler half of the reference trainer (reference gplasdi.py:91-294): same constructor
+    arguments and config keys; `get_new_sample_point` is the B200 hot path."""
+
+    def __init__(self, physics, autoencoder, latent_dynamics, param_space, config):
+        self.autoencoder = autoencoder
+        self.latent_dynamics = latent_dynamics
+        self.physics = physics
+        self.param_space = param_space
+        self.n_samples = config["n_samples"]
+        for k in ("lr", "n_iter", "max_iter", "max_greedy_iter", "ld_weight", "coef_weight"):
+            setattr(self, k, config.get(k))
+        self.path_checkpoint = config.get("path_checkpoint", "checkpoint")
+        self.path_results = config.get("path_results", "results")
+        self.device = config.get("device", "cuda")
+        self.best_loss = np.inf
+        self.best_coefs = None
+        self.restart_iter = 0
+        self.X_train = torch.Tensor([])
+        self.X_test = torch.Tensor([])
+        self.last_max_std = None
+
+    def train(self):
+        raise NotImplementedError(
+            "autoencoder training is outside the B200 greedy-sampling path in this round; "
+            "train with the reference trainer and load `best_coefs` / checkpoint.pt here")
+
+    def load_checkpoint(self):
+        """Best-loss decoder weights written by the training loop (reference gplasdi.py:254)."""
+        import os
+        path = os.path.join(self.path_checkpoint, "checkpoint.pt")
+        if os.path.exists(path):
+            self.autoencoder.load_state_dict(torch.load(path))
+
+    def get_new_sample_point(self, group=None):
+        """Reference gplasdi.py:241-274.  With torch.distributed initialised the test grid is
+        sharded across ranks; every rank returns the same parameter."""
+        assert self.best_coefs is not None
+        ps = self.param_space
+        assert self.best_coefs.shape[0] == ps.n_train()
+        n_test = ps.n_test()
+        print("\n~~~~~~~ Finding New Point ~~~~~~~")
+        ae = self.autoencoder
+        self.load_checkpoint()
+
+        Z0 = np.stack(initial_condition_latent(ps.test_space, self.physics, ae))
+        gp_dictionnary = fit_gps(ps.train_space, self.best_coefs)
+        coef_samples = sample_coefs_all(gp_dictionnary, ps.test_space, self.n_samples)
+
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        bounds = sharding.shard_bounds(n_test, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+
+        eng = _engine_for(ae)
+        dt = float(self.physics.t_grid[1] - self.physics.t_grid[0]) if len(self.physics.t_grid) > 1 else 0.0
+        ms, key = sharding.sharded_greedy_step(eng, coef_samples[lo:hi], Z0[lo:hi], len(self.physics.t_grid), dt,
+                                               lo, group)
+        eng.check_numeric()
+        self.last_max_std = ms.cpu().numpy()
+        _, m_index = sharding.unpack_maxloc(int(key.item()))
+        if m_index < 0:
+            raise RuntimeError("no test parameter has a positive standard deviation")
+        new_sample = ps.test_space[m_index, :].reshape(1, -1)
+        print("New param: " + str(np.round(new_sample, 4)) + "\n")
+        return new_sample
+
+    def export(self):
+        return {"X_train": self.X_train, "X_test": self.X_test, "lr": self.lr, "n_iter": self.n_iter,
+                "n_samples": self.n_samples, "best_coefs": self.best_coefs, "max_iter": self.max_iter,
+                "ld_weight": self.ld_weight, "coef_weight": self.coef_weight, "restart_iter": self.restart_iter}
+
+    def load(self, dict_):
+        self.X_train = dict_["X_train"]
+        self.X_test = dict_["X_test"]
+        self.best_coefs = dict_["best_coefs"]
+        self.restart_iter = dict_["restart_iter"]

@@ -88,7 +88,8 @@ class SINDy(LatentDynamics):
         """One trajectory; returns np.ndarray fp64 [nt, dim] like scipy odeint does in the reference."""
         c = np.asarray(coefs, dtype=np.float64).reshape(1, 1, self.ncoefs)
         z = np.asarray(z0, dtype=np.float32).reshape(1, self.dim)
-        Z = self.engine.rollout(c, z, len(t_grid), _uniform_dt(t_grid))
+        dt = _uniform_dt(t_grid)
+        Z = self.engine.rollout(c, z, len(t_grid), dt)
         return Z[0, 0].cpu().numpy()
 
     def sample(self, coefs_sample, z0_sample, t_grid):
@@ -97,13 +98,15 @@ class SINDy(LatentDynamics):
         z = np.asarray(z0_sample, dtype=np.float32)
         assert len(c) == len(z)
         N = c.shape[0]
-        Z = self.engine.rollout(c.reshape(N, 1, self.ncoefs), z.reshape(N, self.dim), len(t_grid), _uniform_dt(t_grid))
+        dt = _uniform_dt(t_grid)
+        Z = self.engine.rollout(c.reshape(N, 1, self.ncoefs), z.reshape(N, self.dim), len(t_grid), dt)
         return Z[:, 0].cpu().numpy()
 
     def rollout_ensemble(self, coef_samples, Z0, t_grid):
         """[P, S, ncoefs] draws and [P, dim] initial conditions -> CUDA tensor fp64 [P, S, nt, dim]
         (the array the reference fills in gplasdi.py:262-266)."""
-        return self.engine.rollout(coef_samples, Z0, len(t_grid), _uniform_dt(t_grid))
+        dt = _uniform_dt(t_grid)
+        return self.engine.rollout(coef_samples, Z0, len(t_grid), dt)
 
     def export(self):
         d = super().export()

@@ -1,0 +1,62 @@
+"""Multi-GPU sharding of the test-parameter grid for the greedy step.
+
+One process per GPU.  The P test parameters are split into contiguous blocks, rank r owns
+[bounds[r], bounds[r+1]); rollouts, decode and variance are independent per parameter, so the
+only exchange is ONE max-loc all-reduce of a packed 64-bit key per rank:
+
+    key = (float_bits(max_std) << 32) | (0xFFFFFFFF - global_index)
+
+Non-negative floats order like their bit patterns, so an integer MAX picks the largest value and,
+on ties, the SMALLEST global index -- the reference's strict-`>` first-wins rule
+(reference src/lasdi/gplasdi.py:62-72).  A rank with no positive std contributes key 0.
+Works with NCCL (CUDA tensors, NVLink) and with gloo (CPU tensors; used by the CPU tests).
+"""
+from __future__ import annotations
+
+import struct
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(P: int, world: int):
+    """Balanced contiguous blocks: the first P % world ranks get one extra parameter."""
+    base, rem = divmod(P, world)
+    bounds = [0]
+    for r in range(world):
+        bounds.append(bounds[-1] + base + (1 if r < rem else 0))
+    return bounds
+
+
+def pack_maxloc_host(val: float, global_idx: int) -> int:
+    """Host mirror of glasdi_pack_maxloc (csrc/reduce.cu) for CPU-side logic and tests."""
+    if global_idx < 0 or not (val > 0.0):
+        return 0
+    bits = struct.unpack("<I", struct.pack("<f", float(val)))[0]
+    return (bits << 32) | (0xFFFFFFFF - (global_idx & 0xFFFFFFFF))
+
+
+def unpack_maxloc(key: int):
+    """-> (value, global_index) or (0.0, -1) for the empty key."""
+    key = int(key)
+    if key == 0:
+        return 0.0, -1
+    bits = (key >> 32) & 0xFFFFFFFF
+    idx = 0xFFFFFFFF - (key & 0xFFFFFFFF)
+    return struct.unpack("<f", struct.pack("<I", bits))[0], int(idx)
+
+
+def allreduce_maxloc(key: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place MAX all-reduce of the int64 key tensor (one element per rank)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(key, op=dist.ReduceOp.MAX, group=group)
+    return key
+
+
+def sharded_greedy_step(engine, coefs_local, z0_local, T: int, dt: float, index_offset: int, group=None):
+    """Runs the fused greedy step on this rank's block and reduces over ranks.
+    Returns (max_std_local CUDA fp32 [P_local], key CUDA int64 [1] after the all-reduce)."""
+    ms, am, mv = engine.greedy_step(coefs_local, z0_local, T, dt)
+    key = engine.pack_maxloc(mv, am, index_offset)
+    allreduce_maxloc(key, group)
+    return ms, key

@@ -59,7 +59,9 @@ enum glasdi_option {
                                    (3 = fp32-faithful default; see DESIGN.md "precision") */
   GLASDI_OPT_INTEGRATOR = 1,    /* enum glasdi_integrator (default EXPM) */
   GLASDI_OPT_RK4_SUBSTEPS = 2,  /* default 1 */
-  GLASDI_OPT_MAX_CTAS = 3       /* cap on persistent CTAs (0 = one per SM); for tests */
+  GLASDI_OPT_MAX_CTAS = 3,      /* cap on persistent CTAs (0 = one per SM); for tests */
+  GLASDI_OPT_STAGE_TIMING = 4   /* 1: bracket the rollout and decode kernels of the greedy step with
+                                   CUDA events on the caller's stream (read with glasdi_stage_times) */
 };
 
 int glasdi_abi_version(void);
@@ -72,6 +74,12 @@ int glasdi_set_option(glasdi_handle* h, int option, int value);
 int glasdi_get_option(const glasdi_handle* h, int option, int* value);
 /* number of kernels this handle has launched so far (bench.py's `gpu_launches`) */
 int64_t glasdi_launch_count(const glasdi_handle* h);
+
+/* Device time of the stages of the LAST greedy step / decode_max_std call, from CUDA events recorded
+ * on the caller's stream (requires GLASDI_OPT_STAGE_TIMING = 1; synchronises those events).
+ * rollout_ms: latent rollout (or layout conversion) kernels; decode_ms: decode+variance kernels
+ * (summed over parameter slabs); decode_launches: number of decode+variance launches. */
+int glasdi_stage_times(glasdi_handle* h, double* rollout_ms, double* decode_ms, int* decode_launches);
 
 /* decoder weights ------------------------------------------------------------------------------
  * Replaces: the `autoencoder.decoder` nn.Module state consumed by get_fom_max_std

@@ -119,7 +119,9 @@ def gen_gp():
     Y = rs.normal(size=(4, 30))
     gps = fit_gps(X, Y)
     test = np.array([[0.74, 0.98], [0.8, 1.0], [0.9, 1.1]])
-    mean, std = eval_gp(gps, test)
+    # single-point predicts, exactly as sample_coefs evaluates them (gp.py:73)
+    ms = [eval_gp(gps, test[i]) for i in range(len(test))]
+    mean = np.concatenate([m for m, _ in ms]); std = np.concatenate([s for _, s in ms])
     np.random.seed(5)
     samples = [sample_coefs(gps, test[i], 6) for i in range(len(test))]
     np.savez_compressed(os.path.join(HERE, "gp_sampling.npz"), X=X, Y=Y, test=test, mean=mean, std=std,

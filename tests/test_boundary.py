@@ -1,0 +1,99 @@
+"""The drop-in boundary: the C-ABI library loads, exports every symbol the header declares, the
+product never routes through the oracle or a CPU fallback, and fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "glasdi_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(glasdi_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gplasdi_b200 import _lib
+    lib = _lib.load()
+    declared = _header_symbols()
+    assert len(declared) >= 16
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/glasdi_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in gplasdi_b200/_lib.py"
+    assert set(_lib.SIGNATURES) == set(declared)
+    assert lib.glasdi_abi_version() == 1
+
+
+def test_no_cuda_types_in_header():
+    txt = open(os.path.join(ROOT, "include", "glasdi_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)          # signatures only, comments stripped
+    for banned in ("#include <cuda", "torch", "at::", "cudaStream_t", "std::"):
+        assert banned not in code, banned
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gplasdi_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "reference_path" not in src, f
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    from gplasdi_b200 import _lib
+    from gplasdi_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine(0)
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.glasdi_create(ctypes.byref(h), 0) == _lib.ERR_NO_DEVICE
+    # decoder inference has no CPU fallback either
+    from gplasdi_b200.latent_space import MultiLayerPerceptron
+    mlp = MultiLayerPerceptron([5, 16, 64], "sigmoid", reshape_index=-1, reshape_shape=[64])
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        mlp(torch.zeros(3, 5))
+    # ... while the differentiable (training) evaluation is plain torch and works anywhere
+    y = mlp(torch.zeros(3, 5, requires_grad=True))
+    assert y.shape == (3, 64) and y.requires_grad
+
+
+def test_state_dict_keys_match_reference_layout():
+    from gplasdi_b200.latent_space import Autoencoder
+
+    class Phys:
+        qgrid_size = [33]
+
+    ae = Autoencoder(Phys(), {"hidden_units": [12], "latent_dimension": 5})
+    keys = sorted(ae.state_dict().keys())
+    assert keys == ["decoder.fcs.0.bias", "decoder.fcs.0.weight", "decoder.fcs.1.bias", "decoder.fcs.1.weight",
+                    "encoder.fcs.0.bias", "encoder.fcs.0.weight", "encoder.fcs.1.bias", "encoder.fcs.1.weight"]
+    assert ae.decoder.layer_sizes == [5, 12, 33] and ae.n_z == 5
+
+
+def test_registries_use_reference_type_keys():
+    import gplasdi_b200
+    assert set(gplasdi_b200.trainer_dict) == {"gplasdi"}
+    assert set(gplasdi_b200.latent_dict) == {"ae"}
+    assert set(gplasdi_b200.ld_dict) == {"sindy"}
+
+
+def test_sindy_constructor_contract():
+    from gplasdi_b200.latent_dynamics.sindy import SINDy
+    ld = SINDy(5, 101, {"sindy": {"fd_type": "sbp24", "coef_norm_order": "fro"}})
+    assert (ld.dim, ld.nt, ld.ncoefs, ld.fd_type) == (5, 101, 30, "sbp24")
+    assert ld.export() == {"dim": 5, "ncoefs": 30, "fd_type": "sbp24", "coef_norm_order": "fro"}
+    ld.load({"dim": 5, "ncoefs": 30})
+    with pytest.raises(KeyError):
+        SINDy(5, 101, {"sindy": {"fd_type": "weno"}})
+    with pytest.raises(AssertionError):
+        SINDy(5, 7, {"sindy": {"fd_type": "sbp48"}})      # shorter than the boundary closure
+    with pytest.raises(ValueError):
+        ld.simulate(np.zeros(30), np.zeros(5), np.array([0.0, 0.1, 0.3]))   # non-uniform grid

@@ -1,0 +1,175 @@
+"""Drop-in Python API on the GPU: the classes and functions keep the reference's names, argument
+meaning, return types and error behaviour (reference src/lasdi/latent_dynamics/sindy.py,
+src/lasdi/latent_space.py, src/lasdi/gplasdi.py), so these tests read like tests of the reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gplasdi_b200 import synth
+from gplasdi_b200.gplasdi import BayesianGLaSDI, get_fom_max_std, fom_max_std, sample_roms, average_rom
+from gplasdi_b200.gp import fit_gps, eval_gp
+from gplasdi_b200.latent_dynamics.sindy import SINDy
+from gplasdi_b200.latent_space import Autoencoder, initial_condition_latent
+from oracle import reference_path as orc
+
+pytestmark = pytest.mark.gpu
+
+
+class Physics:
+    """Minimal physics object: what the sampler reads (reference src/lasdi/physics/__init__.py:4-79)."""
+
+    def __init__(self, nt=65, nx=301, tmax=1.0):
+        self.qgrid_size = [nx]
+        self.nt = nt
+        self.t_grid = np.linspace(0.0, tmax, nt)
+        self.dt = tmax / (nt - 1)
+        self.x_grid = np.linspace(-3.0, 3.0, nx)
+
+    def initial_condition(self, param):
+        a, w = param
+        return a * np.exp(-self.x_grid ** 2 / 2 / w / w)
+
+
+class ParamSpace:
+    def __init__(self):
+        a = np.linspace(0.7, 0.9, 4); w = np.linspace(0.9, 1.1, 3)
+        A, W = np.meshgrid(a, w, indexing="ij")
+        self.test_space = np.stack([A.ravel(), W.ravel()], axis=1)
+        self.train_space = np.array([[0.7, 0.9], [0.7, 1.1], [0.9, 0.9], [0.9, 1.1]])
+
+    def n_test(self):
+        return self.test_space.shape[0]
+
+    def n_train(self):
+        return self.train_space.shape[0]
+
+
+def _autoencoder(physics, hidden=(100,), act="sigmoid", seed=0):
+    torch.manual_seed(seed)
+    return Autoencoder(physics, {"hidden_units": list(hidden), "latent_dimension": 5, "activation": act})
+
+
+def test_sindy_simulate_and_sample(golden_dir):
+    g = np.load(os.path.join(golden_dir, "greedy_small.npz"))
+    wl = synth.WORKLOADS["small"]
+    inp = synth.make_inputs(wl)
+    ld = SINDy(5, wl.T, {"sindy": {"fd_type": "sbp12"}})
+    Z = ld.simulate(inp["coefs"][3, 4], inp["z0"][3], inp["t_grid"])
+    ref = g["small_Zis"][3, 4]
+    assert isinstance(Z, np.ndarray) and Z.dtype == np.float64 and Z.shape == (wl.T, 5)
+    assert np.max(np.abs(Z - ref)) <= 1e-5 * np.max(np.abs(ref))
+    Zs = ld.sample(inp["coefs"][:, 0], inp["z0"], inp["t_grid"])
+    assert Zs.shape == (wl.P, wl.T, 5)
+    assert np.max(np.abs(Zs - g["small_Zis"][:, 0])) <= 1e-5 * np.max(np.abs(g["small_Zis"]))
+
+
+def test_sindy_calibrate_return_contract(golden_dir):
+    g = np.load(os.path.join(golden_dir, "calibrate.npz"))
+    T = 65; dt = 1.0 / (T - 1)
+    Z = torch.from_numpy(synth.make_latent_series(3, T, 5, dt, seed=7))
+    ld = SINDy(5, T, {"sindy": {"fd_type": "sbp24", "coef_norm_order": 1}})
+    coefs, ls, lc = ld.calibrate(Z, dt, compute_loss=True, numpy=True)
+    assert isinstance(coefs, np.ndarray) and coefs.dtype == np.float64 and coefs.shape == (3, 30)
+    ref = g["sbp24_B3_T65_coefs"]
+    assert np.max(np.abs(coefs - ref)) <= 1e-5 * np.max(np.abs(ref))
+    np.testing.assert_allclose(ls.item(), g["sbp24_B3_T65_loss_sindy"][0], rtol=1e-4, atol=5e-11)
+    np.testing.assert_allclose(lc.item(), g["sbp24_B3_T65_loss_coef"][0], rtol=1e-5)
+    c1 = ld.calibrate(Z[1], dt, compute_loss=False, numpy=False)             # one series, torch out
+    assert isinstance(c1, torch.Tensor) and c1.dtype == torch.float32 and c1.shape == (30,)
+    np.testing.assert_array_equal(c1.numpy().astype(np.float64), coefs[1])
+    c3 = ld.calibrate(Z, dt, compute_loss=False)
+    assert isinstance(c3, torch.Tensor) and c3.shape == (3, 30)
+    dz = ld.compute_time_derivative(Z[0], dt)
+    assert dz.shape == (T, 5) and dz.device.type == "cpu"
+    # fitted coefficients reproduce the series they were fitted to when integrated
+    Zsim = ld.simulate(coefs[0], Z[0, 0].numpy(), np.arange(T) * dt)
+    assert np.max(np.abs(Zsim - Z[0].numpy())) < 5e-2 * np.max(np.abs(Z[0].numpy()))
+
+
+def test_autoencoder_decoder_is_cuda_kernel_and_matches_torch():
+    phys = Physics()
+    ae = _autoencoder(phys)
+    Z = torch.randn(4, 9, 5)
+    with torch.no_grad():
+        X = ae.decoder(Z)                                    # hot path: C-ABI glasdi_decode
+    assert X.shape == (4, 9, 301) and X.device.type == "cpu"
+    Ws = [fc.weight.detach() for fc in ae.decoder.fcs]; bs = [fc.bias.detach() for fc in ae.decoder.fcs]
+    Xr = orc.decoder_forward(Ws, bs, "sigmoid", Z)
+    assert torch.max(torch.abs(X - Xr)) <= 5e-6 * torch.max(torch.abs(Xr))
+    n0 = ae.decoder._engine.launch_count
+    with torch.no_grad():
+        ae.decoder(Z)
+    assert ae.decoder._engine.launch_count == n0 + 1         # one kernel, weights stay packed
+    with torch.no_grad():
+        ae.decoder.fcs[1].bias.add_(1.0)                     # weights changed -> repacked automatically
+        X2 = ae.decoder(Z)
+    assert torch.allclose(X2, X + 1.0, atol=1e-5)
+    Xg = ae.decoder(Z.clone().requires_grad_(True))          # autograd requested: differentiable torch ops
+    assert Xg.requires_grad
+
+
+def test_get_fom_max_std_dropin(golden_dir):
+    g = np.load(os.path.join(golden_dir, "greedy_small.npz"))
+    wl = synth.WORKLOADS["small"]
+    Ws, bs = synth.make_decoder(wl.widths, wl.seed)
+    phys = Physics(nt=wl.T, nx=wl.D)
+    ae = _autoencoder(phys)
+    sd = ae.state_dict()
+    for i, (W, b) in enumerate(zip(Ws, bs)):
+        sd[f"decoder.fcs.{i}.weight"] = torch.from_numpy(W); sd[f"decoder.fcs.{i}.bias"] = torch.from_numpy(b)
+    ae.load_state_dict(sd)
+    m = get_fom_max_std(ae, g["small_Zis"])
+    assert isinstance(m, int) and m == int(g["small_m_index"][0])
+    _, per = fom_max_std(ae, g["small_Zis"])
+    assert np.max(np.abs(per - g["small_max_std"]) - 1e-5 * g["small_max_std"]) <= 2e-6
+    with pytest.raises(RuntimeError):
+        get_fom_max_std(ae, np.repeat(g["small_Zis"][:, :1], 3, axis=1))    # zero spread everywhere
+
+
+def test_get_new_sample_point_end_to_end(tmp_path):
+    """The whole greedy step through the reference-facing trainer API, against the oracle fed with
+    the same GP draws (np.random seeded identically)."""
+    phys = Physics()
+    ps = ParamSpace()
+    ae = _autoencoder(phys)
+    ld = SINDy(5, phys.nt, {"sindy": {"fd_type": "sbp12"}})
+    cfg = {"n_samples": 20, "lr": 1e-3, "n_iter": 1, "max_iter": 1, "max_greedy_iter": 1, "ld_weight": 0.1,
+           "coef_weight": 1e-6, "path_checkpoint": str(tmp_path / "ckpt"), "path_results": str(tmp_path / "res")}
+    trainer = BayesianGLaSDI(phys, ae, ld, ps, cfg)
+    # best_coefs: calibrate encoded training trajectories (smooth synthetic series stand in for the FOM)
+    Ztrain = torch.from_numpy(synth.make_latent_series(4, phys.nt, 5, phys.dt, seed=3))
+    trainer.best_coefs = ld.calibrate(Ztrain, phys.dt, compute_loss=False, numpy=True)
+    np.random.seed(0)
+    new = trainer.get_new_sample_point()
+    assert new.shape == (1, 2)
+
+    # oracle with identical draws
+    from gplasdi_b200.gp import sample_coefs_all
+    Z0 = np.stack(initial_condition_latent(ps.test_space, phys, ae))
+    gps = fit_gps(ps.train_space, trainer.best_coefs)
+    np.random.seed(0)
+    draws = sample_coefs_all(gps, ps.test_space, 20)
+    Ws = [fc.weight.detach().cpu() for fc in ae.decoder.fcs]; bs = [fc.bias.detach().cpu() for fc in ae.decoder.fcs]
+    idx, per, _ = orc.greedy_step(Ws, bs, "sigmoid", draws, Z0, phys.t_grid)
+    assert np.array_equal(new, ps.test_space[idx].reshape(1, -1))
+    assert np.max(np.abs(trainer.last_max_std - per) - 1e-5 * per) <= 2e-6
+
+
+def test_sample_roms_and_average_rom_shapes():
+    phys = Physics(nt=33, nx=64)
+    ps = ParamSpace()
+    ae = _autoencoder(phys, hidden=(16,))
+    ld = SINDy(5, phys.nt, {"sindy": {"fd_type": "sbp12"}})
+    rs = np.random.RandomState(1)
+    gps = fit_gps(ps.train_space, rs.normal(size=(4, 30)))
+    np.random.seed(3)
+    Zis = sample_roms(ae, phys, ld, gps, ps.test_space[:5], 6)
+    assert Zis.shape == (5, 6, 33, 5) and Zis.dtype == np.float64
+    Zavg = average_rom(ae, phys, ld, gps, ps.test_space[:5])
+    assert Zavg.shape == (5, 33, 5)
+    mean, _ = eval_gp(gps, ps.test_space[:5])
+    z0 = initial_condition_latent(ps.test_space[:5], phys, ae)
+    ex = orc.simulate_exact(mean[2], z0[2], phys.dt, phys.nt)
+    assert np.max(np.abs(Zavg[2] - ex)) <= 1e-9 * max(1.0, np.max(np.abs(ex)))

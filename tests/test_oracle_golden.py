@@ -1,0 +1,103 @@
+"""Pins the CPU oracle (oracle/reference_path.py) against fixtures produced by RUNNING THE
+REFERENCE (tests/golden/gen_golden.py imports /root/reference/src/lasdi).  The reference ships
+no tests of its own, so these fixtures are the pin."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gplasdi_b200 import synth
+from oracle import reference_path as orc
+
+SCHEMES = ["sbp12", "sbp24", "sbp36", "sbp48"]
+
+
+@pytest.fixture(scope="module")
+def g_fd(golden_dir):
+    return np.load(os.path.join(golden_dir, "fd_operators.npz"))
+
+
+@pytest.mark.parametrize("name", SCHEMES)
+def test_fd_operator_bit_exact(g_fd, name):
+    for nt in (17, 33):
+        assert np.array_equal(orc.fd_operator_dense(nt, name), g_fd[f"{name}_{nt}"])
+    D = orc.fd_operator_dense(1001, name)
+    assert np.array_equal(D[:12, :24], g_fd[f"{name}_1001_head"])
+    assert np.array_equal(D[-12:, -24:], g_fd[f"{name}_1001_tail"])
+    assert np.array_equal(D[500, 490:511], g_fd[f"{name}_1001_mid"])
+    # survey probe: nnz 2002 / 4000 / 6008 / 8014 (stored zeros of the boundary rows included upstream)
+    assert np.count_nonzero(D) <= int(g_fd[f"{name}_1001_nnz"][0])
+
+
+@pytest.mark.parametrize("name", SCHEMES)
+@pytest.mark.parametrize("case", [(3, 65, 1), (2, 1001, "fro")])
+def test_calibrate_matches_reference(golden_dir, name, case):
+    B, T, order = case
+    g = np.load(os.path.join(golden_dir, "calibrate.npz"))
+    dt = 1.0 / (T - 1)
+    Z = torch.from_numpy(synth.make_latent_series(B, T, 5, dt, seed=7))
+    key = f"{name}_B{B}_T{T}"
+    dz = orc.compute_time_derivative(Z[0], dt, name).numpy()
+    assert np.array_equal(dz, g[key + "_dzdt0"])
+    coefs, ls, lc = orc.calibrate(Z, dt, name, order)
+    assert coefs.dtype == np.float64 and coefs.shape == (B, 30)
+    # LAPACK gelsy in fp32 is not bit-reproducible across thread counts: compare to fp32 accuracy
+    scale = np.max(np.abs(g[key + "_coefs"]))
+    assert np.max(np.abs(coefs - g[key + "_coefs"])) <= 3e-6 * scale
+    # losses ~1e-9 are fp32 rounding noise of dZdt (|dZdt| ~ 30): absolute floor
+    np.testing.assert_allclose(ls, g[key + "_loss_sindy"][0], rtol=1e-4, atol=5e-11)
+    np.testing.assert_allclose(lc, g[key + "_loss_coef"][0], rtol=1e-6)
+
+
+@pytest.mark.parametrize("nm", ["tiny", "small", "small_s200", "small_softplus"])
+def test_greedy_small_matches_reference(golden_dir, nm):
+    g = np.load(os.path.join(golden_dir, "greedy_small.npz"))
+    wl = synth.WORKLOADS[nm]
+    Ws, bs = synth.make_decoder(wl.widths, wl.seed)
+    inp = synth.make_inputs(wl)
+    Zref = g[nm + "_Zis"]
+    # rollouts: identical odeint call sequence -> bit-exact (check a subset to keep the suite short)
+    for p, s in [(0, 0), (wl.P - 1, wl.S - 1), (1, 3)]:
+        assert np.array_equal(orc.simulate(inp["coefs"][p, s], inp["z0"][p], inp["t_grid"]), Zref[p, s])
+    idx, per_param = orc.fom_max_std(Ws, bs, wl.act, Zref)
+    assert idx == int(g[nm + "_m_index"][0])
+    np.testing.assert_array_equal(per_param, g[nm + "_max_std"])
+    # time-chunked evaluation (used for shapes that exceed host RAM) is exact
+    idx2, per2 = orc.fom_max_std(Ws, bs, wl.act, Zref, t_chunk=7)
+    assert idx2 == idx
+    np.testing.assert_allclose(per2, per_param, rtol=2e-6, atol=1e-7)
+
+
+def test_exact_propagator_agrees_with_lsoda(golden_dir):
+    g = np.load(os.path.join(golden_dir, "greedy_small.npz"))
+    wl = synth.WORKLOADS["small"]
+    inp = synth.make_inputs(wl)
+    Zref = g["small_Zis"]
+    worst = 0.0
+    for p, s in [(0, 0), (5, 7), (11, 19)]:
+        ex = orc.simulate_exact(inp["coefs"][p, s], inp["z0"][p], wl.dt, wl.T)
+        worst = max(worst, np.max(np.abs(ex - Zref[p, s])) / np.max(np.abs(Zref[p, s])))
+    assert worst < 2e-6   # LSODA's own tolerance (rtol = atol ~ 1.5e-8, accumulated)
+
+
+def test_burgers1d_shipped_subset(golden_dir):
+    """Config #1 (examples/burgers1d.yml shapes): oracle on a handful of parameters vs the reference run."""
+    g = np.load(os.path.join(golden_dir, "greedy_burgers1d_shipped.npz"))
+    wl = synth.WORKLOADS["burgers1d_shipped"]
+    Ws, bs = synth.make_decoder(wl.widths, wl.seed)
+    m_ref = int(g["burgers1d_shipped_m_index"][0])
+    assert int(np.argmax(g["burgers1d_shipped_max_std"])) == m_ref
+    sel = [m_ref, 5]
+    for p in sel:
+        inp = synth.make_inputs(wl, slice(p, p + 1))
+        Zis = orc.rollout_ensemble(inp["coefs"], inp["z0"], inp["t_grid"])
+        _, per = orc.fom_max_std(Ws, bs, wl.act, Zis)
+        np.testing.assert_allclose(per[0], g["burgers1d_shipped_max_std"][p], rtol=1e-6)
+
+
+def test_vectorised_draws_consume_rng_like_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "gp_sampling.npz"))
+    np.random.seed(int(g["seed"][0]))
+    got = np.stack([orc.sample_coefs_from_moments(g["mean"][i], g["std"][i], 6) for i in range(3)])
+    assert np.array_equal(got, g["samples"])   # same MT19937 stream, same order, same values
