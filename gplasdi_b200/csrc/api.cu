@@ -136,6 +136,10 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
     case GLASDI_OPT_STAGE_TIMING:
       h->opt_timing = value ? 1 : 0;
       return GLASDI_OK;
+    case GLASDI_OPT_DECODE_KERNEL:
+      if (value != 0 && value != 1) return set_error(h, GLASDI_ERR_INVALID, "decode kernel variant must be 0 or 1");
+      h->opt_kernel = value;
+      return GLASDI_OK;
     default: return set_error(h, GLASDI_ERR_INVALID, "unknown option");
   }
 }
@@ -148,6 +152,7 @@ int glasdi_get_option(const glasdi_handle* h, int option, int* value) {
     case GLASDI_OPT_RK4_SUBSTEPS: *value = h->opt_substeps; return GLASDI_OK;
     case GLASDI_OPT_MAX_CTAS: *value = h->opt_max_ctas; return GLASDI_OK;
     case GLASDI_OPT_STAGE_TIMING: *value = h->opt_timing; return GLASDI_OK;
+    case GLASDI_OPT_DECODE_KERNEL: *value = h->opt_kernel; return GLASDI_OK;
     default: return GLASDI_ERR_INVALID;
   }
 }
@@ -199,7 +204,8 @@ int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths, const 
   d.eH = bounded_act(act_id) ? 12 : 4;
   if (ok) {
     const size_t part_halfs = (size_t)d.Kpad * 128;     // [kg][128 rows][8]
-    std::vector<__half> packed((size_t)d.n_tiles * 2 * part_halfs);
+    const int n_tiles_pad = (d.n_tiles + 1) / 2 * 2;   // CTA-pair kernel consumes tiles two at a time
+    std::vector<__half> packed((size_t)n_tiles_pad * 2 * part_halfs, __float2half_rn(0.f));
     for (int tile = 0; tile < d.n_tiles; ++tile) {
       __half* hi = packed.data() + ((size_t)tile * 2 + 0) * part_halfs;
       __half* lo = packed.data() + ((size_t)tile * 2 + 1) * part_halfs;
@@ -295,7 +301,8 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
     if (rc) return rc;
     if ((rc = t_roll.stop())) return rc;
     if ((rc = t_dec.start())) return rc;
-    if (d.tc_ok) rc = launch_decode_var(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
+    if (d.tc_ok && h->opt_kernel == 1) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
+    else if (d.tc_ok) rc = launch_decode_var(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
     else rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
     if (rc) return rc;
     if ((rc = t_dec.stop())) return rc;
@@ -325,6 +332,7 @@ int glasdi_decode(glasdi_handle* h, const float* Z, int64_t rows, float* X_out, 
   if (rows < 0 || (rows > 0 && (!Z || !X_out))) return set_error(h, GLASDI_ERR_INVALID, "decode: bad arguments");
   if (rows == 0) return GLASDI_OK;
   GL_CUDA(h, cudaSetDevice(h->device));
+  if (h->dec.tc_ok && h->opt_kernel == 1) return launch_decode_store_pair(h, Z, rows, X_out, (cudaStream_t)stream);
   if (h->dec.tc_ok) return launch_decode_store(h, Z, rows, X_out, (cudaStream_t)stream);
   return launch_decode_store_simt(h, Z, rows, X_out, (cudaStream_t)stream);
 }

@@ -53,6 +53,7 @@ struct glasdi_handle {
   int opt_substeps = 1;
   int opt_max_ctas = 0;
   int opt_timing = 0;
+  int opt_kernel = 1;                 // 0: one CTA per SM (decode_var.cu), 1: CTA pairs (decode_var2.cu)
   int64_t launches = 0;
   // stage timing (GLASDI_OPT_STAGE_TIMING): event pairs of the last greedy call
   std::vector<cudaEvent_t> ev_pool;
@@ -91,6 +92,10 @@ int launch_decode_var(glasdi_handle* h, const float* Zs, int Spad, int P, int S,
                       unsigned int* maxvar_bits, cudaStream_t st);
 int launch_decode_store(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
 size_t decode_var_smem_bytes(int Kpad, int last_in_w);
+// decode_var2.cu : CTA-pair (cta_group::2) variant of the same kernel
+int launch_decode_var_pair(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
+                           unsigned int* maxvar_bits, cudaStream_t st);
+int launch_decode_store_pair(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
 // simt_fallback.cu : fp32 CUDA-core path for decoder shapes the tcgen05 kernel does not cover
 int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
                            unsigned int* maxvar_bits, cudaStream_t st);
@@ -124,9 +129,43 @@ __device__ __forceinline__ float act_apply(int act, float x) {
   }
 }
 
+// Compile-time activation for the hot producers.  ACT < 0 selects the runtime switch above.
+// sigmoid / softplus / SiLU use the MUFU ex2/rcp/lg2 units (max rel. error ~2^-21, i.e. ~4 fp32 ulp:
+// far inside the 1e-5 parity budget); everything else is the accurate libdevice form.
 template <int ACT>
-__device__ __forceinline__ float act_apply_t(float x) {
-  return act_apply(ACT, x);
+__device__ __forceinline__ float act_apply_t(int act_rt, float x) {
+  if constexpr (ACT == GLASDI_ACT_SIGMOID) {
+    return __fdividef(1.0f, 1.0f + __expf(-x));
+  } else if constexpr (ACT == GLASDI_ACT_SOFTPLUS) {
+    return x > 20.0f ? x : __logf(1.0f + __expf(x));
+  } else if constexpr (ACT == GLASDI_ACT_SILU) {
+    return __fdividef(x, 1.0f + __expf(-x));
+  } else if constexpr (ACT >= 0) {
+    return act_apply(ACT, x);
+  } else {
+    return act_apply(act_rt, x);
+  }
+}
+
+// packed fp32 pairs (Blackwell FFMA2 / FADD2): one instruction for two lanes of the epilogue sums
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b,
+                                                        unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -151,10 +190,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in HW, wake on phase flip
       : "memory");
   return ok != 0;
 }
@@ -248,6 +287,89 @@ __device__ __forceinline__ uint32_t umma_idesc_f16_m128(uint32_t n) {
   // a_format = b_format = 0 (F16); no negate; a_major = b_major = 0 (K-major)
   d |= (n >> 3) << 17;       // n_dim
   d |= (128u >> 4) << 24;    // m_dim
+  return d;
+}
+
+// ---- thread-block clusters / CTA pairs (cta_group::2) -----------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctaid_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// arrive (release at cluster scope) on an mbarrier given by its shared::cluster address (may be remote)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait_cluster(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit all prior MMAs of this thread; arrive on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_2cta(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// CTA-pair MMA: D[tmem, 256 x N split 128 rows per CTA] (+)= A[256 x 16] * B[N x 16]^T, issued by the
+// leader CTA; each CTA supplies its own 128 rows of A and N/2 rows of B from its shared memory.
+__device__ __forceinline__ void tc_mma_f16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 instruction descriptor for the pair: M = 256, N = n
+__device__ __forceinline__ uint32_t umma_idesc_f16_m256(uint32_t n) {
+  uint32_t d = 0;
+  d |= 1u << 4;              // c_format = F32
+  d |= (n >> 3) << 17;       // n_dim
+  d |= (256u >> 4) << 24;    // m_dim
   return d;
 }
 

@@ -1,0 +1,128 @@
+// decode_common.cuh -- pieces shared by the two tcgen05 decode kernels (decode_var.cu: one CTA per SM,
+// decode_var2.cu: CTA pairs with cta_group::2): parameters, shared-memory carve-up, front-MLP producers.
+#pragma once
+#include "common.cuh"
+
+namespace glasdi {
+namespace dv {
+
+constexpr int kTileM = 128;       // DOFs per MMA tile (TMEM lanes)
+constexpr int kChunkN = 128;      // columns (samples or time-step x sample) per chunk
+constexpr int kNtMax = 8;         // DOF tiles per group (accumulator slots per epilogue thread)
+constexpr int kWSlots = 3;        // ring of W part-tiles (hi or lo) in shared memory
+constexpr int kMaxSeg = 16;       // max time steps packed in one chunk when S < kChunkN
+constexpr int kMaxHid = 64;       // max width of intermediate front layers
+constexpr int kEpiWarps = 4;
+constexpr int kLoaderWarp = 4;
+constexpr int kMmaWarp = 5;
+constexpr int kProdWarp0 = 6;
+constexpr int kProdWarps = 8;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;   // 448
+constexpr int kTmemCols = 256;    // 2 accumulators x 128 fp32 columns
+constexpr uint32_t kLBO = kChunkN * 16;   // bytes between the two K halves (k-groups of 8 halfs)
+constexpr uint32_t kSBO = 128;            // bytes between 8-row groups
+
+enum Epi { kVarT1 = 0, kVarSeg = 1, kStore = 2 };
+
+struct Params {
+  // VAR geometry
+  int P, S, T, Spad;
+  int TPC, n_tg, n_chunks;
+  float inv_S;
+  const float* Zs;                  // [P][T][NZ][Spad]
+  unsigned int* maxvar_bits;        // [P]
+  // STORE
+  const float* Zrows;               // [rows][NZ]
+  long long rows;
+  float* X;                         // [rows][D]
+  const float* b_last;              // [D]
+  float out_scale;                  // 2^-(eW+eH)
+  // common
+  int NZ, D, K, Kpad, n_tiles, n_groups, passes;
+  long long n_items;
+  float h_scale;                    // 2^eH
+  int check_overflow;               // unbounded activation: watch the fp16 split range
+  const __half* w_packed;
+  int* flags;
+  FrontMlp front;
+};
+
+struct Smem {
+  uint32_t w, h, wl, pilot, acc, bars, tmem, total;
+  int wl_ld;
+};
+
+// row stride (floats) of the staged last-front-layer weights: [w_0 .. w_{inw-1}, bias, 0-pad] -> 16-byte rows
+__host__ __device__ inline int wl_stride(int last_in_w) { return (last_in_w + 1 + 3) & ~3; }
+
+__host__ __device__ inline Smem carve(int Kpad, int last_in_w) {
+  Smem s;
+  const uint32_t part = (uint32_t)Kpad * 256u;          // one 128-row x Kpad fp16 operand tile
+  uint32_t off = 0;
+  s.w = off; off += kWSlots * part;
+  s.h = off; off += 2 * 2 * part;                      // 2 buffers x (hi, lo)
+  s.wl_ld = wl_stride(last_in_w);
+  s.wl = off; off += (uint32_t)Kpad * (uint32_t)s.wl_ld * 4u;
+  s.pilot = off; off += kMaxSeg * (uint32_t)Kpad * 4u;
+  s.acc = off; off += kNtMax * 2 * 128 * 4u;           // per-thread (sum, sumsq) for 8 tiles
+  s.bars = off; off += 32 * 8;
+  s.tmem = off; off += 16;
+  s.total = off;
+  return s;
+}
+
+// ---- front MLP -------------------------------------------------------------------------------
+// layers 0 .. n_front-2 (small), fp32, weights via the read-only path; result = input of the last
+// front layer.  For a single front layer this is the identity on z.
+template <int ACT>
+__device__ __forceinline__ void front_pre(const FrontMlp& f, const float* zin, float* out) {
+  int w = f.widths[0];
+  for (int i = 0; i < w; ++i) out[i] = zin[i];
+  float tmp[kMaxHid];
+  for (int l = 0; l + 1 < f.n_front; ++l) {
+    const int wo = f.widths[l + 1];
+    const float* __restrict__ W = f.W[l];
+    const float* __restrict__ b = f.b[l];
+    for (int o = 0; o < wo; ++o) {
+      float acc = __ldg(b + o);
+      for (int i = 0; i < w; ++i) acc = fmaf(__ldg(W + (size_t)o * w + i), out[i], acc);
+      tmp[o] = act_apply_t<ACT>(f.act, acc);
+    }
+    for (int o = 0; o < wo; ++o) out[o] = tmp[o];
+    w = wo;
+  }
+}
+
+// 8 consecutive units k0..k0+7 of the last front layer.  Weights come from shared memory rows
+// [w_0..w_{inw-1}, bias, 0...] read as 16-byte vectors (warp-uniform address -> one broadcast
+// wavefront each).  Rows k >= K are all zero, so padded units evaluate to act(0) for every column
+// AND for the pilot: their difference is exactly 0 and needs no predicate.
+template <int ACT, int INW>
+__device__ __forceinline__ void last_front_units(const float* __restrict__ wl, int ld, int inw_rt, int act_rt,
+                                                 int k0, const float* x, float (&hv)[8]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float4* wr = reinterpret_cast<const float4*>(wl + (k0 + u) * ld);
+    float acc;
+    if constexpr (INW == 5) {
+      const float4 a = wr[0], b = wr[1];
+      acc = b.y;
+      acc = fmaf(a.x, x[0], acc);
+      acc = fmaf(a.y, x[1], acc);
+      acc = fmaf(a.z, x[2], acc);
+      acc = fmaf(a.w, x[3], acc);
+      acc = fmaf(b.x, x[4], acc);
+    } else {
+      const float* wf = wl + (k0 + u) * ld;
+      acc = wf[inw_rt];
+      for (int i = 0; i < inw_rt; ++i) acc = fmaf(wf[i], x[i], acc);
+    }
+    hv[u] = act_apply_t<ACT>(act_rt, acc);
+  }
+}
+
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+}  // namespace dv
+}  // namespace glasdi

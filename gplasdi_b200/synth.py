@@ -54,9 +54,9 @@ WORKLOADS = {
     "small_s200": Workload("small_s200", (3, 2), 200, 21, [5, 100, 1001], "sigmoid", 1.0 / 20),
     "small_softplus": Workload("small_softplus", (3, 2), 40, 17, [5, 20, 20, 100, 260], "softplus", 1.0 / 16),
     # ragged shapes: 2 DOF-tile groups (D > 1024), 2 sample chunks with a ragged tail, K not a multiple of 16
-    "ragged": Workload("ragged", (2, 2), 130, 9, [5, 24, 1300], "tanh", 1.0 / 8),
+    "ragged": Workload("ragged", (3, 2), 130, 9, [5, 24, 1300], "tanh", 1.0 / 8),
     # decoder the fused tcgen05 kernel does not cover (K_last > 112) -> CUDA-core path
-    "wide_k": Workload("wide_k", (2, 2), 24, 7, [5, 16, 160, 200], "softplus", 1.0 / 6),
+    "wide_k": Workload("wide_k", (3, 2), 24, 7, [5, 16, 160, 200], "softplus", 1.0 / 6),
 }
 
 

@@ -60,6 +60,8 @@ enum glasdi_option {
   GLASDI_OPT_INTEGRATOR = 1,    /* enum glasdi_integrator (default EXPM) */
   GLASDI_OPT_RK4_SUBSTEPS = 2,  /* default 1 */
   GLASDI_OPT_MAX_CTAS = 3,      /* cap on persistent CTAs (0 = one per SM); for tests */
+  GLASDI_OPT_DECODE_KERNEL = 5, /* 1 (default): CTA-pair tcgen05 kernel (cta_group::2, 256x256 tiles);
+                                   0: single-CTA kernel (128x128 tiles).  Same numerics. */
   GLASDI_OPT_STAGE_TIMING = 4   /* 1: bracket the rollout and decode kernels of the greedy step with
                                    CUDA events on the caller's stream (read with glasdi_stage_times) */
 };

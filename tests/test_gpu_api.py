@@ -123,7 +123,7 @@ def test_get_fom_max_std_dropin(golden_dir):
     m = get_fom_max_std(ae, g["small_Zis"])
     assert isinstance(m, int) and m == int(g["small_m_index"][0])
     _, per = fom_max_std(ae, g["small_Zis"])
-    assert np.max(np.abs(per - g["small_max_std"]) - 1e-5 * g["small_max_std"]) <= 2e-6
+    assert np.max(np.abs(per - g["small_max_std"]) - 1e-5 * g["small_max_std"]) <= 5e-6
     with pytest.raises(RuntimeError):
         get_fom_max_std(ae, np.repeat(g["small_Zis"][:, :1], 3, axis=1))    # zero spread everywhere
 
@@ -154,7 +154,7 @@ def test_get_new_sample_point_end_to_end(tmp_path):
     Ws = [fc.weight.detach().cpu() for fc in ae.decoder.fcs]; bs = [fc.bias.detach().cpu() for fc in ae.decoder.fcs]
     idx, per, _ = orc.greedy_step(Ws, bs, "sigmoid", draws, Z0, phys.t_grid)
     assert np.array_equal(new, ps.test_space[idx].reshape(1, -1))
-    assert np.max(np.abs(trainer.last_max_std - per) - 1e-5 * per) <= 2e-6
+    assert np.max(np.abs(trainer.last_max_std - per) - 1e-5 * per) <= 5e-6
 
 
 def test_sample_roms_and_average_rom_shapes():
