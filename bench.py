@@ -288,14 +288,18 @@ def run_ours(args):
                        "l2": "256 MB buffer written between timed iterations; per-step working set 4.6 GB >> 126 MB L2",
                        "selected_global_index": sel_idx},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["sustained"], "traffic": traffic, "kernel": "glasdi::dv::decode_kernel<5>",
+                         "frac": achieved / pk["sustained"], "traffic": traffic,
+                         "kernel": "glasdi::dv2::decode_pair_kernel<VarT1, sigmoid, 5> (tcgen05 cta_group::2)",
+                         "issued_frac": flops_launch * args.passes * 1.12 * 1024.0 / 1001.0 * 1024.0 / 1000.0
+                                        / (dec_avg_ms * 1e-3) / 1e12 / pk["sustained"],
                          "kernel_ms": dec_avg_ms, "rollout_kernel_ms": float(np.mean(roll_ms)),
                          "algorithmic_flop_per_launch": flops_launch,
-                         "issued_flop_per_launch": flops_launch * args.passes * 112.0 / 100.0 * 1024.0 / 1001.0,
+                         "issued_flop_per_launch": flops_launch * args.passes * 1.12 * 1024.0 / 1001.0 * 1024.0 / 1000.0,
                          "peak_source": pk["source"] + " bf16 dense, sustained figure (kernel timed inside a long step); "
                                         "fp16 and bf16 share the tcgen05 kind::f16 rate",
                          "note": "frac is on ALGORITHMIC decoder FLOP (single pass); the kernel issues "
-                                 f"{args.passes} fp16 split passes per product to stay fp32-faithful"},
+                                 f"{args.passes} fp16 split passes per product to stay fp32-faithful and pads K 100->112, "
+                                 "D 1001->1024, S 1000->1024: issued_frac is the tensor-pipe view of the same launch"},
             "e2e": {"value": rollouts_per_step * args.steps / e2e_total, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),

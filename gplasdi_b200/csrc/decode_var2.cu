@@ -155,14 +155,19 @@ decode_pair_kernel(const __grid_constant__ Params P) {
         uint32_t w_it = 0, h_it = 0, a_it = 0;
         const int nk16 = P.Kpad / 16;
         const uint32_t idesc = umma_idesc_f16_m256((uint32_t)kPairN);
+        constexpr int kDescStep = (2 * kLBO) >> 4;
+        const uint64_t wdesc0 = umma_desc_kmajor(smem_u32(sW), kLBO, kSBO);
+        const uint32_t wslot_step = part_bytes >> 4;          // start-address units (16 B) between ring slots
         for (long long item = pair; item < P.n_items; item += n_pairs) {
           const Item it = decode_item<EPI>(P, item);
           for (int c = 0; c < nchunks; ++c) {
             const uint32_t hb = h_it & 1u;
             mbar_wait_cluster(&B->h_full[hb], (h_it >> 1) & 1u);
             tc_fence_after();
-            const uint32_t hhi = smem_u32(sH + (hb * 2 + 0) * part_bytes);
-            const uint32_t hlo = smem_u32(sH + (hb * 2 + 1) * part_bytes);
+            // descriptors differ only in the 14-bit start-address field: build once, then add k * 256
+            // (= 2 k-groups * kLBO bytes >> 4) per K=16 slice -> ~3 instructions per MMA on the issuing thread
+            const uint64_t bhi0 = umma_desc_kmajor(smem_u32(sH + (hb * 2 + 0) * part_bytes), kLBO, kSBO);
+            const uint64_t blo0 = umma_desc_kmajor(smem_u32(sH + (hb * 2 + 1) * part_bytes), kLBO, kSBO);
             for (int j = 0; j < it.nsteps; ++j) {
               const uint32_t ab = a_it & 1u;
               mbar_wait_cluster(&B->acc_empty[ab], ((a_it >> 1) & 1u) ^ 1u);
@@ -172,14 +177,16 @@ decode_pair_kernel(const __grid_constant__ Params P) {
               mbar_wait(&B->w_full[slot], (w_it / kWSlots) & 1u);
               mbar_wait_cluster(&B->w_peer[slot], (w_it / kWSlots) & 1u);
               tc_fence_after();
-              uint32_t wa = smem_u32(sW + slot * part_bytes);
+              uint64_t a0 = wdesc0 + (uint64_t)(slot * wslot_step);
+#pragma unroll 1
               for (int k = 0; k < nk16; ++k)
-                tc_mma_f16_2cta(d_tmem, umma_desc_kmajor(wa + k * 2 * kLBO, kLBO, kSBO),
-                                umma_desc_kmajor(hhi + k * 2 * kLBO, kLBO, kSBO), idesc, k > 0 ? 1u : 0u);
-              if (P.passes >= 3)
+                tc_mma_f16_2cta(d_tmem, a0 + (uint64_t)(k * kDescStep), bhi0 + (uint64_t)(k * kDescStep), idesc,
+                                k > 0 ? 1u : 0u);
+              if (P.passes >= 3) {
+#pragma unroll 1
                 for (int k = 0; k < nk16; ++k)
-                  tc_mma_f16_2cta(d_tmem, umma_desc_kmajor(wa + k * 2 * kLBO, kLBO, kSBO),
-                                  umma_desc_kmajor(hlo + k * 2 * kLBO, kLBO, kSBO), idesc, 1u);
+                  tc_mma_f16_2cta(d_tmem, a0 + (uint64_t)(k * kDescStep), blo0 + (uint64_t)(k * kDescStep), idesc, 1u);
+              }
               tc_commit_2cta(&B->w_empty[slot], 3);
               ++w_it;
               if (P.passes >= 2) {
@@ -187,10 +194,10 @@ decode_pair_kernel(const __grid_constant__ Params P) {
                 mbar_wait(&B->w_full[slot], (w_it / kWSlots) & 1u);
                 mbar_wait_cluster(&B->w_peer[slot], (w_it / kWSlots) & 1u);
                 tc_fence_after();
-                wa = smem_u32(sW + slot * part_bytes);
+                a0 = wdesc0 + (uint64_t)(slot * wslot_step);
+#pragma unroll 1
                 for (int k = 0; k < nk16; ++k)
-                  tc_mma_f16_2cta(d_tmem, umma_desc_kmajor(wa + k * 2 * kLBO, kLBO, kSBO),
-                                  umma_desc_kmajor(hhi + k * 2 * kLBO, kLBO, kSBO), idesc, 1u);
+                  tc_mma_f16_2cta(d_tmem, a0 + (uint64_t)(k * kDescStep), bhi0 + (uint64_t)(k * kDescStep), idesc, 1u);
                 tc_commit_2cta(&B->w_empty[slot], 3);
                 ++w_it;
               }
