@@ -201,6 +201,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// waiters that run far ahead of the tensor pipe (producers, epilogue, loader, relay): back off instead
+// of polling -- 2.1e9 polling retries per launch showed up in the first profiles and cost power
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -371,6 +376,13 @@ __device__ __forceinline__ uint32_t umma_idesc_f16_m256(uint32_t n) {
   d |= (n >> 3) << 17;       // n_dim
   d |= (256u >> 4) << 24;    // m_dim
   return d;
+}
+
+// one lane of a fully converged warp (warp-uniform control flow keeps MMA operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
           for (int m = 0; m < it.nt; ++m) {
             for (int part = 0; part < nparts; ++part) {
               const uint32_t slot = w_it % kWSlots;
-              mbar_wait(&w_empty[slot], ((w_it / kWSlots) & 1u) ^ 1u);
+              mbar_wait_relaxed(&w_empty[slot], ((w_it / kWSlots) & 1u) ^ 1u);
               mbar_arrive_expect_tx(&w_full[slot], part_bytes);
               const uint8_t* src = reinterpret_cast<const uint8_t*>(P.w_packed) +
                                    ((size_t)(it.tile0 + m) * 2 + part) * part_bytes;
@@ -151,10 +151,15 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
     }
     __syncwarp();
   } else if (warp == kMmaWarp) {
-    // ---- MMA issuer: one thread -----------------------------------------------------------------
-    if (lane == 0) {
+    // ---- MMA issuer: the whole warp walks the loop (warp-uniform control flow keeps the descriptors in
+    // uniform registers); one elected lane issues each tcgen05.mma / commit -------------------------
+    {
       uint32_t w_it = 0, h_it = 0, a_it = 0;
       const int nk16 = P.Kpad / 16;
+      constexpr uint32_t kDescStep = (2 * kLBO) >> 4;
+      const uint64_t wdesc0 = umma_desc_kmajor(smem_u32(sW), kLBO, kSBO);
+      const uint64_t hdesc0 = umma_desc_kmajor(smem_u32(sH), kLBO, kSBO);
+      const uint32_t slot_step = part_bytes >> 4;
       for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const Item it = decode_item<EPI>(P, item);
         for (int c = 0; c < nchunks; ++c) {
@@ -162,42 +167,50 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
           const uint32_t hb = h_it & 1u;
           mbar_wait(&h_full[hb], (h_it >> 1) & 1u);
           tc_fence_after();
-          const uint32_t hhi = smem_u32(sH + (hb * 2 + 0) * part_bytes);
-          const uint32_t hlo = smem_u32(sH + (hb * 2 + 1) * part_bytes);
+          const uint64_t bhi0 = hdesc0 + (uint64_t)((hb * 2 + 0) * slot_step);
+          const uint64_t blo0 = hdesc0 + (uint64_t)((hb * 2 + 1) * slot_step);
           for (int m = 0; m < it.nt; ++m) {
             const uint32_t ab = a_it & 1u;
             mbar_wait(&acc_empty[ab], ((a_it >> 1) & 1u) ^ 1u);
-            tc_fence_after();
             const uint32_t d_tmem = tmem_base + ab * (uint32_t)kChunkN;
-            // W hi part
             uint32_t slot = w_it % kWSlots;
             mbar_wait(&w_full[slot], (w_it / kWSlots) & 1u);
             tc_fence_after();
-            uint32_t wa = smem_u32(sW + slot * part_bytes);
-            for (int k = 0; k < nk16; ++k)
-              tc_mma_f16(d_tmem, umma_desc_kmajor(wa + k * 2 * kLBO, kLBO, kSBO),
-                         umma_desc_kmajor(hhi + k * 2 * kLBO, kLBO, kSBO), idesc, k > 0 ? 1u : 0u);
-            if (P.passes >= 3)
+            uint64_t a0 = wdesc0 + (uint64_t)(slot * slot_step);
+            if (elect_one()) {
+#pragma unroll 1
               for (int k = 0; k < nk16; ++k)
-                tc_mma_f16(d_tmem, umma_desc_kmajor(wa + k * 2 * kLBO, kLBO, kSBO),
-                           umma_desc_kmajor(hlo + k * 2 * kLBO, kLBO, kSBO), idesc, 1u);
-            tc_commit(&w_empty[slot]);
+                tc_mma_f16(d_tmem, a0 + (uint64_t)(k * kDescStep), bhi0 + (uint64_t)(k * kDescStep), idesc,
+                           k > 0 ? 1u : 0u);
+              if (P.passes >= 3) {
+#pragma unroll 1
+                for (int k = 0; k < nk16; ++k)
+                  tc_mma_f16(d_tmem, a0 + (uint64_t)(k * kDescStep), blo0 + (uint64_t)(k * kDescStep), idesc, 1u);
+              }
+              tc_commit(&w_empty[slot]);
+            }
+            __syncwarp();
             ++w_it;
             if (P.passes >= 2) {
               slot = w_it % kWSlots;
               mbar_wait(&w_full[slot], (w_it / kWSlots) & 1u);
               tc_fence_after();
-              wa = smem_u32(sW + slot * part_bytes);
-              for (int k = 0; k < nk16; ++k)
-                tc_mma_f16(d_tmem, umma_desc_kmajor(wa + k * 2 * kLBO, kLBO, kSBO),
-                           umma_desc_kmajor(hhi + k * 2 * kLBO, kLBO, kSBO), idesc, 1u);
-              tc_commit(&w_empty[slot]);
+              a0 = wdesc0 + (uint64_t)(slot * slot_step);
+              if (elect_one()) {
+#pragma unroll 1
+                for (int k = 0; k < nk16; ++k)
+                  tc_mma_f16(d_tmem, a0 + (uint64_t)(k * kDescStep), bhi0 + (uint64_t)(k * kDescStep), idesc, 1u);
+                tc_commit(&w_empty[slot]);
+              }
+              __syncwarp();
               ++w_it;
             }
-            tc_commit(&acc_full[ab]);
+            if (elect_one()) tc_commit(&acc_full[ab]);
+            __syncwarp();
             ++a_it;
           }
-          tc_commit(&h_empty[hb]);
+          if (elect_one()) tc_commit(&h_empty[hb]);
+          __syncwarp();
           ++h_it;
         }
       }
@@ -293,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
         if (c + 1 < nchunks) load_z(it, c + 1, znext, seg_next, valid_next);
 
         // ---- wait until the MMA warp has drained this H buffer --------------------------------
-        mbar_wait(&h_empty[hb], ((h_it >> 1) & 1u) ^ 1u);
+        mbar_wait_relaxed(&h_empty[hb], ((h_it >> 1) & 1u) ^ 1u);
 
         const float* pil = sPilot + seg * P.Kpad;
         for (int kg = kg_begin; kg < kg_end; ++kg) {
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
         const int nmma = mma_n(ncols);
         for (int m = 0; m < it.nt; ++m) {
           const uint32_t ab = a_it & 1u;
-          mbar_wait(&acc_full[ab], (a_it >> 1) & 1u);
+          mbar_wait_relaxed(&acc_full[ab], (a_it >> 1) & 1u);
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + ab * (uint32_t)kChunkN;
           if constexpr (EPI == kVarT1) {

@@ -137,7 +137,7 @@ decode_pair_kernel(const __grid_constant__ Params P) {
             const int tile = it.tile0 + 2 * j + (int)rank;        // < n_tiles rounded up to even (zero padded)
             for (int part = 0; part < nparts; ++part) {
               const uint32_t slot = w_it % kWSlots;
-              mbar_wait(&B->w_empty[slot], ((w_it / kWSlots) & 1u) ^ 1u);
+              mbar_wait_relaxed(&B->w_empty[slot], ((w_it / kWSlots) & 1u) ^ 1u);
               mbar_arrive_expect_tx(&B->w_full[slot], part_bytes);
               const uint8_t* src = reinterpret_cast<const uint8_t*>(P.w_packed) + ((size_t)tile * 2 + part) * part_bytes;
               bulk_g2s(sW + slot * part_bytes, src, part_bytes, &B->w_full[slot]);
@@ -149,35 +149,34 @@ decode_pair_kernel(const __grid_constant__ Params P) {
     }
     __syncwarp();
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
-      if (leader) {
-        // ---- MMA issuer for the pair -------------------------------------------------------------
-        uint32_t w_it = 0, h_it = 0, a_it = 0;
-        const int nk16 = P.Kpad / 16;
-        const uint32_t idesc = umma_idesc_f16_m256((uint32_t)kPairN);
-        constexpr int kDescStep = (2 * kLBO) >> 4;
-        const uint64_t wdesc0 = umma_desc_kmajor(smem_u32(sW), kLBO, kSBO);
-        const uint32_t wslot_step = part_bytes >> 4;          // start-address units (16 B) between ring slots
-        for (long long item = pair; item < P.n_items; item += n_pairs) {
-          const Item it = decode_item<EPI>(P, item);
-          for (int c = 0; c < nchunks; ++c) {
-            const uint32_t hb = h_it & 1u;
-            mbar_wait_cluster(&B->h_full[hb], (h_it >> 1) & 1u);
+    if (leader) {
+      // ---- MMA issuer for the pair.  The WHOLE warp walks the loop (warp-uniform control flow, so the
+      // descriptors stay in uniform registers); one elected lane issues each tcgen05.mma / commit. ----
+      uint32_t w_it = 0, h_it = 0, a_it = 0;
+      const int nk16 = P.Kpad / 16;
+      const uint32_t idesc = umma_idesc_f16_m256((uint32_t)kPairN);
+      constexpr uint32_t kDescStep = (2 * kLBO) >> 4;      // start-address units (16 B) per K=16 slice
+      const uint64_t wdesc0 = umma_desc_kmajor(smem_u32(sW), kLBO, kSBO);
+      const uint32_t wslot_step = part_bytes >> 4;
+      const uint64_t hdesc0 = umma_desc_kmajor(smem_u32(sH), kLBO, kSBO);
+      for (long long item = pair; item < P.n_items; item += n_pairs) {
+        const Item it = decode_item<EPI>(P, item);
+        for (int c = 0; c < nchunks; ++c) {
+          const uint32_t hb = h_it & 1u;
+          mbar_wait_cluster(&B->h_full[hb], (h_it >> 1) & 1u);
+          tc_fence_after();
+          const uint64_t bhi0 = hdesc0 + (uint64_t)((hb * 2 + 0) * wslot_step);
+          const uint64_t blo0 = hdesc0 + (uint64_t)((hb * 2 + 1) * wslot_step);
+          for (int j = 0; j < it.nsteps; ++j) {
+            const uint32_t ab = a_it & 1u;
+            mbar_wait_cluster(&B->acc_empty[ab], ((a_it >> 1) & 1u) ^ 1u);
+            const uint32_t d_tmem = tmem_base + ab * (uint32_t)kPairN;
+            uint32_t slot = w_it % kWSlots;
+            mbar_wait(&B->w_full[slot], (w_it / kWSlots) & 1u);
+            mbar_wait_cluster(&B->w_peer[slot], (w_it / kWSlots) & 1u);
             tc_fence_after();
-            // descriptors differ only in the 14-bit start-address field: build once, then add k * 256
-            // (= 2 k-groups * kLBO bytes >> 4) per K=16 slice -> ~3 instructions per MMA on the issuing thread
-            const uint64_t bhi0 = umma_desc_kmajor(smem_u32(sH + (hb * 2 + 0) * part_bytes), kLBO, kSBO);
-            const uint64_t blo0 = umma_desc_kmajor(smem_u32(sH + (hb * 2 + 1) * part_bytes), kLBO, kSBO);
-            for (int j = 0; j < it.nsteps; ++j) {
-              const uint32_t ab = a_it & 1u;
-              mbar_wait_cluster(&B->acc_empty[ab], ((a_it >> 1) & 1u) ^ 1u);
-              tc_fence_after();
-              const uint32_t d_tmem = tmem_base + ab * (uint32_t)kPairN;
-              uint32_t slot = w_it % kWSlots;
-              mbar_wait(&B->w_full[slot], (w_it / kWSlots) & 1u);
-              mbar_wait_cluster(&B->w_peer[slot], (w_it / kWSlots) & 1u);
-              tc_fence_after();
-              uint64_t a0 = wdesc0 + (uint64_t)(slot * wslot_step);
+            uint64_t a0 = wdesc0 + (uint64_t)(slot * wslot_step);
+            if (elect_one()) {
 #pragma unroll 1
               for (int k = 0; k < nk16; ++k)
                 tc_mma_f16_2cta(d_tmem, a0 + (uint64_t)(k * kDescStep), bhi0 + (uint64_t)(k * kDescStep), idesc,
@@ -188,38 +187,44 @@ decode_pair_kernel(const __grid_constant__ Params P) {
                   tc_mma_f16_2cta(d_tmem, a0 + (uint64_t)(k * kDescStep), blo0 + (uint64_t)(k * kDescStep), idesc, 1u);
               }
               tc_commit_2cta(&B->w_empty[slot], 3);
-              ++w_it;
-              if (P.passes >= 2) {
-                slot = w_it % kWSlots;
-                mbar_wait(&B->w_full[slot], (w_it / kWSlots) & 1u);
-                mbar_wait_cluster(&B->w_peer[slot], (w_it / kWSlots) & 1u);
-                tc_fence_after();
-                a0 = wdesc0 + (uint64_t)(slot * wslot_step);
+            }
+            __syncwarp();
+            ++w_it;
+            if (P.passes >= 2) {
+              slot = w_it % kWSlots;
+              mbar_wait(&B->w_full[slot], (w_it / kWSlots) & 1u);
+              mbar_wait_cluster(&B->w_peer[slot], (w_it / kWSlots) & 1u);
+              tc_fence_after();
+              a0 = wdesc0 + (uint64_t)(slot * wslot_step);
+              if (elect_one()) {
 #pragma unroll 1
                 for (int k = 0; k < nk16; ++k)
                   tc_mma_f16_2cta(d_tmem, a0 + (uint64_t)(k * kDescStep), bhi0 + (uint64_t)(k * kDescStep), idesc, 1u);
                 tc_commit_2cta(&B->w_empty[slot], 3);
-                ++w_it;
               }
-              tc_commit_2cta(&B->acc_full[ab], 3);
-              ++a_it;
+              __syncwarp();
+              ++w_it;
             }
-            tc_commit_2cta(&B->h_empty[hb], 3);
-            ++h_it;
+            if (elect_one()) tc_commit_2cta(&B->acc_full[ab], 3);
+            __syncwarp();
+            ++a_it;
           }
+          if (elect_one()) tc_commit_2cta(&B->h_empty[hb], 3);
+          __syncwarp();
+          ++h_it;
         }
-      } else {
-        // ---- relay (peer CTA): tell the leader when THIS CTA's copy of each W slot has landed ----
-        uint32_t w_it = 0;
-        for (long long item = pair; item < P.n_items; item += n_pairs) {
-          const Item it = decode_item<EPI>(P, item);
-          const int total = nchunks * it.nsteps * nparts;
-          for (int q = 0; q < total; ++q) {
-            const uint32_t slot = w_it % kWSlots;
-            mbar_wait(&B->w_full[slot], (w_it / kWSlots) & 1u);
-            mbar_arrive_cluster(ldr_w_peer0 + slot * 8u);
-            ++w_it;
-          }
+      }
+    } else if (lane == 0) {
+      // ---- relay (peer CTA): tell the leader when THIS CTA's copy of each W slot has landed ----
+      uint32_t w_it = 0;
+      for (long long item = pair; item < P.n_items; item += n_pairs) {
+        const Item it = decode_item<EPI>(P, item);
+        const int total = nchunks * it.nsteps * nparts;
+        for (int q = 0; q < total; ++q) {
+          const uint32_t slot = w_it % kWSlots;
+          mbar_wait_relaxed(&B->w_full[slot], (w_it / kWSlots) & 1u);
+          mbar_arrive_cluster(ldr_w_peer0 + slot * 8u);
+          ++w_it;
         }
       }
     }
@@ -312,7 +317,7 @@ decode_pair_kernel(const __grid_constant__ Params P) {
         bool valid_next = false;
         if (c + 1 < nchunks) load_z(it, c + 1, znext, seg_next, valid_next);
 
-        mbar_wait(&B->h_empty[hb], ((h_it >> 1) & 1u) ^ 1u);
+        mbar_wait_relaxed(&B->h_empty[hb], ((h_it >> 1) & 1u) ^ 1u);
 
         const float* pil = sPilot + seg * P.Kpad;
         for (int kg = kg_begin; kg < kg_end; ++kg) {
@@ -369,7 +374,7 @@ decode_pair_kernel(const __grid_constant__ Params P) {
         const int nread = cols32(ncols);                 // columns beyond are exact zeros: skip them
         for (int j = 0; j < it.nsteps; ++j) {
           const uint32_t ab = a_it & 1u;
-          mbar_wait(&B->acc_full[ab], (a_it >> 1) & 1u);
+          mbar_wait_relaxed(&B->acc_full[ab], (a_it >> 1) & 1u);
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + ab * (uint32_t)kPairN;
           if constexpr (EPI == kVarT1) {
