@@ -40,185 +40,245 @@ static int upload_sbp(glasdi_handle* h) {
   return GLASDI_OK;
 }
 
-// derivative of component i at time row t of one series; z points at element [0][i], row stride = n
-// accumulation in ascending column order, fp32 FMA (the reference's sparse.mm is an fp32 row sum).
-template <typename LoadF>
+// derivative of component i at time row t of one series; `ld(row)` returns Z[row][i].
+// Accumulation in ascending column order, fp32 FMA (the reference's sparse.mm is an fp32 row sum).
+// HW = compile-time interior half-width (1..4): the interior path is fully unrolled with its
+// coefficients read once from the constant bank; only the 2*depth boundary rows take the generic path.
+template <int HW, typename LoadF>
 __device__ __forceinline__ float sbp_row(const SbpF& sc, int t, int T, LoadF ld) {
+  const int depth = sc.depth;
+  if (t >= depth && t < T - depth) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = HW; k >= 1; --k) acc = fmaf(-sc.interior[k - 1], ld(t - k), acc);
+#pragma unroll
+    for (int k = 1; k <= HW; ++k) acc = fmaf(sc.interior[k - 1], ld(t + k), acc);
+    return acc;
+  }
   float acc = 0.f;
-  if (t < sc.depth) {
+  if (t < depth) {
     const int w = sc.widths[t];
     for (int c = 0; c < w; ++c) acc = fmaf(sc.rows[t][c], ld(c), acc);
-  } else if (t >= T - sc.depth) {
+  } else {
     const int r = T - 1 - t;
     const int w = sc.widths[r];
     for (int c = w - 1; c >= 0; --c) acc = fmaf(-sc.rows[r][c], ld(T - 1 - c), acc);
-  } else {
-    for (int k = sc.halfwidth; k >= 1; --k) acc = fmaf(-sc.interior[k - 1], ld(t - k), acc);
-    for (int k = 1; k <= sc.halfwidth; ++k) acc = fmaf(sc.interior[k - 1], ld(t + k), acc);
   }
   return acc;
 }
 
-__global__ void __launch_bounds__(256) fd_dzdt_kernel(const float* __restrict__ Z, int T, int n, int fd_id,
-                                                      float inv_dt, float* __restrict__ dZ) {
+// dZ = (1/dt) D Z.  Flat index f = t*N + i inside a series: every warp load/store is one contiguous
+// 128-byte line and the stencil neighbours sit +-k*N floats away (L1 hits).  Each thread produces
+// kFdPerThread outputs strided by the block size (independent loads in flight); interior rows need no
+// index arithmetic at all (row test on f), only the 2*depth boundary rows recover (t, i).
+constexpr int kFdThreads = 256;
+constexpr int kFdPerThread = 4;
+template <int HW, int N>
+__global__ void __launch_bounds__(kFdThreads) fd_dzdt_kernel(const float* __restrict__ Z, int T, int n_rt, int fd_id,
+                                                             float inv_dt, float* __restrict__ dZ) {
   const SbpF& sc = c_sbp[fd_id];
+  const int n = N > 0 ? N : n_rt;
   const size_t base = (size_t)blockIdx.y * T * n;
   const float* __restrict__ z = Z + base;
+  float* __restrict__ out = dZ + base;
   const int total = T * n;
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
-    const int t = f / n, i = f - t * n;
-    const float v = sbp_row(sc, t, T, [&](int row) { return __ldg(z + row * n + i); });
-    dZ[base + f] = inv_dt * v;
+  const int lo = sc.depth * n, hi = (T - sc.depth) * n;      // interior rows: lo <= f < hi
+  float cf[HW];
+#pragma unroll
+  for (int k = 0; k < HW; ++k) cf[k] = sc.interior[k];
+  const int f0 = blockIdx.x * (kFdThreads * kFdPerThread) + threadIdx.x;
+  float v[kFdPerThread];
+#pragma unroll
+  for (int j = 0; j < kFdPerThread; ++j) {
+    const int f = f0 + j * kFdThreads;
+    v[j] = 0.f;
+    if (f >= lo && f < hi) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = HW; k >= 1; --k) acc = fmaf(-cf[k - 1], __ldg(z + f - k * n), acc);
+#pragma unroll
+      for (int k = 1; k <= HW; ++k) acc = fmaf(cf[k - 1], __ldg(z + f + k * n), acc);
+      v[j] = acc;
+    } else if (f < total) {
+      const int t = f / n, i = f - t * n;
+      v[j] = sbp_row<HW>(sc, t, T, [&](int row) { return __ldg(z + row * n + i); });
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kFdPerThread; ++j) {
+    const int f = f0 + j * kFdThreads;
+    if (f < total) out[f] = inv_dt * v[j];
   }
 }
 
-constexpr int kFitThreads = 256;
+constexpr int kFitThreads = 128;             // 4 warps = 4 training series per CTA
 
-template <int N>
-__global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __restrict__ Z, int T, int fd_id,
+// One WARP per training series.  Lane l owns time rows l, l+32, ...: it forms dZ/dt for its rows with the
+// stencil straight from global memory (the series is 20 KB: L1/L2 resident, HBM sees it once) and
+// accumulates the upper triangle of the (n+1)x(n+1) Gram matrix and the (n+1)xn right-hand side in fp64
+// registers.  A shuffle butterfly sums over lanes; the tiny Cholesky factorisation / substitutions run as
+// rolled loops on a 528-byte per-warp shared-memory scratch (lane 0 factorises, lanes 0..n-1 solve one
+// right-hand side each), which keeps the kernel's code small enough to live in the instruction cache.
+template <int N, int HW>
+__global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __restrict__ Z, int B, int T, int fd_id,
                                                                 float inv_dt, int norm_order,
                                                                 float* __restrict__ coefs_out,
                                                                 float* __restrict__ loss_sindy_out,
                                                                 float* __restrict__ loss_coef_out,
                                                                 int32_t* __restrict__ info_out, int use_smem) {
   constexpr int NA = N + 1;                    // library size [1 | z]
-  constexpr int NG = NA * (NA + 1) / 2;        // upper triangle of the Gram matrix
+  constexpr int NG = NA * (NA + 1) / 2;        // upper triangle of the Gram matrix, row-major
   constexpr int NR = NA * N;                   // right-hand side
   constexpr int NS = NG + NR;
-  extern __shared__ float zs[];                // series [T][N] when it fits
-  __shared__ double red[kFitThreads / 32][NS];
-  __shared__ double sol[NA][N];
-  __shared__ float solf[NA][N];
-  __shared__ double red2[kFitThreads / 32];
-  __shared__ int s_info;
-
+  __shared__ double sG[kFitThreads / 32][NA][NA];
+  __shared__ double sR[kFitThreads / 32][NA][N];
+  __shared__ int sInfo[kFitThreads / 32];
+  extern __shared__ float s_series[];          // [warps per CTA][T*N] when the series fit (else global reads)
   const SbpF& sc = c_sbp[fd_id];
-  const int b = blockIdx.x;
-  const float* __restrict__ zg = Z + (size_t)b * T * N;
-  const float* z = zg;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int b = blockIdx.x * (kFitThreads / 32) + wib;
+  if (b >= B) return;                          // whole warp leaves together (no block barriers below)
+  const float* __restrict__ z = Z + (size_t)b * T * N;
   if (use_smem) {
-    for (int f = threadIdx.x; f < T * N; f += blockDim.x) zs[f] = zg[f];
-    __syncthreads();
-    z = zs;
+    // one coalesced sweep: T*N/32 independent loads per lane in flight, HBM sees the series exactly once
+    float* mine = s_series + (size_t)wib * T * N;
+    for (int f = lane; f < T * N; f += 32) mine[f] = __ldg(z + f);
+    __syncwarp();
+    z = mine;
   }
 
   double acc[NS];
 #pragma unroll
   for (int q = 0; q < NS; ++q) acc[q] = 0.0;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+  for (int t = lane; t < T; t += 32) {
     float x[NA], d[N];
     x[0] = 1.f;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       x[1 + i] = z[t * N + i];
-      d[i] = inv_dt * sbp_row(sc, t, T, [&](int row) { return z[row * N + i]; });
+      d[i] = inv_dt * sbp_row<HW>(sc, t, T, [&](int row) { return z[row * N + i]; });
     }
+    double xd[NA], dd[N];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) xd[a] = (double)x[a];
+#pragma unroll
+    for (int i = 0; i < N; ++i) dd[i] = (double)d[i];
     int q = 0;
 #pragma unroll
     for (int a = 0; a < NA; ++a)
 #pragma unroll
-      for (int c = a; c < NA; ++c) acc[q++] += (double)x[a] * (double)x[c];
+      for (int c = a; c < NA; ++c) { acc[q] = fma(xd[a], xd[c], acc[q]); ++q; }
 #pragma unroll
     for (int a = 0; a < NA; ++a)
 #pragma unroll
-      for (int i = 0; i < N; ++i) acc[q++] += (double)x[a] * (double)d[i];
+      for (int i = 0; i < N; ++i) { acc[q] = fma(xd[a], dd[i], acc[q]); ++q; }
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int q = 0; q < NS; ++q) {
     double v = acc[q];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[warp][q] = v;
+    acc[q] = v;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double G[NA][NA], R[NA][N];
+  if (lane == 0) {
     int q = 0;
+#pragma unroll
     for (int a = 0; a < NA; ++a)
-      for (int c = a; c < NA; ++c) {
-        double v = 0.0;
-        for (int w = 0; w < kFitThreads / 32; ++w) v += red[w][q];
-        G[a][c] = v; G[c][a] = v;
-        ++q;
-      }
+#pragma unroll
+      for (int c = a; c < NA; ++c) { sG[wib][a][c] = acc[q]; sG[wib][c][a] = acc[q]; ++q; }
+#pragma unroll
     for (int a = 0; a < NA; ++a)
-      for (int i = 0; i < N; ++i) {
-        double v = 0.0;
-        for (int w = 0; w < kFitThreads / 32; ++w) v += red[w][q];
-        R[a][i] = v;
-        ++q;
-      }
-    // Cholesky G = L L^T (in place, lower), with a relative pivot test
+#pragma unroll
+      for (int i = 0; i < N; ++i) sR[wib][a][i] = acc[q++];
+    // Cholesky G = L L^T in place (lower), relative pivot test; rolled loops (tiny, latency only)
+    double (*G)[NA] = sG[wib];
     int info = 0;
     double dmax = 0.0;
     for (int a = 0; a < NA; ++a) dmax = fmax(dmax, G[a][a]);
-    for (int j = 0; j < NA && info == 0; ++j) {
-      double s = G[j][j];
-      for (int k = 0; k < j; ++k) s -= G[j][k] * G[j][k];
-      if (!(s > 1e-13 * dmax)) { info = j + 1; break; }
-      const double ljj = sqrt(s);
+#pragma unroll 1
+    for (int j = 0; j < NA; ++j) {
+      double sdiag = G[j][j];
+      for (int k = 0; k < j; ++k) sdiag -= G[j][k] * G[j][k];
+      if (!(sdiag > 1e-13 * dmax)) { info = j + 1; break; }
+      const double ljj = sqrt(sdiag);
       G[j][j] = ljj;
+      const double rl = 1.0 / ljj;
+#pragma unroll 1
       for (int i = j + 1; i < NA; ++i) {
         double v = G[i][j];
         for (int k = 0; k < j; ++k) v -= G[i][k] * G[j][k];
-        G[i][j] = v / ljj;
+        G[i][j] = v * rl;
       }
     }
-    if (info == 0) {
-      for (int c = 0; c < N; ++c) {
-        double y[NA];
-        for (int i = 0; i < NA; ++i) {
-          double v = R[i][c];
-          for (int k = 0; k < i; ++k) v -= G[i][k] * y[k];
-          y[i] = v / G[i][i];
-        }
-        for (int i = NA - 1; i >= 0; --i) {
-          double v = y[i];
-          for (int k = i + 1; k < NA; ++k) v -= G[k][i] * sol[k][c];
-          sol[i][c] = v / G[i][i];
-        }
-      }
-    } else {
-      for (int a = 0; a < NA; ++a)
-        for (int c = 0; c < N; ++c) sol[a][c] = nan("");
+    sInfo[wib] = info;
+  }
+  __syncwarp();
+  const int info = sInfo[wib];
+  if (lane < N && info == 0) {
+    // one right-hand-side column per lane: L y = r, L^T x = y, in place in sR[.][lane]
+    double (*G)[NA] = sG[wib];
+    double (*R)[N] = sR[wib];
+#pragma unroll 1
+    for (int i = 0; i < NA; ++i) {
+      double v = R[i][lane];
+      for (int k = 0; k < i; ++k) v -= G[i][k] * R[k][lane];
+      R[i][lane] = v / G[i][i];
     }
-    double nrm = 0.0;
+#pragma unroll 1
+    for (int i = NA - 1; i >= 0; --i) {
+      double v = R[i][lane];
+      for (int k = i + 1; k < NA; ++k) v -= G[k][i] * R[k][lane];
+      R[i][lane] = v / G[i][i];
+    }
+  }
+  __syncwarp();
+  float Rf[NA][N];
+  double nrm = 0.0;
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      const float cf = info == 0 ? (float)sR[wib][a][c] : nanf("");
+      Rf[a][c] = cf;
+      nrm += (norm_order == 1) ? fabs((double)cf) : (double)cf * (double)cf;
+    }
+  if (lane == 0) {
+#pragma unroll
     for (int a = 0; a < NA; ++a)
-      for (int c = 0; c < N; ++c) {
-        const float cf = (float)sol[a][c];
-        solf[a][c] = cf;
-        coefs_out[(size_t)b * NR + a * N + c] = cf;     // row-major flatten of (n+1, n), sindy.py:80
-        nrm += (norm_order == 1) ? fabs((double)cf) : (double)cf * (double)cf;
-      }
+#pragma unroll
+      for (int c = 0; c < N; ++c) coefs_out[(size_t)b * NR + a * N + c] = Rf[a][c];   // row-major (n+1, n), sindy.py:80
     if (loss_coef_out) loss_coef_out[b] = (float)((norm_order == 1) ? nrm : sqrt(nrm));
-    s_info = info;
     if (info_out) info_out[b] = info;
   }
-  __syncthreads();
   if (!loss_sindy_out) return;
-  // second pass: MSE(dZdt, [1|Z] R) with fp32 coefficients, sindy.py:75
+  // second pass: MSE(dZdt, [1|Z] R) with the fp32 coefficients, sindy.py:75
   double se = 0.0;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+  for (int t = lane; t < T; t += 32) {
+    float zr[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) zr[j] = z[t * N + j];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const float d = inv_dt * sbp_row(sc, t, T, [&](int row) { return z[row * N + i]; });
-      float pred = solf[0][i];
+      const float d = inv_dt * sbp_row<HW>(sc, t, T, [&](int row) { return z[row * N + i]; });
+      float pred = Rf[0][i];
 #pragma unroll
-      for (int j = 0; j < N; ++j) pred = fmaf(z[t * N + j], solf[1 + j][i], pred);
+      for (int j = 0; j < N; ++j) pred = fmaf(zr[j], Rf[1 + j][i], pred);
       const float e = d - pred;
       se += (double)e * (double)e;
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-  if (lane == 0) red2[warp] = se;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double v = 0.0;
-    for (int w = 0; w < kFitThreads / 32; ++w) v += red2[w];
-    loss_sindy_out[b] = (float)(v / ((double)T * N));
-  }
+  if (lane == 0) loss_sindy_out[b] = (float)(se / ((double)T * N));
+}
+
+template <int HW>
+static void launch_fd_hw(const float* Z, int B, int T, int n, int fd_id, float inv_dt, float* dZ, cudaStream_t st) {
+  const int per_block = kFdThreads * kFdPerThread;
+  dim3 grid((T * n + per_block - 1) / per_block, B);
+  if (n == 5) fd_dzdt_kernel<HW, 5><<<grid, kFdThreads, 0, st>>>(Z, T, n, fd_id, inv_dt, dZ);
+  else fd_dzdt_kernel<HW, 0><<<grid, kFdThreads, 0, st>>>(Z, T, n, fd_id, inv_dt, dZ);
 }
 
 int launch_fd_dzdt(glasdi_handle* h, const float* Z, int B, int T, int n, int fd_id, double dt, float* dZ,
@@ -229,23 +289,40 @@ int launch_fd_dzdt(glasdi_handle* h, const float* Z, int B, int T, int n, int fd
   if (B > 65535) return set_error(h, GLASDI_ERR_INVALID, "fd_dzdt: B > 65535");
   int rc = upload_sbp(h);
   if (rc) return rc;
-  const int total = T * n;
-  dim3 grid((total + 255) / 256, B);
-  fd_dzdt_kernel<<<grid, 256, 0, st>>>(Z, T, n, fd_id, (float)(1.0 / dt), dZ);
+  const float inv_dt = (float)(1.0 / dt);
+  switch (kSbpSchemes[fd_id].halfwidth) {
+    case 1: launch_fd_hw<1>(Z, B, T, n, fd_id, inv_dt, dZ, st); break;
+    case 2: launch_fd_hw<2>(Z, B, T, n, fd_id, inv_dt, dZ, st); break;
+    case 3: launch_fd_hw<3>(Z, B, T, n, fd_id, inv_dt, dZ, st); break;
+    default: launch_fd_hw<4>(Z, B, T, n, fd_id, inv_dt, dZ, st); break;
+  }
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "fd_dzdt launch");
+}
+
+template <int N, int HW>
+static void launch_fit_nh(const float* Z, int B, int T, int fd_id, float inv_dt, int norm_order, float* coefs,
+                          float* ls, float* lc, int32_t* info, cudaStream_t st) {
+  const int per_cta = kFitThreads / 32;
+  size_t smem = (size_t)per_cta * T * N * sizeof(float);
+  const int use_smem = smem <= 100 * 1024;            // 2 CTAs per SM keep their series resident
+  if (!use_smem) smem = 0;
+  if (smem > 40 * 1024)
+    cudaFuncSetAttribute(sindy_fit_kernel<N, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sindy_fit_kernel<N, HW><<<(B + per_cta - 1) / per_cta, kFitThreads, smem, st>>>(Z, B, T, fd_id, inv_dt, norm_order,
+                                                                                  coefs, ls, lc, info, use_smem);
 }
 
 template <int N>
 static int launch_fit_n(glasdi_handle* h, const float* Z, int B, int T, int fd_id, double dt, int norm_order,
                         float* coefs, float* ls, float* lc, int32_t* info, cudaStream_t st) {
-  size_t smem = (size_t)T * N * sizeof(float);
-  int use_smem = smem <= 160 * 1024;
-  if (!use_smem) smem = 0;
-  if (smem > 40 * 1024)
-    GL_CUDA(h, cudaFuncSetAttribute(sindy_fit_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sindy_fit_kernel<N><<<B, kFitThreads, smem, st>>>(Z, T, fd_id, (float)(1.0 / dt), norm_order, coefs, ls, lc, info,
-                                                   use_smem);
+  const float inv_dt = (float)(1.0 / dt);
+  switch (kSbpSchemes[fd_id].halfwidth) {
+    case 1: launch_fit_nh<N, 1>(Z, B, T, fd_id, inv_dt, norm_order, coefs, ls, lc, info, st); break;
+    case 2: launch_fit_nh<N, 2>(Z, B, T, fd_id, inv_dt, norm_order, coefs, ls, lc, info, st); break;
+    case 3: launch_fit_nh<N, 3>(Z, B, T, fd_id, inv_dt, norm_order, coefs, ls, lc, info, st); break;
+    default: launch_fit_nh<N, 4>(Z, B, T, fd_id, inv_dt, norm_order, coefs, ls, lc, info, st); break;
+  }
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "sindy_fit launch");
 }
