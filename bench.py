@@ -185,8 +185,11 @@ def run_ours(args):
 
     eng = Engine(local_rank)
     eng.set_decoder(Ws, bs, wl.act)
+    screened = args.mode == "screened"
+    eng.set_option(_lib.OPT_MODE, _lib.MODE_SCREENED if screened else _lib.MODE_DIRECT)
     eng.set_option(_lib.OPT_SPLIT_PASSES, args.passes)
     eng.set_option(_lib.OPT_STAGE_TIMING, 1)
+    issued_passes = 1 if screened else args.passes
 
     coefs_host = torch.from_numpy(inp["coefs"]).pin_memory()
     z0_host = torch.from_numpy(inp["z0"]).pin_memory()
@@ -218,7 +221,8 @@ def run_ours(args):
         time.sleep(0.25)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    dec_ms, roll_ms, dec_launches = [], [], 0
+    dec_ms, roll_ms, ref_ms, dec_launches = [], [], [], 0
+    n_cand, max_dev = 0, 0.0
     barrier()
     launches0 = eng.launch_count
     t_wall0 = time.perf_counter()
@@ -230,6 +234,9 @@ def run_ours(args):
         ev1[k].synchronize()
         r, d, nl = eng.stage_times()
         roll_ms.append(r); dec_ms.append(d); dec_launches += nl
+        if screened:
+            rms, n_cand, max_dev = eng.screen_stats()
+            ref_ms.append(rms)
     barrier()
     t_wall1 = time.perf_counter()
     launches = eng.launch_count - launches0
@@ -281,30 +288,38 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (fp16 split products x%d, fp32 TMEM accumulate; fp64 rollout)" % args.passes,
+            "dtype": ("f32 (one fp16 tensor-core screening pass over the ensemble, fp32 TMEM accumulate; exact fp32 decode + "
+                      "fp64 sample sums at the near-maximum candidates; fp64 rollout)" if screened else
+                      "f32 (fp16 split products x%d, fp32 TMEM accumulate; fp64 rollout)" % args.passes),
             "data": "synthetic",
             "config": {"workload": workload_desc(wl), "params_per_gpu": P, "global_params": P * world,
-                       "split_passes": args.passes, "parallelism": f"test-grid sharding x{world} + 1 max-loc all-reduce",
+                       "mode": args.mode, "split_passes": issued_passes, "parallelism": f"test-grid sharding x{world} + 1 max-loc all-reduce",
                        "l2": "256 MB buffer written between timed iterations; per-step working set 4.6 GB >> 126 MB L2",
                        "selected_global_index": sel_idx},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["sustained"], "traffic": traffic,
                          "kernel": "glasdi::dv2::decode_pair_kernel<VarT1, sigmoid, 5> (tcgen05 cta_group::2)",
-                         "issued_frac": flops_launch * args.passes * 1.12 * 1024.0 / 1001.0 * 1024.0 / 1000.0
+                         "issued_frac": flops_launch * issued_passes * 1.12 * 1024.0 / 1001.0 * 1024.0 / 1000.0
                                         / (dec_avg_ms * 1e-3) / 1e12 / pk["sustained"],
                          "kernel_ms": dec_avg_ms, "rollout_kernel_ms": float(np.mean(roll_ms)),
                          "algorithmic_flop_per_launch": flops_launch,
-                         "issued_flop_per_launch": flops_launch * args.passes * 1.12 * 1024.0 / 1001.0 * 1024.0 / 1000.0,
+                         "issued_flop_per_launch": flops_launch * issued_passes * 1.12 * 1024.0 / 1001.0 * 1024.0 / 1000.0,
                          "peak_source": pk["source"] + " bf16 dense, sustained figure (kernel timed inside a long step); "
                                         "fp16 and bf16 share the tcgen05 kind::f16 rate",
                          "note": "frac is on ALGORITHMIC decoder FLOP (single pass); the kernel issues "
-                                 f"{args.passes} fp16 split passes per product to stay fp32-faithful and pads K 100->112, "
+                                 f"{issued_passes} fp16 pass(es) per product and pads K 100->112, "
                                  "D 1001->1024, S 1000->1024: issued_frac is the tensor-pipe view of the same launch"},
             "e2e": {"value": rollouts_per_step * args.steps / e2e_total, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if screened:
+            line["roofline"]["refine"] = {
+                "select_plus_refine_ms": float(np.mean(ref_ms)), "candidates": int(n_cand),
+                "max_rel_dev_screen_vs_exact": float(max_dev), "margin": 2.0 ** -eng.get_option(_lib.OPT_SCREEN_MARGIN),
+                "note": "candidates = (t, dof) within the margin of a parameter's screened maximum, re-evaluated "
+                        "exactly on the CUDA cores; their maximum is the reported max_std"}
         if world == 1 and not args.no_cpu_baseline:
             v, dt_cpu, threads = cpu_reference_rate(wl, Ws, bs, 2, seed_shift=219)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
@@ -321,7 +336,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--passes", type=int, default=3, help="fp16 split-product passes of the last layer (1..3)")
+    ap.add_argument("--mode", choices=["screened", "direct"], default="screened",
+                    help="screened (default): 1 fp16 pass + exact candidate re-evaluation; direct: --passes split passes")
+    ap.add_argument("--passes", type=int, default=3, help="direct mode: fp16 split-product passes of the last layer (1..3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

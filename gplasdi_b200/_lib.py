@@ -17,6 +17,8 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_READY, ERR_NUMERIC, ERR_OOM = 
 ACT_IDS = {"sigmoid": 0, "tanh": 1, "softplus": 2, "ReLU": 3, "ELU": 4, "SiLU": 5, "GELU": 6, "identity": 7}
 FD_IDS = {"sbp12": 0, "sbp24": 1, "sbp36": 2, "sbp48": 3}
 OPT_SPLIT_PASSES, OPT_INTEGRATOR, OPT_RK4_SUBSTEPS, OPT_MAX_CTAS, OPT_STAGE_TIMING, OPT_DECODE_KERNEL = 0, 1, 2, 3, 4, 5
+OPT_MODE, OPT_SCREEN_MARGIN = 6, 7
+MODE_DIRECT, MODE_SCREENED = 0, 1
 INT_EXPM, INT_RK4 = 0, 1
 
 # name -> (restype, argtypes); must list EVERY symbol of include/glasdi_b200.h (tests check this)
@@ -30,6 +32,7 @@ SIGNATURES = {
     "glasdi_get_option": (_i, [_vp, _i, C.POINTER(_i)]),
     "glasdi_launch_count": (_i64, [_vp]),
     "glasdi_stage_times": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i)]),
+    "glasdi_screen_stats": (_i, [_vp, C.POINTER(_d), C.POINTER(_i64), C.POINTER(C.c_float), _vp]),
     "glasdi_set_decoder": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_vp), _i]),
     "glasdi_rollout": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp]),
     "glasdi_greedy_step": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp]),

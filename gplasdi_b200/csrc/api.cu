@@ -38,6 +38,24 @@ int ensure_maxvar(glasdi_handle* h, size_t n) {
   return GLASDI_OK;
 }
 
+// candidate list + exact-variance bits of the screened mode
+static int ensure_screen_buffers(glasdi_handle* h, size_t P) {
+  if (!h->d_cand) {
+    const size_t cap = (size_t)1 << 20;                        // 16 MB of {p, t, d, var}
+    GL_CUDA(h, cudaMalloc(&h->d_cand, cap * 16));
+    h->cand_cap = cap;
+  }
+  if (!h->d_cand_stats) GL_CUDA(h, cudaMalloc(&h->d_cand_stats, 4 * sizeof(unsigned int)));
+  if (P > h->exact_cap) {
+    if (h->d_exact) cudaFree(h->d_exact);
+    h->d_exact = nullptr;
+    h->exact_cap = 0;
+    GL_CUDA(h, cudaMalloc(&h->d_exact, P * sizeof(unsigned int)));
+    h->exact_cap = P;
+  }
+  return GLASDI_OK;
+}
+
 static void free_decoder(Decoder& d) {
   for (float* p : d.dW) if (p) cudaFree(p);
   for (float* p : d.db) if (p) cudaFree(p);
@@ -56,10 +74,19 @@ static int check_flags(glasdi_handle* h, cudaStream_t st) {
   int flags[4] = {0, 0, 0, 0};
   GL_CUDA(h, cudaMemcpyAsync(flags, h->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
   GL_CUDA(h, cudaStreamSynchronize(st));
-  if (flags[0]) {
+  if (flags[0] || flags[1] || flags[2]) {
     GL_CUDA(h, cudaMemsetAsync(h->d_flags, 0, sizeof(flags), st));
+    if (flags[0])
+      return set_error(h, GLASDI_ERR_NUMERIC,
+                       "hidden activations overflowed the fp16 split range (|h - h_pilot| * 2^eH > 6e4)");
+    if (flags[1])
+      return set_error(h, GLASDI_ERR_NUMERIC,
+                       "screened greedy step: more near-maximum (t, dof) candidates than the candidate buffer holds; "
+                       "use GLASDI_OPT_MODE = 0 (direct) or a larger GLASDI_OPT_SCREEN_MARGIN");
     return set_error(h, GLASDI_ERR_NUMERIC,
-                     "hidden activations overflowed the fp16 split range (|h - h_pilot| * 2^eH > 6e4)");
+                     "screened greedy step: single-pass screening deviates from the exact re-evaluation by more than "
+                     "a quarter of the candidate margin; use GLASDI_OPT_MODE = 0 (direct) or a smaller "
+                     "GLASDI_OPT_SCREEN_MARGIN");
   }
   return GLASDI_OK;
 }
@@ -104,6 +131,9 @@ int glasdi_destroy(glasdi_handle* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->d_maxvar) cudaFree(h->d_maxvar);
   if (h->d_flags) cudaFree(h->d_flags);
+  if (h->d_cand) cudaFree(h->d_cand);
+  if (h->d_cand_stats) cudaFree(h->d_cand_stats);
+  if (h->d_exact) cudaFree(h->d_exact);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   cudaSetDevice(prev);
   delete h;
@@ -140,6 +170,15 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
       if (value != 0 && value != 1) return set_error(h, GLASDI_ERR_INVALID, "decode kernel variant must be 0 or 1");
       h->opt_kernel = value;
       return GLASDI_OK;
+    case GLASDI_OPT_MODE:
+      if (value != GLASDI_MODE_DIRECT && value != GLASDI_MODE_SCREENED)
+        return set_error(h, GLASDI_ERR_INVALID, "mode must be GLASDI_MODE_DIRECT or GLASDI_MODE_SCREENED");
+      h->opt_mode = value;
+      return GLASDI_OK;
+    case GLASDI_OPT_SCREEN_MARGIN:
+      if (value < 4 || value > 16) return set_error(h, GLASDI_ERR_INVALID, "screen margin must be 4..16 (delta = 2^-value)");
+      h->opt_margin_log2 = value;
+      return GLASDI_OK;
     default: return set_error(h, GLASDI_ERR_INVALID, "unknown option");
   }
 }
@@ -153,6 +192,8 @@ int glasdi_get_option(const glasdi_handle* h, int option, int* value) {
     case GLASDI_OPT_MAX_CTAS: *value = h->opt_max_ctas; return GLASDI_OK;
     case GLASDI_OPT_STAGE_TIMING: *value = h->opt_timing; return GLASDI_OK;
     case GLASDI_OPT_DECODE_KERNEL: *value = h->opt_kernel; return GLASDI_OK;
+    case GLASDI_OPT_MODE: *value = h->opt_mode; return GLASDI_OK;
+    case GLASDI_OPT_SCREEN_MARGIN: *value = h->opt_margin_log2; return GLASDI_OK;
     default: return GLASDI_ERR_INVALID;
   }
 }
@@ -275,8 +316,14 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
   if (!max_std_out) return set_error(h, GLASDI_ERR_INVALID, "null output");
   GL_CUDA(h, cudaSetDevice(h->device));
   const int Spad = (S + 31) / 32 * 32;
-  const size_t per_param = (size_t)T * n * Spad * sizeof(float);
-  const size_t budget = (size_t)12 << 30;                      // trajectory scratch per slab
+  // screened mode: one fp16 pass on the tensor cores writes the variance field, refine.cu re-evaluates
+  // the near-maximum candidates exactly.  Only the CTA-pair tcgen05 kernel has the field epilogue.
+  const bool screened = h->opt_mode == GLASDI_MODE_SCREENED && d.tc_ok && h->opt_kernel == 1;
+  const int field_ld = decode_field_ld(d.n_tiles);
+  const size_t traj_bytes = (size_t)T * n * Spad * sizeof(float);
+  const size_t field_bytes = screened ? (size_t)T * field_ld * sizeof(float) : 0;
+  const size_t per_param = traj_bytes + field_bytes;
+  const size_t budget = (size_t)12 << 30;                      // trajectory (+ field) scratch per slab
   int slab = (int)std::max<size_t>(1, std::min<size_t>((size_t)P, budget / per_param));
   slab = std::min(slab, 32768);
   int rc = ensure_workspace(h, per_param * slab);
@@ -284,13 +331,22 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
   rc = ensure_maxvar(h, (size_t)P);
   if (rc) return rc;
   GL_CUDA(h, cudaMemsetAsync(h->d_maxvar, 0, (size_t)P * sizeof(unsigned int), st));
+  if (screened) {
+    if ((rc = ensure_screen_buffers(h, (size_t)P))) return rc;
+    GL_CUDA(h, cudaMemsetAsync(h->d_exact, 0, (size_t)P * sizeof(unsigned int), st));
+    GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats, 0, 4 * sizeof(unsigned int), st));
+  }
   float* Zs = reinterpret_cast<float*>(h->ws);
+  float* field = screened ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->ws) + traj_bytes * slab) : nullptr;
+  const float delta = ldexpf(1.0f, -h->opt_margin_log2);
   h->ev_rollout.clear();
   h->ev_decode.clear();
+  h->ev_refine.clear();
   size_t ev_next = 0;
   for (int p0 = 0; p0 < P; p0 += slab) {
     const int pn = std::min(slab, P - p0);
-    StageTimer t_roll(h, st, &h->ev_rollout, ev_next), t_dec(h, st, &h->ev_decode, ev_next);
+    StageTimer t_roll(h, st, &h->ev_rollout, ev_next), t_dec(h, st, &h->ev_decode, ev_next),
+        t_ref(h, st, &h->ev_refine, ev_next);
     if ((rc = t_roll.start())) return rc;
     if (coefs) {
       rc = launch_rollout(h, coefs + (size_t)p0 * S * n * (n + 1), z0 + (size_t)p0 * n, 0, pn, S, n, T, dt, Zs, Spad,
@@ -301,12 +357,23 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
     if (rc) return rc;
     if ((rc = t_roll.stop())) return rc;
     if ((rc = t_dec.start())) return rc;
-    if (d.tc_ok && h->opt_kernel == 1) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
+    if (screened) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, field, 1, st);
+    else if (d.tc_ok && h->opt_kernel == 1) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, nullptr, 0, st);
     else if (d.tc_ok) rc = launch_decode_var(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
     else rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
     if (rc) return rc;
     if ((rc = t_dec.stop())) return rc;
+    if (screened) {
+      if ((rc = t_ref.start())) return rc;
+      GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats, 0, sizeof(unsigned int), st));      // per-slab count
+      rc = launch_select_candidates(h, field, field_ld, h->d_maxvar + p0, pn, T, d.D, (1.f - delta) * (1.f - delta), st);
+      if (rc) return rc;
+      rc = launch_refine(h, Zs, Spad, S, T, h->d_exact + p0, 0.25f * delta, st);
+      if (rc) return rc;
+      if ((rc = t_ref.stop())) return rc;
+    }
   }
+  if (screened) return launch_finalize(h, h->d_exact, P, 0, max_std_out, argmax_out, maxval_out, st);
   const int scale = d.tc_ok ? (d.eW + d.eH) : 0;
   return launch_finalize(h, h->d_maxvar, P, scale, max_std_out, argmax_out, maxval_out, st);
 }
@@ -352,6 +419,29 @@ int glasdi_stage_times(glasdi_handle* h, double* rollout_ms, double* decode_ms, 
   if (rollout_ms) *rollout_ms = acc[0];
   if (decode_ms) *decode_ms = acc[1];
   if (decode_launches) *decode_launches = (int)h->ev_decode.size();
+  return GLASDI_OK;
+}
+
+int glasdi_screen_stats(glasdi_handle* h, double* refine_ms, int64_t* n_candidates, float* max_rel_dev, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  GL_CUDA(h, cudaSetDevice(h->device));
+  if (refine_ms) {
+    *refine_ms = 0.0;
+    if (h->opt_timing)
+      for (int base : h->ev_refine) {
+        GL_CUDA(h, cudaEventSynchronize(h->ev_pool[base + 1]));
+        float ms = 0.f;
+        GL_CUDA(h, cudaEventElapsedTime(&ms, h->ev_pool[base], h->ev_pool[base + 1]));
+        *refine_ms += ms;
+      }
+  }
+  unsigned int st[4] = {0, 0, 0, 0};
+  if (h->d_cand_stats) {
+    GL_CUDA(h, cudaMemcpyAsync(st, h->d_cand_stats, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GL_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  }
+  if (n_candidates) *n_candidates = (int64_t)st[1];
+  if (max_rel_dev) std::memcpy(max_rel_dev, &st[2], sizeof(float));
   return GLASDI_OK;
 }
 

@@ -63,7 +63,16 @@ struct glasdi_handle {
   size_t ws_bytes = 0;
   unsigned int* d_maxvar = nullptr;   // [P] float bits
   size_t maxvar_cap = 0;
-  int* d_flags = nullptr;             // [4] device error flags
+  int* d_flags = nullptr;             // [4] device error flags: [0] fp16 range, [1] candidate overflow, [2] screening deviation
+  // screened mode (GLASDI_OPT_MODE = 1): candidates of the last greedy call
+  int opt_mode = 1;                   // 0: direct (split passes), 1: single-pass screening + exact refinement
+  int opt_margin_log2 = 8;            // candidates = variance within (1 - 2^-margin)^2 of the screened maximum
+  void* d_cand = nullptr;             // [cand_cap] {p, t, d, approx variance}
+  size_t cand_cap = 0;
+  unsigned int* d_cand_stats = nullptr;   // [0] count (this slab), [1] total count, [2] float bits of max relative deviation
+  unsigned int* d_exact = nullptr;    // [P] float bits of the exact variance
+  size_t exact_cap = 0;
+  std::vector<int> ev_refine;
 };
 
 namespace glasdi {
@@ -93,8 +102,15 @@ int launch_decode_var(glasdi_handle* h, const float* Zs, int Spad, int P, int S,
 int launch_decode_store(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
 size_t decode_var_smem_bytes(int Kpad, int last_in_w);
 // decode_var2.cu : CTA-pair (cta_group::2) variant of the same kernel
+// var_field (optional): [P][T][decode_field_ld] scaled variance of every (t, dof); passes > 0 overrides the handle option
 int launch_decode_var_pair(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
-                           unsigned int* maxvar_bits, cudaStream_t st);
+                           unsigned int* maxvar_bits, float* var_field, int passes, cudaStream_t st);
+inline int decode_field_ld(int n_tiles) { return (n_tiles + 1) / 2 * 2 * 128; }
+// refine.cu : candidate selection on the screened variance field + exact fp32/fp64 re-evaluation
+int launch_select_candidates(glasdi_handle* h, const float* var_field, int field_ld, const unsigned int* approx_bits,
+                             int P, int T, int D, float keep, cudaStream_t st);
+int launch_refine(glasdi_handle* h, const float* Zs, int Spad, int S, int T, unsigned int* exact_bits,
+                  float dev_tol, cudaStream_t st);
 int launch_decode_store_pair(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
 // simt_fallback.cu : fp32 CUDA-core path for decoder shapes the tcgen05 kernel does not cover
 int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
@@ -320,9 +336,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-// arrive (release at cluster scope) on an mbarrier given by its shared::cluster address (may be remote)
+// arrive on an mbarrier given by its shared::cluster address (may be in the peer CTA).  Default semantics
+// (release at CTA scope) compile to the bare SYNCS.ARRIVE; `.release.cluster` costs MEMBAR.ALL.GPU + ERRBAR +
+// CGAERRBAR per arrive, which was 27 % of the epilogue warps' time (profiles/: decode_r1_screen).  What the
+// arrivals publish is either consumed through the async proxy after an explicit fence.proxy.async (operand
+// tiles) or is the completion of tcgen05.ld reads (accumulator release): neither needs the GPU-scope fence.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -32,6 +32,8 @@ struct Params {
   float inv_S;
   const float* Zs;                  // [P][T][NZ][Spad]
   unsigned int* maxvar_bits;        // [P]
+  float* var_field;                 // optional [P][T][field_ld]: scaled variance of every (t, dof) (screening / std field)
+  int field_ld;                     // n_tiles rounded up to even * 128
   // STORE
   const float* Zrows;               // [rows][NZ]
   long long rows;

@@ -335,17 +335,20 @@ decode_pair_kernel(const __grid_constant__ Params P) {
               const float v1 = fmaf(hv[u + 1], hscale, -pv[u + 1]);
               if (P.check_overflow) amax = fmaxf(amax, fmaxf(fabsf(v0), fabsf(v1)));
               const __half2 hh = __floats2half2_rn(v0, v1);
-              const float2 bk = __half22float2(hh);
-              const __half2 hl = __floats2half2_rn(v0 - bk.x, v1 - bk.y);
               uh[u >> 1] = h2_as_u32(hh);
-              ul[u >> 1] = h2_as_u32(hl);
+              if (nparts == 2) {
+                const float2 bk = __half22float2(hh);
+                ul[u >> 1] = h2_as_u32(__floats2half2_rn(v0 - bk.x, v1 - bk.y));
+              } else {
+                ul[u >> 1] = 0u;
+              }
             }
             vhi = make_uint4(uh[0], uh[1], uh[2], uh[3]);
             vlo = make_uint4(ul[0], ul[1], ul[2], ul[3]);
           }
           const uint32_t off = ((uint32_t)kg * 128u + (uint32_t)col) * 16u;
           *reinterpret_cast<uint4*>(Hhi + off) = vhi;
-          *reinterpret_cast<uint4*>(Hlo + off) = vlo;
+          if (nparts == 2) *reinterpret_cast<uint4*>(Hlo + off) = vlo;
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -379,10 +382,7 @@ decode_pair_kernel(const __grid_constant__ Params P) {
           const uint32_t taddr = tmem_base + lane_addr + ab * (uint32_t)kPairN;
           if constexpr (EPI == kVarT1) {
             unsigned long long s2a = 0ull, s2b = 0ull, q2a = 0ull, q2b = 0ull;
-            for (int c0 = 0; c0 < nread; c0 += 32) {
-              uint32_t r[32];
-              tmem_ld_32x32(taddr + c0, r);
-              tmem_ld_wait();
+            auto accumulate = [&](const uint32_t (&r)[32]) {
 #pragma unroll
               for (int q = 0; q < 32; q += 4) {
                 unsigned long long d0, d1;
@@ -392,6 +392,21 @@ decode_pair_kernel(const __grid_constant__ Params P) {
                 s2b = add_f32x2(s2b, d1);
                 q2a = fma_f32x2(d0, d0, q2a);
                 q2b = fma_f32x2(d1, d1, q2b);
+              }
+            };
+            // two register buffers: the TMEM load of the next 32 columns is in flight while the sums of the
+            // current 32 are formed (the un-pipelined loop stalled on every LDTM, profiles/: decode_r1_screen)
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32(taddr, ra);
+            for (int c0 = 0; c0 < nread; c0 += 64) {
+              tmem_ld_wait();
+              const bool more = c0 + 32 < nread;
+              if (more) tmem_ld_32x32(taddr + c0 + 32, rb);
+              accumulate(ra);
+              if (more) {
+                tmem_ld_wait();
+                if (c0 + 64 < nread) tmem_ld_32x32(taddr + c0 + 64, ra);
+                accumulate(rb);
               }
             }
             tc_fence_before();
@@ -410,11 +425,15 @@ decode_pair_kernel(const __grid_constant__ Params P) {
               myAcc[(j * 2 + 1) * 128] = qsum;
             } else {
               const float mean = ssum * P.inv_S;
-              vmax = fmaxf(vmax, fmaf(-mean, mean, qsum * P.inv_S));
+              const float var = fmaf(-mean, mean, qsum * P.inv_S);
+              vmax = fmaxf(vmax, var);
+              if (P.var_field)
+                P.var_field[((size_t)it.p * P.T + it.tg) * P.field_ld + (it.tile0 + 2 * j + (int)rank) * kTileM +
+                            warp * 32 + lane] = var;
             }
           } else if constexpr (EPI == kVarSeg) {
             float ss = 0.f, qq = 0.f;
-            int cnt = 0;
+            int cnt = 0, sg = 0;
             for (int c0 = 0; c0 < nread; c0 += 32) {
               uint32_t r[32];
               tmem_ld_32x32(taddr + c0, r);
@@ -426,8 +445,12 @@ decode_pair_kernel(const __grid_constant__ Params P) {
                 qq = fmaf(d, d, qq);
                 if (++cnt == P.S) {
                   const float mean = ss * P.inv_S;
-                  vmax = fmaxf(vmax, fmaf(-mean, mean, qq * P.inv_S));
-                  ss = 0.f; qq = 0.f; cnt = 0;
+                  const float var = fmaf(-mean, mean, qq * P.inv_S);
+                  vmax = fmaxf(vmax, var);
+                  if (P.var_field && it.tg * P.TPC + sg < P.T)      // zero-padded columns complete phantom segments
+                    P.var_field[((size_t)it.p * P.T + it.tg * P.TPC + sg) * P.field_ld +
+                                (it.tile0 + 2 * j + (int)rank) * kTileM + warp * 32 + lane] = var;
+                  ss = 0.f; qq = 0.f; cnt = 0; ++sg;
                 }
               }
             }
@@ -521,13 +544,16 @@ static int launch_epi2(glasdi_handle* h, const dv::Params& P, cudaStream_t st) {
 }
 
 int launch_decode_var_pair(glasdi_handle* h, const float* Zs, int Spad, int P_, int S, int T,
-                           unsigned int* maxvar_bits, cudaStream_t st) {
+                           unsigned int* maxvar_bits, float* var_field, int passes, cudaStream_t st) {
   dv::Params P{};
   int rc = fill_common2(h, P);
   if (rc) return rc;
   P.P = P_; P.S = S; P.T = T; P.Spad = Spad;
   P.Zs = Zs;
   P.maxvar_bits = maxvar_bits;
+  P.var_field = var_field;
+  P.field_ld = decode_field_ld(h->dec.n_tiles);
+  if (passes > 0) P.passes = passes;
   P.inv_S = 1.0f / (float)S;
   const bool seg = S < dv2::kPairN / 2;          // at least two time steps fit one 256-column chunk
   if (!seg) {

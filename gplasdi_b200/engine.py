@@ -69,6 +69,13 @@ class Engine:
         self._check(self.lib.glasdi_stage_times(self.h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
 
+    def screen_stats(self):
+        """(refine_ms, n_candidates, max_rel_dev) of the last screened greedy call."""
+        ms, n, dev = C.c_double(), C.c_int64(), C.c_float()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_screen_stats(self.h, C.byref(ms), C.byref(n), C.byref(dev), _stream_ptr()))
+        return ms.value, n.value, dev.value
+
     def check_numeric(self):
         with torch.cuda.device(self.device):
             self._check(self.lib.glasdi_check_numeric(self.h, _stream_ptr()))

@@ -62,8 +62,22 @@ enum glasdi_option {
   GLASDI_OPT_MAX_CTAS = 3,      /* cap on persistent CTAs (0 = one per SM); for tests */
   GLASDI_OPT_DECODE_KERNEL = 5, /* 1 (default): CTA-pair tcgen05 kernel (cta_group::2, 256x256 tiles);
                                    0: single-CTA kernel (128x128 tiles).  Same numerics. */
-  GLASDI_OPT_STAGE_TIMING = 4   /* 1: bracket the rollout and decode kernels of the greedy step with
+  GLASDI_OPT_STAGE_TIMING = 4,  /* 1: bracket the rollout and decode kernels of the greedy step with
                                    CUDA events on the caller's stream (read with glasdi_stage_times) */
+  GLASDI_OPT_MODE = 6,          /* enum glasdi_mode (default SCREENED) */
+  GLASDI_OPT_SCREEN_MARGIN = 7  /* m in 4..16 (default 8): screened mode re-evaluates every (t, dof) whose
+                                   single-pass std is within delta = 2^-m of the parameter's screened maximum */
+};
+
+/* how glasdi_greedy_step / glasdi_decode_max_std obtain max_std[p] (same result within the fp32 tolerance) */
+enum glasdi_mode {
+  GLASDI_MODE_DIRECT = 0,    /* GLASDI_OPT_SPLIT_PASSES fp16 split-product passes over the whole ensemble */
+  GLASDI_MODE_SCREENED = 1   /* ONE fp16 pass over the whole ensemble writes an approximate variance field;
+                                the (t, dof) within the margin of each parameter's maximum are then re-evaluated
+                                on the CUDA cores exactly as the reference computes them (fp32 decode, fp64
+                                sample sums).  A screening deviation above delta/4 at any candidate, or a
+                                candidate-buffer overflow, is reported as GLASDI_ERR_NUMERIC by
+                                glasdi_check_numeric -- never silently accepted. */
 };
 
 int glasdi_abi_version(void);
@@ -82,6 +96,12 @@ int64_t glasdi_launch_count(const glasdi_handle* h);
  * rollout_ms: latent rollout (or layout conversion) kernels; decode_ms: decode+variance kernels
  * (summed over parameter slabs); decode_launches: number of decode+variance launches. */
 int glasdi_stage_times(glasdi_handle* h, double* rollout_ms, double* decode_ms, int* decode_launches);
+
+/* Screened mode diagnostics of the LAST greedy call (synchronises `stream`): device time of candidate
+ * selection + exact re-evaluation (0 unless GLASDI_OPT_STAGE_TIMING), number of re-evaluated (t, dof)
+ * candidates, and the largest relative deviation |std_screen - std_exact| / std_exact seen at them. */
+int glasdi_screen_stats(glasdi_handle* h, double* refine_ms, int64_t* n_candidates, float* max_rel_dev,
+                        void* stream);
 
 /* decoder weights ------------------------------------------------------------------------------
  * Replaces: the `autoencoder.decoder` nn.Module state consumed by get_fom_max_std

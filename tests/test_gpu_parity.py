@@ -45,6 +45,8 @@ def setup_wl(engine, nm):
     engine.set_option(_lib.OPT_INTEGRATOR, _lib.INT_EXPM)
     engine.set_option(_lib.OPT_RK4_SUBSTEPS, 1)
     engine.set_option(_lib.OPT_MAX_CTAS, 0)
+    engine.set_option(_lib.OPT_MODE, _lib.MODE_SCREENED)       # library default
+    engine.set_option(_lib.OPT_SCREEN_MARGIN, 8)
     return wl, Ws, bs
 
 
@@ -129,10 +131,47 @@ def test_calibration_flags_rank_deficient_series(engine):
 
 # ---- fused greedy step -------------------------------------------------------------------------
 @pytest.mark.parametrize("nm", ["tiny", "small", "small_s200", "small_softplus"])
+def test_screened_greedy_step_matches_reference(engine, g_small, nm):
+    """Default mode: one fp16 screening pass on the tensor cores + exact re-evaluation of the candidates."""
+    wl, Ws, bs = setup_wl(engine, nm)
+    inp = synth.make_inputs(wl)
+    assert engine.get_option(_lib.OPT_MODE) == _lib.MODE_SCREENED
+    ms, am, mv = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
+    engine.check_numeric()
+    assert int(am) == int(g_small[nm + "_m_index"][0])         # selected parameter: exact
+    std_close(ms.cpu().numpy(), g_small[nm + "_max_std"])
+    assert float(mv) == float(ms.max())
+    _, ncand, dev = engine.screen_stats()
+    assert ncand >= np.count_nonzero(g_small[nm + "_max_std"] > STD_ATOL)   # at least the maximum of every spread-out parameter
+    assert dev <= 0.25 * 2.0 ** -8                             # screening stayed inside a quarter of the margin
+    # a wider margin re-evaluates more candidates and cannot change the result
+    engine.set_option(_lib.OPT_SCREEN_MARGIN, 6)
+    ms6 = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)[0]
+    assert engine.screen_stats()[1] >= ncand
+    assert np.array_equal(ms6.cpu().numpy(), ms.cpu().numpy())
+    engine.set_option(_lib.OPT_SCREEN_MARGIN, 8)
+
+
+def test_screening_deviation_is_reported(engine):
+    """A margin tighter than the single-pass error must raise, never return a possibly wrong maximum."""
+    from gplasdi_b200.engine import GlasdiError
+    wl, Ws, bs = setup_wl(engine, "small")
+    inp = synth.make_inputs(wl)
+    engine.set_option(_lib.OPT_SCREEN_MARGIN, 16)              # delta/4 = 3.8e-6 < fp16 single-pass error
+    engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
+    engine.set_option(_lib.OPT_SCREEN_MARGIN, 8)
+    with pytest.raises(GlasdiError) as e:
+        engine.check_numeric()
+    assert e.value.code == _lib.ERR_NUMERIC
+    engine.check_numeric()
+
+
+@pytest.mark.parametrize("nm", ["tiny", "small", "small_s200", "small_softplus"])
 @pytest.mark.parametrize("passes", [3, 2, 1])
 def test_greedy_step_matches_reference(engine, g_small, nm, passes):
     wl, Ws, bs = setup_wl(engine, nm)
     inp = synth.make_inputs(wl)
+    engine.set_option(_lib.OPT_MODE, _lib.MODE_DIRECT)
     engine.set_option(_lib.OPT_SPLIT_PASSES, passes)
     ms, am, mv = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
     engine.check_numeric()
