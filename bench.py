@@ -185,8 +185,9 @@ def run_ours(args):
 
     eng = Engine(local_rank)
     eng.set_decoder(Ws, bs, wl.act)
-    screened = args.mode == "screened"
-    eng.set_option(_lib.OPT_MODE, _lib.MODE_SCREENED if screened else _lib.MODE_DIRECT)
+    screened = args.mode != "direct"
+    eng.set_option(_lib.OPT_MODE, {"gram": _lib.MODE_SCREENED_GRAM, "screened": _lib.MODE_SCREENED,
+                                   "direct": _lib.MODE_DIRECT}[args.mode])
     eng.set_option(_lib.OPT_SPLIT_PASSES, args.passes)
     eng.set_option(_lib.OPT_STAGE_TIMING, 1)
     issued_passes = 1 if screened else args.passes
@@ -336,8 +337,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--mode", choices=["screened", "direct"], default="screened",
-                    help="screened (default): 1 fp16 pass + exact candidate re-evaluation; direct: --passes split passes")
+    ap.add_argument("--mode", choices=["gram", "screened", "direct"], default="gram",
+                    help="gram (default): covariance-form fp16 screening + exact candidate re-evaluation; screened: "
+                         "decoded-ensemble fp16 screening + the same re-evaluation; direct: --passes split passes")
     ap.add_argument("--passes", type=int, default=3, help="direct mode: fp16 split-product passes of the last layer (1..3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

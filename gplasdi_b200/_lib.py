@@ -18,7 +18,7 @@ ACT_IDS = {"sigmoid": 0, "tanh": 1, "softplus": 2, "ReLU": 3, "ELU": 4, "SiLU": 
 FD_IDS = {"sbp12": 0, "sbp24": 1, "sbp36": 2, "sbp48": 3}
 OPT_SPLIT_PASSES, OPT_INTEGRATOR, OPT_RK4_SUBSTEPS, OPT_MAX_CTAS, OPT_STAGE_TIMING, OPT_DECODE_KERNEL = 0, 1, 2, 3, 4, 5
 OPT_MODE, OPT_SCREEN_MARGIN = 6, 7
-MODE_DIRECT, MODE_SCREENED = 0, 1
+MODE_DIRECT, MODE_SCREENED, MODE_SCREENED_GRAM = 0, 1, 2
 INT_EXPM, INT_RK4 = 0, 1
 
 # name -> (restype, argtypes); must list EVERY symbol of include/glasdi_b200.h (tests check this)

@@ -63,6 +63,9 @@ static void free_decoder(Decoder& d) {
   d.db.clear();
   if (d.w_packed) cudaFree(d.w_packed);
   d.w_packed = nullptr;
+  if (d.v_packed) cudaFree(d.v_packed);
+  d.v_packed = nullptr;
+  d.gram_ok = false;
   d.ready = false;
   d.tc_ok = false;
 }
@@ -171,8 +174,8 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
       h->opt_kernel = value;
       return GLASDI_OK;
     case GLASDI_OPT_MODE:
-      if (value != GLASDI_MODE_DIRECT && value != GLASDI_MODE_SCREENED)
-        return set_error(h, GLASDI_ERR_INVALID, "mode must be GLASDI_MODE_DIRECT or GLASDI_MODE_SCREENED");
+      if (value != GLASDI_MODE_DIRECT && value != GLASDI_MODE_SCREENED && value != GLASDI_MODE_SCREENED_GRAM)
+        return set_error(h, GLASDI_ERR_INVALID, "mode must be GLASDI_MODE_DIRECT, _SCREENED or _SCREENED_GRAM");
       h->opt_mode = value;
       return GLASDI_OK;
     case GLASDI_OPT_SCREEN_MARGIN:
@@ -266,6 +269,12 @@ int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths, const 
     GL_CUDA(h, cudaMalloc(&d.w_packed, packed.size() * sizeof(__half)));
     GL_CUDA(h, cudaMemcpy(d.w_packed, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
+  // covariance-form screening: the constant unit must fit the 128-row tile, shared memory must hold the ring
+  d.gram_ok = ok && d.K + 1 <= 128 && decode_gram_smem_bytes(d.K, last_in_w) <= 227 * 1024;
+  if (d.gram_ok) {
+    int rc = gram_pack_v(h, WL);
+    if (rc) return rc;
+  }
   d.ready = true;
   return GLASDI_OK;
 }
@@ -318,15 +327,20 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
   const int Spad = (S + 31) / 32 * 32;
   // screened mode: one fp16 pass on the tensor cores writes the variance field, refine.cu re-evaluates
   // the near-maximum candidates exactly.  Only the CTA-pair tcgen05 kernel has the field epilogue.
-  const bool screened = h->opt_mode == GLASDI_MODE_SCREENED && d.tc_ok && h->opt_kernel == 1;
+  const bool gram = h->opt_mode == GLASDI_MODE_SCREENED_GRAM && d.gram_ok;
+  const bool screened = gram || (h->opt_mode != GLASDI_MODE_DIRECT && d.tc_ok && h->opt_kernel == 1);
   const int field_ld = decode_field_ld(d.n_tiles);
   const size_t traj_bytes = (size_t)T * n * Spad * sizeof(float);
   const size_t field_bytes = screened ? (size_t)T * field_ld * sizeof(float) : 0;
-  const size_t per_param = traj_bytes + field_bytes;
-  const size_t budget = (size_t)12 << 30;                      // trajectory (+ field) scratch per slab
+  const size_t gram_bytes = gram ? (size_t)T * (gram_nkgQ(d.K) * 16 + sizeof(float)) : 0;   // packed covariances + scales
+  const size_t per_param = traj_bytes + field_bytes + gram_bytes;
+  const size_t budget = (size_t)12 << 30;                      // trajectory (+ field, + covariances) scratch per slab
   int slab = (int)std::max<size_t>(1, std::min<size_t>((size_t)P, budget / per_param));
   slab = std::min(slab, 32768);
-  int rc = ensure_workspace(h, per_param * slab);
+  const size_t a_off = (traj_bytes + field_bytes) * slab;
+  const size_t a_bytes = gram ? gram_a_bytes(d.K, (long long)slab * T) : 0;
+  const size_t fs_bytes = gram ? gram_fscale_bytes((long long)slab * T) : 0;
+  int rc = ensure_workspace(h, a_off + a_bytes + fs_bytes);
   if (rc) return rc;
   rc = ensure_maxvar(h, (size_t)P);
   if (rc) return rc;
@@ -357,7 +371,10 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
     if (rc) return rc;
     if ((rc = t_roll.stop())) return rc;
     if ((rc = t_dec.start())) return rc;
-    if (screened) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, field, 1, st);
+    if (gram) rc = launch_decode_gram(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, field,
+                                      reinterpret_cast<uint8_t*>(h->ws) + a_off,
+                                      reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->ws) + a_off + a_bytes), st);
+    else if (screened) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, field, 1, st);
     else if (d.tc_ok && h->opt_kernel == 1) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, nullptr, 0, st);
     else if (d.tc_ok) rc = launch_decode_var(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
     else rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
@@ -368,7 +385,8 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
       GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats, 0, sizeof(unsigned int), st));      // per-slab count
       rc = launch_select_candidates(h, field, field_ld, h->d_maxvar + p0, pn, T, d.D, (1.f - delta) * (1.f - delta), st);
       if (rc) return rc;
-      rc = launch_refine(h, Zs, Spad, S, T, h->d_exact + p0, 0.25f * delta, st);
+      rc = launch_refine(h, Zs, Spad, S, T, h->d_exact + p0, 0.25f * delta,
+                         gram ? 1.0f : ldexpf(1.0f, -2 * (d.eW + d.eH)), st);
       if (rc) return rc;
       if ((rc = t_ref.stop())) return rc;
     }

@@ -39,6 +39,10 @@ struct Decoder {
   int eW = 0;                       // power-of-two scale applied to W before the fp16 split
   int eH = 0;                       // power-of-two scale applied to the hidden activations
   bool tc_ok = false;               // tcgen05 path supports this shape
+  // covariance-form screening (decode_gram.cu): V[dof, (i<=j)] = (2 - delta_ij) w_i w_j 2^eV, fp16 UMMA tiles
+  __half* v_packed = nullptr;
+  int eV = 0;
+  bool gram_ok = false;
 };
 
 }  // namespace glasdi
@@ -65,7 +69,7 @@ struct glasdi_handle {
   size_t maxvar_cap = 0;
   int* d_flags = nullptr;             // [4] device error flags: [0] fp16 range, [1] candidate overflow, [2] screening deviation
   // screened mode (GLASDI_OPT_MODE = 1): candidates of the last greedy call
-  int opt_mode = 1;                   // 0: direct (split passes), 1: single-pass screening + exact refinement
+  int opt_mode = 2;                   // 0: direct (split passes), 1: x-space screening + refinement, 2: covariance-form screening + refinement
   int opt_margin_log2 = 8;            // candidates = variance within (1 - 2^-margin)^2 of the screened maximum
   void* d_cand = nullptr;             // [cand_cap] {p, t, d, approx variance}
   size_t cand_cap = 0;
@@ -106,11 +110,19 @@ size_t decode_var_smem_bytes(int Kpad, int last_in_w);
 int launch_decode_var_pair(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
                            unsigned int* maxvar_bits, float* var_field, int passes, cudaStream_t st);
 inline int decode_field_ld(int n_tiles) { return (n_tiles + 1) / 2 * 2 * 128; }
+// decode_gram.cu : covariance-form screening pass (gram_kernel + quad_kernel)
+int gram_nkgQ(int K);
+size_t gram_a_bytes(int K, long long n_items);
+size_t gram_fscale_bytes(long long n_items);
+size_t decode_gram_smem_bytes(int K, int last_in_w);
+int gram_pack_v(glasdi_handle* h, const float* WL_host);
+int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T, unsigned int* maxvar_bits,
+                       float* var_field, void* a_ws, float* fscale_ws, cudaStream_t st);
 // refine.cu : candidate selection on the screened variance field + exact fp32/fp64 re-evaluation
 int launch_select_candidates(glasdi_handle* h, const float* var_field, int field_ld, const unsigned int* approx_bits,
                              int P, int T, int D, float keep, cudaStream_t st);
 int launch_refine(glasdi_handle* h, const float* Zs, int Spad, int S, int T, unsigned int* exact_bits,
-                  float dev_tol, cudaStream_t st);
+                  float dev_tol, float unscale, cudaStream_t st);
 int launch_decode_store_pair(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
 // simt_fallback.cu : fp32 CUDA-core path for decoder shapes the tcgen05 kernel does not cover
 int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,

@@ -1,0 +1,643 @@
+// decode_gram.cu -- SCREENING pass of the greedy step in covariance form (GLASDI_MODE_SCREENED_GRAM).
+//
+// Why: the decoded ensemble x[dof, sample] of one (parameter, time step) has D*S outputs but only
+// K = 100 MACs per output; a tcgen05 accumulator leaves TMEM at 64 B/clk/SM (tcgen05.ld), so ANY kernel
+// that materialises x in TMEM is drain-bound at K/256 = 44 % of the tensor peak (measured: 57 ms for the
+// 44.5 TFLOP bench step, profiles/).  The variance over samples does not need x:
+//
+//     sigma^2[dof] = w_dof^T C w_dof,     C = cov_s(h)  (K x K),   h = hidden activations of the last layer,
+//
+// (reference semantics: std(0) of decoder(Z) over the samples, src/lasdi/gplasdi.py:65-67 with the decoder of
+// src/lasdi/latent_space.py:157-164 whose last layer is linear).  Two tensor-core GEMMs whose outputs are tiny:
+//
+//   gram_kernel   per (p, t):  G = H^T H over the S samples (M = N = units, K = samples: MN-major operands,
+//                 both read from the SAME shared-memory tile), an extra constant unit gives the column sums;
+//                 epilogue: C = G/S - m m^T/S^2, per-item power-of-two scale, fp16, packed upper triangle
+//                 written as the A operand of the second GEMM.
+//   quad_kernel   var[(p,t), dof] = sum_q Ctilde[(p,t), q] V[dof, q],  V[dof, (i,j)] = (2 - delta_ij) w_i w_j,
+//                 Q = K(K+1)/2 = 5050: a plain [P*T x Q] x [Q x D] GEMM; epilogue: un-scale, write the variance
+//                 field, atomicMax per parameter.
+//
+// FLOP: K^2 S + Q D per (p, t) instead of K S D: 5x fewer than the direct product at the bench shape.
+// Accuracy: one fp16 pass with cancellation in the quadratic form -> ~1e-4 relative on sigma; this is a
+// SCREENING pass only -- refine.cu re-evaluates every near-maximum (t, dof) exactly and checks the deviation.
+#include "decode_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace glasdi {
+namespace gr {
+
+using namespace dv;
+
+constexpr int kCols = 128;                  // sample columns per chunk
+constexpr int kRing = 4;                    // chunk ring
+constexpr int kGroupsM = 16;                // unit groups of 8 in a tile (M = 128)
+constexpr uint32_t kBufBytes = kGroupsM * kCols * 16;   // 32 KB
+constexpr int kGEpiWarps = 4;
+constexpr int kGMmaWarp = 4;
+constexpr int kGProdWarp0 = 5;
+constexpr int kGProdWarps = 8;
+constexpr int kGProdThreads = kGProdWarps * 32;
+constexpr int kGThreads = (kGProdWarp0 + kGProdWarps) * 32;   // 416
+constexpr int kGTmemCols = 256;             // 2 accumulators x 128 columns
+
+struct GramParams {
+  int P, S, T, Spad, NZ;
+  int K;                 // real hidden units (input width of the last layer); unit index K is the constant unit
+  int nkg;               // unit groups the producers fill = ceil((K + 1) / 8)
+  int Nmma;              // N of the MMA = ceil((K + 1) / 16) * 16 <= 128
+  int nkgQ;              // 16-byte groups of the packed triangle, padded to the quad kernel's K chunk
+  int Q;                 // K (K + 1) / 2
+  float h_scale, inv_S;
+  int exp_base;          // 2 eH + eV : exponent of the fixed part of the scale
+  int check_overflow;
+  long long n_items;     // P * T
+  const float* Zs;       // [P][T][NZ][Spad]
+  __half* A;             // [item block of 128][nkgQ][128 rows][8]  : A operand of the quad kernel
+  float* fscale;         // [n_items] : variance = accumulator * fscale
+  int* flags;
+  FrontMlp front;
+};
+
+struct GBars {
+  uint64_t h_full[kRing], h_empty[kRing], acc_full[2], acc_empty[2];
+};
+
+struct GSmem {
+  uint32_t h, wl, pilot, m, mx, c, bars, tmem, total;
+  int wl_ld, kpu;
+};
+__host__ __device__ inline GSmem gcarve(int nkg, int last_in_w, int nkgQ) {
+  GSmem s;
+  uint32_t off = 0;
+  s.kpu = nkg * 8;
+  s.h = off; off += kRing * kBufBytes;
+  s.wl_ld = wl_stride(last_in_w);
+  s.wl = off; off += (uint32_t)s.kpu * (uint32_t)s.wl_ld * 4u;
+  s.pilot = off; off += (uint32_t)s.kpu * 4u;
+  s.m = off; off += 128 * 4u;
+  s.mx = off; off += 16;
+  off = (off + 15u) & ~15u;
+  s.c = off; off += (uint32_t)nkgQ * 16u;
+  s.bars = off; off += 16 * 8;
+  s.tmem = off; off += 16;
+  s.total = off;
+  return s;
+}
+
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+
+// kind::f16, fp32 accumulate, M = 128, both operands MN-major (the contraction index -- samples -- is the
+// strided one: canonical layout ((8,1,m),(8,k)) : ((1,8,SBO),(8,LBO)) in elements)
+__device__ __forceinline__ uint32_t umma_idesc_f16_m128_mn(uint32_t n) {
+  uint32_t d = 0;
+  d |= 1u << 4;              // c_format = F32
+  d |= 1u << 15;             // a_major = MN
+  d |= 1u << 16;             // b_major = MN
+  d |= (n >> 3) << 17;
+  d |= (128u >> 4) << 24;
+  return d;
+}
+
+template <int ACT, int INW>
+__global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constant__ GramParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int last_in_w = P.front.widths[P.front.n_front - 1];
+  const GSmem L = gcarve(P.nkg, last_in_w, P.nkgQ);
+  uint8_t* sH = smem + L.h;
+  float* sWl = reinterpret_cast<float*>(smem + L.wl);
+  float* sPilot = reinterpret_cast<float*>(smem + L.pilot);
+  float* sM = reinterpret_cast<float*>(smem + L.m);
+  float* sMax = reinterpret_cast<float*>(smem + L.mx);
+  __half* sC = reinterpret_cast<__half*>(smem + L.c);
+  GBars* B = reinterpret_cast<GBars*>(smem + L.bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem);
+  const int nchunks = (P.S + kCols - 1) / kCols;
+
+  // ---- one-time setup -------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(&B->h_full[i], kGProdWarps);
+      mbar_init(&B->h_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&B->acc_full[i], 1);
+      mbar_init(&B->acc_empty[i], kGEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kGMmaWarp) {
+    tmem_alloc(tmem_slot, kGTmemCols);
+    tmem_relinquish();
+  }
+  {
+    const int l = P.front.n_front - 1;
+    const float* __restrict__ W = P.front.W[l];
+    const float* __restrict__ b = P.front.b[l];
+    const int ld = L.wl_ld;
+    for (int idx = threadIdx.x; idx < L.kpu * ld; idx += blockDim.x) {
+      const int k = idx / ld, i = idx - k * ld;
+      float v = 0.f;
+      if (k < P.K) {
+        if (i < last_in_w) v = W[(size_t)k * last_in_w + i];
+        else if (i == last_in_w) v = b[k];
+      }
+      sWl[idx] = v;
+    }
+    // operand tiles (unit groups >= nkg stay zero for ever) and the packed-triangle staging (tail stays zero)
+    uint4* z4 = reinterpret_cast<uint4*>(sH);
+    for (uint32_t idx = threadIdx.x; idx < kRing * kBufBytes / 16; idx += blockDim.x) z4[idx] = make_uint4(0, 0, 0, 0);
+    uint4* c4 = reinterpret_cast<uint4*>(sC);
+    for (int idx = threadIdx.x; idx < P.nkgQ; idx += blockDim.x) c4[idx] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kGMmaWarp) {
+    // ---- MMA issuer ---------------------------------------------------------------------------
+    uint32_t h_it = 0, a_it = 0;
+    const uint32_t idesc = umma_idesc_f16_m128_mn((uint32_t)P.Nmma);
+    // MN-major, no swizzle: LBO = step between 8-sample groups (128 B), SBO = step between 8-unit groups (2 KB)
+    const uint64_t desc0 = umma_desc_kmajor(smem_u32(sH), 128u, (uint32_t)kCols * 16u);
+    for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const uint32_t ab = a_it & 1u;
+      mbar_wait(&B->acc_empty[ab], ((a_it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + ab * 128u;
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t buf = h_it % kRing;
+        mbar_wait(&B->h_full[buf], (h_it / kRing) & 1u);
+        tc_fence_after();
+        const int ncols = min(kCols, P.S - c * kCols);
+        const int nk = (ncols + 15) >> 4;
+        const uint64_t d0 = desc0 + (uint64_t)(buf * (kBufBytes >> 4));
+        if (elect_one()) {
+#pragma unroll 1
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t dk = d0 + (uint64_t)(k * 16);            // 16 samples x 16 B = 256 B per K slice
+            tc_mma_f16(d_tmem, dk, dk, idesc, (c | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&B->h_empty[buf]);
+        }
+        __syncwarp();
+        ++h_it;
+      }
+      if (elect_one()) tc_commit(&B->acc_full[ab]);
+      __syncwarp();
+      ++a_it;
+    }
+  } else if (warp >= kGProdWarp0) {
+    // ---- producers: pilot-centred, scaled activations of 128 sample columns per chunk --------------
+    const int ptid = threadIdx.x - kGProdWarp0 * 32;
+    const int col = ptid & 127;
+    const int half = ptid >> 7;
+    const int kg_begin = half == 0 ? 0 : (P.nkg + 1) / 2;
+    const int kg_end = half == 0 ? (P.nkg + 1) / 2 : P.nkg;
+    const int NZ = P.NZ;
+    const int ld = L.wl_ld;
+    const float hscale = P.h_scale;
+    const int kg_one = P.K >> 3, u_one = P.K & 7;
+    uint32_t h_it = 0;
+    float amax = 0.f;
+    for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const float* __restrict__ zb = P.Zs + (size_t)item * NZ * P.Spad;
+      // pilot = activations of sample 0
+      for (int kg = ptid; kg < P.nkg; kg += kGProdThreads) {
+        float zz[kMaxLatent];
+#pragma unroll
+        for (int i = 0; i < kMaxLatent; ++i) zz[i] = (i < NZ) ? __ldg(zb + (size_t)i * P.Spad) : 0.f;
+        float hv[8];
+        if constexpr (INW > 0) {
+          last_front_units<ACT, INW>(sWl, ld, last_in_w, P.front.act, kg * 8, zz, hv);
+        } else {
+          float x[kMaxHid];
+          front_pre<ACT>(P.front, zz, x);
+          last_front_units<ACT, 0>(sWl, ld, last_in_w, P.front.act, kg * 8, x, hv);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sPilot[kg * 8 + u] = hv[u] * hscale;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c * kCols + col;
+        const bool valid = s < P.S;
+        float zin[kMaxLatent];
+#pragma unroll
+        for (int i = 0; i < kMaxLatent; ++i) zin[i] = (valid && i < NZ) ? __ldg(zb + (size_t)i * P.Spad + s) : 0.f;
+        float xloc[INW > 0 ? 1 : kMaxHid];
+        const float* x = zin;
+        if constexpr (INW == 0) {
+          if (valid) front_pre<ACT>(P.front, zin, xloc);
+          x = xloc;
+        }
+        const uint32_t buf = h_it % kRing;
+        uint8_t* Hb = sH + buf * kBufBytes;
+        mbar_wait_relaxed(&B->h_empty[buf], ((h_it / kRing) & 1u) ^ 1u);
+        for (int kg = kg_begin; kg < kg_end; ++kg) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (valid) {
+            float hv[8];
+            last_front_units<ACT, INW>(sWl, ld, last_in_w, P.front.act, kg * 8, x, hv);
+            const float4 p0 = *reinterpret_cast<const float4*>(sPilot + kg * 8);
+            const float4 p1 = *reinterpret_cast<const float4*>(sPilot + kg * 8 + 4);
+            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            float dv8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              dv8[u] = fmaf(hv[u], hscale, -pv[u]);
+              if (P.check_overflow) amax = fmaxf(amax, fabsf(dv8[u]));
+            }
+            if (kg == kg_one) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) dv8[u] = (u == u_one) ? 1.0f : dv8[u];      // the constant unit
+            }
+            v.x = h2_as_u32(__floats2half2_rn(dv8[0], dv8[1]));
+            v.y = h2_as_u32(__floats2half2_rn(dv8[2], dv8[3]));
+            v.z = h2_as_u32(__floats2half2_rn(dv8[4], dv8[5]));
+            v.w = h2_as_u32(__floats2half2_rn(dv8[6], dv8[7]));
+          }
+          *reinterpret_cast<uint4*>(Hb + ((uint32_t)kg * kCols + (uint32_t)col) * 16u) = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B->h_full[buf]);
+        ++h_it;
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item
+    }
+    if (P.check_overflow && !(amax < 60000.f)) atomicOr(P.flags, 1);
+  } else {
+    // ---- epilogue warps 0..3: thread <-> unit row i of the Gram matrix --------------------------------
+    const int i = warp * 32 + lane;
+    const int K = P.K;
+    const float inv_S = P.inv_S;
+    const int off_i = i * K - (i * (i - 1)) / 2;
+    uint32_t a_it = 0;
+    for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const uint32_t ab = a_it & 1u;
+      mbar_wait_relaxed(&B->acc_full[ab], (a_it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (((uint32_t)(warp * 32)) << 16) + ab * 128u;
+      uint32_t r[32];
+      // step 1: own diagonal entry, own column sum, the row of column sums (from the constant unit's row)
+      tmem_ld_32x32(taddr + warp * 32, r);
+      uint32_t mi_bits;
+      tmem_ld_32x1(taddr + K, mi_bits);
+      tmem_ld_wait();
+      float gii = 0.f;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) gii = (q == lane) ? __uint_as_float(r[q]) : gii;
+      const float mi = __uint_as_float(mi_bits);
+      const float cii = (i < K) ? (gii - mi * mi * inv_S) * inv_S : 0.f;
+      const float wm = warp_max(fmaxf(cii, 0.f));
+      if (lane == 0) sMax[warp] = wm;
+      if (warp == (K >> 5)) {
+        for (int b = 0; b < 4; ++b) {
+          tmem_ld_32x32(taddr + b * 32, r);
+          tmem_ld_wait();
+          if (lane == (K & 31)) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) sM[b * 32 + q] = __uint_as_float(r[q]);
+          }
+        }
+      }
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      const float cmax = fmaxf(fmaxf(sMax[0], sMax[1]), fmaxf(sMax[2], sMax[3]));
+      int e = 0;
+      float f = 0.f;
+      if (cmax > 0.f && cmax < 3.0e38f) {
+        e = max(-60, min(60, 13 - ilogbf(cmax)));
+        f = ldexpf(inv_S, e);
+      }
+      // step 2: upper-triangle entries j >= i of row i, scaled, fp16, packed at off(i) + j - i
+      const float mis = mi * inv_S;
+      for (int b = warp; b < 4; ++b) {                  // blocks left of the diagonal block hold only j < i
+        if (b * 32 >= K) break;
+        tmem_ld_32x32(taddr + b * 32, r);
+        tmem_ld_wait();
+        if (i < K) {
+          const float4* m4 = reinterpret_cast<const float4*>(sM + b * 32);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 mj = m4[q4];
+            const float mjv[4] = {mj.x, mj.y, mj.z, mj.w};
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const int j = b * 32 + q4 * 4 + qq;
+              if (j >= i && j < K) {
+                const float val = fmaf(-mis, mjv[qq], __uint_as_float(r[q4 * 4 + qq])) * f;
+                sC[off_i + j - i] = __float2half_rn(val);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B->acc_empty[ab]);
+      asm volatile("bar.sync 4, 128;" ::: "memory");
+      // copy-out: 16-byte pieces of the packed row into the quad kernel's A tiles
+      {
+        const long long ib = item >> 7;
+        const int row = (int)(item & 127);
+        uint4* dst = reinterpret_cast<uint4*>(P.A) + ((size_t)ib * P.nkgQ) * 128 + row;
+        const uint4* src = reinterpret_cast<const uint4*>(sC);
+        for (int kg = threadIdx.x; kg < P.nkgQ; kg += kGEpiWarps * 32) dst[(size_t)kg * 128] = src[kg];
+        if (threadIdx.x == 0) P.fscale[item] = (f > 0.f) ? ldexpf(1.0f, -(P.exp_base + e)) : 0.f;
+      }
+      ++a_it;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kGMmaWarp) tmem_dealloc(tmem_base, kGTmemCols);
+}
+
+// ================================================================================================
+// quad_kernel: var[item, dof] = sum_q A[item, q] V[dof, q]
+constexpr int kQStages = 4;
+constexpr int kQChunkGroups = 8;                        // 8 groups of 8 = 64 q per stage
+constexpr uint32_t kQABytes = kQChunkGroups * 128 * 16; // 16 KB
+constexpr uint32_t kQBBytes = kQChunkGroups * 256 * 16; // 32 KB
+constexpr uint32_t kQStageBytes = kQABytes + kQBBytes;
+constexpr int kQThreads = 192;                          // 4 epilogue warps, loader, MMA
+constexpr int kQTmemCols = 512;
+
+struct QuadParams {
+  const __half* A;        // [n_ib][nkgQ][128][8]
+  const __half* V;        // [n_db][nkgQ][256][8]
+  const float* fscale;    // [n_items]
+  float* field;           // [n_items][field_ld]
+  unsigned int* maxvar_bits;   // [P]
+  long long n_items;
+  int T, D, field_ld, nkgQ, n_ib, n_db;
+};
+
+struct QBars {
+  uint64_t full[kQStages], empty[kQStages], acc_full[2], acc_empty[2];
+};
+
+__global__ void __launch_bounds__(kQThreads, 1) quad_kernel(const __grid_constant__ QuadParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  QBars* B = reinterpret_cast<QBars*>(smem + kQStages * kQStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kQStages * kQStageBytes + sizeof(QBars));
+  const int nchunks = P.nkgQ / kQChunkGroups;
+  const long long n_tiles = (long long)P.n_ib * P.n_db;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kQStages; ++i) {
+      mbar_init(&B->full[i], 1);
+      mbar_init(&B->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&B->acc_full[i], 1);
+      mbar_init(&B->acc_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, kQTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ---- loader ---------------------------------------------------------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long ib = tile / P.n_db;
+        const int db = (int)(tile - ib * P.n_db);
+        const uint8_t* a0 = reinterpret_cast<const uint8_t*>(P.A) + (size_t)ib * P.nkgQ * 128 * 16;
+        const uint8_t* b0 = reinterpret_cast<const uint8_t*>(P.V) + (size_t)db * P.nkgQ * 256 * 16;
+        for (int kc = 0; kc < nchunks; ++kc) {
+          const uint32_t s = it % kQStages;
+          mbar_wait_relaxed(&B->empty[s], ((it / kQStages) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&B->full[s], kQStageBytes);
+          uint8_t* dst = smem + s * kQStageBytes;
+          bulk_g2s(dst, a0 + (size_t)kc * kQABytes, kQABytes, &B->full[s]);
+          bulk_g2s(dst + kQABytes, b0 + (size_t)kc * kQBBytes, kQBBytes, &B->full[s]);
+          ++it;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ---- MMA issuer -------------------------------------------------------------------------------
+    uint32_t it = 0, a_it = 0;
+    const uint32_t idesc = umma_idesc_f16_m128(256u);
+    const uint64_t adesc0 = umma_desc_kmajor(smem_u32(smem), 128u * 16u, 128u);
+    const uint64_t bdesc0 = umma_desc_kmajor(smem_u32(smem + kQABytes), 256u * 16u, 128u);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint32_t ab = a_it & 1u;
+      mbar_wait(&B->acc_empty[ab], ((a_it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + ab * 256u;
+      for (int kc = 0; kc < nchunks; ++kc) {
+        const uint32_t s = it % kQStages;
+        mbar_wait(&B->full[s], (it / kQStages) & 1u);
+        tc_fence_after();
+        const uint64_t a0 = adesc0 + (uint64_t)(s * (kQStageBytes >> 4));
+        const uint64_t b0 = bdesc0 + (uint64_t)(s * (kQStageBytes >> 4));
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kQChunkGroups / 2; ++kk)
+            tc_mma_f16(d_tmem, a0 + (uint64_t)(kk * ((2 * 128 * 16) >> 4)), b0 + (uint64_t)(kk * ((2 * 256 * 16) >> 4)),
+                       idesc, (kc | kk) != 0 ? 1u : 0u);
+          tc_commit(&B->empty[s]);
+        }
+        __syncwarp();
+        ++it;
+      }
+      if (elect_one()) tc_commit(&B->acc_full[ab]);
+      __syncwarp();
+      ++a_it;
+    }
+  } else {
+    // ---- epilogue: thread <-> item row; un-scale, write the field, per-parameter maximum -----------------
+    uint32_t a_it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long ib = tile / P.n_db;
+      const int db = (int)(tile - ib * P.n_db);
+      const long long item = ib * 128 + warp * 32 + lane;
+      const bool valid = item < P.n_items;
+      const float fs = valid ? __ldg(P.fscale + item) : 0.f;
+      const uint32_t ab = a_it & 1u;
+      mbar_wait_relaxed(&B->acc_full[ab], (a_it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (((uint32_t)(warp * 32)) << 16) + ab * 256u;
+      float* frow = P.field + (size_t)(valid ? item : 0) * P.field_ld + db * 256;
+      float vmax = 0.f;
+      uint32_t ra[32], rb[32];
+      auto emit = [&](const uint32_t (&r)[32], int c0) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          float4 o;
+          o.x = __uint_as_float(r[q]) * fs;
+          o.y = __uint_as_float(r[q + 1]) * fs;
+          o.z = __uint_as_float(r[q + 2]) * fs;
+          o.w = __uint_as_float(r[q + 3]) * fs;
+          vmax = fmaxf(vmax, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
+          if (valid) *reinterpret_cast<float4*>(frow + c0 + q) = o;
+        }
+      };
+      tmem_ld_32x32(taddr, ra);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 64) {
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + c0 + 32, rb);
+        emit(ra, c0);
+        tmem_ld_wait();
+        if (c0 + 64 < 256) tmem_ld_32x32(taddr + c0 + 64, ra);
+        emit(rb, c0 + 32);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B->acc_empty[ab]);
+      {
+        // one atomic per warp when its 32 items belong to one parameter (T >= 32: at most two per warp)
+        const int p = valid ? (int)(item / P.T) : -1;
+        const int p0 = __shfl_sync(0xffffffffu, p, 0);
+        if (__all_sync(0xffffffffu, p == p0)) {
+          const float wm = warp_max(vmax);
+          if (lane == 0 && p0 >= 0 && wm > 0.f) atomicMax(P.maxvar_bits + p0, __float_as_uint(wm));
+        } else if (valid && vmax > 0.f) {
+          atomicMax(P.maxvar_bits + p, __float_as_uint(vmax));
+        }
+      }
+      ++a_it;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, kQTmemCols);
+}
+
+}  // namespace gr
+
+// ---- host side ------------------------------------------------------------------------------------
+int gram_nkgQ(int K) {
+  const int Q = K * (K + 1) / 2;
+  const int g = (Q + 7) / 8;
+  return (g + gr::kQChunkGroups - 1) / gr::kQChunkGroups * gr::kQChunkGroups;
+}
+size_t gram_a_bytes(int K, long long n_items) {
+  const long long n_ib = (n_items + 127) / 128;
+  return (size_t)n_ib * gram_nkgQ(K) * 128 * 16;
+}
+size_t gram_fscale_bytes(long long n_items) { return (size_t)((n_items + 127) / 128 * 128) * sizeof(float); }
+
+// V[dof, q(i,j)] = (2 - delta_ij) w_i w_j 2^eV in fp16, laid out [dof block of 256][nkgQ][256][8]
+int gram_pack_v(glasdi_handle* h, const float* WL /*[D][K] host*/) {
+  Decoder& d = h->dec;
+  const int K = d.K, D = d.D;
+  const int nkgQ = gram_nkgQ(K);
+  const int n_db = (D + 255) / 256;
+  float wmax = 0.f;
+  for (size_t i = 0; i < (size_t)D * K; ++i) wmax = std::max(wmax, std::fabs(WL[i]));
+  d.eV = (wmax > 0.f) ? 13 - std::ilogb(2.0f * wmax * wmax) : 0;
+  d.eV = std::max(-100, std::min(100, d.eV));
+  std::vector<__half> packed((size_t)n_db * nkgQ * 256 * 8, __float2half_rn(0.f));
+  for (int dof = 0; dof < D; ++dof) {
+    const float* w = WL + (size_t)dof * K;
+    const int db = dof / 256, row = dof % 256;
+    __half* base = packed.data() + (size_t)db * nkgQ * 256 * 8;
+    int q = 0;
+    for (int i = 0; i < K; ++i)
+      for (int j = i; j < K; ++j, ++q) {
+        const float v = std::ldexp((i == j ? 1.0f : 2.0f) * w[i] * w[j], d.eV);
+        base[((size_t)(q >> 3) * 256 + row) * 8 + (q & 7)] = __float2half_rn(v);
+      }
+  }
+  if (d.v_packed) cudaFree(d.v_packed);
+  d.v_packed = nullptr;
+  GL_CUDA(h, cudaMalloc(&d.v_packed, packed.size() * sizeof(__half)));
+  GL_CUDA(h, cudaMemcpy(d.v_packed, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  return GLASDI_OK;
+}
+
+static bool unbounded_act_g(int act) { return !(act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH); }
+
+template <int ACT, int INW>
+static int launch_gram_inst(glasdi_handle* h, const gr::GramParams& G, int ctas, size_t smem, cudaStream_t st) {
+  GL_CUDA(h, cudaFuncSetAttribute(gr::gram_kernel<ACT, INW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gr::gram_kernel<ACT, INW><<<ctas, gr::kGThreads, smem, st>>>(G);
+  return GLASDI_OK;
+}
+
+// screening pass in covariance form: fills var_field [P][T][field_ld] (true units) and maxvar_bits [P]
+int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P_, int S, int T, unsigned int* maxvar_bits,
+                       float* var_field, void* a_ws, float* fscale_ws, cudaStream_t st) {
+  const Decoder& d = h->dec;
+  if (!d.ready || !d.gram_ok) return set_error(h, GLASDI_ERR_INVALID, "decoder shape not supported by the Gram kernels");
+  gr::GramParams G{};
+  G.P = P_; G.S = S; G.T = T; G.Spad = Spad; G.NZ = d.widths[0];
+  G.K = d.K;
+  G.nkg = (d.K + 1 + 7) / 8;
+  G.Nmma = (d.K + 1 + 15) / 16 * 16;
+  G.nkgQ = gram_nkgQ(d.K);
+  G.Q = d.K * (d.K + 1) / 2;
+  G.h_scale = ldexpf(1.0f, d.eH);
+  G.inv_S = 1.0f / (float)S;
+  G.exp_base = 2 * d.eH + d.eV;
+  G.check_overflow = unbounded_act_g(d.act) ? 1 : 0;
+  G.n_items = (long long)P_ * T;
+  G.Zs = Zs;
+  G.A = reinterpret_cast<__half*>(a_ws);
+  G.fscale = fscale_ws;
+  G.flags = h->d_flags;
+  G.front.n_front = d.n_linear - 1;
+  G.front.act = d.act;
+  for (int l = 0; l <= G.front.n_front; ++l) G.front.widths[l] = d.widths[l];
+  for (int l = 0; l < G.front.n_front; ++l) { G.front.W[l] = d.dW[l]; G.front.b[l] = d.db[l]; }
+  const int last_in_w = d.widths[d.n_linear - 2];
+  const size_t smem = gr::gcarve(G.nkg, last_in_w, G.nkgQ).total;
+  int ctas = h->num_sms;
+  if (h->opt_max_ctas > 0) ctas = std::max(1, std::min(ctas, h->opt_max_ctas));
+  if ((long long)ctas > G.n_items) ctas = (int)G.n_items;
+  int rc;
+  if (G.front.n_front == 1 && G.NZ == 5 && d.act == GLASDI_ACT_SIGMOID)
+    rc = launch_gram_inst<GLASDI_ACT_SIGMOID, 5>(h, G, ctas, smem, st);
+  else if (d.act == GLASDI_ACT_SOFTPLUS)
+    rc = launch_gram_inst<GLASDI_ACT_SOFTPLUS, 0>(h, G, ctas, smem, st);
+  else
+    rc = launch_gram_inst<-1, 0>(h, G, ctas, smem, st);
+  if (rc) return rc;
+  h->launches++;
+  if ((rc = check_cuda(h, cudaGetLastError(), "gram_kernel launch"))) return rc;
+
+  gr::QuadParams Q{};
+  Q.A = G.A; Q.V = d.v_packed; Q.fscale = fscale_ws; Q.field = var_field; Q.maxvar_bits = maxvar_bits;
+  Q.n_items = G.n_items; Q.T = T; Q.D = d.D; Q.field_ld = decode_field_ld(d.n_tiles); Q.nkgQ = G.nkgQ;
+  Q.n_ib = (int)((G.n_items + 127) / 128);
+  Q.n_db = (d.D + 255) / 256;
+  const size_t qsmem = gr::kQStages * gr::kQStageBytes + sizeof(gr::QBars) + 16;
+  GL_CUDA(h, cudaFuncSetAttribute(gr::quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));
+  int qctas = h->num_sms;
+  if (h->opt_max_ctas > 0) qctas = std::max(1, std::min(qctas, h->opt_max_ctas));
+  const long long n_tiles = (long long)Q.n_ib * Q.n_db;
+  if ((long long)qctas > n_tiles) qctas = (int)n_tiles;
+  gr::quad_kernel<<<qctas, gr::kQThreads, qsmem, st>>>(Q);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "quad_kernel launch");
+}
+
+size_t decode_gram_smem_bytes(int K, int last_in_w) { return gr::gcarve((K + 1 + 7) / 8, last_in_w, gram_nkgQ(K)).total; }
+
+}  // namespace glasdi

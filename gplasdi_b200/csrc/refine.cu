@@ -77,7 +77,7 @@ struct RefParams {
   unsigned int* dev_bits;           // float bits of the max relative deviation screen vs exact
   int* flags;
   int K, Kpad, NZ, S, T, Spad;
-  float unscale;                    // 2^(-2 (eW + eH)): screened variance -> true units
+  float unscale;                    // screened variance -> true units (2^(-2 (eW + eH)) for the x-space screening)
   float dev_tol;
 };
 
@@ -217,7 +217,7 @@ static int launch_refine_inst(glasdi_handle* h, const rf::RefParams& R, size_t s
 }
 
 int launch_refine(glasdi_handle* h, const float* Zs, int Spad, int S, int T, unsigned int* exact_bits, float dev_tol,
-                  cudaStream_t st) {
+                  float unscale, cudaStream_t st) {
   const Decoder& d = h->dec;
   rf::RefParams R{};
   R.front.n_front = d.n_linear - 1;
@@ -233,7 +233,7 @@ int launch_refine(glasdi_handle* h, const float* Zs, int Spad, int S, int T, uns
   R.dev_bits = h->d_cand_stats + 2;
   R.flags = h->d_flags;
   R.K = d.K; R.Kpad = d.Kpad; R.NZ = d.widths[0]; R.S = S; R.T = T; R.Spad = Spad;
-  R.unscale = ldexpf(1.0f, -2 * (d.eW + d.eH));
+  R.unscale = unscale;              // screened variance -> true units
   R.dev_tol = dev_tol;
   const int last_in_w = d.widths[d.n_linear - 2];
   const size_t smem = ((size_t)d.Kpad * dv::wl_stride(last_in_w) + (size_t)rf::kRefWarps * 2 * d.Kpad) * sizeof(float);

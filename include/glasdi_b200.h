@@ -64,7 +64,7 @@ enum glasdi_option {
                                    0: single-CTA kernel (128x128 tiles).  Same numerics. */
   GLASDI_OPT_STAGE_TIMING = 4,  /* 1: bracket the rollout and decode kernels of the greedy step with
                                    CUDA events on the caller's stream (read with glasdi_stage_times) */
-  GLASDI_OPT_MODE = 6,          /* enum glasdi_mode (default SCREENED) */
+  GLASDI_OPT_MODE = 6,          /* enum glasdi_mode (default SCREENED_GRAM) */
   GLASDI_OPT_SCREEN_MARGIN = 7  /* m in 4..16 (default 8): screened mode re-evaluates every (t, dof) whose
                                    single-pass std is within delta = 2^-m of the parameter's screened maximum */
 };
@@ -72,6 +72,12 @@ enum glasdi_option {
 /* how glasdi_greedy_step / glasdi_decode_max_std obtain max_std[p] (same result within the fp32 tolerance) */
 enum glasdi_mode {
   GLASDI_MODE_DIRECT = 0,    /* GLASDI_OPT_SPLIT_PASSES fp16 split-product passes over the whole ensemble */
+  GLASDI_MODE_SCREENED_GRAM = 2, /* default.  Screening in covariance form: per (parameter, time step) the K x K
+                                covariance of the last hidden layer over the samples (one tcgen05 GEMM whose
+                                contraction runs over the samples), then var[dof] = w_dof^T C w_dof for every dof
+                                as a second GEMM against the packed products w_i w_j.  5x fewer FLOP than decoding
+                                the ensemble and no accumulator drain; approximate (fp16, ~1e-4), so the same
+                                exact re-evaluation + deviation check as GLASDI_MODE_SCREENED follows. */
   GLASDI_MODE_SCREENED = 1   /* ONE fp16 pass over the whole ensemble writes an approximate variance field;
                                 the (t, dof) within the margin of each parameter's maximum are then re-evaluated
                                 on the CUDA cores exactly as the reference computes them (fp32 decode, fp64

@@ -45,7 +45,7 @@ def setup_wl(engine, nm):
     engine.set_option(_lib.OPT_INTEGRATOR, _lib.INT_EXPM)
     engine.set_option(_lib.OPT_RK4_SUBSTEPS, 1)
     engine.set_option(_lib.OPT_MAX_CTAS, 0)
-    engine.set_option(_lib.OPT_MODE, _lib.MODE_SCREENED)       # library default
+    engine.set_option(_lib.OPT_MODE, _lib.MODE_SCREENED_GRAM)  # library default
     engine.set_option(_lib.OPT_SCREEN_MARGIN, 8)
     return wl, Ws, bs
 
@@ -131,11 +131,14 @@ def test_calibration_flags_rank_deficient_series(engine):
 
 # ---- fused greedy step -------------------------------------------------------------------------
 @pytest.mark.parametrize("nm", ["tiny", "small", "small_s200", "small_softplus"])
-def test_screened_greedy_step_matches_reference(engine, g_small, nm):
-    """Default mode: one fp16 screening pass on the tensor cores + exact re-evaluation of the candidates."""
+@pytest.mark.parametrize("mode", [_lib.MODE_SCREENED_GRAM, _lib.MODE_SCREENED])
+def test_screened_greedy_step_matches_reference(engine, g_small, nm, mode):
+    """Screened modes: one fp16 screening pass on the tensor cores (covariance form = the default, or the
+    decoded-ensemble form) + exact re-evaluation of the near-maximum candidates."""
     wl, Ws, bs = setup_wl(engine, nm)
     inp = synth.make_inputs(wl)
-    assert engine.get_option(_lib.OPT_MODE) == _lib.MODE_SCREENED
+    assert engine.get_option(_lib.OPT_MODE) == _lib.MODE_SCREENED_GRAM
+    engine.set_option(_lib.OPT_MODE, mode)
     ms, am, mv = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
     engine.check_numeric()
     assert int(am) == int(g_small[nm + "_m_index"][0])         # selected parameter: exact
@@ -208,11 +211,14 @@ def test_decode_max_std_on_reference_trajectories(engine, g_small, nm):
 
 
 @pytest.mark.parametrize("nm", ["ragged", "wide_k"])
-def test_ragged_and_wide_shapes_against_oracle(engine, nm):
+@pytest.mark.parametrize("mode", [_lib.MODE_SCREENED_GRAM, _lib.MODE_SCREENED, _lib.MODE_DIRECT])
+def test_ragged_and_wide_shapes_against_oracle(engine, nm, mode):
     wl, Ws, bs = setup_wl(engine, nm)
     inp = synth.make_inputs(wl)
     idx, per, Zis = orc.greedy_step(Ws, bs, wl.act, inp["coefs"], inp["z0"], inp["t_grid"])
+    engine.set_option(_lib.OPT_MODE, mode)
     ms, am, mv = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
+    engine.check_numeric()
     assert int(am) == idx
     std_close(ms.cpu().numpy(), per)
     Z = engine.rollout(inp["coefs"], inp["z0"], wl.T, wl.dt).cpu().numpy()

@@ -10,7 +10,7 @@ P = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 variant = int(sys.argv[4]) if len(sys.argv) > 4 else 1
-mode = int(sys.argv[5]) if len(sys.argv) > 5 else 1          # 1 = screened (default), 0 = direct
+mode = int(sys.argv[5]) if len(sys.argv) > 5 else 2          # 2 = covariance-form screening (default), 1 = x-space screening, 0 = direct
 wl = synth.WORKLOADS["burgers1d"]
 Ws, bs = synth.make_decoder(wl.widths, wl.seed)
 inp = synth.make_inputs(wl, slice(200, 200 + P))
@@ -25,5 +25,5 @@ for _ in range(reps):
     ms, am, mv = eng.greedy_step(coefs, z0, wl.T, wl.dt)
     torch.cuda.synchronize()
     print("stage ms (rollout, decode, launches):", eng.stage_times(), "idx", int(am),
-          "screen (refine ms, candidates, max dev):", eng.screen_stats() if mode == 1 else None, flush=True)
+          "screen (refine ms, candidates, max dev):", eng.screen_stats() if mode >= 1 else None, flush=True)
 eng.check_numeric()
