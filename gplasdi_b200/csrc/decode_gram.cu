@@ -74,9 +74,9 @@ __host__ __device__ inline GSmem gcarve(int nkg, int last_in_w, int nkgQ) {
   uint32_t off = 0;
   s.kpu = nkg * 8;
   s.h = off; off += kRing * kBufBytes;
-  s.wl_ld = wl_stride(last_in_w);
+  s.wl_ld = wl_stride(last_in_w) > 12 ? wl_stride(last_in_w) : 12;   // fast path rows: 12 floats (duplicated pairs)
   s.wl = off; off += (uint32_t)s.kpu * (uint32_t)s.wl_ld * 4u;
-  s.pilot = off; off += (uint32_t)s.kpu * 4u;
+  s.pilot = off; off += (uint32_t)s.kpu * 8u;                          // fast path: (-p, -p) pairs
   s.m = off; off += 128 * 4u;
   s.mx = off; off += 16;
   off = (off + 15u) & ~15u;
@@ -103,7 +103,71 @@ __device__ __forceinline__ uint32_t umma_idesc_f16_m128_mn(uint32_t n) {
   return d;
 }
 
-template <int ACT, int INW>
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// volatile: a plain asm is a pure function to the compiler, which then hoists the pilot's loads above their
+// `ptid < nkg` guard and executes them for every producer thread -- out of the shared-memory window
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ unsigned long long lds64_volatile(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+constexpr float kNegLog2e = -1.4426950408889634f;
+
+// Fast producer path (one front layer, latent dimension 5): TWO sample columns per thread as packed fp32 pairs
+// (FFMA2 / FADD2), weights staged as duplicated pairs (w, w) so that one LDS.128 feeds two packed FMAs, the
+// sigmoid's -log2(e) folded into the staged weights, MUFU ex2/rcp in their .ftz form (the non-ftz __expf costs
+// three more instructions per value).  d2[u] = (h_A, h_B)[kg*8+u] * 2^eH - pilot: 8.5 issue slots per
+// (unit, sample) instead of 19.6 (profiles/: gram_r1).
+template <int ACT>
+__device__ __forceinline__ void units8_pair(uint32_t sW2_addr, uint32_t sNP2_addr, int kg, const unsigned long long (&z2)[5],
+                                            unsigned long long hs2, int act_rt, bool sub_pilot,
+                                            unsigned long long (&d2)[8]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint32_t a = sW2_addr + (uint32_t)(kg * 8 + u) * 48u;
+    const float4 w01 = lds128(a), w23 = lds128(a + 16), w4b = lds128(a + 32);
+    unsigned long long acc = pack_f32x2(w4b.z, w4b.w);
+    acc = fma_f32x2(pack_f32x2(w01.x, w01.y), z2[0], acc);
+    acc = fma_f32x2(pack_f32x2(w01.z, w01.w), z2[1], acc);
+    acc = fma_f32x2(pack_f32x2(w23.x, w23.y), z2[2], acc);
+    acc = fma_f32x2(pack_f32x2(w23.z, w23.w), z2[3], acc);
+    acc = fma_f32x2(pack_f32x2(w4b.x, w4b.y), z2[4], acc);
+    float xa, xb;
+    unpack_f32x2(acc, xa, xb);
+    unsigned long long h2;
+    if constexpr (ACT == GLASDI_ACT_SIGMOID) {
+      // acc = -log2(e) * pre-activation  ->  sigmoid = 1 / (1 + 2^acc)
+      const unsigned long long t2 = add_f32x2(pack_f32x2(ex2_ftz(xa), ex2_ftz(xb)), pack_f32x2(1.0f, 1.0f));
+      float ta, tb;
+      unpack_f32x2(t2, ta, tb);
+      h2 = pack_f32x2(rcp_ftz(ta), rcp_ftz(tb));
+    } else {
+      h2 = pack_f32x2(act_apply_t<ACT>(act_rt, xa), act_apply_t<ACT>(act_rt, xb));
+    }
+    if (sub_pilot) {
+      d2[u] = fma_f32x2(h2, hs2, lds64_volatile(sNP2_addr + (uint32_t)(kg * 8 + u) * 8u));
+    } else {
+      d2[u] = h2;
+    }
+  }
+}
+
+template <int ACT, int INW, bool FAST>
 __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constant__ GramParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -141,14 +205,25 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
     const float* __restrict__ W = P.front.W[l];
     const float* __restrict__ b = P.front.b[l];
     const int ld = L.wl_ld;
-    for (int idx = threadIdx.x; idx < L.kpu * ld; idx += blockDim.x) {
-      const int k = idx / ld, i = idx - k * ld;
-      float v = 0.f;
-      if (k < P.K) {
-        if (i < last_in_w) v = W[(size_t)k * last_in_w + i];
-        else if (i == last_in_w) v = b[k];
+    if constexpr (FAST) {
+      // rows of 12 floats: (w0,w0,w1,w1 | w2,w2,w3,w3 | w4,w4,b,b), times -log2(e) for the sigmoid
+      const float cf = (ACT == GLASDI_ACT_SIGMOID) ? kNegLog2e : 1.0f;
+      for (int idx = threadIdx.x; idx < L.kpu * 12; idx += blockDim.x) {
+        const int k = idx / 12, i = (idx - k * 12) >> 1;
+        float v = 0.f;
+        if (k < P.K) v = cf * (i < 5 ? W[(size_t)k * 5 + i] : b[k]);
+        sWl[k * 12 + (idx - k * 12)] = v;
       }
-      sWl[idx] = v;
+    } else {
+      for (int idx = threadIdx.x; idx < L.kpu * ld; idx += blockDim.x) {
+        const int k = idx / ld, i = idx - k * ld;
+        float v = 0.f;
+        if (k < P.K) {
+          if (i < last_in_w) v = W[(size_t)k * last_in_w + i];
+          else if (i == last_in_w) v = b[k];
+        }
+        sWl[idx] = v;
+      }
     }
     // operand tiles (unit groups >= nkg stay zero for ever) and the packed-triangle staging (tail stays zero)
     uint4* z4 = reinterpret_cast<uint4*>(sH);
@@ -198,6 +273,99 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
   } else if (warp >= kGProdWarp0) {
     // ---- producers: pilot-centred, scaled activations of 128 sample columns per chunk --------------
     const int ptid = threadIdx.x - kGProdWarp0 * 32;
+    if constexpr (FAST) {
+      // thread <-> sample columns (cp, cp + 64) of the chunk x one quarter of the unit groups
+      const int cp = ptid & 63;
+      const int quarter = ptid >> 6;
+      const int kg_begin = (P.nkg * quarter) / 4, kg_end = (P.nkg * (quarter + 1)) / 4;
+      const uint32_t sW2 = smem_u32(sWl), sNP2 = smem_u32(sPilot);
+      const float hscale = P.h_scale;
+      const unsigned long long hs2 = pack_f32x2(hscale, hscale);
+      const int kg_one = P.K >> 3, u_one = P.K & 7;
+      uint32_t h_it = 0;
+      float amax = 0.f;
+      auto load_z2 = [&](const float* __restrict__ zb, int c, unsigned long long (&z2)[5]) {
+        const int sa = c * kCols + cp, sb = sa + 64;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const float za = sa < P.S ? __ldg(zb + (size_t)i * P.Spad + sa) : 0.f;
+          const float zbv = sb < P.S ? __ldg(zb + (size_t)i * P.Spad + sb) : 0.f;
+          z2[i] = pack_f32x2(za, zbv);
+        }
+      };
+      long long item = blockIdx.x;
+      unsigned long long znext[5];
+      if (item < P.n_items) load_z2(P.Zs + (size_t)item * 5 * P.Spad, 0, znext);
+      for (; item < P.n_items; item += gridDim.x) {
+        const float* __restrict__ zb = P.Zs + (size_t)item * 5 * P.Spad;
+        // pilot = activations of sample 0, stored negated, scaled and duplicated
+        if (ptid < P.nkg) {
+          unsigned long long z0[5], pv[8];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const float zv = __ldg(zb + (size_t)i * P.Spad);
+            z0[i] = pack_f32x2(zv, zv);
+          }
+          units8_pair<ACT>(sW2, sNP2, ptid, z0, hs2, P.front.act, false, pv);
+          float2* dst = reinterpret_cast<float2*>(sPilot) + ptid * 8;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float ha, hb;
+            unpack_f32x2(pv[u], ha, hb);
+            dst[u] = make_float2(-ha * hscale, -ha * hscale);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
+        for (int c = 0; c < nchunks; ++c) {
+          unsigned long long z2[5];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) z2[i] = znext[i];
+          // next chunk's (or next item's first) latent states: in flight while this chunk is computed
+          if (c + 1 < nchunks) load_z2(zb, c + 1, znext);
+          else if (item + gridDim.x < P.n_items) load_z2(P.Zs + (size_t)(item + gridDim.x) * 5 * P.Spad, 0, znext);
+          const bool va = c * kCols + cp < P.S, vb = c * kCols + cp + 64 < P.S;
+          const uint32_t buf = h_it % kRing;
+          uint8_t* Hb = sH + buf * kBufBytes;
+          mbar_wait_relaxed(&B->h_empty[buf], ((h_it / kRing) & 1u) ^ 1u);
+          for (int kg = kg_begin; kg < kg_end; ++kg) {
+            unsigned long long d2[8];
+            units8_pair<ACT>(sW2, sNP2, kg, z2, hs2, P.front.act, true, d2);
+            float da[8], db[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              unpack_f32x2(d2[u], da[u], db[u]);
+              if (P.check_overflow) amax = fmaxf(amax, fmaxf(va ? fabsf(da[u]) : 0.f, vb ? fabsf(db[u]) : 0.f));
+            }
+            if (kg == kg_one) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                da[u] = (u == u_one) ? 1.0f : da[u];                  // the constant unit
+                db[u] = (u == u_one) ? 1.0f : db[u];
+              }
+            }
+            uint4 va4, vb4;
+            va4.x = h2_as_u32(__floats2half2_rn(da[0], da[1]));
+            va4.y = h2_as_u32(__floats2half2_rn(da[2], da[3]));
+            va4.z = h2_as_u32(__floats2half2_rn(da[4], da[5]));
+            va4.w = h2_as_u32(__floats2half2_rn(da[6], da[7]));
+            vb4.x = h2_as_u32(__floats2half2_rn(db[0], db[1]));
+            vb4.y = h2_as_u32(__floats2half2_rn(db[2], db[3]));
+            vb4.z = h2_as_u32(__floats2half2_rn(db[4], db[5]));
+            vb4.w = h2_as_u32(__floats2half2_rn(db[6], db[7]));
+            if (!va) va4 = make_uint4(0, 0, 0, 0);
+            if (!vb) vb4 = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(Hb + ((uint32_t)kg * kCols + (uint32_t)cp) * 16u) = va4;
+            *reinterpret_cast<uint4*>(Hb + ((uint32_t)kg * kCols + (uint32_t)cp + 64u) * 16u) = vb4;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&B->h_full[buf]);
+          ++h_it;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item
+      }
+      if (P.check_overflow && !(amax < 60000.f)) atomicOr(P.flags, 1);
+    } else {
     const int col = ptid & 127;
     const int half = ptid >> 7;
     const int kg_begin = half == 0 ? 0 : (P.nkg + 1) / 2;
@@ -227,12 +395,20 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         for (int u = 0; u < 8; ++u) sPilot[kg * 8 + u] = hv[u] * hscale;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
+      float znext[kMaxLatent];
+#pragma unroll
+      for (int i = 0; i < kMaxLatent; ++i) znext[i] = (col < P.S && i < NZ) ? __ldg(zb + (size_t)i * P.Spad + col) : 0.f;
       for (int c = 0; c < nchunks; ++c) {
         const int s = c * kCols + col;
         const bool valid = s < P.S;
         float zin[kMaxLatent];
 #pragma unroll
-        for (int i = 0; i < kMaxLatent; ++i) zin[i] = (valid && i < NZ) ? __ldg(zb + (size_t)i * P.Spad + s) : 0.f;
+        for (int i = 0; i < kMaxLatent; ++i) zin[i] = znext[i];
+        if (c + 1 < nchunks) {               // next chunk's latent state: in flight while this chunk is computed
+#pragma unroll
+          for (int i = 0; i < kMaxLatent; ++i)
+            znext[i] = (s + kCols < P.S && i < NZ) ? __ldg(zb + (size_t)i * P.Spad + s + kCols) : 0.f;
+        }
         float xloc[INW > 0 ? 1 : kMaxHid];
         const float* x = zin;
         if constexpr (INW == 0) {
@@ -275,6 +451,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item
     }
     if (P.check_overflow && !(amax < 60000.f)) atomicOr(P.flags, 1);
+    }
   } else {
     // ---- epilogue warps 0..3: thread <-> unit row i of the Gram matrix --------------------------------
     const int i = warp * 32 + lane;
@@ -574,10 +751,10 @@ int gram_pack_v(glasdi_handle* h, const float* WL /*[D][K] host*/) {
 
 static bool unbounded_act_g(int act) { return !(act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH); }
 
-template <int ACT, int INW>
+template <int ACT, int INW, bool FAST>
 static int launch_gram_inst(glasdi_handle* h, const gr::GramParams& G, int ctas, size_t smem, cudaStream_t st) {
-  GL_CUDA(h, cudaFuncSetAttribute(gr::gram_kernel<ACT, INW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gr::gram_kernel<ACT, INW><<<ctas, gr::kGThreads, smem, st>>>(G);
+  GL_CUDA(h, cudaFuncSetAttribute(gr::gram_kernel<ACT, INW, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gr::gram_kernel<ACT, INW, FAST><<<ctas, gr::kGThreads, smem, st>>>(G);
   return GLASDI_OK;
 }
 
@@ -613,11 +790,11 @@ int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P_, int 
   if ((long long)ctas > G.n_items) ctas = (int)G.n_items;
   int rc;
   if (G.front.n_front == 1 && G.NZ == 5 && d.act == GLASDI_ACT_SIGMOID)
-    rc = launch_gram_inst<GLASDI_ACT_SIGMOID, 5>(h, G, ctas, smem, st);
+    rc = launch_gram_inst<GLASDI_ACT_SIGMOID, 5, true>(h, G, ctas, smem, st);
   else if (d.act == GLASDI_ACT_SOFTPLUS)
-    rc = launch_gram_inst<GLASDI_ACT_SOFTPLUS, 0>(h, G, ctas, smem, st);
+    rc = launch_gram_inst<GLASDI_ACT_SOFTPLUS, 0, false>(h, G, ctas, smem, st);
   else
-    rc = launch_gram_inst<-1, 0>(h, G, ctas, smem, st);
+    rc = launch_gram_inst<-1, 0, false>(h, G, ctas, smem, st);
   if (rc) return rc;
   h->launches++;
   if ((rc = check_cuda(h, cudaGetLastError(), "gram_kernel launch"))) return rc;
