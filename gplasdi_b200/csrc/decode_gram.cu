@@ -76,7 +76,7 @@ __host__ __device__ inline GSmem gcarve(int nkg, int last_in_w, int nkgQ) {
   s.h = off; off += kRing * kBufBytes;
   s.wl_ld = wl_stride(last_in_w) > 12 ? wl_stride(last_in_w) : 12;   // fast path rows: 12 floats (duplicated pairs)
   s.wl = off; off += (uint32_t)s.kpu * (uint32_t)s.wl_ld * 4u;
-  s.pilot = off; off += (uint32_t)s.kpu * 8u;                          // fast path: (-p, -p) pairs
+  s.pilot = off; off += 2u * (uint32_t)s.kpu * 8u;                     // fast path: (-p, -p) pairs, double buffered
   s.m = off; off += 128 * 4u;
   s.mx = off; off += 16;
   off = (off + 15u) & ~15u;
@@ -134,37 +134,98 @@ constexpr float kNegLog2e = -1.4426950408889634f;
 // three more instructions per value).  d2[u] = (h_A, h_B)[kg*8+u] * 2^eH - pilot: 8.5 issue slots per
 // (unit, sample) instead of 19.6 (profiles/: gram_r1).
 template <int ACT>
-__device__ __forceinline__ void units8_pair(uint32_t sW2_addr, uint32_t sNP2_addr, int kg, const unsigned long long (&z2)[5],
-                                            unsigned long long hs2, int act_rt, bool sub_pilot,
-                                            unsigned long long (&d2)[8]) {
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const uint32_t a = sW2_addr + (uint32_t)(kg * 8 + u) * 48u;
-    const float4 w01 = lds128(a), w23 = lds128(a + 16), w4b = lds128(a + 32);
-    unsigned long long acc = pack_f32x2(w4b.z, w4b.w);
-    acc = fma_f32x2(pack_f32x2(w01.x, w01.y), z2[0], acc);
-    acc = fma_f32x2(pack_f32x2(w01.z, w01.w), z2[1], acc);
-    acc = fma_f32x2(pack_f32x2(w23.x, w23.y), z2[2], acc);
-    acc = fma_f32x2(pack_f32x2(w23.z, w23.w), z2[3], acc);
-    acc = fma_f32x2(pack_f32x2(w4b.x, w4b.y), z2[4], acc);
-    float xa, xb;
-    unpack_f32x2(acc, xa, xb);
-    unsigned long long h2;
-    if constexpr (ACT == GLASDI_ACT_SIGMOID) {
-      // acc = -log2(e) * pre-activation  ->  sigmoid = 1 / (1 + 2^acc)
-      const unsigned long long t2 = add_f32x2(pack_f32x2(ex2_ftz(xa), ex2_ftz(xb)), pack_f32x2(1.0f, 1.0f));
-      float ta, tb;
-      unpack_f32x2(t2, ta, tb);
-      h2 = pack_f32x2(rcp_ftz(ta), rcp_ftz(tb));
-    } else {
-      h2 = pack_f32x2(act_apply_t<ACT>(act_rt, xa), act_apply_t<ACT>(act_rt, xb));
-    }
-    if (sub_pilot) {
-      d2[u] = fma_f32x2(h2, hs2, lds64_volatile(sNP2_addr + (uint32_t)(kg * 8 + u) * 8u));
-    } else {
-      d2[u] = h2;
-    }
+__device__ __forceinline__ unsigned long long unit_pair(uint32_t sW2_addr, int k, const unsigned long long (&z2)[5],
+                                                        int act_rt) {
+  const uint32_t a = sW2_addr + (uint32_t)k * 48u;
+  const float4 w01 = lds128(a), w23 = lds128(a + 16), w4b = lds128(a + 32);
+  unsigned long long acc = pack_f32x2(w4b.z, w4b.w);
+  acc = fma_f32x2(pack_f32x2(w01.x, w01.y), z2[0], acc);
+  acc = fma_f32x2(pack_f32x2(w01.z, w01.w), z2[1], acc);
+  acc = fma_f32x2(pack_f32x2(w23.x, w23.y), z2[2], acc);
+  acc = fma_f32x2(pack_f32x2(w23.z, w23.w), z2[3], acc);
+  acc = fma_f32x2(pack_f32x2(w4b.x, w4b.y), z2[4], acc);
+  float xa, xb;
+  unpack_f32x2(acc, xa, xb);
+  if constexpr (ACT == GLASDI_ACT_SIGMOID) {
+    // acc = -log2(e) * pre-activation  ->  sigmoid = 1 / (1 + 2^acc)
+    const unsigned long long t2 = add_f32x2(pack_f32x2(ex2_ftz(xa), ex2_ftz(xb)), pack_f32x2(1.0f, 1.0f));
+    float ta, tb;
+    unpack_f32x2(t2, ta, tb);
+    return pack_f32x2(rcp_ftz(ta), rcp_ftz(tb));
+  } else {
+    return pack_f32x2(act_apply_t<ACT>(act_rt, xa), act_apply_t<ACT>(act_rt, xb));
   }
+}
+
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// packed log2-domain pre-activation of unit k for the two columns: acc = cf * (w . z + b)
+__device__ __forceinline__ unsigned long long preact_pair(uint32_t sW2_addr, int k, const unsigned long long (&z2)[5]) {
+  const uint32_t a = sW2_addr + (uint32_t)k * 48u;
+  const float4 w01 = lds128(a), w23 = lds128(a + 16), w4b = lds128(a + 32);
+  unsigned long long acc = pack_f32x2(w4b.z, w4b.w);
+  acc = fma_f32x2(pack_f32x2(w01.x, w01.y), z2[0], acc);
+  acc = fma_f32x2(pack_f32x2(w01.z, w01.w), z2[1], acc);
+  acc = fma_f32x2(pack_f32x2(w23.x, w23.y), z2[2], acc);
+  acc = fma_f32x2(pack_f32x2(w23.z, w23.w), z2[3], acc);
+  acc = fma_f32x2(pack_f32x2(w4b.x, w4b.y), z2[4], acc);
+  return acc;
+}
+
+// Sigmoids of FOUR units x two columns with TWO reciprocals instead of eight (simultaneous inversion: the
+// reciprocal of the product of the four denominators, then back-substitution with packed multiplies).  The MUFU
+// (XU) pipe issues a warp instruction every 8 cycles per SM sub-partition and bounds this kernel (profiles/:
+// gram_r1b, XU 46 % busy with everything else waiting on it): 1.25 instead of 2 MUFU per value.
+// acc = -log2(e) x, clamped to <= 30 so that the product of four denominators (< 2^124) stays finite;
+// sigmoid(-20.8) = 9e-10 is the smallest value a unit can take.
+__device__ __forceinline__ void sigmoid4_pair(const unsigned long long (&acc)[4], unsigned long long (&h)[4]) {
+  const unsigned long long one2 = pack_f32x2(1.0f, 1.0f);
+  unsigned long long t[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float xa, xb;
+    unpack_f32x2(acc[j], xa, xb);
+    t[j] = add_f32x2(pack_f32x2(ex2_ftz(fminf(xa, 30.0f)), ex2_ftz(fminf(xb, 30.0f))), one2);
+  }
+  const unsigned long long p12 = mul_f32x2(t[0], t[1]);
+  const unsigned long long p123 = mul_f32x2(p12, t[2]);
+  const unsigned long long p1234 = mul_f32x2(p123, t[3]);
+  float pa, pb;
+  unpack_f32x2(p1234, pa, pb);
+  const unsigned long long r4 = pack_f32x2(rcp_ftz(pa), rcp_ftz(pb));      // 1 / (t1 t2 t3 t4)
+  h[3] = mul_f32x2(r4, p123);
+  const unsigned long long r3 = mul_f32x2(r4, t[3]);                        // 1 / (t1 t2 t3)
+  h[2] = mul_f32x2(r3, p12);
+  const unsigned long long r2 = mul_f32x2(r3, t[2]);                        // 1 / (t1 t2)
+  h[1] = mul_f32x2(r2, t[0]);
+  h[0] = mul_f32x2(r2, t[1]);
+}
+
+template <int ACT>
+__device__ __forceinline__ void units8_pair(uint32_t sW2_addr, uint32_t sNP2_addr, int kg, const unsigned long long (&z2)[5],
+                                            unsigned long long hs2, int act_rt, unsigned long long (&d2)[8]) {
+  unsigned long long h2[8];
+  if constexpr (ACT == GLASDI_ACT_SIGMOID) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      unsigned long long acc[4], h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = preact_pair(sW2_addr, kg * 8 + g * 4 + j, z2);
+      sigmoid4_pair(acc, h);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h2[g * 4 + j] = h[j];
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) h2[u] = unit_pair<ACT>(sW2_addr, kg * 8 + u, z2, act_rt);
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    d2[u] = fma_f32x2(h2[u], hs2, lds64_volatile(sNP2_addr + (uint32_t)(kg * 8 + u) * 8u));
 }
 
 template <int ACT, int INW, bool FAST>
@@ -274,62 +335,74 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
     // ---- producers: pilot-centred, scaled activations of 128 sample columns per chunk --------------
     const int ptid = threadIdx.x - kGProdWarp0 * 32;
     if constexpr (FAST) {
-      // thread <-> sample columns (cp, cp + 64) of the chunk x one quarter of the unit groups
+      // thread <-> sample columns (cp, cp + 64) of the chunk x every 4th unit group.  nkg is rarely a multiple
+      // of 4 (13 at K = 100): the left-over groups rotate over the four thread quarters from chunk to chunk.
       const int cp = ptid & 63;
       const int quarter = ptid >> 6;
-      const int kg_begin = (P.nkg * quarter) / 4, kg_end = (P.nkg * (quarter + 1)) / 4;
+      const int nkg4 = P.nkg & ~3;
       const uint32_t sW2 = smem_u32(sWl), sNP2 = smem_u32(sPilot);
+      const uint32_t pilot_bytes = (uint32_t)L.kpu * 8u;
       const float hscale = P.h_scale;
       const unsigned long long hs2 = pack_f32x2(hscale, hscale);
       const int kg_one = P.K >> 3, u_one = P.K & 7;
-      uint32_t h_it = 0;
+      uint32_t h_it = 0, n_it = 0;
       float amax = 0.f;
-      auto load_z2 = [&](const float* __restrict__ zb, int c, unsigned long long (&z2)[5]) {
+      // prefetched latent states stay UNPACKED scalars until they are used: packing at load time puts a register
+      // move behind every load, and the move waits for the load (profiles/: gram_r1c, 10 % of the kernel)
+      auto load_z = [&](const float* __restrict__ zb, int c, float (&za)[5], float (&zbv)[5]) {
         const int sa = c * kCols + cp, sb = sa + 64;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-          const float za = sa < P.S ? __ldg(zb + (size_t)i * P.Spad + sa) : 0.f;
-          const float zbv = sb < P.S ? __ldg(zb + (size_t)i * P.Spad + sb) : 0.f;
-          z2[i] = pack_f32x2(za, zbv);
+          za[i] = 0.f;
+          zbv[i] = 0.f;
+          if (sa < P.S) za[i] = __ldg(zb + (size_t)i * P.Spad + sa);
+          if (sb < P.S) zbv[i] = __ldg(zb + (size_t)i * P.Spad + sb);
         }
       };
+      auto load_zp = [&](const float* __restrict__ zb, float (&zp)[5]) {      // sample 0 = the pilot
+#pragma unroll
+        for (int i = 0; i < 5; ++i) zp[i] = __ldg(zb + (size_t)i * P.Spad);
+      };
       long long item = blockIdx.x;
-      unsigned long long znext[5];
-      if (item < P.n_items) load_z2(P.Zs + (size_t)item * 5 * P.Spad, 0, znext);
-      for (; item < P.n_items; item += gridDim.x) {
+      float znA[5], znB[5], zp[5];
+      if (item < P.n_items) {
+        load_z(P.Zs + (size_t)item * 5 * P.Spad, 0, znA, znB);
+        load_zp(P.Zs + (size_t)item * 5 * P.Spad, zp);
+      }
+      for (; item < P.n_items; item += gridDim.x, ++n_it) {
         const float* __restrict__ zb = P.Zs + (size_t)item * 5 * P.Spad;
-        // pilot = activations of sample 0, stored negated, scaled and duplicated
-        if (ptid < P.nkg) {
-          unsigned long long z0[5], pv[8];
+        // pilot = activations of sample 0, one unit per thread, stored negated, scaled and duplicated.  Two pilot
+        // buffers alternate from item to item: a thread can only write buffer b again after every producer
+        // thread has passed the barrier of the item in between, i.e. has finished reading b.
+        const uint32_t sNPb = sNP2 + (n_it & 1u) * pilot_bytes;
+        if (ptid < L.kpu) {
+          unsigned long long zp2[5];
 #pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            const float zv = __ldg(zb + (size_t)i * P.Spad);
-            z0[i] = pack_f32x2(zv, zv);
-          }
-          units8_pair<ACT>(sW2, sNP2, ptid, z0, hs2, P.front.act, false, pv);
-          float2* dst = reinterpret_cast<float2*>(sPilot) + ptid * 8;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            float ha, hb;
-            unpack_f32x2(pv[u], ha, hb);
-            dst[u] = make_float2(-ha * hscale, -ha * hscale);
-          }
+          for (int i = 0; i < 5; ++i) zp2[i] = pack_f32x2(zp[i], zp[i]);
+          float ha, hb;
+          unpack_f32x2(unit_pair<ACT>(sW2, ptid, zp2, P.front.act), ha, hb);
+          reinterpret_cast<float2*>(sPilot)[(n_it & 1u) * L.kpu + ptid] = make_float2(-ha * hscale, -ha * hscale);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
         for (int c = 0; c < nchunks; ++c) {
           unsigned long long z2[5];
 #pragma unroll
-          for (int i = 0; i < 5; ++i) z2[i] = znext[i];
+          for (int i = 0; i < 5; ++i) z2[i] = pack_f32x2(znA[i], znB[i]);
           // next chunk's (or next item's first) latent states: in flight while this chunk is computed
-          if (c + 1 < nchunks) load_z2(zb, c + 1, znext);
-          else if (item + gridDim.x < P.n_items) load_z2(P.Zs + (size_t)(item + gridDim.x) * 5 * P.Spad, 0, znext);
+          if (c + 1 < nchunks) {
+            load_z(zb, c + 1, znA, znB);
+          } else if (item + gridDim.x < P.n_items) {
+            load_z(P.Zs + (size_t)(item + gridDim.x) * 5 * P.Spad, 0, znA, znB);
+            load_zp(P.Zs + (size_t)(item + gridDim.x) * 5 * P.Spad, zp);
+          }
           const bool va = c * kCols + cp < P.S, vb = c * kCols + cp + 64 < P.S;
           const uint32_t buf = h_it % kRing;
           uint8_t* Hb = sH + buf * kBufBytes;
           mbar_wait_relaxed(&B->h_empty[buf], ((h_it / kRing) & 1u) ^ 1u);
-          for (int kg = kg_begin; kg < kg_end; ++kg) {
+          const int rot = (quarter + 4 - (int)(h_it & 3u)) & 3;         // this quarter's slot among the left-over groups
+          auto do_group = [&](int kg) {
             unsigned long long d2[8];
-            units8_pair<ACT>(sW2, sNP2, kg, z2, hs2, P.front.act, true, d2);
+            units8_pair<ACT>(sW2, sNPb, kg, z2, hs2, P.front.act, d2);
             float da[8], db[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -356,13 +429,15 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             if (!vb) vb4 = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(Hb + ((uint32_t)kg * kCols + (uint32_t)cp) * 16u) = va4;
             *reinterpret_cast<uint4*>(Hb + ((uint32_t)kg * kCols + (uint32_t)cp + 64u) * 16u) = vb4;
-          }
+          };
+#pragma unroll 1
+          for (int kg = quarter; kg < nkg4; kg += 4) do_group(kg);
+          if (nkg4 + rot < P.nkg) do_group(nkg4 + rot);                 // left-over group, if this quarter has one
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&B->h_full[buf]);
           ++h_it;
         }
-        asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item
       }
       if (P.check_overflow && !(amax < 60000.f)) atomicOr(P.flags, 1);
     } else {
