@@ -271,6 +271,8 @@ int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths, const 
   }
   // covariance-form screening: the constant unit must fit the 128-row tile, shared memory must hold the ring
   d.gram_ok = ok && d.K + 1 <= 128 && decode_gram_smem_bytes(d.K, last_in_w) <= 227 * 1024;
+  d.h_front_last_W.assign(W_host[n_linear - 2], W_host[n_linear - 2] + (size_t)d.K * last_in_w);
+  d.h_front_last_b.assign(b_host[n_linear - 2], b_host[n_linear - 2] + d.K);
   if (d.gram_ok) {
     int rc = gram_pack_v(h, WL);
     if (rc) return rc;
@@ -324,7 +326,7 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
   if (P <= 0 || S <= 0 || T <= 0) return set_error(h, GLASDI_ERR_INVALID, "empty ensemble");
   if (!max_std_out) return set_error(h, GLASDI_ERR_INVALID, "null output");
   GL_CUDA(h, cudaSetDevice(h->device));
-  const int Spad = (S + 31) / 32 * 32;
+  const int Spad = (S + 127) / 128 * 128;        // whole 128-sample chunks (covariance-form producers)
   // screened mode: one fp16 pass on the tensor cores writes the variance field, refine.cu re-evaluates
   // the near-maximum candidates exactly.  Only the CTA-pair tcgen05 kernel has the field epilogue.
   const bool gram = h->opt_mode == GLASDI_MODE_SCREENED_GRAM && d.gram_ok;
@@ -369,6 +371,7 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
       rc = launch_zis_to_soa(h, Zis + (size_t)p0 * S * T * n, pn, S, T, n, Zs, Spad, st);
     }
     if (rc) return rc;
+    if (gram && (rc = launch_pad_columns(h, Zs, (long long)pn * T * n, S, Spad, st))) return rc;
     if ((rc = t_roll.stop())) return rc;
     if ((rc = t_dec.start())) return rc;
     if (gram) rc = launch_decode_gram(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, field,

@@ -43,6 +43,7 @@ struct Decoder {
   __half* v_packed = nullptr;
   int eV = 0;
   bool gram_ok = false;
+  std::vector<float> h_front_last_W, h_front_last_b;   // host copy of the last FRONT layer (kernel-parameter weights)
 };
 
 }  // namespace glasdi
@@ -100,6 +101,7 @@ int launch_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z
                    cudaStream_t st);
 int launch_zis_to_soa(glasdi_handle* h, const double* Zis, int P, int S, int T, int n, float* Zs, int Spad,
                       cudaStream_t st);
+int launch_pad_columns(glasdi_handle* h, float* Zs, long long rows, int S, int Spad, cudaStream_t st);
 // decode_var.cu
 int launch_decode_var(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
                       unsigned int* maxvar_bits, cudaStream_t st);

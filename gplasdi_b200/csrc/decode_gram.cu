@@ -35,13 +35,16 @@ constexpr int kCols = 128;                  // sample columns per chunk
 constexpr int kRing = 4;                    // chunk ring
 constexpr int kGroupsM = 16;                // unit groups of 8 in a tile (M = 128)
 constexpr uint32_t kBufBytes = kGroupsM * kCols * 16;   // 32 KB
+// Roles: warps 0..3 = consumers (warp 0 also issues the MMAs, then all four run the epilogue of the item),
+// warps 4..19 = producers.  20 warps = 640 threads leave 96 registers per thread: the producers are bound by
+// instruction latency (MUFU, shared-memory loads), which four producer warps per SM sub-partition hide where
+// two could not (profiles/: gram_r1d: 48 % issue, 32 % XU with two).
 constexpr int kGEpiWarps = 4;
-constexpr int kGMmaWarp = 4;
-constexpr int kGProdWarp0 = 5;
-constexpr int kGProdWarps = 8;
+constexpr int kGProdWarp0 = 4;
+constexpr int kGProdWarps = 16;
 constexpr int kGProdThreads = kGProdWarps * 32;
-constexpr int kGThreads = (kGProdWarp0 + kGProdWarps) * 32;   // 416
-constexpr int kGTmemCols = 256;             // 2 accumulators x 128 columns
+constexpr int kGThreads = (kGProdWarp0 + kGProdWarps) * 32;   // 640
+constexpr int kGTmemCols = 128;             // one 128 x 128 fp32 accumulator
 
 struct GramParams {
   int P, S, T, Spad, NZ;
@@ -59,10 +62,16 @@ struct GramParams {
   float* fscale;         // [n_items] : variance = accumulator * fscale
   int* flags;
   FrontMlp front;
+  // fast path (one front layer, latent dimension 5): rows (w0..w4, b) of the front layer, times -log2(e) for the
+  // sigmoid, as KERNEL PARAMETERS: they are read through the constant bank / uniform datapath (every lane of a
+  // warp works on the same units), which costs no shared-memory bandwidth.  Staged in shared memory they were the
+  // bound: 28 LDS.128 x 4 cycles of the 128 B/clk shared-memory datapath per 16 (unit, sample) values = 23 k of
+  // the 31 k cycles per (parameter, time step) (profiles/: gram_r1d).
+  float w6[128 * 6];
 };
 
 struct GBars {
-  uint64_t h_full[kRing], h_empty[kRing], acc_full[2], acc_empty[2];
+  uint64_t h_full[kRing], h_empty[kRing], acc_full;
 };
 
 struct GSmem {
@@ -85,6 +94,17 @@ __host__ __device__ inline GSmem gcarve(int nkg, int last_in_w, int nkgQ) {
   s.tmem = off; off += 16;
   s.total = off;
   return s;
+}
+
+// Byte offset of the 16-byte vector (unit group kg = 8 consecutive units, sample column col) in an operand tile.
+// Canonical MN-major SWIZZLE_128B layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in elements: a swizzle atom is
+// 8 samples x 64 units (8 rows of 128 B), the 16-byte chunk index is XORed with the row (sample mod 8).
+// The un-swizzled MN-major layout works too but every MMA then takes ~480 instead of ~60 cycles: for a fixed
+// sample the 16 unit groups sit a multiple of 128 B apart, i.e. in the same four banks (16-way conflict in the
+// operand fetch; measured: the kernel's time did not move when the producers' work was halved).
+__device__ __forceinline__ uint32_t h_offset(int kg, int col) {
+  const uint32_t r = (uint32_t)col & 7u;
+  return ((uint32_t)kg >> 3) * 16384u + ((uint32_t)col >> 3) * 1024u + r * 128u + ((((uint32_t)kg & 7u) ^ r) << 4);
 }
 
 __device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
@@ -134,16 +154,7 @@ constexpr float kNegLog2e = -1.4426950408889634f;
 // three more instructions per value).  d2[u] = (h_A, h_B)[kg*8+u] * 2^eH - pilot: 8.5 issue slots per
 // (unit, sample) instead of 19.6 (profiles/: gram_r1).
 template <int ACT>
-__device__ __forceinline__ unsigned long long unit_pair(uint32_t sW2_addr, int k, const unsigned long long (&z2)[5],
-                                                        int act_rt) {
-  const uint32_t a = sW2_addr + (uint32_t)k * 48u;
-  const float4 w01 = lds128(a), w23 = lds128(a + 16), w4b = lds128(a + 32);
-  unsigned long long acc = pack_f32x2(w4b.z, w4b.w);
-  acc = fma_f32x2(pack_f32x2(w01.x, w01.y), z2[0], acc);
-  acc = fma_f32x2(pack_f32x2(w01.z, w01.w), z2[1], acc);
-  acc = fma_f32x2(pack_f32x2(w23.x, w23.y), z2[2], acc);
-  acc = fma_f32x2(pack_f32x2(w23.z, w23.w), z2[3], acc);
-  acc = fma_f32x2(pack_f32x2(w4b.x, w4b.y), z2[4], acc);
+__device__ __forceinline__ unsigned long long act_pair(unsigned long long acc, int act_rt) {
   float xa, xb;
   unpack_f32x2(acc, xa, xb);
   if constexpr (ACT == GLASDI_ACT_SIGMOID) {
@@ -163,25 +174,23 @@ __device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, un
   return d;
 }
 
-// packed log2-domain pre-activation of unit k for the two columns: acc = cf * (w . z + b)
-__device__ __forceinline__ unsigned long long preact_pair(uint32_t sW2_addr, int k, const unsigned long long (&z2)[5]) {
-  const uint32_t a = sW2_addr + (uint32_t)k * 48u;
-  const float4 w01 = lds128(a), w23 = lds128(a + 16), w4b = lds128(a + 32);
-  unsigned long long acc = pack_f32x2(w4b.z, w4b.w);
-  acc = fma_f32x2(pack_f32x2(w01.x, w01.y), z2[0], acc);
-  acc = fma_f32x2(pack_f32x2(w01.z, w01.w), z2[1], acc);
-  acc = fma_f32x2(pack_f32x2(w23.x, w23.y), z2[2], acc);
-  acc = fma_f32x2(pack_f32x2(w23.z, w23.w), z2[3], acc);
-  acc = fma_f32x2(pack_f32x2(w4b.x, w4b.y), z2[4], acc);
+// packed log2-domain pre-activation of unit k for the two columns: acc = cf * (w . z + b); k is warp-uniform
+__device__ __forceinline__ unsigned long long preact_pair(const float* __restrict__ w6, int k,
+                                                          const unsigned long long (&z2)[5]) {
+  const float* w = w6 + k * 6;
+  unsigned long long acc = pack_f32x2(w[5], w[5]);
+  acc = fma_f32x2(pack_f32x2(w[0], w[0]), z2[0], acc);
+  acc = fma_f32x2(pack_f32x2(w[1], w[1]), z2[1], acc);
+  acc = fma_f32x2(pack_f32x2(w[2], w[2]), z2[2], acc);
+  acc = fma_f32x2(pack_f32x2(w[3], w[3]), z2[3], acc);
+  acc = fma_f32x2(pack_f32x2(w[4], w[4]), z2[4], acc);
   return acc;
 }
 
-// Sigmoids of FOUR units x two columns with TWO reciprocals instead of eight (simultaneous inversion: the
-// reciprocal of the product of the four denominators, then back-substitution with packed multiplies).  The MUFU
-// (XU) pipe issues a warp instruction every 8 cycles per SM sub-partition and bounds this kernel (profiles/:
-// gram_r1b, XU 46 % busy with everything else waiting on it): 1.25 instead of 2 MUFU per value.
-// acc = -log2(e) x, clamped to <= 30 so that the product of four denominators (< 2^124) stays finite;
-// sigmoid(-20.8) = 9e-10 is the smallest value a unit can take.
+// Sigmoids of FOUR units x two columns with FOUR reciprocals instead of eight (pairwise simultaneous inversion:
+// 1/(t0 t1), then h0 = t1/(t0 t1), h1 = t0/(t0 t1) as packed multiplies).  acc = -log2(e) x.  No clamp: 2^acc
+// overflows only for x < -88, where the products become inf/NaN; the epilogue of gram_kernel raises the numeric
+// flag on any non-finite Gram diagonal instead of clamping every value here (two more instructions per value).
 __device__ __forceinline__ void sigmoid4_pair(const unsigned long long (&acc)[4], unsigned long long (&h)[4]) {
   const unsigned long long one2 = pack_f32x2(1.0f, 1.0f);
   unsigned long long t[4];
@@ -189,43 +198,35 @@ __device__ __forceinline__ void sigmoid4_pair(const unsigned long long (&acc)[4]
   for (int j = 0; j < 4; ++j) {
     float xa, xb;
     unpack_f32x2(acc[j], xa, xb);
-    t[j] = add_f32x2(pack_f32x2(ex2_ftz(fminf(xa, 30.0f)), ex2_ftz(fminf(xb, 30.0f))), one2);
+    t[j] = add_f32x2(pack_f32x2(ex2_ftz(xa), ex2_ftz(xb)), one2);
   }
-  const unsigned long long p12 = mul_f32x2(t[0], t[1]);
-  const unsigned long long p123 = mul_f32x2(p12, t[2]);
-  const unsigned long long p1234 = mul_f32x2(p123, t[3]);
-  float pa, pb;
-  unpack_f32x2(p1234, pa, pb);
-  const unsigned long long r4 = pack_f32x2(rcp_ftz(pa), rcp_ftz(pb));      // 1 / (t1 t2 t3 t4)
-  h[3] = mul_f32x2(r4, p123);
-  const unsigned long long r3 = mul_f32x2(r4, t[3]);                        // 1 / (t1 t2 t3)
-  h[2] = mul_f32x2(r3, p12);
-  const unsigned long long r2 = mul_f32x2(r3, t[2]);                        // 1 / (t1 t2)
-  h[1] = mul_f32x2(r2, t[0]);
-  h[0] = mul_f32x2(r2, t[1]);
+#pragma unroll
+  for (int j = 0; j < 4; j += 2) {
+    float pa, pb;
+    unpack_f32x2(mul_f32x2(t[j], t[j + 1]), pa, pb);
+    const unsigned long long r = pack_f32x2(rcp_ftz(pa), rcp_ftz(pb));
+    h[j] = mul_f32x2(r, t[j + 1]);
+    h[j + 1] = mul_f32x2(r, t[j]);
+  }
 }
 
+// four consecutive units k0..k0+3 x two columns: d2[j] = (h_A, h_B)[k0 + j] * 2^eH - pilot
 template <int ACT>
-__device__ __forceinline__ void units8_pair(uint32_t sW2_addr, uint32_t sNP2_addr, int kg, const unsigned long long (&z2)[5],
-                                            unsigned long long hs2, int act_rt, unsigned long long (&d2)[8]) {
-  unsigned long long h2[8];
+__device__ __forceinline__ void units4_pair(const float* __restrict__ w6, uint32_t sNP2_addr, int k0,
+                                            const unsigned long long (&z2)[5], unsigned long long hs2, int act_rt,
+                                            unsigned long long (&d2)[4]) {
+  unsigned long long h[4];
   if constexpr (ACT == GLASDI_ACT_SIGMOID) {
+    unsigned long long acc[4];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      unsigned long long acc[4], h[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = preact_pair(sW2_addr, kg * 8 + g * 4 + j, z2);
-      sigmoid4_pair(acc, h);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) h2[g * 4 + j] = h[j];
-    }
+    for (int j = 0; j < 4; ++j) acc[j] = preact_pair(w6, k0 + j, z2);
+    sigmoid4_pair(acc, h);
   } else {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) h2[u] = unit_pair<ACT>(sW2_addr, kg * 8 + u, z2, act_rt);
+    for (int j = 0; j < 4; ++j) h[j] = act_pair<ACT>(preact_pair(w6, k0 + j, z2), act_rt);
   }
 #pragma unroll
-  for (int u = 0; u < 8; ++u)
-    d2[u] = fma_f32x2(h2[u], hs2, lds64_volatile(sNP2_addr + (uint32_t)(kg * 8 + u) * 8u));
+  for (int j = 0; j < 4; ++j) d2[j] = fma_f32x2(h[j], hs2, lds64_volatile(sNP2_addr + (uint32_t)(k0 + j) * 8u));
 }
 
 template <int ACT, int INW, bool FAST>
@@ -251,13 +252,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       mbar_init(&B->h_full[i], kGProdWarps);
       mbar_init(&B->h_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&B->acc_full[i], 1);
-      mbar_init(&B->acc_empty[i], kGEpiWarps);
-    }
+    mbar_init(&B->acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == kGMmaWarp) {
+  if (warp == 0) {
     tmem_alloc(tmem_slot, kGTmemCols);
     tmem_relinquish();
   }
@@ -266,16 +264,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
     const float* __restrict__ W = P.front.W[l];
     const float* __restrict__ b = P.front.b[l];
     const int ld = L.wl_ld;
-    if constexpr (FAST) {
-      // rows of 12 floats: (w0,w0,w1,w1 | w2,w2,w3,w3 | w4,w4,b,b), times -log2(e) for the sigmoid
-      const float cf = (ACT == GLASDI_ACT_SIGMOID) ? kNegLog2e : 1.0f;
-      for (int idx = threadIdx.x; idx < L.kpu * 12; idx += blockDim.x) {
-        const int k = idx / 12, i = (idx - k * 12) >> 1;
-        float v = 0.f;
-        if (k < P.K) v = cf * (i < 5 ? W[(size_t)k * 5 + i] : b[k]);
-        sWl[k * 12 + (idx - k * 12)] = v;
-      }
-    } else {
+    if constexpr (!FAST) {
       for (int idx = threadIdx.x; idx < L.kpu * ld; idx += blockDim.x) {
         const int k = idx / ld, i = idx - k * ld;
         float v = 0.f;
@@ -298,65 +287,34 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == kGMmaWarp) {
-    // ---- MMA issuer ---------------------------------------------------------------------------
-    uint32_t h_it = 0, a_it = 0;
-    const uint32_t idesc = umma_idesc_f16_m128_mn((uint32_t)P.Nmma);
-    // MN-major, no swizzle: LBO = step between 8-sample groups (128 B), SBO = step between 8-unit groups (2 KB)
-    const uint64_t desc0 = umma_desc_kmajor(smem_u32(sH), 128u, (uint32_t)kCols * 16u);
-    for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-      const uint32_t ab = a_it & 1u;
-      mbar_wait(&B->acc_empty[ab], ((a_it >> 1) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + ab * 128u;
-      for (int c = 0; c < nchunks; ++c) {
-        const uint32_t buf = h_it % kRing;
-        mbar_wait(&B->h_full[buf], (h_it / kRing) & 1u);
-        tc_fence_after();
-        const int ncols = min(kCols, P.S - c * kCols);
-        const int nk = (ncols + 15) >> 4;
-        const uint64_t d0 = desc0 + (uint64_t)(buf * (kBufBytes >> 4));
-        if (elect_one()) {
-#pragma unroll 1
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t dk = d0 + (uint64_t)(k * 16);            // 16 samples x 16 B = 256 B per K slice
-            tc_mma_f16(d_tmem, dk, dk, idesc, (c | k) != 0 ? 1u : 0u);
-          }
-          tc_commit(&B->h_empty[buf]);
-        }
-        __syncwarp();
-        ++h_it;
-      }
-      if (elect_one()) tc_commit(&B->acc_full[ab]);
-      __syncwarp();
-      ++a_it;
-    }
-  } else if (warp >= kGProdWarp0) {
+  if (warp >= kGProdWarp0) {
     // ---- producers: pilot-centred, scaled activations of 128 sample columns per chunk --------------
     const int ptid = threadIdx.x - kGProdWarp0 * 32;
+    const float hscale = P.h_scale;
+    const int kg_one = P.K >> 3, u_one = P.K & 7;
+    uint32_t h_it = 0, n_it = 0;
+    float amax = 0.f;
     if constexpr (FAST) {
-      // thread <-> sample columns (cp, cp + 64) of the chunk x every 4th unit group.  nkg is rarely a multiple
-      // of 4 (13 at K = 100): the left-over groups rotate over the four thread quarters from chunk to chunk.
+      // thread <-> sample columns (cp, cp + 64) of the chunk x every 8th TASK; a task = 4 consecutive units
+      // (half a 16-byte operand vector).  The tasks that do not divide evenly rotate over the eight thread
+      // groups from chunk to chunk.
       const int cp = ptid & 63;
-      const int quarter = ptid >> 6;
-      const int nkg4 = P.nkg & ~3;
-      const uint32_t sW2 = smem_u32(sWl), sNP2 = smem_u32(sPilot);
+      const int eighth = __shfl_sync(0xffffffffu, ptid >> 6, 0);      // warp-uniform: weights come through the uniform datapath
+      const int ntask = 2 * P.nkg;
+      const int ntask8 = ntask & ~7;
+      const uint32_t sNP2 = smem_u32(sPilot);
       const uint32_t pilot_bytes = (uint32_t)L.kpu * 8u;
-      const float hscale = P.h_scale;
       const unsigned long long hs2 = pack_f32x2(hscale, hscale);
-      const int kg_one = P.K >> 3, u_one = P.K & 7;
-      uint32_t h_it = 0, n_it = 0;
-      float amax = 0.f;
       // prefetched latent states stay UNPACKED scalars until they are used: packing at load time puts a register
       // move behind every load, and the move waits for the load (profiles/: gram_r1c, 10 % of the kernel)
+      // Spad is a multiple of 128 and the columns [S, Spad) hold copies of sample 0 (launch_pad_columns): no
+      // bounds predicate anywhere, the padding cancels against the pilot
       auto load_z = [&](const float* __restrict__ zb, int c, float (&za)[5], float (&zbv)[5]) {
-        const int sa = c * kCols + cp, sb = sa + 64;
+        const float* __restrict__ src = zb + c * kCols + cp;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-          za[i] = 0.f;
-          zbv[i] = 0.f;
-          if (sa < P.S) za[i] = __ldg(zb + (size_t)i * P.Spad + sa);
-          if (sb < P.S) zbv[i] = __ldg(zb + (size_t)i * P.Spad + sb);
+          za[i] = __ldg(src + (size_t)i * P.Spad);
+          zbv[i] = __ldg(src + (size_t)i * P.Spad + 64);
         }
       };
       auto load_zp = [&](const float* __restrict__ zb, float (&zp)[5]) {      // sample 0 = the pilot
@@ -376,11 +334,25 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         // thread has passed the barrier of the item in between, i.e. has finished reading b.
         const uint32_t sNPb = sNP2 + (n_it & 1u) * pilot_bytes;
         if (ptid < L.kpu) {
-          unsigned long long zp2[5];
+          // same arithmetic as the samples (the group of four units, own unit picked): the columns that pad S up
+          // to a multiple of 128 hold the pilot's latent state and must cancel to exactly 0
+          unsigned long long zp2[5], hq[4];
 #pragma unroll
           for (int i = 0; i < 5; ++i) zp2[i] = pack_f32x2(zp[i], zp[i]);
+          if constexpr (ACT == GLASDI_ACT_SIGMOID) {
+            unsigned long long acc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = preact_pair(P.w6, (ptid & ~3) + j, zp2);
+            sigmoid4_pair(acc, hq);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hq[j] = act_pair<ACT>(preact_pair(P.w6, (ptid & ~3) + j, zp2), P.front.act);
+          }
+          unsigned long long mine = hq[0];
+#pragma unroll
+          for (int j = 1; j < 4; ++j) mine = ((ptid & 3) == j) ? hq[j] : mine;
           float ha, hb;
-          unpack_f32x2(unit_pair<ACT>(sW2, ptid, zp2, P.front.act), ha, hb);
+          unpack_f32x2(mine, ha, hb);
           reinterpret_cast<float2*>(sPilot)[(n_it & 1u) * L.kpu + ptid] = make_float2(-ha * hscale, -ha * hscale);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
@@ -395,150 +367,170 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             load_z(P.Zs + (size_t)(item + gridDim.x) * 5 * P.Spad, 0, znA, znB);
             load_zp(P.Zs + (size_t)(item + gridDim.x) * 5 * P.Spad, zp);
           }
-          const bool va = c * kCols + cp < P.S, vb = c * kCols + cp + 64 < P.S;
           const uint32_t buf = h_it % kRing;
           uint8_t* Hb = sH + buf * kBufBytes;
           mbar_wait_relaxed(&B->h_empty[buf], ((h_it / kRing) & 1u) ^ 1u);
-          const int rot = (quarter + 4 - (int)(h_it & 3u)) & 3;         // this quarter's slot among the left-over groups
-          auto do_group = [&](int kg) {
-            unsigned long long d2[8];
-            units8_pair<ACT>(sW2, sNPb, kg, z2, hs2, P.front.act, d2);
-            float da[8], db[8];
+          auto do_task = [&](int task) {
+            const int k0 = task * 4;
+            unsigned long long d2[4];
+            units4_pair<ACT>(P.w6, sNPb, k0, z2, hs2, P.front.act, d2);
+            float da[4], db[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              unpack_f32x2(d2[u], da[u], db[u]);
-              if (P.check_overflow) amax = fmaxf(amax, fmaxf(va ? fabsf(da[u]) : 0.f, vb ? fabsf(db[u]) : 0.f));
+            for (int j = 0; j < 4; ++j) {
+              unpack_f32x2(d2[j], da[j], db[j]);
+              if (P.check_overflow) amax = fmaxf(amax, fmaxf(fabsf(da[j]), fabsf(db[j])));
             }
-            if (kg == kg_one) {
+            if ((k0 >> 2) == (P.K >> 2)) {
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                da[u] = (u == u_one) ? 1.0f : da[u];                  // the constant unit
-                db[u] = (u == u_one) ? 1.0f : db[u];
+              for (int j = 0; j < 4; ++j) {
+                da[j] = (j == (P.K & 3)) ? 1.0f : da[j];               // the constant unit
+                db[j] = (j == (P.K & 3)) ? 1.0f : db[j];
               }
             }
-            uint4 va4, vb4;
-            va4.x = h2_as_u32(__floats2half2_rn(da[0], da[1]));
-            va4.y = h2_as_u32(__floats2half2_rn(da[2], da[3]));
-            va4.z = h2_as_u32(__floats2half2_rn(da[4], da[5]));
-            va4.w = h2_as_u32(__floats2half2_rn(da[6], da[7]));
-            vb4.x = h2_as_u32(__floats2half2_rn(db[0], db[1]));
-            vb4.y = h2_as_u32(__floats2half2_rn(db[2], db[3]));
-            vb4.z = h2_as_u32(__floats2half2_rn(db[4], db[5]));
-            vb4.w = h2_as_u32(__floats2half2_rn(db[6], db[7]));
-            if (!va) va4 = make_uint4(0, 0, 0, 0);
-            if (!vb) vb4 = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(Hb + ((uint32_t)kg * kCols + (uint32_t)cp) * 16u) = va4;
-            *reinterpret_cast<uint4*>(Hb + ((uint32_t)kg * kCols + (uint32_t)cp + 64u) * 16u) = vb4;
+            uint2 va2, vb2;
+            va2.x = h2_as_u32(__floats2half2_rn(da[0], da[1]));
+            va2.y = h2_as_u32(__floats2half2_rn(da[2], da[3]));
+            vb2.x = h2_as_u32(__floats2half2_rn(db[0], db[1]));
+            vb2.y = h2_as_u32(__floats2half2_rn(db[2], db[3]));
+            const uint32_t off = h_offset(task >> 1, cp) + (uint32_t)(task & 1) * 8u;    // cp + 64: same row, 8 atoms on
+            *reinterpret_cast<uint2*>(Hb + off) = va2;
+            *reinterpret_cast<uint2*>(Hb + off + 8u * 1024u) = vb2;
           };
 #pragma unroll 1
-          for (int kg = quarter; kg < nkg4; kg += 4) do_group(kg);
-          if (nkg4 + rot < P.nkg) do_group(nkg4 + rot);                 // left-over group, if this quarter has one
+          for (int task = eighth; task < ntask8; task += 8) do_task(task);
+          {
+            const int extra = ntask8 + ((eighth + 8 - (int)(h_it & 7u)) & 7);   // left-over tasks rotate
+            if (extra < ntask) do_task(extra);
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&B->h_full[buf]);
           ++h_it;
         }
       }
-      if (P.check_overflow && !(amax < 60000.f)) atomicOr(P.flags, 1);
     } else {
-    const int col = ptid & 127;
-    const int half = ptid >> 7;
-    const int kg_begin = half == 0 ? 0 : (P.nkg + 1) / 2;
-    const int kg_end = half == 0 ? (P.nkg + 1) / 2 : P.nkg;
-    const int NZ = P.NZ;
-    const int ld = L.wl_ld;
-    const float hscale = P.h_scale;
-    const int kg_one = P.K >> 3, u_one = P.K & 7;
-    uint32_t h_it = 0;
-    float amax = 0.f;
-    for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-      const float* __restrict__ zb = P.Zs + (size_t)item * NZ * P.Spad;
-      // pilot = activations of sample 0
-      for (int kg = ptid; kg < P.nkg; kg += kGProdThreads) {
-        float zz[kMaxLatent];
+      // generic front MLP: thread <-> one sample column x a quarter of the unit groups
+      const int col = ptid & 127;
+      const int part = ptid >> 7;
+      const int kg_begin = (P.nkg * part) / 4, kg_end = (P.nkg * (part + 1)) / 4;
+      const int NZ = P.NZ;
+      const int ld = L.wl_ld;
+      for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const float* __restrict__ zb = P.Zs + (size_t)item * NZ * P.Spad;
+        // pilot = activations of sample 0
+        for (int kg = ptid; kg < P.nkg; kg += kGProdThreads) {
+          float zz[kMaxLatent];
 #pragma unroll
-        for (int i = 0; i < kMaxLatent; ++i) zz[i] = (i < NZ) ? __ldg(zb + (size_t)i * P.Spad) : 0.f;
-        float hv[8];
-        if constexpr (INW > 0) {
-          last_front_units<ACT, INW>(sWl, ld, last_in_w, P.front.act, kg * 8, zz, hv);
-        } else {
-          float x[kMaxHid];
-          front_pre<ACT>(P.front, zz, x);
-          last_front_units<ACT, 0>(sWl, ld, last_in_w, P.front.act, kg * 8, x, hv);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) sPilot[kg * 8 + u] = hv[u] * hscale;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
-      float znext[kMaxLatent];
-#pragma unroll
-      for (int i = 0; i < kMaxLatent; ++i) znext[i] = (col < P.S && i < NZ) ? __ldg(zb + (size_t)i * P.Spad + col) : 0.f;
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c * kCols + col;
-        const bool valid = s < P.S;
-        float zin[kMaxLatent];
-#pragma unroll
-        for (int i = 0; i < kMaxLatent; ++i) zin[i] = znext[i];
-        if (c + 1 < nchunks) {               // next chunk's latent state: in flight while this chunk is computed
-#pragma unroll
-          for (int i = 0; i < kMaxLatent; ++i)
-            znext[i] = (s + kCols < P.S && i < NZ) ? __ldg(zb + (size_t)i * P.Spad + s + kCols) : 0.f;
-        }
-        float xloc[INW > 0 ? 1 : kMaxHid];
-        const float* x = zin;
-        if constexpr (INW == 0) {
-          if (valid) front_pre<ACT>(P.front, zin, xloc);
-          x = xloc;
-        }
-        const uint32_t buf = h_it % kRing;
-        uint8_t* Hb = sH + buf * kBufBytes;
-        mbar_wait_relaxed(&B->h_empty[buf], ((h_it / kRing) & 1u) ^ 1u);
-        for (int kg = kg_begin; kg < kg_end; ++kg) {
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (valid) {
-            float hv[8];
-            last_front_units<ACT, INW>(sWl, ld, last_in_w, P.front.act, kg * 8, x, hv);
-            const float4 p0 = *reinterpret_cast<const float4*>(sPilot + kg * 8);
-            const float4 p1 = *reinterpret_cast<const float4*>(sPilot + kg * 8 + 4);
-            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-            float dv8[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              dv8[u] = fmaf(hv[u], hscale, -pv[u]);
-              if (P.check_overflow) amax = fmaxf(amax, fabsf(dv8[u]));
-            }
-            if (kg == kg_one) {
-#pragma unroll
-              for (int u = 0; u < 8; ++u) dv8[u] = (u == u_one) ? 1.0f : dv8[u];      // the constant unit
-            }
-            v.x = h2_as_u32(__floats2half2_rn(dv8[0], dv8[1]));
-            v.y = h2_as_u32(__floats2half2_rn(dv8[2], dv8[3]));
-            v.z = h2_as_u32(__floats2half2_rn(dv8[4], dv8[5]));
-            v.w = h2_as_u32(__floats2half2_rn(dv8[6], dv8[7]));
+          for (int i = 0; i < kMaxLatent; ++i) zz[i] = (i < NZ) ? __ldg(zb + (size_t)i * P.Spad) : 0.f;
+          float hv[8];
+          if constexpr (INW > 0) {
+            last_front_units<ACT, INW>(sWl, ld, last_in_w, P.front.act, kg * 8, zz, hv);
+          } else {
+            float x[kMaxHid];
+            front_pre<ACT>(P.front, zz, x);
+            last_front_units<ACT, 0>(sWl, ld, last_in_w, P.front.act, kg * 8, x, hv);
           }
-          *reinterpret_cast<uint4*>(Hb + ((uint32_t)kg * kCols + (uint32_t)col) * 16u) = v;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) sPilot[kg * 8 + u] = hv[u] * hscale;
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&B->h_full[buf]);
-        ++h_it;
+        asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
+        float znext[kMaxLatent];
+#pragma unroll
+        for (int i = 0; i < kMaxLatent; ++i) znext[i] = (col < P.S && i < NZ) ? __ldg(zb + (size_t)i * P.Spad + col) : 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+          const int s = c * kCols + col;
+          const bool valid = s < P.S;
+          float zin[kMaxLatent];
+#pragma unroll
+          for (int i = 0; i < kMaxLatent; ++i) zin[i] = znext[i];
+          if (c + 1 < nchunks) {               // next chunk's latent state: in flight while this chunk is computed
+#pragma unroll
+            for (int i = 0; i < kMaxLatent; ++i)
+              znext[i] = (s + kCols < P.S && i < NZ) ? __ldg(zb + (size_t)i * P.Spad + s + kCols) : 0.f;
+          }
+          float xloc[INW > 0 ? 1 : kMaxHid];
+          const float* x = zin;
+          if constexpr (INW == 0) {
+            if (valid) front_pre<ACT>(P.front, zin, xloc);
+            x = xloc;
+          }
+          const uint32_t buf = h_it % kRing;
+          uint8_t* Hb = sH + buf * kBufBytes;
+          mbar_wait_relaxed(&B->h_empty[buf], ((h_it / kRing) & 1u) ^ 1u);
+          for (int kg = kg_begin; kg < kg_end; ++kg) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (valid) {
+              float hv[8];
+              last_front_units<ACT, INW>(sWl, ld, last_in_w, P.front.act, kg * 8, x, hv);
+              const float4 p0 = *reinterpret_cast<const float4*>(sPilot + kg * 8);
+              const float4 p1 = *reinterpret_cast<const float4*>(sPilot + kg * 8 + 4);
+              const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+              float dv8[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                dv8[u] = fmaf(hv[u], hscale, -pv[u]);
+                if (P.check_overflow) amax = fmaxf(amax, fabsf(dv8[u]));
+              }
+              if (kg == kg_one) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dv8[u] = (u == u_one) ? 1.0f : dv8[u];      // the constant unit
+              }
+              v.x = h2_as_u32(__floats2half2_rn(dv8[0], dv8[1]));
+              v.y = h2_as_u32(__floats2half2_rn(dv8[2], dv8[3]));
+              v.z = h2_as_u32(__floats2half2_rn(dv8[4], dv8[5]));
+              v.w = h2_as_u32(__floats2half2_rn(dv8[6], dv8[7]));
+            }
+            *reinterpret_cast<uint4*>(Hb + h_offset(kg, col)) = v;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&B->h_full[buf]);
+          ++h_it;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item
       }
-      asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item
     }
     if (P.check_overflow && !(amax < 60000.f)) atomicOr(P.flags, 1);
-    }
   } else {
-    // ---- epilogue warps 0..3: thread <-> unit row i of the Gram matrix --------------------------------
+    // ---- consumer warps 0..3.  Warp 0 first issues the item's MMAs (G += H_chunk^T H_chunk as the producers
+    // deliver the chunks); then thread <-> unit row i of the Gram matrix for the epilogue.  The next item's
+    // MMAs start after this item's epilogue: the 4-deep chunk ring keeps the producers busy meanwhile. --------
     const int i = warp * 32 + lane;
     const int K = P.K;
     const float inv_S = P.inv_S;
     const int off_i = i * K - (i * (i - 1)) / 2;
-    uint32_t a_it = 0;
-    for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-      const uint32_t ab = a_it & 1u;
-      mbar_wait_relaxed(&B->acc_full[ab], (a_it >> 1) & 1u);
+    const uint32_t idesc = umma_idesc_f16_m128_mn((uint32_t)P.Nmma);
+    // MN-major, 128-byte swizzle (see h_offset): LBO = step between 64-unit blocks (16 KB), SBO = step between
+    // 8-sample groups (1 KB)
+    const uint64_t desc0 = umma_desc_kmajor(smem_u32(sH), 16384u, 1024u) | (2ull << 61);
+    const uint32_t taddr = tmem_base + (((uint32_t)(warp * 32)) << 16);
+    uint32_t h_it = 0, n_it = 0;
+    for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x, ++n_it) {
+      if (warp == 0) {
+        tc_fence_after();                               // the other warps' TMEM reads of the previous item (bar 4)
+        for (int c = 0; c < nchunks; ++c) {
+          const uint32_t buf = h_it % kRing;
+          mbar_wait(&B->h_full[buf], (h_it / kRing) & 1u);
+          tc_fence_after();
+          const int ncols = min(kCols, P.S - c * kCols);     // fast path: padding columns beyond hold exact zeros
+          const int nk = (ncols + 15) >> 4;
+          const uint64_t d0 = desc0 + (uint64_t)(buf * (kBufBytes >> 4));
+          if (elect_one()) {
+#pragma unroll 1
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t dk = d0 + (uint64_t)(k * 128);           // 16 samples = two 1 KB swizzle atoms per K slice
+              tc_mma_f16(tmem_base, dk, dk, idesc, (c | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(&B->h_empty[buf]);
+          }
+          __syncwarp();
+          ++h_it;
+        }
+        if (elect_one()) tc_commit(&B->acc_full);
+        __syncwarp();
+      }
+      mbar_wait_relaxed(&B->acc_full, n_it & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (((uint32_t)(warp * 32)) << 16) + ab * 128u;
       uint32_t r[32];
       // step 1: own diagonal entry, own column sum, the row of column sums (from the constant unit's row)
       tmem_ld_32x32(taddr + warp * 32, r);
@@ -552,6 +544,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       const float cii = (i < K) ? (gii - mi * mi * inv_S) * inv_S : 0.f;
       const float wm = warp_max(fmaxf(cii, 0.f));
       if (lane == 0) sMax[warp] = wm;
+      if (__any_sync(0xffffffffu, i < K && !(fabsf(gii) < 3.0e38f)) && lane == 0) atomicOr(P.flags, 1);   // NaN / inf activations
       if (warp == (K >> 5)) {
         for (int b = 0; b < 4; ++b) {
           tmem_ld_32x32(taddr + b * 32, r);
@@ -593,9 +586,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&B->acc_empty[ab]);
+      tc_fence_before();                                // TMEM reads done before warp 0 overwrites the accumulator
       asm volatile("bar.sync 4, 128;" ::: "memory");
       // copy-out: 16-byte pieces of the packed row into the quad kernel's A tiles
       {
@@ -606,13 +597,12 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         for (int kg = threadIdx.x; kg < P.nkgQ; kg += kGEpiWarps * 32) dst[(size_t)kg * 128] = src[kg];
         if (threadIdx.x == 0) P.fscale[item] = (f > 0.f) ? ldexpf(1.0f, -(P.exp_base + e)) : 0.f;
       }
-      ++a_it;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kGMmaWarp) tmem_dealloc(tmem_base, kGTmemCols);
+  if (warp == 0) tmem_dealloc(tmem_base, kGTmemCols);
 }
 
 // ================================================================================================
@@ -859,12 +849,19 @@ int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P_, int 
   for (int l = 0; l <= G.front.n_front; ++l) G.front.widths[l] = d.widths[l];
   for (int l = 0; l < G.front.n_front; ++l) { G.front.W[l] = d.dW[l]; G.front.b[l] = d.db[l]; }
   const int last_in_w = d.widths[d.n_linear - 2];
+  const bool fast = G.front.n_front == 1 && G.NZ == 5 && d.act == GLASDI_ACT_SIGMOID;
+  if (fast) {
+    const float cf = gr::kNegLog2e;                   // the fast path is instantiated for the sigmoid only
+    for (int k = 0; k < 128; ++k)
+      for (int i = 0; i < 6; ++i)
+        G.w6[k * 6 + i] = k < d.K ? cf * (i < 5 ? d.h_front_last_W[(size_t)k * 5 + i] : d.h_front_last_b[k]) : 0.f;
+  }
   const size_t smem = gr::gcarve(G.nkg, last_in_w, G.nkgQ).total;
   int ctas = h->num_sms;
   if (h->opt_max_ctas > 0) ctas = std::max(1, std::min(ctas, h->opt_max_ctas));
   if ((long long)ctas > G.n_items) ctas = (int)G.n_items;
   int rc;
-  if (G.front.n_front == 1 && G.NZ == 5 && d.act == GLASDI_ACT_SIGMOID)
+  if (fast)
     rc = launch_gram_inst<GLASDI_ACT_SIGMOID, 5, true>(h, G, ctas, smem, st);
   else if (d.act == GLASDI_ACT_SOFTPLUS)
     rc = launch_gram_inst<GLASDI_ACT_SOFTPLUS, 0, false>(h, G, ctas, smem, st);

@@ -14,6 +14,8 @@
 // (the reference's layout, for the simulate / sample_roms drop-ins).
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace glasdi {
 
 template <int N>
@@ -254,6 +256,27 @@ int launch_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z
     case 8: return launch_rollout_n<8>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
     default: return set_error(h, GLASDI_ERR_INVALID, "rollout: latent dimension must be 1..8");
   }
+}
+
+// columns [S, Spad) of every (p, t, i) row := the row's sample 0 (the pilot of the decode kernels): padding then
+// cancels exactly against the pilot and the covariance-form producers need no bounds predicates
+__global__ void pad_columns_kernel(float* __restrict__ Zs, long long rows, int S, int Spad) {
+  const int npad = Spad - S;
+  const long long total = rows * npad;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = e / npad;
+    const int c = (int)(e - row * npad);
+    Zs[row * Spad + S + c] = Zs[row * Spad];
+  }
+}
+
+int launch_pad_columns(glasdi_handle* h, float* Zs, long long rows, int S, int Spad, cudaStream_t st) {
+  if (Spad <= S || rows <= 0) return GLASDI_OK;
+  const long long total = rows * (Spad - S);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 16);
+  pad_columns_kernel<<<blocks, 256, 0, st>>>(Zs, rows, S, Spad);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "pad_columns launch");
 }
 
 int launch_zis_to_soa(glasdi_handle* h, const double* Zis, int P, int S, int T, int n, float* Zs, int Spad,
