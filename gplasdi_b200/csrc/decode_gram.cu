@@ -43,7 +43,8 @@ constexpr int kGEpiWarps = 4;
 constexpr int kGProdWarp0 = 4;
 constexpr int kGProdWarps = 16;
 constexpr int kGProdThreads = kGProdWarps * 32;
-constexpr int kGThreads = (kGProdWarp0 + kGProdWarps) * 32;   // 640
+constexpr int kGThreads = (kGProdWarp0 + kGProdWarps) * 32;
+constexpr int kGParts = kGProdThreads / 64;   // thread groups a chunk's tasks are dealt to (fast path)
 constexpr int kGTmemCols = 128;             // one 128 x 128 fp32 accumulator
 
 struct GramParams {
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       const int cp = ptid & 63;
       const int eighth = __shfl_sync(0xffffffffu, ptid >> 6, 0);      // warp-uniform: weights come through the uniform datapath
       const int ntask = 2 * P.nkg;
-      const int ntask8 = ntask & ~7;
+      const int ntask8 = ntask - ntask % kGParts;
       const uint32_t sNP2 = smem_u32(sPilot);
       const uint32_t pilot_bytes = (uint32_t)L.kpu * 8u;
       const unsigned long long hs2 = pack_f32x2(hscale, hscale);
@@ -397,9 +398,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             *reinterpret_cast<uint2*>(Hb + off + 8u * 1024u) = vb2;
           };
 #pragma unroll 1
-          for (int task = eighth; task < ntask8; task += 8) do_task(task);
+          for (int task = eighth; task < ntask8; task += kGParts) do_task(task);
           {
-            const int extra = ntask8 + ((eighth + 8 - (int)(h_it & 7u)) & 7);   // left-over tasks rotate
+            const int extra = ntask8 + ((eighth + kGParts - (int)(h_it % kGParts)) % kGParts);   // left-over tasks rotate
             if (extra < ntask) do_task(extra);
           }
           fence_proxy_async_smem();
@@ -529,7 +530,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         if (elect_one()) tc_commit(&B->acc_full);
         __syncwarp();
       }
-      mbar_wait_relaxed(&B->acc_full, n_it & 1u);
+      while (!mbar_try_wait(&B->acc_full, n_it & 1u)) __nanosleep(warp == 0 ? 64 : 1024);   // an item takes ~10 us
       tc_fence_after();
       uint32_t r[32];
       // step 1: own diagonal entry, own column sum, the row of column sums (from the constant unit's row)
