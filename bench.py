@@ -222,7 +222,7 @@ def run_ours(args):
         time.sleep(0.25)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    dec_ms, roll_ms, ref_ms, dec_launches = [], [], [], 0
+    dec_ms, roll_ms, ref_ms, quad_ms, dec_launches = [], [], [], [], 0
     n_cand, max_dev = 0, 0.0
     barrier()
     launches0 = eng.launch_count
@@ -237,7 +237,7 @@ def run_ours(args):
         roll_ms.append(r); dec_ms.append(d); dec_launches += nl
         if screened:
             rms, n_cand, max_dev = eng.screen_stats()
-            ref_ms.append(rms)
+            ref_ms.append(rms); quad_ms.append(eng.last_quad_ms)
     barrier()
     t_wall1 = time.perf_counter()
     launches = eng.launch_count - launches0
@@ -280,41 +280,64 @@ def run_ours(args):
         achieved = flops_launch / (dec_avg_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "decode_kernel_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.mode == "gram":
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        K = wl.widths[-2]
+        pad = 1.12 * 1024.0 / 1001.0 * 1024.0 / 1000.0
+        if args.mode == "gram":
+            n_items = P * T
+            nmma = -(-S // 16)
+            q_pad = -(-(K * (K + 1) // 2) // 64) * 64
+            issued = n_items * nmma * 2.0 * 128 * (-(-(K + 1) // 16) * 16) * 16          # gram_kernel MMAs
+            issued_quad = -(-n_items // 128) * 128 * 2.0 * (-(-wl.D // 256) * 256) * q_pad   # quad_kernel MMAs
+            kernel = "glasdi::gr::gram_kernel<sigmoid, 5, fast> (tcgen05 cta_group::1, MN-major SW128 operands, M=128 N=112 K=16)"
+            note = ("frac is on the ALGORITHMIC decoder FLOP of the reference formulation (decode every sample, then std). "
+                    "The covariance form reaches the same variances with 5x fewer FLOP (K^2 S + K(K+1)/2 D instead of K S D per "
+                    "(parameter, time step)), so frac > 1 is algebra, not a faster tensor pipe: gram_kernel issues "
+                    f"{issued:.3e} tensor FLOP (+ {issued_quad:.3e} in quad_kernel) and is bound by the CUDA-core work that "
+                    "feeds it -- P*S*T*K = 2.2e10 sigmoid evaluations (MUFU ex2 + rcp, 60 % issue-slot utilisation in "
+                    "profiles/r01_gram_quad_kernels_bench_full_ncu.json).  kernel_ms is gram_kernel alone; quad_kernel_ms "
+                    "is the second GEMM (79 % tensor-pipe active)")
+        else:
+            issued = flops_launch * issued_passes * pad
+            issued_quad = 0.0
+            kernel = "glasdi::dv2::decode_pair_kernel<VarT1, sigmoid, 5> (tcgen05 cta_group::2)"
+            note = ("frac is on ALGORITHMIC decoder FLOP (single pass); the kernel issues "
+                    f"{issued_passes} fp16 pass(es) per product and pads K 100->112, D 1001->1024, S 1000->1024: "
+                    "issued_frac is the tensor-pipe view of the same launch.  Decoding the ensemble into TMEM is bound by "
+                    "the accumulator drain (tcgen05.ld, 64 B/clk/SM): K/256 = 44 % of the tensor peak per pass")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": ("f32 (one fp16 tensor-core screening pass over the ensemble, fp32 TMEM accumulate; exact fp32 decode + "
+            "dtype": ("f32 (fp16 tensor-core screening pass over the ensemble, fp32 TMEM accumulate; exact fp32 decode + "
                       "fp64 sample sums at the near-maximum candidates; fp64 rollout)" if screened else
                       "f32 (fp16 split products x%d, fp32 TMEM accumulate; fp64 rollout)" % args.passes),
             "data": "synthetic",
             "config": {"workload": workload_desc(wl), "params_per_gpu": P, "global_params": P * world,
-                       "mode": args.mode, "split_passes": issued_passes, "parallelism": f"test-grid sharding x{world} + 1 max-loc all-reduce",
-                       "l2": "256 MB buffer written between timed iterations; per-step working set 4.6 GB >> 126 MB L2",
+                       "mode": args.mode, "split_passes": issued_passes,
+                       "parallelism": f"test-grid sharding x{world} + 1 max-loc all-reduce",
+                       "l2": "256 MB buffer written between timed iterations; per-step working set 7.7 GB >> 126 MB L2",
                        "selected_global_index": sel_idx},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["sustained"], "traffic": traffic,
-                         "kernel": "glasdi::dv2::decode_pair_kernel<VarT1, sigmoid, 5> (tcgen05 cta_group::2)",
-                         "issued_frac": flops_launch * issued_passes * 1.12 * 1024.0 / 1001.0 * 1024.0 / 1000.0
-                                        / (dec_avg_ms * 1e-3) / 1e12 / pk["sustained"],
+                         "frac": achieved / pk["sustained"], "traffic": traffic, "kernel": kernel,
+                         "issued_frac": issued / (dec_avg_ms * 1e-3) / 1e12 / pk["sustained"],
                          "kernel_ms": dec_avg_ms, "rollout_kernel_ms": float(np.mean(roll_ms)),
-                         "algorithmic_flop_per_launch": flops_launch,
-                         "issued_flop_per_launch": flops_launch * issued_passes * 1.12 * 1024.0 / 1001.0 * 1024.0 / 1000.0,
+                         "algorithmic_flop_per_launch": flops_launch, "issued_flop_per_launch": issued,
                          "peak_source": pk["source"] + " bf16 dense, sustained figure (kernel timed inside a long step); "
                                         "fp16 and bf16 share the tcgen05 kind::f16 rate",
-                         "note": "frac is on ALGORITHMIC decoder FLOP (single pass); the kernel issues "
-                                 f"{issued_passes} fp16 pass(es) per product and pads K 100->112, "
-                                 "D 1001->1024, S 1000->1024: issued_frac is the tensor-pipe view of the same launch"},
+                         "note": note},
             "e2e": {"value": rollouts_per_step * args.steps / e2e_total, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if args.mode == "gram":
+            line["roofline"]["quad_kernel_ms"] = float(np.mean(quad_ms))
+            line["roofline"]["quad_issued_flop_per_launch"] = issued_quad
         if screened:
             line["roofline"]["refine"] = {
                 "select_plus_refine_ms": float(np.mean(ref_ms)), "candidates": int(n_cand),
@@ -322,9 +345,10 @@ def run_ours(args):
                 "note": "candidates = (t, dof) within the margin of a parameter's screened maximum, re-evaluated "
                         "exactly on the CUDA cores; their maximum is the reported max_std"}
         if world == 1 and not args.no_cpu_baseline:
-            v, dt_cpu, threads = cpu_reference_rate(wl, Ws, bs, 2, seed_shift=219)
+            ncpu = 8
+            v, dt_cpu, threads = cpu_reference_rate(wl, Ws, bs, ncpu, seed_shift=216)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"2 of 441 test parameters x {S} samples (2000 rollouts, {dt_cpu:.1f} s): "
+                                    "sample": f"{ncpu} of 441 test parameters x {S} samples ({ncpu * S} rollouts, {dt_cpu:.1f} s): "
                                               f"odeint loop + time-chunked decode + numpy std; torch threads={threads}"}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -32,7 +32,7 @@ SIGNATURES = {
     "glasdi_get_option": (_i, [_vp, _i, C.POINTER(_i)]),
     "glasdi_launch_count": (_i64, [_vp]),
     "glasdi_stage_times": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i)]),
-    "glasdi_screen_stats": (_i, [_vp, C.POINTER(_d), C.POINTER(_i64), C.POINTER(C.c_float), _vp]),
+    "glasdi_screen_stats": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i64), C.POINTER(C.c_float), _vp]),
     "glasdi_set_decoder": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_vp), _i]),
     "glasdi_rollout": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp]),
     "glasdi_greedy_step": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp]),

@@ -358,11 +358,12 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
   h->ev_rollout.clear();
   h->ev_decode.clear();
   h->ev_refine.clear();
+  h->ev_quad.clear();
   size_t ev_next = 0;
   for (int p0 = 0; p0 < P; p0 += slab) {
     const int pn = std::min(slab, P - p0);
     StageTimer t_roll(h, st, &h->ev_rollout, ev_next), t_dec(h, st, &h->ev_decode, ev_next),
-        t_ref(h, st, &h->ev_refine, ev_next);
+        t_ref(h, st, &h->ev_refine, ev_next), t_quad(h, st, &h->ev_quad, ev_next);
     if ((rc = t_roll.start())) return rc;
     if (coefs) {
       rc = launch_rollout(h, coefs + (size_t)p0 * S * n * (n + 1), z0 + (size_t)p0 * n, 0, pn, S, n, T, dt, Zs, Spad,
@@ -374,8 +375,7 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
     if (gram && (rc = launch_pad_columns(h, Zs, (long long)pn * T * n, S, Spad, st))) return rc;
     if ((rc = t_roll.stop())) return rc;
     if ((rc = t_dec.start())) return rc;
-    if (gram) rc = launch_decode_gram(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, field,
-                                      reinterpret_cast<uint8_t*>(h->ws) + a_off,
+    if (gram) rc = launch_decode_gram(h, Zs, Spad, pn, S, T, reinterpret_cast<uint8_t*>(h->ws) + a_off,
                                       reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->ws) + a_off + a_bytes), st);
     else if (screened) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, field, 1, st);
     else if (d.tc_ok && h->opt_kernel == 1) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, nullptr, 0, st);
@@ -383,6 +383,13 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
     else rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
     if (rc) return rc;
     if ((rc = t_dec.stop())) return rc;
+    if (gram) {
+      if ((rc = t_quad.start())) return rc;
+      rc = launch_decode_quad(h, pn, T, h->d_maxvar + p0, field, reinterpret_cast<uint8_t*>(h->ws) + a_off,
+                              reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->ws) + a_off + a_bytes), st);
+      if (rc) return rc;
+      if ((rc = t_quad.stop())) return rc;
+    }
     if (screened) {
       if ((rc = t_ref.start())) return rc;
       GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats, 0, sizeof(unsigned int), st));      // per-slab count
@@ -443,17 +450,21 @@ int glasdi_stage_times(glasdi_handle* h, double* rollout_ms, double* decode_ms, 
   return GLASDI_OK;
 }
 
-int glasdi_screen_stats(glasdi_handle* h, double* refine_ms, int64_t* n_candidates, float* max_rel_dev, void* stream) {
+int glasdi_screen_stats(glasdi_handle* h, double* refine_ms, double* quad_ms, int64_t* n_candidates, float* max_rel_dev,
+                        void* stream) {
   if (!h) return GLASDI_ERR_INVALID;
   GL_CUDA(h, cudaSetDevice(h->device));
-  if (refine_ms) {
-    *refine_ms = 0.0;
+  double* outs[2] = {refine_ms, quad_ms};
+  const std::vector<int>* lists[2] = {&h->ev_refine, &h->ev_quad};
+  for (int k = 0; k < 2; ++k) {
+    if (!outs[k]) continue;
+    *outs[k] = 0.0;
     if (h->opt_timing)
-      for (int base : h->ev_refine) {
+      for (int base : *lists[k]) {
         GL_CUDA(h, cudaEventSynchronize(h->ev_pool[base + 1]));
         float ms = 0.f;
         GL_CUDA(h, cudaEventElapsedTime(&ms, h->ev_pool[base], h->ev_pool[base + 1]));
-        *refine_ms += ms;
+        *outs[k] += ms;
       }
   }
   unsigned int st[4] = {0, 0, 0, 0};

@@ -77,7 +77,7 @@ struct glasdi_handle {
   unsigned int* d_cand_stats = nullptr;   // [0] count (this slab), [1] total count, [2] float bits of max relative deviation
   unsigned int* d_exact = nullptr;    // [P] float bits of the exact variance
   size_t exact_cap = 0;
-  std::vector<int> ev_refine;
+  std::vector<int> ev_refine, ev_quad;
 };
 
 namespace glasdi {
@@ -118,8 +118,10 @@ size_t gram_a_bytes(int K, long long n_items);
 size_t gram_fscale_bytes(long long n_items);
 size_t decode_gram_smem_bytes(int K, int last_in_w);
 int gram_pack_v(glasdi_handle* h, const float* WL_host);
-int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T, unsigned int* maxvar_bits,
-                       float* var_field, void* a_ws, float* fscale_ws, cudaStream_t st);
+int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T, void* a_ws, float* fscale_ws,
+                       cudaStream_t st);
+int launch_decode_quad(glasdi_handle* h, int P, int T, unsigned int* maxvar_bits, float* var_field, const void* a_ws,
+                       const float* fscale_ws, cudaStream_t st);
 // refine.cu : candidate selection on the screened variance field + exact fp32/fp64 re-evaluation
 int launch_select_candidates(glasdi_handle* h, const float* var_field, int field_ld, const unsigned int* approx_bits,
                              int P, int T, int D, float keep, cudaStream_t st);

@@ -824,9 +824,9 @@ static int launch_gram_inst(glasdi_handle* h, const gr::GramParams& G, int ctas,
   return GLASDI_OK;
 }
 
-// screening pass in covariance form: fills var_field [P][T][field_ld] (true units) and maxvar_bits [P]
-int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P_, int S, int T, unsigned int* maxvar_bits,
-                       float* var_field, void* a_ws, float* fscale_ws, cudaStream_t st) {
+// first GEMM of the screening pass in covariance form: packed, scaled fp16 covariances of every (p, t) -> a_ws
+int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P_, int S, int T, void* a_ws, float* fscale_ws,
+                       cudaStream_t st) {
   const Decoder& d = h->dec;
   if (!d.ready || !d.gram_ok) return set_error(h, GLASDI_ERR_INVALID, "decoder shape not supported by the Gram kernels");
   gr::GramParams G{};
@@ -872,10 +872,18 @@ int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P_, int 
   h->launches++;
   if ((rc = check_cuda(h, cudaGetLastError(), "gram_kernel launch"))) return rc;
 
+  return GLASDI_OK;
+}
+
+// second GEMM of the screening pass: var[(p,t), dof] = Ctilde[(p,t), :] . V[dof, :], field + per-parameter maximum
+int launch_decode_quad(glasdi_handle* h, int P_, int T, unsigned int* maxvar_bits, float* var_field, const void* a_ws,
+                       const float* fscale_ws, cudaStream_t st) {
+  const Decoder& d = h->dec;
   gr::QuadParams Q{};
-  Q.A = G.A; Q.V = d.v_packed; Q.fscale = fscale_ws; Q.field = var_field; Q.maxvar_bits = maxvar_bits;
-  Q.n_items = G.n_items; Q.T = T; Q.D = d.D; Q.field_ld = decode_field_ld(d.n_tiles); Q.nkgQ = G.nkgQ;
-  Q.n_ib = (int)((G.n_items + 127) / 128);
+  Q.A = reinterpret_cast<const __half*>(a_ws); Q.V = d.v_packed; Q.fscale = fscale_ws; Q.field = var_field;
+  Q.maxvar_bits = maxvar_bits;
+  Q.n_items = (long long)P_ * T; Q.T = T; Q.D = d.D; Q.field_ld = decode_field_ld(d.n_tiles); Q.nkgQ = gram_nkgQ(d.K);
+  Q.n_ib = (int)((Q.n_items + 127) / 128);
   Q.n_db = (d.D + 255) / 256;
   const size_t qsmem = gr::kQStages * gr::kQStageBytes + sizeof(gr::QBars) + 16;
   GL_CUDA(h, cudaFuncSetAttribute(gr::quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));

@@ -70,10 +70,13 @@ class Engine:
         return a.value, b.value, n.value
 
     def screen_stats(self):
-        """(refine_ms, n_candidates, max_rel_dev) of the last screened greedy call."""
-        ms, n, dev = C.c_double(), C.c_int64(), C.c_float()
+        """(refine_ms, n_candidates, max_rel_dev) of the last screened greedy call; `self.last_quad_ms` = device
+        time of the second screening GEMM (covariance form; needs OPT_STAGE_TIMING)."""
+        ms, qms, n, dev = C.c_double(), C.c_double(), C.c_int64(), C.c_float()
         with torch.cuda.device(self.device):
-            self._check(self.lib.glasdi_screen_stats(self.h, C.byref(ms), C.byref(n), C.byref(dev), _stream_ptr()))
+            self._check(self.lib.glasdi_screen_stats(self.h, C.byref(ms), C.byref(qms), C.byref(n), C.byref(dev),
+                                                     _stream_ptr()))
+        self.last_quad_ms = qms.value
         return ms.value, n.value, dev.value
 
     def check_numeric(self):

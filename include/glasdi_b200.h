@@ -104,10 +104,12 @@ int64_t glasdi_launch_count(const glasdi_handle* h);
 int glasdi_stage_times(glasdi_handle* h, double* rollout_ms, double* decode_ms, int* decode_launches);
 
 /* Screened mode diagnostics of the LAST greedy call (synchronises `stream`): device time of candidate
- * selection + exact re-evaluation (0 unless GLASDI_OPT_STAGE_TIMING), number of re-evaluated (t, dof)
- * candidates, and the largest relative deviation |std_screen - std_exact| / std_exact seen at them. */
-int glasdi_screen_stats(glasdi_handle* h, double* refine_ms, int64_t* n_candidates, float* max_rel_dev,
-                        void* stream);
+ * selection + exact re-evaluation and of the second screening GEMM (quad_kernel; covariance form only) --
+ * both 0 unless GLASDI_OPT_STAGE_TIMING; glasdi_stage_times' decode_ms is then the first screening kernel
+ * alone --, number of re-evaluated (t, dof) candidates, and the largest relative deviation
+ * |std_screen - std_exact| / std_exact seen at them. */
+int glasdi_screen_stats(glasdi_handle* h, double* refine_ms, double* quad_ms, int64_t* n_candidates,
+                        float* max_rel_dev, void* stream);
 
 /* decoder weights ------------------------------------------------------------------------------
  * Replaces: the `autoencoder.decoder` nn.Module state consumed by get_fom_max_std
