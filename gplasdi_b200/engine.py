@@ -140,6 +140,32 @@ class Engine:
                                                     ms.data_ptr(), am.data_ptr(), mv.data_ptr(), _stream_ptr()))
         return ms, am, mv
 
+    def checked(self, call):
+        """Runs `call()` (a greedy_step / decode_max_std closure), then glasdi_check_numeric.  A screened mode that
+        reports GLASDI_ERR_NUMERIC (screening deviation above a quarter of the candidate margin, candidate overflow,
+        fp16 range) is never trusted: the call is repeated in GLASDI_MODE_DIRECT with three split passes, whose only
+        failure mode (fp16 range of unbounded activations) is raised to the caller."""
+        out = call()
+        try:
+            self.check_numeric()
+            return out
+        except GlasdiError as e:
+            mode = self.get_option(_lib.OPT_MODE)
+            if e.code != _lib.ERR_NUMERIC or mode == _lib.MODE_DIRECT:
+                raise
+            import warnings
+            warnings.warn(f"gplasdi_b200: {e}; repeating the step in direct mode (3 split passes)")
+            passes = self.get_option(_lib.OPT_SPLIT_PASSES)
+            self.set_option(_lib.OPT_MODE, _lib.MODE_DIRECT)
+            self.set_option(_lib.OPT_SPLIT_PASSES, 3)
+            try:
+                out = call()
+                self.check_numeric()
+            finally:
+                self.set_option(_lib.OPT_MODE, mode)
+                self.set_option(_lib.OPT_SPLIT_PASSES, passes)
+            return out
+
     def decode_max_std(self, Zis):
         """Zis [P,S,T,n] fp64 -> (max_std [P], argmax [1], maxval [1])."""
         Zis = self._dev(Zis, torch.float64)

@@ -58,8 +58,8 @@ def sample_roms(autoencoder, physics, latent_dynamics, gp_dictionary, param_grid
 def fom_max_std(autoencoder, Zis):
     """(m_index, max_std[P]) for caller-supplied trajectories Zis [P, S, nt, n_z]."""
     eng = _engine_for(autoencoder)
-    ms, am, _ = eng.decode_max_std(torch.as_tensor(np.ascontiguousarray(Zis)))
-    eng.check_numeric()
+    Zt = torch.as_tensor(np.ascontiguousarray(Zis))
+    ms, am, _ = eng.checked(lambda: eng.decode_max_std(Zt))
     return int(am.item()), ms.cpu().numpy()
 
 
@@ -131,7 +131,6 @@ class BayesianGLaSDI:
         dt = float(self.physics.t_grid[1] - self.physics.t_grid[0]) if len(self.physics.t_grid) > 1 else 0.0
         ms, key = sharding.sharded_greedy_step(eng, coef_samples[lo:hi], Z0[lo:hi], len(self.physics.t_grid), dt,
                                                lo, group)
-        eng.check_numeric()
         self.last_max_std = ms.cpu().numpy()
         _, m_index = sharding.unpack_maxloc(int(key.item()))
         if m_index < 0:

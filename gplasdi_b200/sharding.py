@@ -56,7 +56,9 @@ def allreduce_maxloc(key: torch.Tensor, group=None) -> torch.Tensor:
 def sharded_greedy_step(engine, coefs_local, z0_local, T: int, dt: float, index_offset: int, group=None):
     """Runs the fused greedy step on this rank's block and reduces over ranks.
     Returns (max_std_local CUDA fp32 [P_local], key CUDA int64 [1] after the all-reduce)."""
-    ms, am, mv = engine.greedy_step(coefs_local, z0_local, T, dt)
+    # numeric flags are checked (and a flagged screened step repeated in direct mode) BEFORE the exchange, so that
+    # every rank contributes a trusted key
+    ms, am, mv = engine.checked(lambda: engine.greedy_step(coefs_local, z0_local, T, dt))
     key = engine.pack_maxloc(mv, am, index_offset)
     allreduce_maxloc(key, group)
     return ms, key

@@ -169,6 +169,23 @@ def test_screening_deviation_is_reported(engine):
     engine.check_numeric()
 
 
+def test_flagged_screening_falls_back_to_direct_mode(engine, g_small):
+    """Engine.checked: a screened step whose numeric flag is raised is repeated in direct mode, the caller's
+    options are restored, and the result is the direct-mode (3 split passes) result."""
+    wl, Ws, bs = setup_wl(engine, "small")
+    inp = synth.make_inputs(wl)
+    engine.set_option(_lib.OPT_SCREEN_MARGIN, 16)              # forces the deviation flag (see the test above)
+    with pytest.warns(UserWarning, match="direct mode"):
+        ms, am, mv = engine.checked(lambda: engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt))
+    assert engine.get_option(_lib.OPT_MODE) == _lib.MODE_SCREENED_GRAM and engine.get_option(_lib.OPT_SPLIT_PASSES) == 3
+    engine.set_option(_lib.OPT_SCREEN_MARGIN, 8)
+    assert int(am) == int(g_small["small_m_index"][0])
+    std_close(ms.cpu().numpy(), g_small["small_max_std"])
+    engine.set_option(_lib.OPT_MODE, _lib.MODE_DIRECT)
+    direct = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)[0].cpu().numpy()
+    assert np.array_equal(ms.cpu().numpy(), direct)
+
+
 @pytest.mark.parametrize("nm", ["tiny", "small", "small_s200", "small_softplus"])
 @pytest.mark.parametrize("passes", [3, 2, 1])
 def test_greedy_step_matches_reference(engine, g_small, nm, passes):
