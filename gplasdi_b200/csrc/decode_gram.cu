@@ -354,7 +354,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
           for (int j = 1; j < 4; ++j) mine = ((ptid & 3) == j) ? hq[j] : mine;
           float ha, hb;
           unpack_f32x2(mine, ha, hb);
-          reinterpret_cast<float2*>(sPilot)[(n_it & 1u) * L.kpu + ptid] = make_float2(-ha * hscale, -ha * hscale);
+          // the constant unit K (all-zero weights: h = 1/2 for every column) gets the pilot entry 1 - h 2^eH, so that
+          // its "difference" h 2^eH + (1 - h 2^eH) is the constant 1 without a special case in the hot loop
+          const float np = (ptid == P.K ? 1.0f : 0.0f) - ha * hscale;
+          reinterpret_cast<float2*>(sPilot)[(n_it & 1u) * L.kpu + ptid] = make_float2(np, np);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
         for (int c = 0; c < nchunks; ++c) {
@@ -379,13 +382,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               unpack_f32x2(d2[j], da[j], db[j]);
-              if (P.check_overflow) amax = fmaxf(amax, fmaxf(fabsf(da[j]), fabsf(db[j])));
-            }
-            if ((k0 >> 2) == (P.K >> 2)) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                da[j] = (j == (P.K & 3)) ? 1.0f : da[j];               // the constant unit
-                db[j] = (j == (P.K & 3)) ? 1.0f : db[j];
+              if constexpr (ACT != GLASDI_ACT_SIGMOID && ACT != GLASDI_ACT_TANH) {
+                if (P.check_overflow) amax = fmaxf(amax, fmaxf(fabsf(da[j]), fabsf(db[j])));
               }
             }
             uint2 va2, vb2;
@@ -511,7 +509,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         tc_fence_after();                               // the other warps' TMEM reads of the previous item (bar 4)
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t buf = h_it % kRing;
-          mbar_wait(&B->h_full[buf], (h_it / kRing) & 1u);
+          while (!mbar_try_wait(&B->h_full[buf], (h_it / kRing) & 1u)) __nanosleep(64);   // a chunk takes ~1.5 us
           tc_fence_after();
           const int ncols = min(kCols, P.S - c * kCols);     // fast path: padding columns beyond hold exact zeros
           const int nk = (ncols + 15) >> 4;
