@@ -45,7 +45,9 @@ constexpr int kGProdWarps = 16;
 constexpr int kGProdThreads = kGProdWarps * 32;
 constexpr int kGThreads = (kGProdWarp0 + kGProdWarps) * 32;
 constexpr int kGParts = kGProdThreads / 64;   // thread groups a chunk's tasks are dealt to (fast path)
-constexpr int kGTmemCols = 128;             // one 128 x 128 fp32 accumulator
+constexpr int kGTmemCols = 128;             // generic path: one 128 x 128 fp32 accumulator
+constexpr int kGTmemColsFast = 512;         // fast path: + three 128-column pre-activation buffers
+constexpr uint32_t kA1Bytes = 4 * 2048;     // dz tile: 128 samples x 16 tf32 (hi | lo), K-major, 4 K chunks of 16 B
 
 struct GramParams {
   int P, S, T, Spad, NZ;
@@ -72,11 +74,11 @@ struct GramParams {
 };
 
 struct GBars {
-  uint64_t h_full[kRing], h_empty[kRing], acc_full;
+  uint64_t h_full[kRing], h_empty[kRing], a1_full[kRing], a1_empty[kRing], d1_full[3], acc_full, acc_empty;
 };
 
 struct GSmem {
-  uint32_t h, wl, pilot, m, mx, c, bars, tmem, total;
+  uint32_t h, a1, b1, wl, pilot, m, mx, c, bars, tmem, total;
   int wl_ld, kpu;
 };
 __host__ __device__ inline GSmem gcarve(int nkg, int last_in_w, int nkgQ) {
@@ -84,14 +86,16 @@ __host__ __device__ inline GSmem gcarve(int nkg, int last_in_w, int nkgQ) {
   uint32_t off = 0;
   s.kpu = nkg * 8;
   s.h = off; off += kRing * kBufBytes;
+  s.a1 = off; off += kRing * kA1Bytes;                                  // fast path: latent differences (tf32 A operand)
+  s.b1 = off; off += 4 * 2048;                                          // fast path: front-layer weights (tf32 hi | lo B operand)
   s.wl_ld = wl_stride(last_in_w) > 12 ? wl_stride(last_in_w) : 12;   // fast path rows: 12 floats (duplicated pairs)
   s.wl = off; off += (uint32_t)s.kpu * (uint32_t)s.wl_ld * 4u;
   s.pilot = off; off += 2u * (uint32_t)s.kpu * 8u;                     // fast path: (-p, -p) pairs, double buffered
-  s.m = off; off += 128 * 4u;
-  s.mx = off; off += 16;
+  s.m = off; off += 2 * 128 * 4u;                                       // column sums, double buffered by item parity
+  s.mx = off; off += 2 * 16;
   off = (off + 15u) & ~15u;
-  s.c = off; off += (uint32_t)nkgQ * 16u;
-  s.bars = off; off += 16 * 8;
+  s.c = off; off += 2u * (uint32_t)nkgQ * 16u;                          // packed triangle staging, double buffered
+  s.bars = off; off += 24 * 8;
   s.tmem = off; off += 16;
   s.total = off;
   return s;
@@ -106,6 +110,41 @@ __host__ __device__ inline GSmem gcarve(int nkg, int last_in_w, int nkgQ) {
 __device__ __forceinline__ uint32_t h_offset(int kg, int col) {
   const uint32_t r = (uint32_t)col & 7u;
   return ((uint32_t)kg >> 3) * 16384u + ((uint32_t)col >> 3) * 1024u + r * 128u + ((((uint32_t)kg & 7u) ^ r) << 4);
+}
+
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t (&r)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32 (fp32 containers, 10-bit mantissa, fp32 accumulate), K = 8
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::tf32 instruction descriptor: tf32 A/B (K-major both), fp32 accumulator, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_tf32_m128(uint32_t n) {
+  uint32_t d = 0;
+  d |= 1u << 4;              // c_format = F32
+  d |= 2u << 7;              // a_format = TF32
+  d |= 2u << 10;             // b_format = TF32
+  d |= (n >> 3) << 17;
+  d |= (128u >> 4) << 24;
+  return d;
 }
 
 __device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
@@ -252,20 +291,38 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
     for (int i = 0; i < kRing; ++i) {
       mbar_init(&B->h_full[i], kGProdWarps);
       mbar_init(&B->h_empty[i], 1);
+      mbar_init(&B->a1_full[i], 4);
+      mbar_init(&B->a1_empty[i], 1);
     }
+    mbar_init(&B->d1_full[0], 1);
+    mbar_init(&B->d1_full[1], 1);
+    mbar_init(&B->d1_full[2], 1);
     mbar_init(&B->acc_full, 1);
+    mbar_init(&B->acc_empty, kGEpiWarps - 1);
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, kGTmemCols);
+    tmem_alloc(tmem_slot, FAST ? kGTmemColsFast : kGTmemCols);
     tmem_relinquish();
   }
+  uint8_t* sA1 = smem + L.a1;
+  uint8_t* sB1 = smem + L.b1;
   {
     const int l = P.front.n_front - 1;
     const float* __restrict__ W = P.front.W[l];
     const float* __restrict__ b = P.front.b[l];
     const int ld = L.wl_ld;
-    if constexpr (!FAST) {
+    if constexpr (FAST) {
+      // B operand of the pre-activation MMA: -log2(e) W0 as tf32, [unit][k < 8] K-major (k >= 5 and units >= K zero)
+      for (int idx = threadIdx.x; idx < 128 * 8; idx += blockDim.x) {
+        const int u = idx >> 3, k = idx & 7;
+        const float v = (u < P.K && k < 5) ? P.w6[u * 6 + k] : 0.f;
+        const float vh = round_tf32(v);
+        uint8_t* dst = sB1 + (k >> 2) * 2048 + (u >> 3) * 128 + (u & 7) * 16 + (k & 3) * 4;
+        *reinterpret_cast<float*>(dst) = vh;                       // K chunks 0,1: tf32(W)
+        *reinterpret_cast<float*>(dst + 4096) = v - vh;            // K chunks 2,3: the remainder
+      }
+    } else {
       for (int idx = threadIdx.x; idx < L.kpu * ld; idx += blockDim.x) {
         const int k = idx / ld, i = idx - k * ld;
         float v = 0.f;
@@ -280,7 +337,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
     uint4* z4 = reinterpret_cast<uint4*>(sH);
     for (uint32_t idx = threadIdx.x; idx < kRing * kBufBytes / 16; idx += blockDim.x) z4[idx] = make_uint4(0, 0, 0, 0);
     uint4* c4 = reinterpret_cast<uint4*>(sC);
-    for (int idx = threadIdx.x; idx < P.nkgQ; idx += blockDim.x) c4[idx] = make_uint4(0, 0, 0, 0);
+    for (int idx = threadIdx.x; idx < 2 * P.nkgQ; idx += blockDim.x) c4[idx] = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -296,115 +353,173 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
     uint32_t h_it = 0, n_it = 0;
     float amax = 0.f;
     if constexpr (FAST) {
-      // thread <-> sample columns (cp, cp + 64) of the chunk x every 8th TASK; a task = 4 consecutive units
-      // (half a 16-byte operand vector).  The tasks that do not divide evenly rotate over the eight thread
-      // groups from chunk to chunk.
-      const int cp = ptid & 63;
-      const int eighth = __shfl_sync(0xffffffffu, ptid >> 6, 0);      // warp-uniform: weights come through the uniform datapath
-      const int ntask = 2 * P.nkg;
-      const int ntask8 = ntask - ntask % kGParts;
-      const uint32_t sNP2 = smem_u32(sPilot);
-      const uint32_t pilot_bytes = (uint32_t)L.kpu * 8u;
+      // Pre-activations come from the TENSOR CORE: a(s) = a(pilot) + (-log2 e) W0 (z(s) - z(pilot)), the second term
+      // as one tf32 MMA pair per chunk (samples on the TMEM lanes, units on the columns; dz split hi + lo so that only
+      // W0 is rounded to tf32: a 5e-5 systematic effect on sigma, inside the screening budget).  That removes the
+      // 5 FMAs + 3 weight loads per (unit, sample) that dominated the instruction count (profiles/: gram_r1e: 60 k
+      // warp-instructions per (p, t), 60 % issue utilisation) and gives the natural mapping
+      //   thread <-> one sample (TMEM lane) x 8 consecutive units (one 16-byte operand vector).
+      const int q = warp & 3;                               // TMEM lane quadrant = 32-sample block of the chunk
+      const int jg = (warp - kGProdWarp0) >> 2;             // 0..3: unit groups jg, jg + 4, ... (+ rotating left-over)
+      const int col = q * 32 + lane;
+      const bool phase_a = jg == 0;                         // warps 4..7 also write the latent differences
+      const int nkg4 = P.nkg & ~3;
       const unsigned long long hs2 = pack_f32x2(hscale, hscale);
-      // prefetched latent states stay UNPACKED scalars until they are used: packing at load time puts a register
-      // move behind every load, and the move waits for the load (profiles/: gram_r1c, 10 % of the kernel)
-      // Spad is a multiple of 128 and the columns [S, Spad) hold copies of sample 0 (launch_pad_columns): no
-      // bounds predicate anywhere, the padding cancels against the pilot
-      auto load_z = [&](const float* __restrict__ zb, int c, float (&za)[5], float (&zbv)[5]) {
-        const float* __restrict__ src = zb + c * kCols + cp;
+      const unsigned long long one2 = pack_f32x2(1.0f, 1.0f);
+      const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+      uint32_t g = 0;                                       // chunk counter over the whole kernel
+      long long item = blockIdx.x;
+      // Phase A (warps 4..7) walks the CTA's stream of chunks ONE AHEAD of phase B, so that the pre-activation MMA
+      // of chunk c + 1 runs while chunk c is being processed.  Its latent states are prefetched two stream elements
+      // ahead (zq[2], a two-entry queue), the pilot's one item ahead (zpa = item of the queue head, zpn = the next).
+      float zq[2][5], zpa[5], zpn[5], zpt[5], zptn[5];
+      long long item_l = item;                              // position of the next stream element to LOAD
+      int c_l = 0;
+      uint32_t ga = 0;                                      // stream index of the next phase-A element (= queue head)
+      int c_a = 0;                                          // its chunk index inside its item
+      long long item_a = item;                              // its item
+      const uint32_t n_elems = item < P.n_items
+                                   ? (uint32_t)((P.n_items - item + gridDim.x - 1) / gridDim.x) * (uint32_t)nchunks : 0u;
+      auto load_col = [&](long long it, int c, float (&z)[5]) {
+        const float* __restrict__ src = P.Zs + (size_t)it * 5 * P.Spad + c * kCols + col;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          za[i] = __ldg(src + (size_t)i * P.Spad);
-          zbv[i] = __ldg(src + (size_t)i * P.Spad + 64);
+        for (int i = 0; i < 5; ++i) z[i] = __ldg(src + (size_t)i * P.Spad);
+      };
+      auto load_zp = [&](long long it, float (&z)[5]) {      // sample 0 = the pilot
+        const float* __restrict__ src = P.Zs + (size_t)it * 5 * P.Spad;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) z[i] = __ldg(src + (size_t)i * P.Spad);
+      };
+      auto load_next = [&](float (&z)[5]) {                  // next element of the stream, if any
+        if (item_l < P.n_items) {
+          load_col(item_l, c_l, z);
+          if (++c_l == nchunks) { c_l = 0; item_l += gridDim.x; }
         }
       };
-      auto load_zp = [&](const float* __restrict__ zb, float (&zp)[5]) {      // sample 0 = the pilot
-#pragma unroll
-        for (int i = 0; i < 5; ++i) zp[i] = __ldg(zb + (size_t)i * P.Spad);
-      };
-      long long item = blockIdx.x;
-      float znA[5], znB[5], zp[5];
-      if (item < P.n_items) {
-        load_z(P.Zs + (size_t)item * 5 * P.Spad, 0, znA, znB);
-        load_zp(P.Zs + (size_t)item * 5 * P.Spad, zp);
+      if (phase_a && item < P.n_items) {
+        load_next(zq[0]);
+        load_next(zq[1]);
+        load_zp(item, zpa);
+        load_zp(item, zpt);
+        if (item + gridDim.x < P.n_items) {
+          load_zp(item + gridDim.x, zpn);
+          load_zp(item + gridDim.x, zptn);
+        }
       }
+      // dz = z - z_pilot of this thread's sample as the tf32 A operand (hi in K 0..7, lo in K 8..15) of stream element ga
+      auto phase_a_step = [&]() {
+        const uint32_t slot = ga % kRing;
+        float hi[5], lo[5];
+        if (ga & 1u) {
+#pragma unroll
+          for (int i = 0; i < 5; ++i) { const float dz = zq[1][i] - zpa[i]; hi[i] = round_tf32(dz); lo[i] = dz - hi[i]; }
+          load_next(zq[1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 5; ++i) { const float dz = zq[0][i] - zpa[i]; hi[i] = round_tf32(dz); lo[i] = dz - hi[i]; }
+          load_next(zq[0]);
+        }
+        mbar_wait_relaxed(&B->a1_empty[slot], ((ga / kRing) & 1u) ^ 1u);
+        uint8_t* dst = sA1 + slot * kA1Bytes + (col >> 3) * 128 + (col & 7) * 16;
+        *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(dst + 2048) = make_float4(hi[4], 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(dst + 4096) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(dst + 6144) = make_float4(lo[4], 0.f, 0.f, 0.f);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B->a1_full[slot]);
+        ++ga;
+        if (++c_a == nchunks) {                              // the queue head moves to the next item: its pilot
+          c_a = 0;
+          item_a += gridDim.x;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) zpa[i] = zpn[i];
+          if (item_a + gridDim.x < P.n_items) load_zp(item_a + gridDim.x, zpn);
+        }
+      };
+      if (phase_a && n_elems > 0) phase_a_step();           // stream elements 0 and 1: phase A runs TWO ahead of phase B
+      if (phase_a && n_elems > 1) phase_a_step();
       for (; item < P.n_items; item += gridDim.x, ++n_it) {
-        const float* __restrict__ zb = P.Zs + (size_t)item * 5 * P.Spad;
-        // pilot = activations of sample 0, one unit per thread, stored negated, scaled and duplicated.  Two pilot
-        // buffers alternate from item to item: a thread can only write buffer b again after every producer
-        // thread has passed the barrier of the item in between, i.e. has finished reading b.
-        const uint32_t sNPb = sNP2 + (n_it & 1u) * pilot_bytes;
-        if (ptid < L.kpu) {
-          // same arithmetic as the samples (the group of four units, own unit picked): the columns that pad S up
-          // to a multiple of 128 hold the pilot's latent state and must cancel to exactly 0
-          unsigned long long zp2[5], hq[4];
+        // pilot tables of this item (double buffered, see the barrier comment of the generic path): a(pilot) in the
+        // log2 domain and -(h(pilot) 2^eH), with the SAME pairwise arithmetic as the samples so that the padding
+        // columns (copies of sample 0, dz = 0) cancel to exactly 0.  The constant unit K (zero weights, h = 1/2)
+        // gets 1 - h 2^eH: its "difference" is the constant 1.
+        float* tabA = sPilot + (n_it & 1u) * 2 * L.kpu;
+        float* tabN = tabA + L.kpu;
+        if (ptid < L.kpu) {                                  // ptid < 128: phase-A warps, zpt = this item's pilot
+          const int k = ptid, kp = ptid ^ 1;
+          const float* wk = P.w6 + k * 6;
+          const float* wp = P.w6 + kp * 6;
+          float ak = wk[5], ap = wp[5];
 #pragma unroll
-          for (int i = 0; i < 5; ++i) zp2[i] = pack_f32x2(zp[i], zp[i]);
-          if constexpr (ACT == GLASDI_ACT_SIGMOID) {
-            unsigned long long acc[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = preact_pair(P.w6, (ptid & ~3) + j, zp2);
-            sigmoid4_pair(acc, hq);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) hq[j] = act_pair<ACT>(preact_pair(P.w6, (ptid & ~3) + j, zp2), P.front.act);
+          for (int i = 0; i < 5; ++i) {
+            ak = fmaf(wk[i], zpt[i], ak);
+            ap = fmaf(wp[i], zpt[i], ap);
           }
-          unsigned long long mine = hq[0];
-#pragma unroll
-          for (int j = 1; j < 4; ++j) mine = ((ptid & 3) == j) ? hq[j] : mine;
-          float ha, hb;
-          unpack_f32x2(mine, ha, hb);
-          // the constant unit K (all-zero weights: h = 1/2 for every column) gets the pilot entry 1 - h 2^eH, so that
-          // its "difference" h 2^eH + (1 - h 2^eH) is the constant 1 without a special case in the hot loop
-          const float np = (ptid == P.K ? 1.0f : 0.0f) - ha * hscale;
-          reinterpret_cast<float2*>(sPilot)[(n_it & 1u) * L.kpu + ptid] = make_float2(np, np);
+          const float tk = ex2_ftz(ak) + 1.0f, tp = ex2_ftz(ap) + 1.0f;
+          const float te = (k & 1) ? tp : tk, to = (k & 1) ? tk : tp;
+          const float r = rcp_ftz(te * to);
+          const float hk = r * ((k & 1) ? te : to);
+          tabA[k] = ak;
+          tabN[k] = (k == P.K ? 1.0f : 0.0f) - hk * hscale;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
-        for (int c = 0; c < nchunks; ++c) {
-          unsigned long long z2[5];
-#pragma unroll
-          for (int i = 0; i < 5; ++i) z2[i] = pack_f32x2(znA[i], znB[i]);
-          // next chunk's (or next item's first) latent states: in flight while this chunk is computed
-          if (c + 1 < nchunks) {
-            load_z(zb, c + 1, znA, znB);
-          } else if (item + gridDim.x < P.n_items) {
-            load_z(P.Zs + (size_t)(item + gridDim.x) * 5 * P.Spad, 0, znA, znB);
-            load_zp(P.Zs + (size_t)(item + gridDim.x) * 5 * P.Spad, zp);
-          }
-          const uint32_t buf = h_it % kRing;
-          uint8_t* Hb = sH + buf * kBufBytes;
-          mbar_wait_relaxed(&B->h_empty[buf], ((h_it / kRing) & 1u) ^ 1u);
-          auto do_task = [&](int task) {
-            const int k0 = task * 4;
-            unsigned long long d2[4];
-            units4_pair<ACT>(P.w6, sNPb, k0, z2, hs2, P.front.act, d2);
-            float da[4], db[4];
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          if (phase_a && ga < n_elems) phase_a_step();        // stream element g + 2
+          // ---- phase B: sigmoid of (a_pilot + da), pilot-centred, scaled, fp16, into the Gram operand tile
+          const uint32_t db = g % 3u, hb = g % kRing;
+          while (!mbar_try_wait(&B->d1_full[db], (g / 3u) & 1u)) __nanosleep(32);
+          tc_fence_after();
+          mbar_wait_relaxed(&B->h_empty[hb], ((g / kRing) & 1u) ^ 1u);
+          uint8_t* Hb = sH + hb * kBufBytes;
+          const uint32_t taddr = tmem_base + lane_addr + 128u + db * 128u;   // D1[g mod 3]
+          auto do_group = [&](int kg) {
+            uint32_t d[8];
+            tmem_ld_32x8(taddr + kg * 8, d);
+            const float4 a0 = *reinterpret_cast<const float4*>(tabA + kg * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(tabA + kg * 8 + 4);
+            tmem_ld_wait();
+            unsigned long long acc[4];
+            acc[0] = add_f32x2(pack_f32x2(a0.x, a0.y), pack_f32x2(__uint_as_float(d[0]), __uint_as_float(d[1])));
+            acc[1] = add_f32x2(pack_f32x2(a0.z, a0.w), pack_f32x2(__uint_as_float(d[2]), __uint_as_float(d[3])));
+            acc[2] = add_f32x2(pack_f32x2(a1.x, a1.y), pack_f32x2(__uint_as_float(d[4]), __uint_as_float(d[5])));
+            acc[3] = add_f32x2(pack_f32x2(a1.z, a1.w), pack_f32x2(__uint_as_float(d[6]), __uint_as_float(d[7])));
+            const float4 n0 = *reinterpret_cast<const float4*>(tabN + kg * 8);
+            const float4 n1 = *reinterpret_cast<const float4*>(tabN + kg * 8 + 4);
+            const unsigned long long np[4] = {pack_f32x2(n0.x, n0.y), pack_f32x2(n0.z, n0.w), pack_f32x2(n1.x, n1.y),
+                                              pack_f32x2(n1.z, n1.w)};
+            uint32_t out[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              unpack_f32x2(d2[j], da[j], db[j]);
-              if constexpr (ACT != GLASDI_ACT_SIGMOID && ACT != GLASDI_ACT_TANH) {
-                if (P.check_overflow) amax = fmaxf(amax, fmaxf(fabsf(da[j]), fabsf(db[j])));
-              }
+              float xe, xo;
+              unpack_f32x2(acc[j], xe, xo);
+              float te, to;
+              unpack_f32x2(add_f32x2(pack_f32x2(ex2_ftz(xe), ex2_ftz(xo)), one2), te, to);
+              const float r = rcp_ftz(te * to);
+              float de, dod;
+              unpack_f32x2(fma_f32x2(pack_f32x2(r * to, r * te), hs2, np[j]), de, dod);
+              out[j] = h2_as_u32(__floats2half2_rn(de, dod));
             }
-            uint2 va2, vb2;
-            va2.x = h2_as_u32(__floats2half2_rn(da[0], da[1]));
-            va2.y = h2_as_u32(__floats2half2_rn(da[2], da[3]));
-            vb2.x = h2_as_u32(__floats2half2_rn(db[0], db[1]));
-            vb2.y = h2_as_u32(__floats2half2_rn(db[2], db[3]));
-            const uint32_t off = h_offset(task >> 1, cp) + (uint32_t)(task & 1) * 8u;    // cp + 64: same row, 8 atoms on
-            *reinterpret_cast<uint2*>(Hb + off) = va2;
-            *reinterpret_cast<uint2*>(Hb + off + 8u * 1024u) = vb2;
+            *reinterpret_cast<uint4*>(Hb + h_offset(kg, col)) = make_uint4(out[0], out[1], out[2], out[3]);
           };
 #pragma unroll 1
-          for (int task = eighth; task < ntask8; task += kGParts) do_task(task);
-          {
-            const int extra = ntask8 + ((eighth + kGParts - (int)(h_it % kGParts)) % kGParts);   // left-over tasks rotate
-            if (extra < ntask) do_task(extra);
+          for (int kg = jg; kg < nkg4; kg += 4) do_group(kg);
+          if (jg > 0) {
+            // left-over groups rotate over the warp groups 1..3; group 0 (the phase-A warps) has its extra work already.
+            // Per chunk the warps are therefore NOT equally loaded: three pre-activation buffers (below) let them
+            // drift up to two chunks apart, so that only the average matters.
+            const int extra = nkg4 + (int)((uint32_t)(jg - 1 + 3 - (int)(g % 3u)) % 3u);
+            if (extra < P.nkg) do_group(extra);
           }
+          tc_fence_before();
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&B->h_full[buf]);
-          ++h_it;
+          if (lane == 0) mbar_arrive(&B->h_full[hb]);
+        }
+        if (phase_a) {                                        // pilot of the next item's tables (prefetched an item ago)
+#pragma unroll
+          for (int i = 0; i < 5; ++i) zpt[i] = zptn[i];
+          if (item + 2 * (long long)gridDim.x < P.n_items) load_zp(item + 2 * (long long)gridDim.x, zptn);
         }
       }
     } else {
@@ -497,19 +612,74 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
     const int i = warp * 32 + lane;
     const int K = P.K;
     const float inv_S = P.inv_S;
-    const int off_i = i * K - (i * (i - 1)) / 2;
+    const int off_i = (i * (i + 1)) / 2;                    // packed LOWER triangle, row-major: q(i, j <= i) = i (i + 1) / 2 + j
     const uint32_t idesc = umma_idesc_f16_m128_mn((uint32_t)P.Nmma);
     // MN-major, 128-byte swizzle (see h_offset): LBO = step between 64-unit blocks (16 KB), SBO = step between
     // 8-sample groups (1 KB)
     const uint64_t desc0 = umma_desc_kmajor(smem_u32(sH), 16384u, 1024u) | (2ull << 61);
     const uint32_t taddr = tmem_base + (((uint32_t)(warp * 32)) << 16);
-    uint32_t h_it = 0, n_it = 0;
+    uint32_t h_it = 0, n_it = 0, g1 = 0;
     for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x, ++n_it) {
-      if (warp == 0) {
+      if (warp == 0 && FAST) {
+        // The pre-activation MMAs run ONE stream element (chunk) ahead of the Gram MMAs over the whole kernel:
+        // D1[g & 1] = dz (hi, lo) x (-log2 e W0)^T (hi, lo), then G += H^T H.  D1[(g + 1) & 1] is free when element
+        // g + 1 is issued: its last readers (phase B of element g - 1) arrived on h_full before the previous Gram MMAs.
+        tc_fence_after();                               // the other warps' TMEM reads of the previous item (bar 4)
+        const uint32_t idesc1 = umma_idesc_tf32_m128((uint32_t)P.Nmma);
+        const uint64_t adesc1 = umma_desc_kmajor(smem_u32(sA1), 2048u, 128u);
+        const uint64_t bdesc1 = umma_desc_kmajor(smem_u32(sB1), 2048u, 128u);
+        const uint32_t n_elems = (uint32_t)((P.n_items - blockIdx.x + gridDim.x - 1) / gridDim.x) * (uint32_t)nchunks;
+        auto issue_mma1 = [&]() {
+          const uint32_t slot = g1 % kRing;
+          while (!mbar_try_wait(&B->a1_full[slot], (g1 / kRing) & 1u)) __nanosleep(32);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d1 = tmem_base + 128u + (g1 % 3u) * 128u;
+            const uint64_t a = adesc1 + (uint64_t)(slot * (kA1Bytes >> 4));
+            tc_mma_tf32(d1, a, bdesc1, idesc1, 0u);                                          // dz_hi W_hi
+            tc_mma_tf32(d1, a + (uint64_t)(4096 >> 4), bdesc1, idesc1, 1u);                  // dz_lo W_hi
+            tc_mma_tf32(d1, a, bdesc1 + (uint64_t)(4096 >> 4), idesc1, 1u);                  // dz_hi W_lo
+            tc_commit(&B->a1_empty[slot]);
+            tc_commit(&B->d1_full[g1 % 3u]);
+          }
+          __syncwarp();
+          ++g1;
+        };
+        if (g1 == 0) {                                  // stream elements 0 and 1
+          issue_mma1();
+          if (g1 < n_elems) issue_mma1();
+        }
+        for (int c = 0; c < nchunks; ++c) {
+          if (g1 < n_elems && g1 <= h_it + 2u) issue_mma1();      // element h_it + 2 (its buffer: element h_it - 1, drained)
+          const uint32_t buf = h_it % kRing;
+          while (!mbar_try_wait(&B->h_full[buf], (h_it / kRing) & 1u)) __nanosleep(64);   // a chunk takes ~1 us
+          if (c == 0 && n_it > 0) mbar_wait(&B->acc_empty, (n_it - 1u) & 1u);             // previous accumulator drained
+          tc_fence_after();
+          const int ncols = min(kCols, P.S - c * kCols);       // padding columns beyond hold exact zeros
+          const int nk = (ncols + 15) >> 4;
+          const uint64_t d0 = desc0 + (uint64_t)(buf * (kBufBytes >> 4));
+          if (elect_one()) {
+#pragma unroll 1
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t dk = d0 + (uint64_t)(k * 128);             // 16 samples = two 1 KB swizzle atoms per K slice
+              tc_mma_f16(tmem_base, dk, dk, idesc, (c | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(&B->h_empty[buf]);
+          }
+          __syncwarp();
+          ++h_it;
+        }
+        if (elect_one()) tc_commit(&B->acc_full);
+        __syncwarp();
+        // the epilogue below keeps this warp away for ~2 chunk times: put a second pre-activation MMA in flight
+        // (both D1 buffers are free: every phase B of this item has arrived) so that the producers do not starve
+        if (g1 < n_elems && g1 <= h_it + 2u) issue_mma1();
+      } else if (warp == 0) {
         tc_fence_after();                               // the other warps' TMEM reads of the previous item (bar 4)
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t buf = h_it % kRing;
           while (!mbar_try_wait(&B->h_full[buf], (h_it / kRing) & 1u)) __nanosleep(64);   // a chunk takes ~1.5 us
+          if (c == 0 && n_it > 0) mbar_wait(&B->acc_empty, (n_it - 1u) & 1u);             // previous accumulator drained
           tc_fence_after();
           const int ncols = min(kCols, P.S - c * kCols);     // fast path: padding columns beyond hold exact zeros
           const int nk = (ncols + 15) >> 4;
@@ -530,6 +700,12 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       }
       while (!mbar_try_wait(&B->acc_full, n_it & 1u)) __nanosleep(warp == 0 ? 64 : 1024);   // an item takes ~10 us
       tc_fence_after();
+      // Warp 0 also issues the MMAs, so its share of the epilogue is kept minimal: row i packs the LOWER triangle
+      // j <= i (rows 0..31: one 32-column block), it only ARRIVES on the barrier that separates packing from the
+      // copy-out, and warps 1..3 do the copy-out.  Everything per-item in shared memory is double buffered.
+      float* sMb = sM + (n_it & 1u) * 128;
+      float* sMaxb = sMax + (n_it & 1u) * 4;
+      __half* sCb = sC + (size_t)(n_it & 1u) * P.nkgQ * 8;
       uint32_t r[32];
       // step 1: own diagonal entry, own column sum, the row of column sums (from the constant unit's row)
       tmem_ld_32x32(taddr + warp * 32, r);
@@ -542,7 +718,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       const float mi = __uint_as_float(mi_bits);
       const float cii = (i < K) ? (gii - mi * mi * inv_S) * inv_S : 0.f;
       const float wm = warp_max(fmaxf(cii, 0.f));
-      if (lane == 0) sMax[warp] = wm;
+      if (lane == 0) sMaxb[warp] = wm;
       if (__any_sync(0xffffffffu, i < K && !(fabsf(gii) < 3.0e38f)) && lane == 0) atomicOr(P.flags, 1);   // NaN / inf activations
       if (warp == (K >> 5)) {
         for (int b = 0; b < 4; ++b) {
@@ -550,26 +726,26 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
           tmem_ld_wait();
           if (lane == (K & 31)) {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) sM[b * 32 + q] = __uint_as_float(r[q]);
+            for (int q = 0; q < 32; ++q) sMb[b * 32 + q] = __uint_as_float(r[q]);
           }
         }
       }
       asm volatile("bar.sync 3, 128;" ::: "memory");
-      const float cmax = fmaxf(fmaxf(sMax[0], sMax[1]), fmaxf(sMax[2], sMax[3]));
+      const float cmax = fmaxf(fmaxf(sMaxb[0], sMaxb[1]), fmaxf(sMaxb[2], sMaxb[3]));
       int e = 0;
       float f = 0.f;
       if (cmax > 0.f && cmax < 3.0e38f) {
         e = max(-60, min(60, 13 - ilogbf(cmax)));
         f = ldexpf(inv_S, e);
       }
-      // step 2: upper-triangle entries j >= i of row i, scaled, fp16, packed at off(i) + j - i
+      // step 2: lower-triangle entries j <= i of row i, scaled, fp16, packed at off(i) + j
       const float mis = mi * inv_S;
-      for (int b = warp; b < 4; ++b) {                  // blocks left of the diagonal block hold only j < i
+      for (int b = 0; b <= warp; ++b) {                 // blocks right of the diagonal block hold only j > i
         if (b * 32 >= K) break;
         tmem_ld_32x32(taddr + b * 32, r);
         tmem_ld_wait();
         if (i < K) {
-          const float4* m4 = reinterpret_cast<const float4*>(sM + b * 32);
+          const float4* m4 = reinterpret_cast<const float4*>(sMb + b * 32);
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             const float4 mj = m4[q4];
@@ -577,31 +753,35 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
               const int j = b * 32 + q4 * 4 + qq;
-              if (j >= i && j < K) {
+              if (j <= i) {
                 const float val = fmaf(-mis, mjv[qq], __uint_as_float(r[q4 * 4 + qq])) * f;
-                sC[off_i + j - i] = __float2half_rn(val);
+                sCb[off_i + j] = __float2half_rn(val);
               }
             }
           }
         }
       }
-      tc_fence_before();                                // TMEM reads done before warp 0 overwrites the accumulator
-      asm volatile("bar.sync 4, 128;" ::: "memory");
-      // copy-out: 16-byte pieces of the packed row into the quad kernel's A tiles
-      {
+      tc_fence_before();                                // this warp's TMEM reads of the item are done
+      if (warp == 0) {
+        asm volatile("bar.arrive 4, 128;" ::: "memory");                 // packed its rows; back to issuing MMAs
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B->acc_empty);                         // warp 0 may overwrite the accumulator
+        asm volatile("bar.sync 4, 128;" ::: "memory");
+        // copy-out: 16-byte pieces of the packed row into the quad kernel's A tiles
         const long long ib = item >> 7;
         const int row = (int)(item & 127);
         uint4* dst = reinterpret_cast<uint4*>(P.A) + ((size_t)ib * P.nkgQ) * 128 + row;
-        const uint4* src = reinterpret_cast<const uint4*>(sC);
-        for (int kg = threadIdx.x; kg < P.nkgQ; kg += kGEpiWarps * 32) dst[(size_t)kg * 128] = src[kg];
-        if (threadIdx.x == 0) P.fscale[item] = (f > 0.f) ? ldexpf(1.0f, -(P.exp_base + e)) : 0.f;
+        const uint4* src = reinterpret_cast<const uint4*>(sCb);
+        for (int kg = threadIdx.x - 32; kg < P.nkgQ; kg += (kGEpiWarps - 1) * 32) dst[(size_t)kg * 128] = src[kg];
+        if (threadIdx.x == 32) P.fscale[item] = (f > 0.f) ? ldexpf(1.0f, -(P.exp_base + e)) : 0.f;
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, kGTmemCols);
+  if (warp == 0) tmem_dealloc(tmem_base, FAST ? kGTmemColsFast : kGTmemCols);
 }
 
 // ================================================================================================
@@ -801,7 +981,7 @@ int gram_pack_v(glasdi_handle* h, const float* WL /*[D][K] host*/) {
     __half* base = packed.data() + (size_t)db * nkgQ * 256 * 8;
     int q = 0;
     for (int i = 0; i < K; ++i)
-      for (int j = i; j < K; ++j, ++q) {
+      for (int j = 0; j <= i; ++j, ++q) {                      // same order as the epilogue of gram_kernel
         const float v = std::ldexp((i == j ? 1.0f : 2.0f) * w[i] * w[j], d.eV);
         base[((size_t)(q >> 3) * 256 + row) * 8 + (q & 7)] = __float2half_rn(v);
       }
