@@ -74,7 +74,7 @@ struct GramParams {
 };
 
 struct GBars {
-  uint64_t h_full[kRing], h_empty[kRing], a1_full[kRing], a1_empty[kRing], d1_full[3], acc_full, acc_empty;
+  uint64_t h_full[kRing], h_empty[kRing], a1_full[kRing], a1_empty[kRing], d1_full[3], tab_full[4], acc_full, acc_empty;
 };
 
 struct GSmem {
@@ -90,12 +90,12 @@ __host__ __device__ inline GSmem gcarve(int nkg, int last_in_w, int nkgQ) {
   s.b1 = off; off += 4 * 2048;                                          // fast path: front-layer weights (tf32 hi | lo B operand)
   s.wl_ld = wl_stride(last_in_w) > 12 ? wl_stride(last_in_w) : 12;   // fast path rows: 12 floats (duplicated pairs)
   s.wl = off; off += (uint32_t)s.kpu * (uint32_t)s.wl_ld * 4u;
-  s.pilot = off; off += 2u * (uint32_t)s.kpu * 8u;                     // fast path: (-p, -p) pairs, double buffered
+  s.pilot = off; off += 4u * (uint32_t)s.kpu * 8u;                     // fast path: 4 buffers x (a_pilot, -h_pilot 2^eH) tables
   s.m = off; off += 2 * 128 * 4u;                                       // column sums, double buffered by item parity
   s.mx = off; off += 2 * 16;
   off = (off + 15u) & ~15u;
   s.c = off; off += 2u * (uint32_t)nkgQ * 16u;                          // packed triangle staging, double buffered
-  s.bars = off; off += 24 * 8;
+  s.bars = off; off += 32 * 8;
   s.tmem = off; off += 16;
   s.total = off;
   return s;
@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
     mbar_init(&B->d1_full[0], 1);
     mbar_init(&B->d1_full[1], 1);
     mbar_init(&B->d1_full[2], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&B->tab_full[i], 4);
     mbar_init(&B->acc_full, 1);
     mbar_init(&B->acc_empty, kGEpiWarps - 1);
     fence_barrier_init();
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       // Phase A (warps 4..7) walks the CTA's stream of chunks ONE AHEAD of phase B, so that the pre-activation MMA
       // of chunk c + 1 runs while chunk c is being processed.  Its latent states are prefetched two stream elements
       // ahead (zq[2], a two-entry queue), the pilot's one item ahead (zpa = item of the queue head, zpn = the next).
-      float zq[2][5], zpa[5], zpn[5], zpt[5], zptn[5];
+      float zq[2][5], zpa[5], zpn[5], zpt[5];              // zpt: pilot of the item whose tables are made next (warps 8..11)
       long long item_l = item;                              // position of the next stream element to LOAD
       int c_l = 0;
       uint32_t ga = 0;                                      // stream index of the next phase-A element (= queue head)
@@ -400,11 +401,42 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         load_next(zq[0]);
         load_next(zq[1]);
         load_zp(item, zpa);
-        load_zp(item, zpt);
-        if (item + gridDim.x < P.n_items) {
-          load_zp(item + gridDim.x, zpn);
-          load_zp(item + gridDim.x, zptn);
+        if (item + gridDim.x < P.n_items) load_zp(item + gridDim.x, zpn);
+      }
+      // Pilot tables a(pilot) (log2 domain) and -(h(pilot) 2^eH) of an item: made ONE ITEM AHEAD by warps 8..11 into
+      // a ring of four buffers and published through an mbarrier, so that no CTA-wide barrier ties the producer
+      // warps together at item boundaries (they drift up to two chunks apart).  Same pairwise arithmetic as the
+      // samples: the padding columns (copies of sample 0, dz = 0) cancel to exactly 0.  The constant unit K (zero
+      // weights, h = 1/2) gets 1 - h 2^eH: its "difference" is the constant 1.
+      const bool tab_warp = jg == 1;
+      auto make_tables = [&](uint32_t nseq) {
+        float* tA = sPilot + (nseq & 3u) * 2 * L.kpu;
+        float* tN = tA + L.kpu;
+        const int k = ptid - 128;
+        if (k < L.kpu) {
+          const int kp = k ^ 1;
+          const float* wk = P.w6 + k * 6;
+          const float* wp = P.w6 + kp * 6;
+          float ak = wk[5], ap = wp[5];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            ak = fmaf(wk[i], zpt[i], ak);
+            ap = fmaf(wp[i], zpt[i], ap);
+          }
+          const float tk = ex2_ftz(ak) + 1.0f, tp = ex2_ftz(ap) + 1.0f;
+          const float te = (k & 1) ? tp : tk, to = (k & 1) ? tk : tp;
+          const float r = rcp_ftz(te * to);
+          const float hk = r * ((k & 1) ? te : to);
+          tA[k] = ak;
+          tN[k] = (k == P.K ? 1.0f : 0.0f) - hk * hscale;
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B->tab_full[nseq & 3u]);
+      };
+      if (tab_warp && item < P.n_items) {
+        load_zp(item, zpt);
+        make_tables(0);
+        if (item + gridDim.x < P.n_items) load_zp(item + gridDim.x, zpt);
       }
       // dz = z - z_pilot of this thread's sample as the tf32 A operand (hi in K 0..7, lo in K 8..15) of stream element ga
       auto phase_a_step = [&]() {
@@ -440,30 +472,13 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       if (phase_a && n_elems > 0) phase_a_step();           // stream elements 0 and 1: phase A runs TWO ahead of phase B
       if (phase_a && n_elems > 1) phase_a_step();
       for (; item < P.n_items; item += gridDim.x, ++n_it) {
-        // pilot tables of this item (double buffered, see the barrier comment of the generic path): a(pilot) in the
-        // log2 domain and -(h(pilot) 2^eH), with the SAME pairwise arithmetic as the samples so that the padding
-        // columns (copies of sample 0, dz = 0) cancel to exactly 0.  The constant unit K (zero weights, h = 1/2)
-        // gets 1 - h 2^eH: its "difference" is the constant 1.
-        float* tabA = sPilot + (n_it & 1u) * 2 * L.kpu;
-        float* tabN = tabA + L.kpu;
-        if (ptid < L.kpu) {                                  // ptid < 128: phase-A warps, zpt = this item's pilot
-          const int k = ptid, kp = ptid ^ 1;
-          const float* wk = P.w6 + k * 6;
-          const float* wp = P.w6 + kp * 6;
-          float ak = wk[5], ap = wp[5];
-#pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            ak = fmaf(wk[i], zpt[i], ak);
-            ap = fmaf(wp[i], zpt[i], ap);
-          }
-          const float tk = ex2_ftz(ak) + 1.0f, tp = ex2_ftz(ap) + 1.0f;
-          const float te = (k & 1) ? tp : tk, to = (k & 1) ? tk : tp;
-          const float r = rcp_ftz(te * to);
-          const float hk = r * ((k & 1) ? te : to);
-          tabA[k] = ak;
-          tabN[k] = (k == P.K ? 1.0f : 0.0f) - hk * hscale;
+        if (tab_warp && item + gridDim.x < P.n_items) {       // tables of the NEXT item (zpt was prefetched an item ago)
+          make_tables(n_it + 1u);
+          if (item + 2 * (long long)gridDim.x < P.n_items) load_zp(item + 2 * (long long)gridDim.x, zpt);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
+        const float* tabA = sPilot + (n_it & 3u) * 2 * L.kpu;
+        const float* tabN = tabA + L.kpu;
+        while (!mbar_try_wait(&B->tab_full[n_it & 3u], (n_it >> 2) & 1u)) __nanosleep(32);
         for (int c = 0; c < nchunks; ++c, ++g) {
           if (phase_a && ga < n_elems) phase_a_step();        // stream element g + 2
           // ---- phase B: sigmoid of (a_pilot + da), pilot-centred, scaled, fp16, into the Gram operand tile
@@ -515,11 +530,6 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&B->h_full[hb]);
-        }
-        if (phase_a) {                                        // pilot of the next item's tables (prefetched an item ago)
-#pragma unroll
-          for (int i = 0; i < 5; ++i) zpt[i] = zptn[i];
-          if (item + 2 * (long long)gridDim.x < P.n_items) load_zp(item + 2 * (long long)gridDim.x, zptn);
         }
       }
     } else {
