@@ -291,16 +291,18 @@ def run_ours(args):
             n_items = P * T
             nmma = -(-S // 16)
             q_pad = -(-(K * (K + 1) // 2) // 64) * 64
-            issued = n_items * nmma * 2.0 * 128 * (-(-(K + 1) // 16) * 16) * 16          # gram_kernel MMAs
+            issued = n_items * nmma * 2.0 * 128 * (-(-(K + 1) // 16) * 16) * 16          # gram_kernel: Gram MMAs
+            issued += n_items * (-(-S // 128)) * 3 * 2.0 * 128 * (-(-(K + 1) // 16) * 16) * 8   # + tf32 pre-activation MMAs
             issued_quad = -(-n_items // 128) * 128 * 2.0 * (-(-wl.D // 256) * 256) * q_pad   # quad_kernel MMAs
-            kernel = "glasdi::gr::gram_kernel<sigmoid, 5, fast> (tcgen05 cta_group::1, MN-major SW128 operands, M=128 N=112 K=16)"
+            kernel = ("glasdi::gr::gram_kernel<sigmoid, 5, fast> (tcgen05 cta_group::1: tf32 pre-activation MMAs + f16 Gram MMAs on "
+                      "MN-major SW128 tiles, M=128 N=112 K=16)")
             note = ("frac is on the ALGORITHMIC decoder FLOP of the reference formulation (decode every sample, then std). "
                     "The covariance form reaches the same variances with 5x fewer FLOP (K^2 S + K(K+1)/2 D instead of K S D per "
                     "(parameter, time step)), so frac > 1 is algebra, not a faster tensor pipe: gram_kernel issues "
                     f"{issued:.3e} tensor FLOP (+ {issued_quad:.3e} in quad_kernel) and is bound by the CUDA-core work that "
-                    "feeds it -- P*S*T*K = 2.2e10 sigmoid evaluations (MUFU ex2 + rcp, 60 % issue-slot utilisation in "
+                    "feeds it -- P*S*T*K = 2.2e10 sigmoid evaluations (MUFU ex2 + rcp: XU pipe 50 %, issue slots 55 % busy in "
                     "profiles/r01_gram_quad_kernels_bench_full_ncu.json).  kernel_ms is gram_kernel alone; quad_kernel_ms "
-                    "is the second GEMM (79 % tensor-pipe active)")
+                    "is the second GEMM (80 % tensor-pipe active)")
         else:
             issued = flops_launch * issued_passes * pad
             issued_quad = 0.0
