@@ -86,10 +86,25 @@ __device__ __forceinline__ void front_pre(const FrontMlp& f, const float* zin, f
     const int wo = f.widths[l + 1];
     const float* __restrict__ W = f.W[l];
     const float* __restrict__ b = f.b[l];
-    for (int o = 0; o < wo; ++o) {
-      float acc = __ldg(b + o);
-      for (int i = 0; i < w; ++i) acc = fmaf(__ldg(W + (size_t)o * w + i), out[i], acc);
-      tmp[o] = act_apply_t<ACT>(f.act, acc);
+    // four output units at a time, inputs in the outer loop: four independent FMA chains and one read of the
+    // (local-memory) input per step instead of one serial chain per unit
+    for (int o0 = 0; o0 < wo; o0 += 4) {
+      float acc[4];
+      const float* wr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int o = min(o0 + u, wo - 1);
+        acc[u] = __ldg(b + o);
+        wr[u] = W + (size_t)o * w;
+      }
+      for (int i = 0; i < w; ++i) {
+        const float xi = out[i];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fmaf(__ldg(wr[u] + i), xi, acc[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (o0 + u < wo) tmp[o0 + u] = act_apply_t<ACT>(f.act, acc[u]);
     }
     for (int o = 0; o < wo; ++o) out[o] = tmp[o];
     w = wo;
@@ -103,24 +118,43 @@ __device__ __forceinline__ void front_pre(const FrontMlp& f, const float* zin, f
 template <int ACT, int INW>
 __device__ __forceinline__ void last_front_units(const float* __restrict__ wl, int ld, int inw_rt, int act_rt,
                                                  int k0, const float* x, float (&hv)[8]) {
+  if constexpr (INW == 5) {
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const float4* wr = reinterpret_cast<const float4*>(wl + (k0 + u) * ld);
-    float acc;
-    if constexpr (INW == 5) {
+    for (int u = 0; u < 8; ++u) {
+      const float4* wr = reinterpret_cast<const float4*>(wl + (k0 + u) * ld);
       const float4 a = wr[0], b = wr[1];
-      acc = b.y;
+      float acc = b.y;
       acc = fmaf(a.x, x[0], acc);
       acc = fmaf(a.y, x[1], acc);
       acc = fmaf(a.z, x[2], acc);
       acc = fmaf(a.w, x[3], acc);
       acc = fmaf(b.x, x[4], acc);
-    } else {
-      const float* wf = wl + (k0 + u) * ld;
-      acc = wf[inw_rt];
-      for (int i = 0; i < inw_rt; ++i) acc = fmaf(wf[i], x[i], acc);
+      hv[u] = act_apply_t<ACT>(act_rt, acc);
     }
-    hv[u] = act_apply_t<ACT>(act_rt, acc);
+  } else {
+    // inputs in the outer loop (four at a time), the eight units as independent chains
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = wl[(k0 + u) * ld + inw_rt];
+    int i = 0;
+    for (; i + 4 <= inw_rt; i += 4) {
+      const float x0 = x[i], x1 = x[i + 1], x2 = x[i + 2], x3 = x[i + 3];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wl + (k0 + u) * ld + i);     // ld is a multiple of 4
+        acc[u] = fmaf(w4.x, x0, acc[u]);
+        acc[u] = fmaf(w4.y, x1, acc[u]);
+        acc[u] = fmaf(w4.z, x2, acc[u]);
+        acc[u] = fmaf(w4.w, x3, acc[u]);
+      }
+    }
+    for (; i < inw_rt; ++i) {
+      const float xi = x[i];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = fmaf(wl[(k0 + u) * ld + i], xi, acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) hv[u] = act_apply_t<ACT>(act_rt, acc[u]);
   }
 }
 

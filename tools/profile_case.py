@@ -11,7 +11,7 @@ passes = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 variant = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 mode = int(sys.argv[5]) if len(sys.argv) > 5 else 2          # 2 = covariance-form screening (default), 1 = x-space screening, 0 = direct
-wl = synth.WORKLOADS["burgers1d"]
+wl = synth.WORKLOADS[os.environ.get("GLASDI_WORKLOAD", "burgers1d")]
 Ws, bs = synth.make_decoder(wl.widths, wl.seed)
 inp = synth.make_inputs(wl, slice(200, 200 + P))
 eng = Engine(0)
