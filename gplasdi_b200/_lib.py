@@ -37,6 +37,7 @@ SIGNATURES = {
     "glasdi_rollout": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp]),
     "glasdi_greedy_step": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp]),
     "glasdi_decode_max_std": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "glasdi_decode_stat_fields": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "glasdi_decode": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "glasdi_check_numeric": (_i, [_vp, _vp]),
     "glasdi_argmax_first": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),

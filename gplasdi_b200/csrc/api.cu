@@ -421,6 +421,54 @@ int glasdi_decode_max_std(glasdi_handle* h, const double* Zis, int P, int S, int
                      (cudaStream_t)stream);
 }
 
+int glasdi_decode_stat_fields(glasdi_handle* h, const double* Zis, int P, int S, int T, int n, float* mean_out,
+                              float* std_out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  const Decoder& d = h->dec;
+  if (!d.ready) return set_error(h, GLASDI_ERR_NOT_READY, "decoder weights not set (glasdi_set_decoder)");
+  if (!d.tc_ok) return set_error(h, GLASDI_ERR_INVALID, "stat fields: decoder shape not supported by the tcgen05 kernel");
+  if (!Zis || (!mean_out && !std_out)) return set_error(h, GLASDI_ERR_INVALID, "stat fields: null pointer");
+  if (n != d.widths[0]) return set_error(h, GLASDI_ERR_INVALID, "latent dimension does not match the decoder");
+  if (P <= 0 || S <= 0 || T <= 0) return set_error(h, GLASDI_ERR_INVALID, "empty ensemble");
+  cudaStream_t st = (cudaStream_t)stream;
+  GL_CUDA(h, cudaSetDevice(h->device));
+  const int Spad = (S + 127) / 128 * 128;
+  const int field_ld = decode_field_ld(d.n_tiles);
+  const size_t traj_bytes = (size_t)T * n * Spad * sizeof(float);
+  const size_t field_bytes = (size_t)T * field_ld * sizeof(float);
+  const size_t rows_bytes = ((size_t)T * n * sizeof(float) + 255) / 256 * 256;
+  const size_t per_param = traj_bytes + 2 * field_bytes + rows_bytes;
+  const size_t budget = (size_t)12 << 30;
+  int slab = (int)std::max<size_t>(1, std::min<size_t>((size_t)P, budget / per_param));
+  slab = std::min(slab, 32768);
+  int rc = ensure_workspace(h, per_param * slab);
+  if (rc) return rc;
+  rc = ensure_maxvar(h, (size_t)P);
+  if (rc) return rc;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(h->ws);
+  float* Zs = reinterpret_cast<float*>(ws);
+  float* varf = reinterpret_cast<float*>(ws + traj_bytes * slab);
+  float* meanf = reinterpret_cast<float*>(ws + (traj_bytes + field_bytes) * slab);
+  float* zrows = reinterpret_cast<float*>(ws + (traj_bytes + 2 * field_bytes) * slab);
+  for (int p0 = 0; p0 < P; p0 += slab) {
+    const int pn = std::min(slab, P - p0);
+    const long long rows = (long long)pn * T;
+    if ((rc = launch_zis_to_soa(h, Zis + (size_t)p0 * S * T * n, pn, S, T, n, Zs, Spad, st))) return rc;
+    GL_CUDA(h, cudaMemsetAsync(h->d_maxvar, 0, (size_t)pn * sizeof(unsigned int), st));
+    // three split passes: the fields are fp32-faithful (this is an output, not a screening pass)
+    if ((rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar, varf, 3, st, meanf))) return rc;
+    float* mean_p = mean_out ? mean_out + (size_t)p0 * T * d.D : nullptr;
+    if (mean_p) {
+      if ((rc = launch_gather_pilot_rows(h, Zs, Spad, rows, n, zrows, st))) return rc;
+      if ((rc = launch_decode_store_pair(h, zrows, rows, mean_p, st))) return rc;     // decode(pilot), exact fp32
+    }
+    if ((rc = launch_finalize_fields(h, meanf, varf, field_ld, rows, d.D, d.eW + d.eH, mean_p,
+                                     std_out ? std_out + (size_t)p0 * T * d.D : nullptr, st)))
+      return rc;
+  }
+  return GLASDI_OK;
+}
+
 int glasdi_decode(glasdi_handle* h, const float* Z, int64_t rows, float* X_out, void* stream) {
   if (!h) return GLASDI_ERR_INVALID;
   if (!h->dec.ready) return set_error(h, GLASDI_ERR_NOT_READY, "decoder weights not set (glasdi_set_decoder)");

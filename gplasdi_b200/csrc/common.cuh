@@ -110,7 +110,8 @@ size_t decode_var_smem_bytes(int Kpad, int last_in_w);
 // decode_var2.cu : CTA-pair (cta_group::2) variant of the same kernel
 // var_field (optional): [P][T][decode_field_ld] scaled variance of every (t, dof); passes > 0 overrides the handle option
 int launch_decode_var_pair(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
-                           unsigned int* maxvar_bits, float* var_field, int passes, cudaStream_t st);
+                           unsigned int* maxvar_bits, float* var_field, int passes, cudaStream_t st,
+                           float* mean_field = nullptr);
 inline int decode_field_ld(int n_tiles) { return (n_tiles + 1) / 2 * 2 * 128; }
 // decode_gram.cu : covariance-form screening pass (gram_kernel + quad_kernel)
 int gram_nkgQ(int K);
@@ -138,6 +139,11 @@ int launch_finalize(glasdi_handle* h, const unsigned int* maxvar_bits, int P, in
 int launch_argmax_first(glasdi_handle* h, const float* vals, int P, int64_t* idx, float* val, cudaStream_t st);
 int launch_pack_maxloc(glasdi_handle* h, const float* val, const int64_t* idx, int64_t off, int64_t* key,
                        cudaStream_t st);
+// sample-statistics fields (reduce.cu): pilot rows of Zs -> [rows][n]; scaled (mean, var) fields -> mean / std [rows][D]
+int launch_gather_pilot_rows(glasdi_handle* h, const float* Zs, int Spad, long long rows, int n, float* Zrows,
+                             cudaStream_t st);
+int launch_finalize_fields(glasdi_handle* h, const float* mean_f, const float* var_f, int field_ld, long long rows, int D,
+                           int scale_exp2, float* mean_io, float* std_out, cudaStream_t st);
 // calibrate.cu
 int launch_fd_dzdt(glasdi_handle* h, const float* Z, int B, int T, int n, int fd_id, double dt, float* dZ,
                    cudaStream_t st);

@@ -33,6 +33,7 @@ struct Params {
   const float* Zs;                  // [P][T][NZ][Spad]
   unsigned int* maxvar_bits;        // [P]
   float* var_field;                 // optional [P][T][field_ld]: scaled variance of every (t, dof) (screening / std field)
+  float* mean_field;                // optional, same layout: scaled mean over the samples of x(s) - x(pilot)
   int field_ld;                     // n_tiles rounded up to even * 128
   // STORE
   const float* Zrows;               // [rows][NZ]

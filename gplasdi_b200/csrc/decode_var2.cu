@@ -427,9 +427,12 @@ decode_pair_kernel(const __grid_constant__ Params P) {
               const float mean = ssum * P.inv_S;
               const float var = fmaf(-mean, mean, qsum * P.inv_S);
               vmax = fmaxf(vmax, var);
-              if (P.var_field)
-                P.var_field[((size_t)it.p * P.T + it.tg) * P.field_ld + (it.tile0 + 2 * j + (int)rank) * kTileM +
-                            warp * 32 + lane] = var;
+              if (P.var_field) {
+                const size_t fo = ((size_t)it.p * P.T + it.tg) * P.field_ld + (it.tile0 + 2 * j + (int)rank) * kTileM +
+                                  warp * 32 + lane;
+                P.var_field[fo] = var;
+                if (P.mean_field) P.mean_field[fo] = mean;
+              }
             }
           } else if constexpr (EPI == kVarSeg) {
             float ss = 0.f, qq = 0.f;
@@ -447,9 +450,12 @@ decode_pair_kernel(const __grid_constant__ Params P) {
                   const float mean = ss * P.inv_S;
                   const float var = fmaf(-mean, mean, qq * P.inv_S);
                   vmax = fmaxf(vmax, var);
-                  if (P.var_field && it.tg * P.TPC + sg < P.T)      // zero-padded columns complete phantom segments
-                    P.var_field[((size_t)it.p * P.T + it.tg * P.TPC + sg) * P.field_ld +
-                                (it.tile0 + 2 * j + (int)rank) * kTileM + warp * 32 + lane] = var;
+                  if (P.var_field && it.tg * P.TPC + sg < P.T) {    // zero-padded columns complete phantom segments
+                    const size_t fo = ((size_t)it.p * P.T + it.tg * P.TPC + sg) * P.field_ld +
+                                      (it.tile0 + 2 * j + (int)rank) * kTileM + warp * 32 + lane;
+                    P.var_field[fo] = var;
+                    if (P.mean_field) P.mean_field[fo] = mean;
+                  }
                   ss = 0.f; qq = 0.f; cnt = 0; ++sg;
                 }
               }
@@ -544,7 +550,8 @@ static int launch_epi2(glasdi_handle* h, const dv::Params& P, cudaStream_t st) {
 }
 
 int launch_decode_var_pair(glasdi_handle* h, const float* Zs, int Spad, int P_, int S, int T,
-                           unsigned int* maxvar_bits, float* var_field, int passes, cudaStream_t st) {
+                           unsigned int* maxvar_bits, float* var_field, int passes, cudaStream_t st,
+                           float* mean_field) {
   dv::Params P{};
   int rc = fill_common2(h, P);
   if (rc) return rc;
@@ -552,6 +559,7 @@ int launch_decode_var_pair(glasdi_handle* h, const float* Zs, int Spad, int P_, 
   P.Zs = Zs;
   P.maxvar_bits = maxvar_bits;
   P.var_field = var_field;
+  P.mean_field = mean_field;
   P.field_ld = decode_field_ld(h->dec.n_tiles);
   if (passes > 0) P.passes = passes;
   P.inv_S = 1.0f / (float)S;

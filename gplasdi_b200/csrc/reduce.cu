@@ -5,6 +5,8 @@
 // m_index = m; max_std = max_std_m` -> the SMALLEST index attaining the maximum, provided it is > 0.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace glasdi {
 
 struct ValIdx {
@@ -81,6 +83,47 @@ __global__ void pack_maxloc_kernel(const float* val, const int64_t* idx, int64_t
   const unsigned long long vb = (unsigned long long)__float_as_uint(*val);      // non-negative float
   const unsigned long long gi = (unsigned long long)(li + off);
   *key = (int64_t)((vb << 32) | (0xFFFFFFFFull - (gi & 0xFFFFFFFFull)));
+}
+
+// pilot (sample 0) latent states of every (p, t): Zs [rows][n][Spad] -> Zrows [rows][n]
+__global__ void gather_pilot_rows_kernel(const float* __restrict__ Zs, int Spad, long long rows, int n,
+                                         float* __restrict__ Zrows) {
+  const long long total = rows * n;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+    Zrows[e] = Zs[e * Spad];
+}
+
+// mean[r][d] = decode(pilot)[r][d] + mean_f 2^-e ; std[r][d] = sqrt(max(var_f, 0)) 2^-e
+__global__ void finalize_fields_kernel(const float* __restrict__ mean_f, const float* __restrict__ var_f, int field_ld,
+                                       long long rows, int D, float sc, float* __restrict__ mean_io,
+                                       float* __restrict__ std_out) {
+  const long long total = rows * D;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / D;
+    const int d = (int)(e - r * D);
+    const size_t fo = (size_t)r * field_ld + d;
+    if (mean_io) mean_io[e] = fmaf(mean_f[fo], sc, mean_io[e]);
+    if (std_out) std_out[e] = sqrtf(fmaxf(var_f[fo], 0.f)) * sc;
+  }
+}
+
+int launch_gather_pilot_rows(glasdi_handle* h, const float* Zs, int Spad, long long rows, int n, float* Zrows,
+                             cudaStream_t st) {
+  const long long total = rows * n;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 16);
+  gather_pilot_rows_kernel<<<blocks, 256, 0, st>>>(Zs, Spad, rows, n, Zrows);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "gather_pilot_rows launch");
+}
+
+int launch_finalize_fields(glasdi_handle* h, const float* mean_f, const float* var_f, int field_ld, long long rows, int D,
+                           int scale_exp2, float* mean_io, float* std_out, cudaStream_t st) {
+  const long long total = rows * D;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 32);
+  finalize_fields_kernel<<<blocks, 256, 0, st>>>(mean_f, var_f, field_ld, rows, D, ldexpf(1.0f, -scale_exp2), mean_io,
+                                                 std_out);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "finalize_fields launch");
 }
 
 int launch_finalize(glasdi_handle* h, const unsigned int* bits, int P, int scale_exp2, float* max_std,

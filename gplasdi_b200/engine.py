@@ -178,6 +178,20 @@ class Engine:
                                                        am.data_ptr(), mv.data_ptr(), _stream_ptr()))
         return ms, am, mv
 
+    def decode_stat_fields(self, Zis, want_mean: bool = True):
+        """Zis [P,S,T,n] fp64 -> (mean [P,T,D] or None, std [P,T,D]): sample mean / population std of the decoded
+        ensemble at every (t, dof), without ever writing the ensemble."""
+        Zis = self._dev(Zis, torch.float64)
+        P, S, T, n = Zis.shape
+        D = self.decoder_widths[-1]
+        std = torch.empty((P, T, D), dtype=torch.float32, device=self.tdev)
+        mean = torch.empty((P, T, D), dtype=torch.float32, device=self.tdev) if want_mean else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_decode_stat_fields(self.h, Zis.data_ptr(), P, S, T, n,
+                                                           mean.data_ptr() if want_mean else None, std.data_ptr(),
+                                                           _stream_ptr()))
+        return mean, std
+
     def decode(self, Z) -> torch.Tensor:
         """Z [..., n_z] fp32 -> X [..., D] fp32."""
         Z = self._dev(Z, torch.float32)

@@ -63,6 +63,19 @@ def fom_max_std(autoencoder, Zis):
     return int(am.item()), ms.cpu().numpy()
 
 
+def fom_mean_std(autoencoder, Zis):
+    """(mean, std) fields [P, nt, *qgrid_size] of the decoded ensemble Zis [P, S, nt, n_z] -- what
+    `plot_prediction` computes with `pred.mean(0)`, `pred.std(0)` (reference src/lasdi/postprocess.py:32-34),
+    for every parameter at once and without materialising `pred`."""
+    eng = _engine_for(autoencoder)
+    Zt = torch.as_tensor(np.ascontiguousarray(Zis))
+    mean, std = eng.decode_stat_fields(Zt)
+    eng.check_numeric()
+    q = list(getattr(autoencoder, "qgrid_size", [mean.shape[-1]]))
+    P, T = mean.shape[:2]
+    return mean.cpu().numpy().reshape(P, T, *q), std.cpu().numpy().reshape(P, T, *q)
+
+
 def get_fom_max_std(autoencoder, Zis):
     """Index of the test parameter with the largest decoded sample std (reference gplasdi.py:52-74)."""
     m_index, _ = fom_max_std(autoencoder, Zis)

@@ -147,6 +147,14 @@ int glasdi_greedy_step(glasdi_handle* h, const double* coefs, const float* z0,
 int glasdi_decode_max_std(glasdi_handle* h, const double* Zis, int P, int S, int T, int n,
                           float* max_std_out, int64_t* argmax_out, float* maxval_out, void* stream);
 
+/* Sample statistics of the decoded ensemble as FIELDS.
+ * Replaces: `pred = autoencoder.decoder(torch.Tensor(Z)); pred.mean(0); pred.std(0)` of plot_prediction
+ *   (src/lasdi/postprocess.py:32-34; examples/burgers1d.ipynb) for every parameter of Zis fp64 [P, S, T, n].
+ * mean_out / std_out fp32 [P, T, D] (either may be NULL).  Three fp16 split passes on the tensor cores (fp32-faithful),
+ * mean = decode(sample 0) + mean_s(x(s) - x(0)); the decoded ensemble is never written.  tcgen05-covered decoders only. */
+int glasdi_decode_stat_fields(glasdi_handle* h, const double* Zis, int P, int S, int T, int n, float* mean_out,
+                              float* std_out, void* stream);
+
 /* Replaces: autoencoder.decoder(Z) forward (latent_space.py:135-171; call sites gplasdi.py:66,182,
  * postprocess.py:32).  Z fp32 [rows, n_z] -> X fp32 [rows, D]. */
 int glasdi_decode(glasdi_handle* h, const float* Z, int64_t rows, float* X_out, void* stream);

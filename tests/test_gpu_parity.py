@@ -268,6 +268,29 @@ def test_config1_burgers1d_shipped_full(engine, golden_dir):
     assert (top2[1] - top2[0]) / top2[1] > 0.01                # visible top-1 margin of the fixture
 
 
+# ---- sample-statistics fields -------------------------------------------------
+@pytest.mark.parametrize("nm", ["tiny", "small", "small_s200", "small_softplus", "ragged"])
+def test_stat_fields_match_decoded_ensemble(engine, g_small, nm):
+    """glasdi_decode_stat_fields against `pred.mean(0)`, `pred.std(0)` of the decoded ensemble
+    (reference src/lasdi/postprocess.py:32-34), for every parameter, (t, dof)."""
+    wl, Ws, bs = setup_wl(engine, nm)
+    if nm + "_Zis" in g_small.files:
+        Zis = g_small[nm + "_Zis"]
+    else:
+        inp = synth.make_inputs(wl)
+        Zis = engine.rollout(inp["coefs"], inp["z0"], wl.T, wl.dt).cpu().numpy()
+    mean, std = engine.decode_stat_fields(Zis)
+    mean = mean.cpu().numpy(); std = std.cpu().numpy()
+    tW = [torch.from_numpy(w) for w in Ws]; tb = [torch.from_numpy(b) for b in bs]
+    for p in range(wl.P):
+        X = orc.decoder_forward(tW, tb, wl.act, torch.from_numpy(Zis[p].astype(np.float32))).numpy().astype(np.float64)
+        rm, rs = X.mean(0), X.std(0)
+        assert np.max(np.abs(mean[p] - rm)) <= FIELD_RTOL * np.max(np.abs(rm))
+        assert np.max(np.abs(std[p] - rs)) <= STD_RTOL * np.max(rs) + STD_ATOL
+    _, std_only = engine.decode_stat_fields(Zis, want_mean=False)
+    assert np.array_equal(std_only.cpu().numpy(), std)
+
+
 # ---- decoder -----------------------------------------------------------------------------------
 @pytest.mark.parametrize("nm", ["tiny", "small", "small_softplus", "ragged", "wide_k"])
 def test_decoder_forward_matches_torch(engine, nm):
