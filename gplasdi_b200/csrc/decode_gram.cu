@@ -517,8 +517,17 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             }
             *reinterpret_cast<uint4*>(Hb + h_offset(kg, col)) = make_uint4(out[0], out[1], out[2], out[3]);
           };
+          // The warps of group 0 also write dz (phase A, ~2/3 of a group's work): every 4th chunk their last fixed
+          // group goes to one of the other warp groups instead, so that all four carry the same average load.
+          const int give = nkg4 - 4;                                   // group 0's last fixed unit group
+          const bool given = nkg4 >= 8 && (g & 3u) == 3u;
+          const int taker = 1 + (int)((g >> 2) % 3u);
 #pragma unroll 1
-          for (int kg = jg; kg < nkg4; kg += 4) do_group(kg);
+          for (int kg = jg; kg < nkg4; kg += 4) {
+            if (given && kg == give) continue;
+            do_group(kg);
+          }
+          if (given && jg == taker) do_group(give);
           if (jg > 0) {
             // left-over groups rotate over the warp groups 1..3; group 0 (the phase-A warps) has its extra work already.
             // Per chunk the warps are therefore NOT equally loaded: three pre-activation buffers (below) let them

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from gplasdi_b200 import synth
-from gplasdi_b200.gplasdi import BayesianGLaSDI, get_fom_max_std, fom_max_std, sample_roms, average_rom
+from gplasdi_b200.gplasdi import BayesianGLaSDI, get_fom_max_std, fom_max_std, fom_mean_std, sample_roms, average_rom
 from gplasdi_b200.gp import fit_gps, eval_gp
 from gplasdi_b200.latent_dynamics.sindy import SINDy
 from gplasdi_b200.latent_space import Autoencoder, initial_condition_latent
@@ -155,6 +155,23 @@ def test_get_new_sample_point_end_to_end(tmp_path):
     idx, per, _ = orc.greedy_step(Ws, bs, "sigmoid", draws, Z0, phys.t_grid)
     assert np.array_equal(new, ps.test_space[idx].reshape(1, -1))
     assert np.max(np.abs(trainer.last_max_std - per) - 1e-5 * per) <= 5e-6
+
+
+def test_fom_mean_std_matches_plot_prediction_statistics(golden_dir):
+    """`fom_mean_std` = the `pred.mean(0)`, `pred.std(0)` of reference postprocess.plot_prediction (:32-34)."""
+    g = np.load(os.path.join(golden_dir, "greedy_small.npz"))
+    wl = synth.WORKLOADS["small"]
+    phys = Physics(nt=wl.T, nx=wl.D)
+    ae = _autoencoder(phys)
+    Zis = g["small_Zis"][:2]
+    mean, std = fom_mean_std(ae, Zis)
+    assert mean.shape == std.shape == (2, wl.T, wl.D)
+    with torch.no_grad():
+        pred = torch.nn.Sequential()  # reference path: the module's own differentiable torch evaluation on the CPU
+        Ws = [fc.weight.detach() for fc in ae.decoder.fcs]; bs = [fc.bias.detach() for fc in ae.decoder.fcs]
+        X = orc.decoder_forward(Ws, bs, "sigmoid", torch.from_numpy(Zis[1].astype(np.float32))).numpy().astype(np.float64)
+    assert np.max(np.abs(mean[1] - X.mean(0))) <= 5e-6 * np.max(np.abs(X))
+    assert np.max(np.abs(std[1] - X.std(0))) <= 1e-5 * np.max(X.std(0)) + 5e-6
 
 
 def test_sample_roms_and_average_rom_shapes():
