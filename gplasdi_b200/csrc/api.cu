@@ -270,7 +270,9 @@ int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths, const 
     GL_CUDA(h, cudaMemcpy(d.w_packed, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
   // covariance-form screening: the constant unit must fit the 128-row tile, shared memory must hold the ring
-  d.gram_ok = ok && d.K + 1 <= 128 && decode_gram_smem_bytes(d.K, last_in_w) <= 227 * 1024;
+  int xw = 0;
+  for (int l = 1; l < n_linear - 1; ++l) xw = std::max(xw, (widths[l] + 3) / 4 * 4);
+  d.gram_ok = ok && d.K + 1 <= 128 && decode_gram_smem_bytes(d.K, last_in_w, xw) <= 227 * 1024;
   d.h_front_last_W.assign(W_host[n_linear - 2], W_host[n_linear - 2] + (size_t)d.K * last_in_w);
   d.h_front_last_b.assign(b_host[n_linear - 2], b_host[n_linear - 2] + d.K);
   if (d.gram_ok) {

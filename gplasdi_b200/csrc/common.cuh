@@ -117,7 +117,7 @@ inline int decode_field_ld(int n_tiles) { return (n_tiles + 1) / 2 * 2 * 128; }
 int gram_nkgQ(int K);
 size_t gram_a_bytes(int K, long long n_items);
 size_t gram_fscale_bytes(long long n_items);
-size_t decode_gram_smem_bytes(int K, int last_in_w);
+size_t decode_gram_smem_bytes(int K, int last_in_w, int xw /* widest intermediate front layer, rounded up to 4; 0 if none */);
 int gram_pack_v(glasdi_handle* h, const float* WL_host);
 int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T, void* a_ws, float* fscale_ws,
                        cudaStream_t st);

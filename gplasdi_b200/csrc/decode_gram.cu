@@ -59,6 +59,7 @@ struct GramParams {
   float h_scale, inv_S;
   int exp_base;          // 2 eH + eV : exponent of the fixed part of the scale
   int check_overflow;
+  int xw;                // generic path with >= 2 front layers: widest intermediate layer, rounded up to 4 (else 0)
   long long n_items;     // P * T
   const float* Zs;       // [P][T][NZ][Spad]
   __half* A;             // [item block of 128][nkgQ][128 rows][8]  : A operand of the quad kernel
@@ -78,16 +79,24 @@ struct GBars {
 };
 
 struct GSmem {
-  uint32_t h, a1, b1, wl, pilot, m, mx, c, bars, tmem, total;
-  int wl_ld, kpu;
+  uint32_t h, a1, b1, wl, pilot, m, mx, c, xb, bars, tmem, total;
+  int wl_ld, kpu, xw;
 };
-__host__ __device__ inline GSmem gcarve(int nkg, int last_in_w, int nkgQ) {
+__host__ __device__ inline GSmem gcarve(int nkg, int last_in_w, int nkgQ, int xw = 0) {
   GSmem s;
   uint32_t off = 0;
   s.kpu = nkg * 8;
   s.h = off; off += kRing * kBufBytes;
-  s.a1 = off; off += kRing * kA1Bytes;                                  // fast path: latent differences (tf32 A operand)
-  s.b1 = off; off += 4 * 2048;                                          // fast path: front-layer weights (tf32 hi | lo B operand)
+  // fast path: latent differences (tf32 A operand ring) + front-layer weights (tf32 hi | lo B operand);
+  // generic path with deep fronts: two activation buffers x (128 columns + pilot) x widest hidden layer -- same bytes
+  s.a1 = off;
+  s.b1 = off + kRing * kA1Bytes;
+  s.xb = off;
+  s.xw = xw;
+  {
+    const uint32_t fast_bytes = kRing * kA1Bytes + 4u * 2048u, gen_bytes = 2u * 129u * (uint32_t)xw * 4u;
+    off += fast_bytes > gen_bytes ? fast_bytes : ((gen_bytes + 15u) & ~15u);
+  }
   s.wl_ld = wl_stride(last_in_w) > 12 ? wl_stride(last_in_w) : 12;   // fast path rows: 12 floats (duplicated pairs)
   s.wl = off; off += (uint32_t)s.kpu * (uint32_t)s.wl_ld * 4u;
   s.pilot = off; off += 4u * (uint32_t)s.kpu * 8u;                     // fast path: 4 buffers x (a_pilot, -h_pilot 2^eH) tables
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int last_in_w = P.front.widths[P.front.n_front - 1];
-  const GSmem L = gcarve(P.nkg, last_in_w, P.nkgQ);
+  const GSmem L = gcarve(P.nkg, last_in_w, P.nkgQ, P.xw);
   uint8_t* sH = smem + L.h;
   float* sWl = reinterpret_cast<float*>(smem + L.wl);
   float* sPilot = reinterpret_cast<float*>(smem + L.pilot);
@@ -542,34 +551,62 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         }
       }
     } else {
-      // generic front MLP: thread <-> one sample column x a quarter of the unit groups
+      // generic front MLP: thread <-> one sample column x a quarter of the unit groups.  With two or more front
+      // layers the layers before the last one are evaluated COOPERATIVELY: the four threads of a column each compute
+      // a quarter of every layer's units and exchange them through shared memory (one named barrier per layer).
+      // Every thread evaluating the whole front on its own (and from local-memory arrays) cost 265 us per (p, t) at
+      // the Burgers2D-shaped decoder [5,20,20,20,100,3600].
       const int col = ptid & 127;
       const int part = ptid >> 7;
       const int kg_begin = (P.nkg * part) / 4, kg_end = (P.nkg * (part + 1)) / 4;
       const int NZ = P.NZ;
       const int ld = L.wl_ld;
+      const int n_pre = P.front.n_front - 1;               // layers before the last front layer
+      float* xbuf = reinterpret_cast<float*>(smem + L.xb);
+      const int xw = L.xw;
+      // layers 0 .. n_pre-1 for column `cx` of the activation buffers (cx = 128: the pilot); returns the final buffer
+      auto coop_layers = [&](const float (&z)[kMaxLatent], bool also_pilot, const float (&zpil)[kMaxLatent]) {
+        asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");      // readers of the previous final buffer
+        for (int l = 0; l < n_pre; ++l) {
+          const int wi = P.front.widths[l], wo = P.front.widths[l + 1];
+          const float* __restrict__ W = P.front.W[l];
+          const float* __restrict__ bb = P.front.b[l];
+          const int o_begin = (wo * part) / 4, o_end = (wo * (part + 1)) / 4;
+          float* dst = xbuf + (size_t)(l & 1) * 129 * xw;
+          const float* src = xbuf + (size_t)((l & 1) ^ 1) * 129 * xw;
+          for (int pass = 0; pass < (also_pilot ? 2 : 1); ++pass) {
+            const int cx = pass ? 128 : col;
+            for (int o0 = o_begin; o0 < o_end; o0 += 4) {
+              float acc[4];
+              const float* wr[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int o = min(o0 + u, o_end - 1);
+                acc[u] = __ldg(bb + o);
+                wr[u] = W + (size_t)o * wi;
+              }
+              for (int i = 0; i < wi; ++i) {
+                const float xi = (l == 0) ? (pass ? zpil[i] : z[i]) : src[cx * xw + i];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[u] = fmaf(__ldg(wr[u] + i), xi, acc[u]);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (o0 + u < o_end) dst[cx * xw + o0 + u] = act_apply_t<ACT>(P.front.act, acc[u]);
+            }
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");
+        }
+      };
+      const float* xfinal = xbuf + (size_t)((n_pre - 1) & 1) * 129 * xw;       // valid when n_pre >= 1
       for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const float* __restrict__ zb = P.Zs + (size_t)item * NZ * P.Spad;
-        // pilot = activations of sample 0
-        for (int kg = ptid; kg < P.nkg; kg += kGProdThreads) {
-          float zz[kMaxLatent];
+        float znext[kMaxLatent], zpil[kMaxLatent];
 #pragma unroll
-          for (int i = 0; i < kMaxLatent; ++i) zz[i] = (i < NZ) ? __ldg(zb + (size_t)i * P.Spad) : 0.f;
-          float hv[8];
-          if constexpr (INW > 0) {
-            last_front_units<ACT, INW>(sWl, ld, last_in_w, P.front.act, kg * 8, zz, hv);
-          } else {
-            float x[kMaxHid];
-            front_pre<ACT>(P.front, zz, x);
-            last_front_units<ACT, 0>(sWl, ld, last_in_w, P.front.act, kg * 8, x, hv);
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) sPilot[kg * 8 + u] = hv[u] * hscale;
+        for (int i = 0; i < kMaxLatent; ++i) {
+          znext[i] = (col < P.S && i < NZ) ? __ldg(zb + (size_t)i * P.Spad + col) : 0.f;
+          zpil[i] = (i < NZ) ? __ldg(zb + (size_t)i * P.Spad) : 0.f;          // sample 0 = the pilot
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
-        float znext[kMaxLatent];
-#pragma unroll
-        for (int i = 0; i < kMaxLatent; ++i) znext[i] = (col < P.S && i < NZ) ? __ldg(zb + (size_t)i * P.Spad + col) : 0.f;
         for (int c = 0; c < nchunks; ++c) {
           const int s = c * kCols + col;
           const bool valid = s < P.S;
@@ -581,11 +618,25 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             for (int i = 0; i < kMaxLatent; ++i)
               znext[i] = (s + kCols < P.S && i < NZ) ? __ldg(zb + (size_t)i * P.Spad + s + kCols) : 0.f;
           }
-          float xloc[INW > 0 ? 1 : kMaxHid];
           const float* x = zin;
           if constexpr (INW == 0) {
-            if (valid) front_pre<ACT>(P.front, zin, xloc);
-            x = xloc;
+            if (n_pre > 0) {
+              coop_layers(zin, c == 0 && col == 0, zpil);
+              x = xfinal + col * xw;
+            }
+          }
+          if (c == 0) {
+            // pilot = activations of sample 0 (its front layers were evaluated with chunk 0's, column 128)
+            for (int kg = ptid; kg < P.nkg; kg += kGProdThreads) {
+              float hv[8];
+              if (INW == 0 && n_pre > 0)
+                last_front_units<ACT, 0>(sWl, ld, last_in_w, P.front.act, kg * 8, xfinal + 128 * xw, hv);
+              else
+                last_front_units<ACT, INW>(sWl, ld, last_in_w, P.front.act, kg * 8, zpil, hv);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) sPilot[kg * 8 + u] = hv[u] * hscale;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
           }
           const uint32_t buf = h_it % kRing;
           uint8_t* Hb = sH + buf * kBufBytes;
@@ -620,7 +671,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
           if (lane == 0) mbar_arrive(&B->h_full[buf]);
           ++h_it;
         }
-        asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item
+        asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item
       }
     }
     if (P.check_overflow && !(amax < 60000.f)) atomicOr(P.flags, 1);
@@ -1054,7 +1105,10 @@ int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P_, int 
       for (int i = 0; i < 6; ++i)
         G.w6[k * 6 + i] = k < d.K ? cf * (i < 5 ? d.h_front_last_W[(size_t)k * 5 + i] : d.h_front_last_b[k]) : 0.f;
   }
-  const size_t smem = gr::gcarve(G.nkg, last_in_w, G.nkgQ).total;
+  G.xw = 0;
+  if (!fast)
+    for (int l = 1; l < G.front.n_front; ++l) G.xw = std::max(G.xw, (d.widths[l] + 3) / 4 * 4);
+  const size_t smem = gr::gcarve(G.nkg, last_in_w, G.nkgQ, G.xw).total;
   int ctas = h->num_sms;
   if (h->opt_max_ctas > 0) ctas = std::max(1, std::min(ctas, h->opt_max_ctas));
   if ((long long)ctas > G.n_items) ctas = (int)G.n_items;
@@ -1093,6 +1147,6 @@ int launch_decode_quad(glasdi_handle* h, int P_, int T, unsigned int* maxvar_bit
   return check_cuda(h, cudaGetLastError(), "quad_kernel launch");
 }
 
-size_t decode_gram_smem_bytes(int K, int last_in_w) { return gr::gcarve((K + 1 + 7) / 8, last_in_w, gram_nkgQ(K)).total; }
+size_t decode_gram_smem_bytes(int K, int last_in_w, int xw) { return gr::gcarve((K + 1 + 7) / 8, last_in_w, gram_nkgQ(K), xw).total; }
 
 }  // namespace glasdi

@@ -166,10 +166,8 @@ def test_fom_mean_std_matches_plot_prediction_statistics(golden_dir):
     Zis = g["small_Zis"][:2]
     mean, std = fom_mean_std(ae, Zis)
     assert mean.shape == std.shape == (2, wl.T, wl.D)
-    with torch.no_grad():
-        pred = torch.nn.Sequential()  # reference path: the module's own differentiable torch evaluation on the CPU
-        Ws = [fc.weight.detach() for fc in ae.decoder.fcs]; bs = [fc.bias.detach() for fc in ae.decoder.fcs]
-        X = orc.decoder_forward(Ws, bs, "sigmoid", torch.from_numpy(Zis[1].astype(np.float32))).numpy().astype(np.float64)
+    Ws = [fc.weight.detach() for fc in ae.decoder.fcs]; bs = [fc.bias.detach() for fc in ae.decoder.fcs]
+    X = orc.decoder_forward(Ws, bs, "sigmoid", torch.from_numpy(Zis[1].astype(np.float32))).numpy().astype(np.float64)
     assert np.max(np.abs(mean[1] - X.mean(0))) <= 5e-6 * np.max(np.abs(X))
     assert np.max(np.abs(std[1] - X.std(0))) <= 1e-5 * np.max(X.std(0)) + 5e-6
 
