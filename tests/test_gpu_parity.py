@@ -242,6 +242,54 @@ def test_ragged_and_wide_shapes_against_oracle(engine, nm, mode):
     assert np.max(np.abs(Z - Zis)) <= TRAJ_RTOL * np.max(np.abs(Zis))
 
 
+@pytest.mark.parametrize("K,S,D,T,act", [
+    (8, 1, 5, 1, "sigmoid"), (8, 2, 128, 3, "sigmoid"), (31, 17, 257, 3, "sigmoid"), (64, 128, 129, 2, "sigmoid"),
+    (100, 129, 1300, 2, "sigmoid"), (105, 300, 64, 3, "sigmoid"), (111, 40, 300, 2, "sigmoid"),
+    (112, 256, 513, 1, "sigmoid"), (100, 257, 260, 2, "tanh"), (24, 130, 1300, 3, "softplus"), (112, 33, 70, 2, "ReLU"),
+])
+def test_covariance_form_shape_sweep(engine, K, S, D, T, act):
+    """Edge shapes of the default mode (unit-group left-overs 0..3, single/ragged sample chunks, S = 1, dof-block
+    tails, K up to the 112 limit; sigmoid = tensor-core pre-activation path, others = generic producers) against
+    the direct mode (three split passes, parity-tested against the reference above)."""
+    from dataclasses import replace
+    wl = replace(synth.WORKLOADS["tiny"], S=S, T=T, widths=[5, K, D], act=act, dt=1.0 / max(T - 1, 1), seed=K + S)
+    Ws, bs = synth.make_decoder(wl.widths, wl.seed)
+    engine.set_decoder(Ws, bs, act)
+    inp = synth.make_inputs(wl)
+    engine.set_option(_lib.OPT_SPLIT_PASSES, 3)
+    engine.set_option(_lib.OPT_MODE, _lib.MODE_DIRECT)
+    ref, ram, _ = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
+    engine.check_numeric()
+    engine.set_option(_lib.OPT_MODE, _lib.MODE_SCREENED_GRAM)
+    ms, am, _ = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
+    engine.check_numeric()
+    assert int(am) == int(ram)
+    std_close(ms.cpu().numpy(), ref.cpu().numpy())
+    # twice in a row: bit-identical (persistent schedule, atomics on maxima only)
+    ms2 = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)[0]
+    assert np.array_equal(ms2.cpu().numpy(), ms.cpu().numpy())
+
+
+def test_saturated_units_raise_the_numeric_flag(engine):
+    """Sigmoid pre-activations below -88 make the fast producers' 2^x overflow: the Gram diagonal turns non-finite
+    and glasdi_check_numeric must report it (Engine.checked then repeats the step in direct mode)."""
+    from gplasdi_b200.engine import GlasdiError
+    wl, Ws, bs = setup_wl(engine, "tiny")
+    Ws = [w.copy() for w in Ws]; bs = [b.copy() for b in bs]
+    bs[0][:4] = -3000.0                                          # four dead units: sigmoid(-3000) = 0 exactly
+    engine.set_decoder(Ws, bs, wl.act)
+    inp = synth.make_inputs(wl)
+    engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
+    with pytest.raises(GlasdiError) as e:
+        engine.check_numeric()
+    assert e.value.code == _lib.ERR_NUMERIC
+    with pytest.warns(UserWarning, match="direct mode"):
+        ms, am, mv = engine.checked(lambda: engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt))
+    idx, per, _ = orc.greedy_step(Ws, bs, wl.act, inp["coefs"], inp["z0"], inp["t_grid"])
+    assert int(am) == idx
+    std_close(ms.cpu().numpy(), per)
+
+
 def test_persistent_schedule_independent_of_cta_count(engine, g_small):
     wl, Ws, bs = setup_wl(engine, "small_s200")
     inp = synth.make_inputs(wl)
