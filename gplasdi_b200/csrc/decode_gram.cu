@@ -66,12 +66,6 @@ struct GramParams {
   float* fscale;         // [n_items] : variance = accumulator * fscale
   int* flags;
   FrontMlp front;
-  // fast path (one front layer, latent dimension 5): rows (w0..w4, b) of the front layer, times -log2(e) for the
-  // sigmoid, as KERNEL PARAMETERS: they are read through the constant bank / uniform datapath (every lane of a
-  // warp works on the same units), which costs no shared-memory bandwidth.  Staged in shared memory they were the
-  // bound: 28 LDS.128 x 4 cycles of the 128 B/clk shared-memory datapath per 16 (unit, sample) values = 23 k of
-  // the 31 k cycles per (parameter, time step) (profiles/: gram_r1d).
-  float w6[128 * 6];
 };
 
 struct GBars {
@@ -202,82 +196,6 @@ constexpr float kNegLog2e = -1.4426950408889634f;
 // sigmoid's -log2(e) folded into the staged weights, MUFU ex2/rcp in their .ftz form (the non-ftz __expf costs
 // three more instructions per value).  d2[u] = (h_A, h_B)[kg*8+u] * 2^eH - pilot: 8.5 issue slots per
 // (unit, sample) instead of 19.6 (profiles/: gram_r1).
-template <int ACT>
-__device__ __forceinline__ unsigned long long act_pair(unsigned long long acc, int act_rt) {
-  float xa, xb;
-  unpack_f32x2(acc, xa, xb);
-  if constexpr (ACT == GLASDI_ACT_SIGMOID) {
-    // acc = -log2(e) * pre-activation  ->  sigmoid = 1 / (1 + 2^acc)
-    const unsigned long long t2 = add_f32x2(pack_f32x2(ex2_ftz(xa), ex2_ftz(xb)), pack_f32x2(1.0f, 1.0f));
-    float ta, tb;
-    unpack_f32x2(t2, ta, tb);
-    return pack_f32x2(rcp_ftz(ta), rcp_ftz(tb));
-  } else {
-    return pack_f32x2(act_apply_t<ACT>(act_rt, xa), act_apply_t<ACT>(act_rt, xb));
-  }
-}
-
-__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-// packed log2-domain pre-activation of unit k for the two columns: acc = cf * (w . z + b); k is warp-uniform
-__device__ __forceinline__ unsigned long long preact_pair(const float* __restrict__ w6, int k,
-                                                          const unsigned long long (&z2)[5]) {
-  const float* w = w6 + k * 6;
-  unsigned long long acc = pack_f32x2(w[5], w[5]);
-  acc = fma_f32x2(pack_f32x2(w[0], w[0]), z2[0], acc);
-  acc = fma_f32x2(pack_f32x2(w[1], w[1]), z2[1], acc);
-  acc = fma_f32x2(pack_f32x2(w[2], w[2]), z2[2], acc);
-  acc = fma_f32x2(pack_f32x2(w[3], w[3]), z2[3], acc);
-  acc = fma_f32x2(pack_f32x2(w[4], w[4]), z2[4], acc);
-  return acc;
-}
-
-// Sigmoids of FOUR units x two columns with FOUR reciprocals instead of eight (pairwise simultaneous inversion:
-// 1/(t0 t1), then h0 = t1/(t0 t1), h1 = t0/(t0 t1) as packed multiplies).  acc = -log2(e) x.  No clamp: 2^acc
-// overflows only for x < -88, where the products become inf/NaN; the epilogue of gram_kernel raises the numeric
-// flag on any non-finite Gram diagonal instead of clamping every value here (two more instructions per value).
-__device__ __forceinline__ void sigmoid4_pair(const unsigned long long (&acc)[4], unsigned long long (&h)[4]) {
-  const unsigned long long one2 = pack_f32x2(1.0f, 1.0f);
-  unsigned long long t[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float xa, xb;
-    unpack_f32x2(acc[j], xa, xb);
-    t[j] = add_f32x2(pack_f32x2(ex2_ftz(xa), ex2_ftz(xb)), one2);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; j += 2) {
-    float pa, pb;
-    unpack_f32x2(mul_f32x2(t[j], t[j + 1]), pa, pb);
-    const unsigned long long r = pack_f32x2(rcp_ftz(pa), rcp_ftz(pb));
-    h[j] = mul_f32x2(r, t[j + 1]);
-    h[j + 1] = mul_f32x2(r, t[j]);
-  }
-}
-
-// four consecutive units k0..k0+3 x two columns: d2[j] = (h_A, h_B)[k0 + j] * 2^eH - pilot
-template <int ACT>
-__device__ __forceinline__ void units4_pair(const float* __restrict__ w6, uint32_t sNP2_addr, int k0,
-                                            const unsigned long long (&z2)[5], unsigned long long hs2, int act_rt,
-                                            unsigned long long (&d2)[4]) {
-  unsigned long long h[4];
-  if constexpr (ACT == GLASDI_ACT_SIGMOID) {
-    unsigned long long acc[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = preact_pair(w6, k0 + j, z2);
-    sigmoid4_pair(acc, h);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = act_pair<ACT>(preact_pair(w6, k0 + j, z2), act_rt);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) d2[j] = fma_f32x2(h[j], hs2, lds64_volatile(sNP2_addr + (uint32_t)(k0 + j) * 8u));
-}
-
 template <int ACT, int INW, bool FAST>
 __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constant__ GramParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -323,15 +241,18 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
     const float* __restrict__ b = P.front.b[l];
     const int ld = L.wl_ld;
     if constexpr (FAST) {
-      // B operand of the pre-activation MMA: -log2(e) W0 as tf32, [unit][k < 8] K-major (k >= 5 and units >= K zero)
+      // B operand of the pre-activation MMA: cf W0 as tf32 (hi | remainder), [unit][k < 8] K-major (k >= NZ and units
+      // >= K zero); cf = -log2(e) for the sigmoid (2^x domain), 1 otherwise.  Biases (times cf) go to a table.
+      const float cf = (ACT == GLASDI_ACT_SIGMOID) ? kNegLog2e : 1.0f;
       for (int idx = threadIdx.x; idx < 128 * 8; idx += blockDim.x) {
         const int u = idx >> 3, k = idx & 7;
-        const float v = (u < P.K && k < 5) ? P.w6[u * 6 + k] : 0.f;
+        const float v = (u < P.K && k < P.NZ) ? cf * W[(size_t)u * P.NZ + k] : 0.f;
         const float vh = round_tf32(v);
         uint8_t* dst = sB1 + (k >> 2) * 2048 + (u >> 3) * 128 + (u & 7) * 16 + (k & 3) * 4;
         *reinterpret_cast<float*>(dst) = vh;                       // K chunks 0,1: tf32(W)
         *reinterpret_cast<float*>(dst + 4096) = v - vh;            // K chunks 2,3: the remainder
       }
+      for (int k = threadIdx.x; k < L.kpu; k += blockDim.x) sWl[k] = k < P.K ? cf * b[k] : 0.f;
     } else {
       for (int idx = threadIdx.x; idx < L.kpu * ld; idx += blockDim.x) {
         const int k = idx / ld, i = idx - k * ld;
@@ -382,7 +303,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       // Phase A (warps 4..7) walks the CTA's stream of chunks ONE AHEAD of phase B, so that the pre-activation MMA
       // of chunk c + 1 runs while chunk c is being processed.  Its latent states are prefetched two stream elements
       // ahead (zq[2], a two-entry queue), the pilot's one item ahead (zpa = item of the queue head, zpn = the next).
-      float zq[2][5], zpa[5], zpn[5], zpt[5];              // zpt: pilot of the item whose tables are made next (warps 8..11)
+      constexpr int NL = INW > 0 ? INW : kMaxLatent;       // fast path: INW = compile-time latent dimension (5) or 0 = up to 8
+      const int NZ = P.NZ;
+      float zq[2][NL], zpa[NL], zpn[NL], zpt[NL];          // zpt: pilot of the item whose tables are made next (warps 8..11)
       long long item_l = item;                              // position of the next stream element to LOAD
       int c_l = 0;
       uint32_t ga = 0;                                      // stream index of the next phase-A element (= queue head)
@@ -390,17 +313,17 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       long long item_a = item;                              // its item
       const uint32_t n_elems = item < P.n_items
                                    ? (uint32_t)((P.n_items - item + gridDim.x - 1) / gridDim.x) * (uint32_t)nchunks : 0u;
-      auto load_col = [&](long long it, int c, float (&z)[5]) {
-        const float* __restrict__ src = P.Zs + (size_t)it * 5 * P.Spad + c * kCols + col;
+      auto load_col = [&](long long it, int c, float (&z)[NL]) {
+        const float* __restrict__ src = P.Zs + (size_t)it * NZ * P.Spad + c * kCols + col;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) z[i] = __ldg(src + (size_t)i * P.Spad);
+        for (int i = 0; i < NL; ++i) z[i] = (INW > 0 || i < NZ) ? __ldg(src + (size_t)i * P.Spad) : 0.f;
       };
-      auto load_zp = [&](long long it, float (&z)[5]) {      // sample 0 = the pilot
-        const float* __restrict__ src = P.Zs + (size_t)it * 5 * P.Spad;
+      auto load_zp = [&](long long it, float (&z)[NL]) {     // sample 0 = the pilot
+        const float* __restrict__ src = P.Zs + (size_t)it * NZ * P.Spad;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) z[i] = __ldg(src + (size_t)i * P.Spad);
+        for (int i = 0; i < NL; ++i) z[i] = (INW > 0 || i < NZ) ? __ldg(src + (size_t)i * P.Spad) : 0.f;
       };
-      auto load_next = [&](float (&z)[5]) {                  // next element of the stream, if any
+      auto load_next = [&](float (&z)[NL]) {                 // next element of the stream, if any
         if (item_l < P.n_items) {
           load_col(item_l, c_l, z);
           if (++c_l == nchunks) { c_l = 0; item_l += gridDim.x; }
@@ -416,26 +339,35 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       // a ring of four buffers and published through an mbarrier, so that no CTA-wide barrier ties the producer
       // warps together at item boundaries (they drift up to two chunks apart).  Same pairwise arithmetic as the
       // samples: the padding columns (copies of sample 0, dz = 0) cancel to exactly 0.  The constant unit K (zero
-      // weights, h = 1/2) gets 1 - h 2^eH: its "difference" is the constant 1.
+      // weights, h = act(0)) gets 1 - h 2^eH: its "difference" is the constant 1.
       const bool tab_warp = jg == 1;
       auto make_tables = [&](uint32_t nseq) {
         float* tA = sPilot + (nseq & 3u) * 2 * L.kpu;
         float* tN = tA + L.kpu;
         const int k = ptid - 128;
         if (k < L.kpu) {
-          const int kp = k ^ 1;
-          const float* wk = P.w6 + k * 6;
-          const float* wp = P.w6 + kp * 6;
-          float ak = wk[5], ap = wp[5];
+          // a(pilot) of unit k and of its pair partner from the staged weights (hi + remainder = the fp32 weight)
+          auto preact = [&](int u) {
+            float a = sWl[u];
+            const uint8_t* w = sB1 + (u >> 3) * 128 + (u & 7) * 16;
 #pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            ak = fmaf(wk[i], zpt[i], ak);
-            ap = fmaf(wp[i], zpt[i], ap);
+            for (int i = 0; i < NL; ++i) {
+              const uint8_t* wi = w + (i >> 2) * 2048 + (i & 3) * 4;
+              a = fmaf(*reinterpret_cast<const float*>(wi) + *reinterpret_cast<const float*>(wi + 4096), zpt[i], a);
+            }
+            return a;
+          };
+          const float ak = preact(k);
+          float hk;
+          if constexpr (ACT == GLASDI_ACT_SIGMOID) {
+            const float ap = preact(k ^ 1);
+            const float tk = ex2_ftz(ak) + 1.0f, tp = ex2_ftz(ap) + 1.0f;
+            const float te = (k & 1) ? tp : tk, to = (k & 1) ? tk : tp;
+            const float r = rcp_ftz(te * to);
+            hk = r * ((k & 1) ? te : to);
+          } else {
+            hk = act_apply_t<ACT>(P.front.act, ak);
           }
-          const float tk = ex2_ftz(ak) + 1.0f, tp = ex2_ftz(ap) + 1.0f;
-          const float te = (k & 1) ? tp : tk, to = (k & 1) ? tk : tp;
-          const float r = rcp_ftz(te * to);
-          const float hk = r * ((k & 1) ? te : to);
           tA[k] = ak;
           tN[k] = (k == P.K ? 1.0f : 0.0f) - hk * hscale;
         }
@@ -450,22 +382,23 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       // dz = z - z_pilot of this thread's sample as the tf32 A operand (hi in K 0..7, lo in K 8..15) of stream element ga
       auto phase_a_step = [&]() {
         const uint32_t slot = ga % kRing;
-        float hi[5], lo[5];
+        float hi[NL], lo[NL];
         if (ga & 1u) {
 #pragma unroll
-          for (int i = 0; i < 5; ++i) { const float dz = zq[1][i] - zpa[i]; hi[i] = round_tf32(dz); lo[i] = dz - hi[i]; }
+          for (int i = 0; i < NL; ++i) { const float dz = zq[1][i] - zpa[i]; hi[i] = round_tf32(dz); lo[i] = dz - hi[i]; }
           load_next(zq[1]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 5; ++i) { const float dz = zq[0][i] - zpa[i]; hi[i] = round_tf32(dz); lo[i] = dz - hi[i]; }
+          for (int i = 0; i < NL; ++i) { const float dz = zq[0][i] - zpa[i]; hi[i] = round_tf32(dz); lo[i] = dz - hi[i]; }
           load_next(zq[0]);
         }
         mbar_wait_relaxed(&B->a1_empty[slot], ((ga / kRing) & 1u) ^ 1u);
         uint8_t* dst = sA1 + slot * kA1Bytes + (col >> 3) * 128 + (col & 7) * 16;
-        *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(dst + 2048) = make_float4(hi[4], 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(dst + 4096) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<float4*>(dst + 6144) = make_float4(lo[4], 0.f, 0.f, 0.f);
+        auto comp = [&](const float (&v)[NL], int i) { return i < NL ? v[i < NL ? i : 0] : 0.f; };
+        *reinterpret_cast<float4*>(dst) = make_float4(comp(hi, 0), comp(hi, 1), comp(hi, 2), comp(hi, 3));
+        *reinterpret_cast<float4*>(dst + 2048) = make_float4(comp(hi, 4), comp(hi, 5), comp(hi, 6), comp(hi, 7));
+        *reinterpret_cast<float4*>(dst + 4096) = make_float4(comp(lo, 0), comp(lo, 1), comp(lo, 2), comp(lo, 3));
+        *reinterpret_cast<float4*>(dst + 6144) = make_float4(comp(lo, 4), comp(lo, 5), comp(lo, 6), comp(lo, 7));
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&B->a1_full[slot]);
@@ -474,7 +407,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
           c_a = 0;
           item_a += gridDim.x;
 #pragma unroll
-          for (int i = 0; i < 5; ++i) zpa[i] = zpn[i];
+          for (int i = 0; i < NL; ++i) zpa[i] = zpn[i];
           if (item_a + gridDim.x < P.n_items) load_zp(item_a + gridDim.x, zpn);
         }
       };
@@ -517,11 +450,20 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             for (int j = 0; j < 4; ++j) {
               float xe, xo;
               unpack_f32x2(acc[j], xe, xo);
-              float te, to;
-              unpack_f32x2(add_f32x2(pack_f32x2(ex2_ftz(xe), ex2_ftz(xo)), one2), te, to);
-              const float r = rcp_ftz(te * to);
+              unsigned long long h2;
+              if constexpr (ACT == GLASDI_ACT_SIGMOID) {
+                float te, to;
+                unpack_f32x2(add_f32x2(pack_f32x2(ex2_ftz(xe), ex2_ftz(xo)), one2), te, to);
+                const float r = rcp_ftz(te * to);
+                h2 = pack_f32x2(r * to, r * te);
+              } else {
+                h2 = pack_f32x2(act_apply_t<ACT>(P.front.act, xe), act_apply_t<ACT>(P.front.act, xo));
+              }
               float de, dod;
-              unpack_f32x2(fma_f32x2(pack_f32x2(r * to, r * te), hs2, np[j]), de, dod);
+              unpack_f32x2(fma_f32x2(h2, hs2, np[j]), de, dod);
+              if constexpr (ACT != GLASDI_ACT_SIGMOID && ACT != GLASDI_ACT_TANH) {
+                if (P.check_overflow) amax = fmaxf(amax, fmaxf(fabsf(de), fabsf(dod)));
+              }
               out[j] = h2_as_u32(__floats2half2_rn(de, dod));
             }
             *reinterpret_cast<uint4*>(Hb + h_offset(kg, col)) = make_uint4(out[0], out[1], out[2], out[3]);
@@ -1098,13 +1040,7 @@ int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P_, int 
   for (int l = 0; l <= G.front.n_front; ++l) G.front.widths[l] = d.widths[l];
   for (int l = 0; l < G.front.n_front; ++l) { G.front.W[l] = d.dW[l]; G.front.b[l] = d.db[l]; }
   const int last_in_w = d.widths[d.n_linear - 2];
-  const bool fast = G.front.n_front == 1 && G.NZ == 5 && d.act == GLASDI_ACT_SIGMOID;
-  if (fast) {
-    const float cf = gr::kNegLog2e;                   // the fast path is instantiated for the sigmoid only
-    for (int k = 0; k < 128; ++k)
-      for (int i = 0; i < 6; ++i)
-        G.w6[k * 6 + i] = k < d.K ? cf * (i < 5 ? d.h_front_last_W[(size_t)k * 5 + i] : d.h_front_last_b[k]) : 0.f;
-  }
+  const bool fast = G.front.n_front == 1;            // one front layer: pre-activations on the tensor core
   G.xw = 0;
   if (!fast)
     for (int l = 1; l < G.front.n_front; ++l) G.xw = std::max(G.xw, (d.widths[l] + 3) / 4 * 4);
@@ -1113,8 +1049,14 @@ int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P_, int 
   if (h->opt_max_ctas > 0) ctas = std::max(1, std::min(ctas, h->opt_max_ctas));
   if ((long long)ctas > G.n_items) ctas = (int)G.n_items;
   int rc;
-  if (fast)
-    rc = launch_gram_inst<GLASDI_ACT_SIGMOID, 5, true>(h, G, ctas, smem, st);
+  if (fast && d.act == GLASDI_ACT_SIGMOID && G.NZ == 5)
+    rc = launch_gram_inst<GLASDI_ACT_SIGMOID, 5, true>(h, G, ctas, smem, st);     // the shipped Burgers decoder
+  else if (fast && d.act == GLASDI_ACT_SIGMOID)
+    rc = launch_gram_inst<GLASDI_ACT_SIGMOID, 0, true>(h, G, ctas, smem, st);
+  else if (fast && d.act == GLASDI_ACT_SOFTPLUS)
+    rc = launch_gram_inst<GLASDI_ACT_SOFTPLUS, 0, true>(h, G, ctas, smem, st);
+  else if (fast)
+    rc = launch_gram_inst<-1, 0, true>(h, G, ctas, smem, st);
   else if (d.act == GLASDI_ACT_SOFTPLUS)
     rc = launch_gram_inst<GLASDI_ACT_SOFTPLUS, 0, false>(h, G, ctas, smem, st);
   else
