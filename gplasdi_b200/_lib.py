@@ -39,11 +39,14 @@ SIGNATURES = {
     "glasdi_decode_max_std": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "glasdi_decode_stat_fields": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "glasdi_decode": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "glasdi_set_encoder": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_vp), _i]),
+    "glasdi_encode": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "glasdi_check_numeric": (_i, [_vp, _vp]),
     "glasdi_argmax_first": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "glasdi_pack_maxloc": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "glasdi_fd_dzdt": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp]),
     "glasdi_sindy_fit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp]),
+    "glasdi_sindy_fit_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _i, _vp, _vp]),
 }
 
 

@@ -45,6 +45,11 @@ static int ensure_screen_buffers(glasdi_handle* h, size_t P) {
     GL_CUDA(h, cudaMalloc(&h->d_cand, cap * 16));
     h->cand_cap = cap;
   }
+  if (!h->d_groups) {
+    const size_t gcap = (size_t)1 << 19;                       // 8 MB of {p, t, first, count}
+    GL_CUDA(h, cudaMalloc(&h->d_groups, gcap * 16));
+    h->group_cap = gcap;
+  }
   if (!h->d_cand_stats) GL_CUDA(h, cudaMalloc(&h->d_cand_stats, 4 * sizeof(unsigned int)));
   if (P > h->exact_cap) {
     if (h->d_exact) cudaFree(h->d_exact);
@@ -68,6 +73,14 @@ static void free_decoder(Decoder& d) {
   d.gram_ok = false;
   d.ready = false;
   d.tc_ok = false;
+}
+
+static void free_encoder(Encoder& e) {
+  for (float* p : e.dW) if (p) cudaFree(p);
+  for (float* p : e.db) if (p) cudaFree(p);
+  e.dW.clear();
+  e.db.clear();
+  e.ready = false;
 }
 
 static bool bounded_act(int act) { return act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH; }
@@ -131,10 +144,12 @@ int glasdi_destroy(glasdi_handle* h) {
   cudaGetDevice(&prev);
   cudaSetDevice(h->device);
   free_decoder(h->dec);
+  free_encoder(h->enc);
   if (h->ws) cudaFree(h->ws);
   if (h->d_maxvar) cudaFree(h->d_maxvar);
   if (h->d_flags) cudaFree(h->d_flags);
   if (h->d_cand) cudaFree(h->d_cand);
+  if (h->d_groups) cudaFree(h->d_groups);
   if (h->d_cand_stats) cudaFree(h->d_cand_stats);
   if (h->d_exact) cudaFree(h->d_exact);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -394,7 +409,8 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
     }
     if (screened) {
       if ((rc = t_ref.start())) return rc;
-      GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats, 0, sizeof(unsigned int), st));      // per-slab count
+      GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats, 0, sizeof(unsigned int), st));      // per-slab candidate count
+      GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats + 3, 0, sizeof(unsigned int), st));  // per-slab row-group count
       rc = launch_select_candidates(h, field, field_ld, h->d_maxvar + p0, pn, T, d.D, (1.f - delta) * (1.f - delta), st);
       if (rc) return rc;
       rc = launch_refine(h, Zs, Spad, S, T, h->d_exact + p0, 0.25f * delta,
@@ -564,6 +580,52 @@ int glasdi_sindy_fit(glasdi_handle* h, const float* Z, int B, int T, int n, int 
   GL_CUDA(h, cudaSetDevice(h->device));
   return launch_sindy_fit(h, Z, B, T, n, fd_id, dt, norm_order, coefs_out, loss_sindy_out, loss_coef_out, info_out,
                           (cudaStream_t)stream);
+}
+
+int glasdi_set_encoder(glasdi_handle* h, int n_linear, const int* widths, const float* const* W_host,
+                       const float* const* b_host, int act_id) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (n_linear < 1 || n_linear > 16) return set_error(h, GLASDI_ERR_INVALID, "encoder needs 1..16 linear layers");
+  if (!widths || !W_host || !b_host) return set_error(h, GLASDI_ERR_INVALID, "null encoder arrays");
+  if (act_id < 0 || act_id > GLASDI_ACT_IDENTITY) return set_error(h, GLASDI_ERR_INVALID, "unknown activation id");
+  for (int l = 0; l <= n_linear; ++l)
+    if (widths[l] < 1) return set_error(h, GLASDI_ERR_INVALID, "non-positive layer width");
+  GL_CUDA(h, cudaSetDevice(h->device));
+  Encoder& e = h->enc;
+  free_encoder(e);
+  e.n_linear = n_linear;
+  e.act = act_id;
+  e.widths.assign(widths, widths + n_linear + 1);
+  e.dW.assign(n_linear, nullptr);
+  e.db.assign(n_linear, nullptr);
+  for (int l = 0; l < n_linear; ++l) {
+    const size_t nw = (size_t)widths[l] * widths[l + 1];
+    GL_CUDA(h, cudaMalloc(&e.dW[l], nw * sizeof(float)));
+    GL_CUDA(h, cudaMalloc(&e.db[l], (size_t)widths[l + 1] * sizeof(float)));
+    GL_CUDA(h, cudaMemcpy(e.dW[l], W_host[l], nw * sizeof(float), cudaMemcpyHostToDevice));
+    GL_CUDA(h, cudaMemcpy(e.db[l], b_host[l], (size_t)widths[l + 1] * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  e.ready = true;
+  return GLASDI_OK;
+}
+
+int glasdi_encode(glasdi_handle* h, const float* U, int64_t rows, float* Z_out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!h->enc.ready) return set_error(h, GLASDI_ERR_NOT_READY, "encoder weights not set (glasdi_set_encoder)");
+  if (rows < 0 || (rows > 0 && (!U || !Z_out))) return set_error(h, GLASDI_ERR_INVALID, "encode: bad arguments");
+  if (rows == 0) return GLASDI_OK;
+  GL_CUDA(h, cudaSetDevice(h->device));
+  return launch_encode_simt(h, U, rows, Z_out, (cudaStream_t)stream);
+}
+
+int glasdi_sindy_fit_backward(glasdi_handle* h, const float* Z, const float* coefs, const float* grad_loss_sindy,
+                              const float* grad_loss_coef, int B, int T, int n, int fd_id, double dt, int norm_order,
+                              float* grad_Z_out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!Z || !coefs || !grad_Z_out) return set_error(h, GLASDI_ERR_INVALID, "sindy_fit_backward: null pointer");
+  GL_CUDA(h, cudaSetDevice(h->device));
+  return launch_sindy_fit_backward(h, Z, coefs, grad_loss_sindy, grad_loss_coef, B, T, n, fd_id, dt, norm_order,
+                                   grad_Z_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -273,6 +273,275 @@ __global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __r
   if (lane == 0) loss_sindy_out[b] = (float)(se / ((double)T * N));
 }
 
+// ---- backward of the fit -------------------------------------------------------------------------------------
+// D[r][c] of the SBP operator (without 1/dt): interior rows are antisymmetric bands, the first/last `depth` rows
+// dense closures (right boundary = negated mirror of the left, reference src/lasdi/fd.py:39).
+template <int HW>
+__device__ __forceinline__ float sbp_entry(const SbpF& sc, int r, int c, int T) {
+  const int depth = sc.depth;
+  if (r < depth) return c < sc.widths[r] ? sc.rows[r][c] : 0.f;
+  if (r >= T - depth) {
+    const int rr = T - 1 - r, cc = T - 1 - c;
+    return cc < sc.widths[rr] ? -sc.rows[rr][cc] : 0.f;
+  }
+  const int k = c - r;
+  if (k == 0 || k > HW || k < -HW) return 0.f;
+  return k > 0 ? sc.interior[k - 1] : -sc.interior[-k - 1];
+}
+
+constexpr int kBwdThreads = 128;
+
+// Gradient of  L = sum_b gs[b] * loss_sindy[b] + gc[b] * loss_coef[b]  with respect to Z, where (reference
+// sindy.py:66-77, differentiated by torch autograd through sparse.mm / lstsq / MSELoss / norm in gplasdi.py:186-197)
+//   Y = (1/dt) D Z,  X = [1 | Z],  R = argmin |Y - X R|,  E = Y - X R,
+//   loss_sindy = |E|^2 / (T n),  loss_coef = |R|_1 or |R|_F.
+// With M = (X^T X)^-1:  dR = M (dX^T E - X^T dX R + X^T dY), so for Rbar = dL/dR and Bm = M Rbar
+//   Ybar = X Bm + c E,   Xbar = E Bm^T - Ybar R^T,   c = 2 gs / (T n),
+//   Rbar = gc * d|R|/dR - c X^T E      (X^T E = 0 for the exact minimiser; kept because R is rounded to fp32),
+//   Zbar = Xbar[:, 1:] + (1/dt) D^T Ybar.
+// One CTA per series: the series and Ybar live in shared memory, X^T X / X^T E are accumulated and solved in fp64,
+// D^T is applied as a gather in ascending row order (deterministic, no atomics).
+template <int N, int HW>
+__global__ void __launch_bounds__(kBwdThreads) sindy_fit_bwd_kernel(const float* __restrict__ Z,
+                                                                    const float* __restrict__ coefs,
+                                                                    const float* __restrict__ g_sindy,
+                                                                    const float* __restrict__ g_coef, int T, int fd_id,
+                                                                    float inv_dt, int norm_order,
+                                                                    float* __restrict__ Zbar) {
+  constexpr int NA = N + 1;
+  constexpr int NG = NA * (NA + 1) / 2;
+  constexpr int NR = NA * N;
+  constexpr int NS = NG + NR;
+  constexpr int NW = kBwdThreads / 32;
+  __shared__ double sRed[NW][NS];
+  __shared__ double sG[NA][NA];
+  __shared__ double sB[NA][N];
+  __shared__ float sBm[NA][N];
+  __shared__ float sRf[NA][N];
+  __shared__ int sInfo;
+  extern __shared__ float s_bwd[];
+  float* sZ = s_bwd;                    // [T][N] series, later Xbar[:, 1:]
+  float* sY = s_bwd + (size_t)T * N;    // [T][N] residual E, later Ybar
+  const SbpF& sc = c_sbp[fd_id];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const float* __restrict__ z = Z + (size_t)b * T * N;
+  for (int f = tid; f < T * N; f += kBwdThreads) sZ[f] = __ldg(z + f);
+  if (tid < NR) sRf[tid / N][tid % N] = __ldg(coefs + (size_t)b * NR + tid);
+  __syncthreads();
+  const float gs = g_sindy ? __ldg(g_sindy + b) : 0.f;
+  const float gc = g_coef ? __ldg(g_coef + b) : 0.f;
+  const float c = 2.f * gs / ((float)T * (float)N);
+
+  float Rf[NA][N];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int i = 0; i < N; ++i) Rf[a][i] = sRf[a][i];
+
+  // pass A: residual rows, X^T X (upper triangle) and X^T E in fp64
+  double acc[NS];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) acc[q] = 0.0;
+  for (int t = tid; t < T; t += kBwdThreads) {
+    float x[NA], e[N];
+    x[0] = 1.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[1 + j] = sZ[t * N + j];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float d = inv_dt * sbp_row<HW>(sc, t, T, [&](int row) { return sZ[row * N + i]; });
+      float pred = Rf[0][i];
+#pragma unroll
+      for (int j = 0; j < N; ++j) pred = fmaf(x[1 + j], Rf[1 + j][i], pred);
+      e[i] = d - pred;
+      sY[t * N + i] = e[i];
+    }
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int cc = a; cc < NA; ++cc) { acc[q] = fma((double)x[a], (double)x[cc], acc[q]); ++q; }
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int i = 0; i < N; ++i) { acc[q] = fma((double)x[a], (double)e[i], acc[q]); ++q; }
+  }
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    double v = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sRed[warp][q] = v;
+  }
+  __syncthreads();
+  if (tid < NS) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += sRed[w][tid];
+    sRed[0][tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int q = 0;
+    for (int a = 0; a < NA; ++a)
+      for (int cc = a; cc < NA; ++cc) { sG[a][cc] = sRed[0][q]; sG[cc][a] = sRed[0][q]; ++q; }
+    // Rbar = gc * d|R|_p/dR - c X^T E
+    double nrm = 0.0;
+    for (int a = 0; a < NA; ++a)
+      for (int i = 0; i < N; ++i) nrm += (double)sRf[a][i] * (double)sRf[a][i];
+    nrm = sqrt(nrm);
+    for (int a = 0; a < NA; ++a)
+      for (int i = 0; i < N; ++i) {
+        const double r = (double)sRf[a][i];
+        double dn;
+        if (norm_order == 1) dn = (r > 0.0) - (r < 0.0);
+        else dn = nrm > 0.0 ? r / nrm : 0.0;
+        sB[a][i] = (double)gc * dn - (double)c * sRed[0][NG + a * N + i];
+      }
+    int info = 0;
+    double dmax = 0.0;
+    for (int a = 0; a < NA; ++a) dmax = fmax(dmax, sG[a][a]);
+#pragma unroll 1
+    for (int j = 0; j < NA; ++j) {
+      double sdiag = sG[j][j];
+      for (int k = 0; k < j; ++k) sdiag -= sG[j][k] * sG[j][k];
+      if (!(sdiag > 1e-13 * dmax)) { info = j + 1; break; }
+      const double ljj = sqrt(sdiag);
+      sG[j][j] = ljj;
+      const double rl = 1.0 / ljj;
+#pragma unroll 1
+      for (int i = j + 1; i < NA; ++i) {
+        double v = sG[i][j];
+        for (int k = 0; k < j; ++k) v -= sG[i][k] * sG[j][k];
+        sG[i][j] = v * rl;
+      }
+    }
+    sInfo = info;
+  }
+  __syncthreads();
+  const int info = sInfo;
+  if (tid < N && info == 0) {
+#pragma unroll 1
+    for (int i = 0; i < NA; ++i) {
+      double v = sB[i][tid];
+      for (int k = 0; k < i; ++k) v -= sG[i][k] * sB[k][tid];
+      sB[i][tid] = v / sG[i][i];
+    }
+#pragma unroll 1
+    for (int i = NA - 1; i >= 0; --i) {
+      double v = sB[i][tid];
+      for (int k = i + 1; k < NA; ++k) v -= sG[k][i] * sB[k][tid];
+      sB[i][tid] = v / sG[i][i];
+    }
+    for (int i = 0; i < NA; ++i) sBm[i][tid] = (float)sB[i][tid];
+  }
+  __syncthreads();
+  float* __restrict__ out = Zbar + (size_t)b * T * N;
+  if (info != 0) {                       // rank-deficient series: the forward returned NaN coefficients
+    for (int f = tid; f < T * N; f += kBwdThreads) out[f] = nanf("");
+    return;
+  }
+  float Bm[NA][N];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int i = 0; i < N; ++i) Bm[a][i] = sBm[a][i];
+  // pass B: Ybar = X Bm + c E (over E), Xbar[:, 1:] = E Bm^T - Ybar R^T (over Z); every thread touches its own rows
+  for (int t = tid; t < T; t += kBwdThreads) {
+    float zr[N], e[N], yb[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) { zr[j] = sZ[t * N + j]; e[j] = sY[t * N + j]; }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float v = Bm[0][i];
+#pragma unroll
+      for (int j = 0; j < N; ++j) v = fmaf(zr[j], Bm[1 + j][i], v);
+      yb[i] = fmaf(c, e[i], v);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < N; ++i) v = fmaf(e[i], Bm[1 + j][i], v);
+#pragma unroll
+      for (int i = 0; i < N; ++i) v = fmaf(-yb[i], Rf[1 + j][i], v);
+      sZ[t * N + j] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) sY[t * N + i] = yb[i];
+  }
+  __syncthreads();
+  // Zbar = Xbar[:, 1:] + (1/dt) D^T Ybar: column t of D gathers rows [t-HW, t+HW] of the interior band and, within
+  // SBP_MAXW of an end, the dense boundary rows
+  const int depth = sc.depth;
+  for (int f = tid; f < T * N; f += kBwdThreads) {
+    const int t = f / N, i = f - t * N;
+    float a = 0.f;
+    if (t < SBP_MAXW)
+      for (int r = 0; r < depth; ++r) a = fmaf(sbp_entry<HW>(sc, r, t, T), sY[r * N + i], a);
+    const int r0 = max(t - HW, depth), r1 = min(t + HW, T - depth - 1);
+    for (int r = r0; r <= r1; ++r) a = fmaf(sbp_entry<HW>(sc, r, t, T), sY[r * N + i], a);
+    if (T - 1 - t < SBP_MAXW)
+      for (int r = T - depth; r < T; ++r) a = fmaf(sbp_entry<HW>(sc, r, t, T), sY[r * N + i], a);
+    out[f] = fmaf(inv_dt, a, sZ[f]);
+  }
+}
+
+template <int N, int HW>
+static cudaError_t launch_bwd_nh(const float* Z, const float* coefs, const float* gs, const float* gc, int B, int T,
+                                 int fd_id, float inv_dt, int norm_order, float* Zbar, cudaStream_t st) {
+  const size_t smem = (size_t)2 * T * N * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  if (smem > 40 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(sindy_fit_bwd_kernel<N, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  sindy_fit_bwd_kernel<N, HW><<<B, kBwdThreads, smem, st>>>(Z, coefs, gs, gc, T, fd_id, inv_dt, norm_order, Zbar);
+  return cudaGetLastError();
+}
+
+template <int N>
+static cudaError_t launch_bwd_n(const float* Z, const float* coefs, const float* gs, const float* gc, int B, int T,
+                                int fd_id, float inv_dt, int norm_order, float* Zbar, cudaStream_t st) {
+  switch (kSbpSchemes[fd_id].halfwidth) {
+    case 1: return launch_bwd_nh<N, 1>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st);
+    case 2: return launch_bwd_nh<N, 2>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st);
+    case 3: return launch_bwd_nh<N, 3>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st);
+    default: return launch_bwd_nh<N, 4>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st);
+  }
+}
+
+int launch_sindy_fit_backward(glasdi_handle* h, const float* Z, const float* coefs, const float* gs, const float* gc,
+                              int B, int T, int n, int fd_id, double dt, int norm_order, float* Zbar, cudaStream_t st) {
+  if (fd_id < 0 || fd_id >= SBP_NSCHEMES) return set_error(h, GLASDI_ERR_INVALID, "unknown fd scheme id");
+  if (B <= 0) return set_error(h, GLASDI_ERR_INVALID, "sindy_fit_backward: empty batch");
+  if (T < 2 * kSbpSchemes[fd_id].depth)
+    return set_error(h, GLASDI_ERR_INVALID, "sindy_fit_backward: series shorter than 2*boundary depth");
+  if (norm_order != 1 && norm_order != 2)
+    return set_error(h, GLASDI_ERR_INVALID, "sindy_fit_backward: norm_order must be 1 or 2 ('fro')");
+  if ((size_t)2 * T * n * sizeof(float) > 200 * 1024)
+    return set_error(h, GLASDI_ERR_INVALID, "sindy_fit_backward: series longer than 25600 values (T * n)");
+  int rc = upload_sbp(h);
+  if (rc) return rc;
+  const float inv_dt = (float)(1.0 / dt);
+  cudaError_t e;
+  switch (n) {
+    case 1: e = launch_bwd_n<1>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st); break;
+    case 2: e = launch_bwd_n<2>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st); break;
+    case 3: e = launch_bwd_n<3>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st); break;
+    case 4: e = launch_bwd_n<4>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st); break;
+    case 5: e = launch_bwd_n<5>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st); break;
+    case 6: e = launch_bwd_n<6>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st); break;
+    case 7: e = launch_bwd_n<7>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st); break;
+    case 8: e = launch_bwd_n<8>(Z, coefs, gs, gc, B, T, fd_id, inv_dt, norm_order, Zbar, st); break;
+    default: return set_error(h, GLASDI_ERR_INVALID, "sindy_fit_backward: latent dimension must be 1..8");
+  }
+  h->launches++;
+  return check_cuda(h, e, "sindy_fit_backward launch");
+}
+
+
 template <int HW>
 static void launch_fd_hw(const float* Z, int B, int T, int n, int fd_id, float inv_dt, float* dZ, cudaStream_t st) {
   const int per_block = kFdThreads * kFdPerThread;

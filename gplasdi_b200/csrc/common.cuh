@@ -46,6 +46,15 @@ struct Decoder {
   std::vector<float> h_front_last_W, h_front_last_b;   // host copy of the last FRONT layer (kernel-parameter weights)
 };
 
+// Encoder MLP (reference Autoencoder.encoder, latent_space.py:223): plain fp32 device copies, evaluated layer by layer.
+struct Encoder {
+  bool ready = false;
+  int n_linear = 0;
+  int act = 0;
+  std::vector<int> widths;          // widths[0] = number of dofs ... widths[n_linear] = n_z
+  std::vector<float*> dW, db;
+};
+
 }  // namespace glasdi
 
 struct glasdi_handle {
@@ -53,6 +62,7 @@ struct glasdi_handle {
   int num_sms = 0;
   std::string err;
   glasdi::Decoder dec;
+  glasdi::Encoder enc;
   int opt_passes = 3;
   int opt_integrator = GLASDI_INT_EXPM;
   int opt_substeps = 1;
@@ -74,7 +84,9 @@ struct glasdi_handle {
   int opt_margin_log2 = 8;            // candidates = variance within (1 - 2^-margin)^2 of the screened maximum
   void* d_cand = nullptr;             // [cand_cap] {p, t, d, approx variance}
   size_t cand_cap = 0;
-  unsigned int* d_cand_stats = nullptr;   // [0] count (this slab), [1] total count, [2] float bits of max relative deviation
+  void* d_groups = nullptr;           // [group_cap] {p, t, first, count}: the candidates of one (p, t) row of the field
+  size_t group_cap = 0;
+  unsigned int* d_cand_stats = nullptr;   // [0] count (this slab), [1] total count, [2] float bits of max relative deviation, [3] row groups (this slab)
   unsigned int* d_exact = nullptr;    // [P] float bits of the exact variance
   size_t exact_cap = 0;
   std::vector<int> ev_refine, ev_quad;
@@ -133,6 +145,7 @@ int launch_decode_store_pair(glasdi_handle* h, const float* Z, int64_t rows, flo
 int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
                            unsigned int* maxvar_bits, cudaStream_t st);
 int launch_decode_store_simt(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
+int launch_encode_simt(glasdi_handle* h, const float* U, int64_t rows, float* Z, cudaStream_t st);
 // reduce.cu
 int launch_finalize(glasdi_handle* h, const unsigned int* maxvar_bits, int P, int scale_exp2,
                     float* max_std, int64_t* argmax, float* maxval, cudaStream_t st);
@@ -149,6 +162,9 @@ int launch_fd_dzdt(glasdi_handle* h, const float* Z, int B, int T, int n, int fd
                    cudaStream_t st);
 int launch_sindy_fit(glasdi_handle* h, const float* Z, int B, int T, int n, int fd_id, double dt, int norm_order,
                      float* coefs, float* loss_sindy, float* loss_coef, int32_t* info, cudaStream_t st);
+int launch_sindy_fit_backward(glasdi_handle* h, const float* Z, const float* coefs, const float* g_sindy,
+                              const float* g_coef, int B, int T, int n, int fd_id, double dt, int norm_order,
+                              float* Zbar, cudaStream_t st);
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -1,16 +1,20 @@
-// refine.cu -- second half of the SCREENED greedy step (GLASDI_OPT_MODE = 1).
+// refine.cu -- second half of the SCREENED greedy step (GLASDI_MODE_SCREENED_GRAM / GLASDI_MODE_SCREENED).
 //
-// The tcgen05 kernel (decode_var2.cu) is run with ONE fp16 pass (W_hi * H_hi: ~2^-11 per operand) and
-// writes the approximate variance of every (t, dof) next to the per-parameter maximum.  The maximum of
-// the reference's fp32 result can only sit where the screened variance is within a factor (1 - delta)^2
-// of the screened maximum as long as the screening error is below delta / 2 (measured: 7e-5 relative on
-// sigma at the bench shape; delta = 2^-8 by default).  Those few candidates are re-evaluated here on the
-// CUDA cores -- front MLP in fp32 exactly as the reference does (src/lasdi/latent_space.py:157-164),
-// last layer as an fp32 FMA chain on the pilot-centred activations, sample sums in fp64 -- and the
-// maximum over the candidates of a parameter is its max variance (reference src/lasdi/gplasdi.py:65-69).
-// The deviation |sigma_screen - sigma_exact| / sigma_exact of every candidate is checked against
-// delta / 4; a violation raises a device flag (GLASDI_ERR_NUMERIC from glasdi_check_numeric), it is never
-// silently accepted.
+// The tensor-core screening pass (decode_gram.cu: covariance form; decode_var2.cu: one fp16 pass over the decoded
+// ensemble) writes the approximate variance of every (t, dof) next to the per-parameter maximum.  The maximum of
+// the reference's fp32 result can only sit where the screened variance is within a factor (1 - delta)^2 of the
+// screened maximum as long as the screening error is below delta / 2 (measured: 5e-5 relative on sigma for the
+// random-weight bench decoder, 5e-4 for a smooth one; delta = 2^-8 by default).  Those candidates are re-evaluated
+// here on the CUDA cores -- front MLP in fp32 exactly as the reference does (src/lasdi/latent_space.py:157-164),
+// last layer as an fp32 FMA chain on the pilot-centred activations, sample sums in fp64 -- and the maximum over the
+// candidates of a parameter is its max variance (reference src/lasdi/gplasdi.py:65-69).
+// The deviation |sigma_screen - sigma_exact| / sigma_exact of every candidate is checked against delta / 4; a
+// violation raises a device flag (GLASDI_ERR_NUMERIC from glasdi_check_numeric), it is never silently accepted.
+//
+// Candidates are collected PER (parameter, time step) ROW of the field: trained decoders are smooth in the dof
+// index, so a row that holds one near-maximum dof holds dozens of them (72 candidates per parameter for a smooth
+// last layer, 6 for the random-weight bench decoder).  All candidates of a row share the hidden activations of its
+// S samples; one warp evaluates them once and dots them with up to 8 rows of the last layer at a time.
 #include "decode_common.cuh"
 
 #include <algorithm>
@@ -22,47 +26,71 @@ using namespace dv;
 
 struct Cand {
   int p, t, d;
-  float var;       // screened variance (scaled units)
+  float var;       // screened variance (field units)
+};
+struct Group {
+  int p, t;
+  unsigned int first, count;      // candidates [first, first + count) of cand[]
 };
 
-constexpr int kSelThreads = 256;
-constexpr int kSelPerThread = 16;     // floats per thread (4 x float4)
+constexpr int kSelWarps = 8;          // rows per block of select_rows_kernel
 constexpr int kRefWarps = 8;
+constexpr int kNC = 8;                // candidates a warp evaluates per pass over the samples
 
-// candidates of parameter p: every (t, dof) whose screened variance is >= keep * screened max of p
-__global__ void __launch_bounds__(kSelThreads) select_kernel(const float* __restrict__ field, int field_ld,
-                                                             const unsigned int* __restrict__ approx_bits, int T,
-                                                             int D, float keep, Cand* __restrict__ cand,
-                                                             unsigned int cap, unsigned int* __restrict__ stats,
-                                                             int* __restrict__ flags) {
-  const int p = blockIdx.y;
+// one warp per (p, t) row of the field: candidates = dofs whose screened variance is >= keep * screened max of p
+__global__ void __launch_bounds__(kSelWarps * 32) select_rows_kernel(const float* __restrict__ field, int field_ld,
+                                                                    const unsigned int* __restrict__ approx_bits,
+                                                                    long long n_rows, int T, int D, float keep,
+                                                                    Cand* __restrict__ cand, unsigned int cap,
+                                                                    Group* __restrict__ groups, unsigned int gcap,
+                                                                    unsigned int* __restrict__ stats,
+                                                                    int* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kSelWarps + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int p = (int)(row / T), t = (int)(row - (long long)p * T);
   const float vmax = __uint_as_float(approx_bits[p]);
   if (!(vmax > 0.f)) return;
   const float thr = vmax * keep;
-  const long long n4 = (long long)T * field_ld / 4;                 // field_ld is a multiple of 256
-  const float4* __restrict__ f4 = reinterpret_cast<const float4*>(field + (size_t)p * T * field_ld);
-  const long long base = (long long)blockIdx.x * (kSelThreads * kSelPerThread / 4);
-#pragma unroll
-  for (int u = 0; u < kSelPerThread / 4; ++u) {
-    const long long i4 = base + u * kSelThreads + threadIdx.x;
-    if (i4 >= n4) break;
+  const float4* __restrict__ f4 = reinterpret_cast<const float4*>(field + (size_t)row * field_ld);
+  const int n4 = field_ld / 4;                                      // field_ld is a multiple of 256
+  // pass 1: count
+  int mine = 0;
+  for (int i4 = lane; i4 < n4; i4 += 32) {
     const float4 v = __ldg(f4 + i4);
-    const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-    if (m >= thr) {
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-      const long long e0 = i4 * 4;
-      const int t = (int)(e0 / field_ld);
-      const int d0 = (int)(e0 - (long long)t * field_ld);
+    const int d0 = i4 * 4;
+    mine += (v.x >= thr && d0 < D) + (v.y >= thr && d0 + 1 < D) + (v.z >= thr && d0 + 2 < D) + (v.w >= thr && d0 + 3 < D);
+  }
+  int incl = mine;                                                  // inclusive prefix sum over the lanes
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (vv[q] >= thr && d0 + q < D) {
-          const unsigned int slot = atomicAdd(stats + 0, 1u);
-          atomicAdd(stats + 1, 1u);
-          if (slot < cap) cand[slot] = Cand{p, t, d0 + q, vv[q]};
-          else atomicOr(flags + 1, 1);
-        }
-      }
-    }
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  // one work unit (= one warp of refine_kernel) per kNC candidates of the row
+  const unsigned int nunits = ((unsigned int)total + kNC - 1) / kNC;
+  unsigned int base = 0, gslot = 0;
+  if (lane == 0) {
+    base = atomicAdd(stats + 0, (unsigned int)total);
+    atomicAdd(stats + 1, (unsigned int)total);
+    gslot = atomicAdd(stats + 3, nunits);
+    if (base + (unsigned int)total > cap || gslot + nunits > gcap) atomicOr(flags + 1, 1);
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  gslot = __shfl_sync(0xffffffffu, gslot, 0);
+  if (base + (unsigned int)total > cap || gslot + nunits > gcap) return;
+  for (unsigned int u = lane; u < nunits; u += 32)
+    groups[gslot + u] = Group{p, t, base + u * kNC, min((unsigned int)kNC, (unsigned int)total - u * kNC)};
+  // pass 2: write (the row is in L1/L2); lanes own interleaved float4s, so the order inside a row is by lane
+  unsigned int w = base + (unsigned int)(incl - mine);
+  for (int i4 = lane; i4 < n4; i4 += 32) {
+    const float4 v = __ldg(f4 + i4);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (vv[q] >= thr && i4 * 4 + q < D) cand[w++] = Cand{p, t, i4 * 4 + q, vv[q]};
   }
 }
 
@@ -71,8 +99,9 @@ struct RefParams {
   const float* Wlast;               // [D][K] fp32, nn.Linear layout
   const float* Zs;                  // [P][T][NZ][Spad]
   const Cand* cand;
+  const Group* groups;
   const unsigned int* stats;
-  unsigned int cap;
+  unsigned int gcap;
   unsigned int* exact_bits;         // [P] float bits of the exact variance (true units)
   unsigned int* dev_bits;           // float bits of the max relative deviation screen vs exact
   int* flags;
@@ -87,16 +116,108 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// one warp per candidate; lanes stride the samples
-template <int ACT, int INW>
-__global__ void __launch_bounds__(kRefWarps * 32) refine_kernel(const __grid_constant__ RefParams R) {
+// One work unit: the hidden activations of the row's S samples, dotted with NC rows of the last layer.
+template <int ACT, int INW, int NC>
+__device__ __forceinline__ void refine_unit(const RefParams& R, const Group& gr, const float* __restrict__ sWl, int ld,
+                                            int last_in_w, float* sWd, const float* sPil, int lane) {
+  const int nc = (int)gr.count;
+  const int nkg = R.Kpad / 8;
+  const Cand* __restrict__ cd = R.cand + gr.first;
+  const float* __restrict__ zb = R.Zs + ((size_t)gr.p * R.T + gr.t) * R.NZ * R.Spad;
+  // rows of the last layer of the unit's candidates (unused slots: zero rows)
+  for (int idx = lane; idx < NC * R.Kpad; idx += 32) {
+    const int c = idx / R.Kpad, k = idx - c * R.Kpad;
+    sWd[idx] = (c < nc && k < R.K) ? __ldg(R.Wlast + (size_t)cd[c].d * R.K + k) : 0.f;
+  }
+  __syncwarp();
+  // sum_k |w_k| |h_k(pilot)| per candidate: scale of the fp32 rounding noise of a decoded value
+  float xabs[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    float a = 0.f;
+    for (int k = lane; k < R.Kpad; k += 32) a = fmaf(fabsf(sWd[c * R.Kpad + k]), fabsf(sPil[k]), a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    xabs[c] = a;
+  }
+  double s1[NC], s2[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
+  for (int s = lane; s < R.S; s += 32) {
+    float zz[kMaxLatent];
+#pragma unroll
+    for (int i = 0; i < kMaxLatent; ++i) zz[i] = (i < R.NZ) ? __ldg(zb + (size_t)i * R.Spad + s) : 0.f;
+    float xp[INW > 0 ? 1 : kMaxHid];
+    const float* xin = zz;
+    if constexpr (INW == 0) {
+      front_pre<ACT>(R.front, zz, xp);
+      xin = xp;
+    }
+    float dsum[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) dsum[c] = 0.f;
+    for (int kg = 0; kg < nkg; ++kg) {
+      float hv[8];
+      last_front_units<ACT, INW>(sWl, ld, last_in_w, R.front.act, kg * 8, xin, hv);
+      const float4 p0 = *reinterpret_cast<const float4*>(sPil + kg * 8);
+      const float4 p1 = *reinterpret_cast<const float4*>(sPil + kg * 8 + 4);
+      const float dh[8] = {hv[0] - p0.x, hv[1] - p0.y, hv[2] - p0.z, hv[3] - p0.w,
+                           hv[4] - p1.x, hv[5] - p1.y, hv[6] - p1.z, hv[7] - p1.w};
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sWd + c * R.Kpad + kg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sWd + c * R.Kpad + kg * 8 + 4);
+        float d = dsum[c];                          // same FMA order as one chain over k = 0 .. K-1
+        d = fmaf(w0.x, dh[0], d);
+        d = fmaf(w0.y, dh[1], d);
+        d = fmaf(w0.z, dh[2], d);
+        d = fmaf(w0.w, dh[3], d);
+        d = fmaf(w1.x, dh[4], d);
+        d = fmaf(w1.y, dh[5], d);
+        d = fmaf(w1.z, dh[6], d);
+        d = fmaf(w1.w, dh[7], d);
+        dsum[c] = d;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      s1[c] += (double)dsum[c];
+      s2[c] = fma((double)dsum[c], (double)dsum[c], s2[c]);
+    }
+  }
+  const double inv_S = 1.0 / (double)R.S;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const double t1 = warp_sum(s1[c]), t2 = warp_sum(s2[c]);
+    if (lane == 0 && c < nc) {
+      const double mean = t1 * inv_S;
+      const float var = (float)fmax(t2 * inv_S - mean * mean, 0.0);
+      atomicMax(R.exact_bits + gr.p, __float_as_uint(var));
+      // Screening check.  Below ~2^-24 * sum|w||h| (half an ulp of the decoded value's terms) a spread is fp32
+      // rounding noise in the reference as much as here (sigma of near-identical samples, e.g. at the GP's
+      // training points, where the activations h(s) - h(pilot) themselves carry 1e-2 relative rounding error):
+      // deviations inside that floor say nothing about the screening and are not counted.
+      const float se = sqrtf(var), sa = sqrtf(fmaxf(cd[c].var, 0.f) * R.unscale);
+      const float excess = fabsf(sa - se) - 6.0e-8f * xabs[c];
+      const float dev = (se > 0.f && excess > 0.f) ? excess / se : 0.f;
+      atomicMax(R.dev_bits, __float_as_uint(dev));
+      if (dev > R.dev_tol) atomicOr(R.flags + 2, 1);
+    }
+  }
+}
+
+// One warp per work unit (<= kNC candidates of one row); lanes stride the samples.  Two instantiations share the unit
+// list: NC = 2 takes the units with one or two candidates (64 registers, four CTAs per SM -- the kernel is bound by
+// the latency of the activation chains, so resident warps are what counts), NC = kNC the fuller ones.
+template <int ACT, int INW, int NC>
+__global__ void __launch_bounds__(kRefWarps * 32, NC <= 2 ? 4 : 2) refine_kernel(const __grid_constant__ RefParams R) {
   extern __shared__ __align__(16) float rsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int last_in_w = R.front.widths[R.front.n_front - 1];
   const int ld = wl_stride(last_in_w);
-  float* sWl = rsm;                                    // [Kpad][ld] rows [w.., bias, 0..] of the last FRONT layer
-  float* sWd = rsm + R.Kpad * ld + warp * 2 * R.Kpad;  // this warp's row of the LAST layer
-  float* sPil = sWd + R.Kpad;                          // this warp's pilot activations
+  float* sWl = rsm;                                              // [Kpad][ld] rows [w.., bias, 0..] of the last FRONT layer
+  float* sWd = rsm + R.Kpad * ld + warp * (kNC + 1) * R.Kpad;    // this warp's kNC rows of the LAST layer
+  float* sPil = sWd + kNC * R.Kpad;                              // this warp's pilot activations
   {
     const int l = R.front.n_front - 1;
     const float* __restrict__ W = R.front.W[l];
@@ -112,19 +233,18 @@ __global__ void __launch_bounds__(kRefWarps * 32) refine_kernel(const __grid_con
     }
   }
   __syncthreads();
-  const unsigned int n = min(R.stats[0], R.cap);
+  const unsigned int nunits = min(R.stats[3], R.gcap);
   const int nkg = R.Kpad / 8;
-  const double inv_S = 1.0 / (double)R.S;
-  for (unsigned int c = blockIdx.x * kRefWarps + warp; c < n; c += gridDim.x * kRefWarps) {
-    const Cand cd = R.cand[c];
-    for (int k = lane; k < R.Kpad; k += 32) sWd[k] = k < R.K ? __ldg(R.Wlast + (size_t)cd.d * R.K + k) : 0.f;
-    const float* __restrict__ zb = R.Zs + ((size_t)cd.p * R.T + cd.t) * R.NZ * R.Spad;
+  // unit u -> CTA u % gridDim.x: consecutive units (= neighbouring rows of one parameter) spread over the SMs
+  for (unsigned int gi = blockIdx.x + gridDim.x * warp; gi < nunits; gi += gridDim.x * kRefWarps) {
+    const Group gr = R.groups[gi];
+    if ((gr.count <= 2) != (NC <= 2)) continue;
+    const float* __restrict__ zb = R.Zs + ((size_t)gr.p * R.T + gr.t) * R.NZ * R.Spad;
     __syncwarp();
-    float xabs = 0.f;                 // sum_k |w_k| |h_k(pilot)|: scale of the fp32 rounding noise of a decoded value
-    {
+    {   // pilot activations of this row (sample 0)
       float zz[kMaxLatent];
 #pragma unroll
-      for (int i = 0; i < kMaxLatent; ++i) zz[i] = (i < R.NZ) ? __ldg(zb + (size_t)i * R.Spad) : 0.f;   // sample 0
+      for (int i = 0; i < kMaxLatent; ++i) zz[i] = (i < R.NZ) ? __ldg(zb + (size_t)i * R.Spad) : 0.f;
       float xp[INW > 0 ? 1 : kMaxHid];
       const float* xin = zz;
       if constexpr (INW == 0) {
@@ -135,63 +255,11 @@ __global__ void __launch_bounds__(kRefWarps * 32) refine_kernel(const __grid_con
         float hv[8];
         last_front_units<ACT, INW>(sWl, ld, last_in_w, R.front.act, kg * 8, xin, hv);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          sPil[kg * 8 + u] = hv[u];
-          xabs = fmaf(fabsf(sWd[kg * 8 + u]), fabsf(hv[u]), xabs);
-        }
+        for (int u = 0; u < 8; ++u) sPil[kg * 8 + u] = hv[u];
       }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) xabs += __shfl_xor_sync(0xffffffffu, xabs, o);
-    __syncwarp();
-    double s1 = 0.0, s2 = 0.0;
-    for (int s = lane; s < R.S; s += 32) {
-      float zz[kMaxLatent];
-#pragma unroll
-      for (int i = 0; i < kMaxLatent; ++i) zz[i] = (i < R.NZ) ? __ldg(zb + (size_t)i * R.Spad + s) : 0.f;
-      float xp[INW > 0 ? 1 : kMaxHid];
-      const float* xin = zz;
-      if constexpr (INW == 0) {
-        front_pre<ACT>(R.front, zz, xp);
-        xin = xp;
-      }
-      float dsum = 0.f;
-      for (int kg = 0; kg < nkg; ++kg) {
-        float hv[8];
-        last_front_units<ACT, INW>(sWl, ld, last_in_w, R.front.act, kg * 8, xin, hv);
-        const float4 w0 = *reinterpret_cast<const float4*>(sWd + kg * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(sWd + kg * 8 + 4);
-        const float4 p0 = *reinterpret_cast<const float4*>(sPil + kg * 8);
-        const float4 p1 = *reinterpret_cast<const float4*>(sPil + kg * 8 + 4);
-        dsum = fmaf(w0.x, hv[0] - p0.x, dsum);
-        dsum = fmaf(w0.y, hv[1] - p0.y, dsum);
-        dsum = fmaf(w0.z, hv[2] - p0.z, dsum);
-        dsum = fmaf(w0.w, hv[3] - p0.w, dsum);
-        dsum = fmaf(w1.x, hv[4] - p1.x, dsum);
-        dsum = fmaf(w1.y, hv[5] - p1.y, dsum);
-        dsum = fmaf(w1.z, hv[6] - p1.z, dsum);
-        dsum = fmaf(w1.w, hv[7] - p1.w, dsum);
-      }
-      s1 += (double)dsum;
-      s2 = fma((double)dsum, (double)dsum, s2);
-    }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) {
-      const double mean = s1 * inv_S;
-      const float var = (float)fmax(s2 * inv_S - mean * mean, 0.0);
-      atomicMax(R.exact_bits + cd.p, __float_as_uint(var));
-      // Screening check.  Below ~2^-24 * sum|w||h| (half an ulp of the decoded value's terms) a spread is fp32
-      // rounding noise in the reference as much as here (sigma of near-identical samples, e.g. at the GP's
-      // training points, where the activations h(s) - h(pilot) themselves carry 1e-2 relative rounding error):
-      // deviations inside that floor say nothing about the screening and are not counted.
-      const float se = sqrtf(var), sa = sqrtf(fmaxf(cd.var, 0.f) * R.unscale);
-      const float excess = fabsf(sa - se) - 6.0e-8f * xabs;
-      const float dev = (se > 0.f && excess > 0.f) ? excess / se : 0.f;
-      atomicMax(R.dev_bits, __float_as_uint(dev));
-      if (dev > R.dev_tol) atomicOr(R.flags + 2, 1);
     }
     __syncwarp();
+    refine_unit<ACT, INW, NC>(R, gr, sWl, ld, last_in_w, sWd, sPil, lane);
   }
 }
 
@@ -199,20 +267,23 @@ __global__ void __launch_bounds__(kRefWarps * 32) refine_kernel(const __grid_con
 
 int launch_select_candidates(glasdi_handle* h, const float* var_field, int field_ld, const unsigned int* approx_bits,
                              int P, int T, int D, float keep, cudaStream_t st) {
-  const long long n4 = (long long)T * field_ld / 4;
-  const int per_block = rf::kSelThreads * rf::kSelPerThread / 4;
-  dim3 grid((unsigned)((n4 + per_block - 1) / per_block), (unsigned)P);
-  rf::select_kernel<<<grid, rf::kSelThreads, 0, st>>>(var_field, field_ld, approx_bits, T, D, keep,
-                                                     reinterpret_cast<rf::Cand*>(h->d_cand), (unsigned)h->cand_cap,
-                                                     h->d_cand_stats, h->d_flags);
+  const long long n_rows = (long long)P * T;
+  const unsigned int blocks = (unsigned int)((n_rows + rf::kSelWarps - 1) / rf::kSelWarps);
+  rf::select_rows_kernel<<<blocks, rf::kSelWarps * 32, 0, st>>>(
+      var_field, field_ld, approx_bits, n_rows, T, D, keep, reinterpret_cast<rf::Cand*>(h->d_cand),
+      (unsigned)h->cand_cap, reinterpret_cast<rf::Group*>(h->d_groups), (unsigned)h->group_cap, h->d_cand_stats,
+      h->d_flags);
   h->launches++;
-  return check_cuda(h, cudaGetLastError(), "select_kernel launch");
+  return check_cuda(h, cudaGetLastError(), "select_rows_kernel launch");
 }
 
 template <int ACT, int INW>
 static int launch_refine_inst(glasdi_handle* h, const rf::RefParams& R, size_t smem, cudaStream_t st) {
-  GL_CUDA(h, cudaFuncSetAttribute(rf::refine_kernel<ACT, INW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rf::refine_kernel<ACT, INW><<<h->num_sms * 4, rf::kRefWarps * 32, smem, st>>>(R);
+  GL_CUDA(h, cudaFuncSetAttribute(rf::refine_kernel<ACT, INW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GL_CUDA(h, cudaFuncSetAttribute(rf::refine_kernel<ACT, INW, rf::kNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rf::refine_kernel<ACT, INW, 2><<<h->num_sms * 4, rf::kRefWarps * 32, smem, st>>>(R);
+  rf::refine_kernel<ACT, INW, rf::kNC><<<h->num_sms * 2, rf::kRefWarps * 32, smem, st>>>(R);
+  h->launches++;
   return GLASDI_OK;
 }
 
@@ -227,8 +298,9 @@ int launch_refine(glasdi_handle* h, const float* Zs, int Spad, int S, int T, uns
   R.Wlast = d.dW[d.n_linear - 1];
   R.Zs = Zs;
   R.cand = reinterpret_cast<const rf::Cand*>(h->d_cand);
+  R.groups = reinterpret_cast<const rf::Group*>(h->d_groups);
   R.stats = h->d_cand_stats;
-  R.cap = (unsigned)h->cand_cap;
+  R.gcap = (unsigned)h->group_cap;
   R.exact_bits = exact_bits;
   R.dev_bits = h->d_cand_stats + 2;
   R.flags = h->d_flags;
@@ -236,7 +308,8 @@ int launch_refine(glasdi_handle* h, const float* Zs, int Spad, int S, int T, uns
   R.unscale = unscale;              // screened variance -> true units
   R.dev_tol = dev_tol;
   const int last_in_w = d.widths[d.n_linear - 2];
-  const size_t smem = ((size_t)d.Kpad * dv::wl_stride(last_in_w) + (size_t)rf::kRefWarps * 2 * d.Kpad) * sizeof(float);
+  const size_t smem =
+      ((size_t)d.Kpad * dv::wl_stride(last_in_w) + (size_t)rf::kRefWarps * (rf::kNC + 1) * d.Kpad) * sizeof(float);
   int rc;
   // accurate libdevice activations (ACT >= 0 resolves the switch at compile time; -1 = runtime switch)
   if (R.front.n_front == 1 && R.NZ == 5) rc = launch_refine_inst<-1, 5>(h, R, smem, st);

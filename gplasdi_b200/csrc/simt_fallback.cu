@@ -237,4 +237,30 @@ int launch_decode_store_simt(glasdi_handle* h, const float* Z, int64_t rows, flo
   return rc;
 }
 
+// Encoder forward (reference latent_space.py:157-164 with reshape_index = 0): act(fc_i(x)) for the hidden layers, a
+// linear last layer.  U fp32 [rows, D] -> Z fp32 [rows, n_z].  The first layer reads U once (HBM-bound at D inputs per
+// row); the rest is a few KB per row.
+int launch_encode_simt(glasdi_handle* h, const float* U, int64_t rows, float* Z, cudaStream_t st) {
+  const Encoder& e = h->enc;
+  int maxw = 1;
+  for (int l = 1; l < e.n_linear; ++l) maxw = std::max(maxw, e.widths[l]);
+  float* scratch = nullptr;
+  if (e.n_linear > 1) GL_CUDA(h, cudaMallocAsync((void**)&scratch, (size_t)rows * maxw * 2 * sizeof(float), st));
+  float* bufs[2] = {scratch, scratch ? scratch + (size_t)rows * maxw : nullptr};
+  const float* cur = U;
+  int rc = GLASDI_OK;
+  for (int l = 0; l < e.n_linear && rc == GLASDI_OK; ++l) {
+    const bool last = l == e.n_linear - 1;
+    float* dst = last ? Z : bufs[l & 1];
+    dim3 grid((unsigned)((rows + simt::BM - 1) / simt::BM), (e.widths[l + 1] + simt::BN - 1) / simt::BN);
+    simt::linear_act_kernel<<<grid, 256, 0, st>>>(cur, e.dW[l], e.db[l], dst, rows, e.widths[l], e.widths[l + 1],
+                                                  last ? GLASDI_ACT_IDENTITY : e.act);
+    h->launches++;
+    rc = check_cuda(h, cudaGetLastError(), "encoder linear_act launch");
+    cur = dst;
+  }
+  if (scratch) cudaFreeAsync(scratch, st);
+  return rc;
+}
+
 }  // namespace glasdi

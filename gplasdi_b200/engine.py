@@ -34,6 +34,8 @@ class Engine:
         self.decoder_widths = None
         self.decoder_act = None
         self.decoder_owner = None   # module whose weights are currently packed in the handle
+        self.encoder_widths = None
+        self.encoder_owner = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -106,6 +108,35 @@ class Engine:
             self._check(self.lib.glasdi_set_decoder(self.h, n, wa, Wp, bp, _lib.ACT_IDS[act]))
         self.decoder_widths = widths
         self.decoder_act = act
+
+    def set_encoder(self, weights, biases, act: str):
+        """Encoder MLP, weights[l] [out, in] (nn.Linear layout); any widths."""
+        if act not in _lib.ACT_IDS:
+            raise ValueError(f"activation {act!r} is not supported by the CUDA encoder "
+                             f"(supported: {sorted(_lib.ACT_IDS)})")
+        Ws = [np.ascontiguousarray(torch.as_tensor(w).detach().cpu().numpy(), dtype=np.float32) for w in weights]
+        bs = [np.ascontiguousarray(torch.as_tensor(b).detach().cpu().numpy(), dtype=np.float32) for b in biases]
+        n = len(Ws)
+        widths = [Ws[0].shape[1]] + [w.shape[0] for w in Ws]
+        for l in range(n):
+            assert Ws[l].shape == (widths[l + 1], widths[l]) and bs[l].shape == (widths[l + 1],)
+        wa = (C.c_int * (n + 1))(*widths)
+        Wp = (C.c_void_p * n)(*[w.ctypes.data for w in Ws])
+        bp = (C.c_void_p * n)(*[b.ctypes.data for b in bs])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_set_encoder(self.h, n, wa, Wp, bp, _lib.ACT_IDS[act]))
+        self.encoder_widths = widths
+
+    def encode(self, U) -> torch.Tensor:
+        """U [..., D] fp32 -> Z [..., n_z] fp32."""
+        U = self._dev(U, torch.float32)
+        lead = U.shape[:-1]
+        rows = int(np.prod(lead)) if len(lead) else 1
+        assert U.shape[-1] == self.encoder_widths[0]
+        Z = torch.empty((rows, self.encoder_widths[-1]), dtype=torch.float32, device=self.tdev)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_encode(self.h, U.data_ptr(), rows, Z.data_ptr(), _stream_ptr()))
+        return Z.reshape(*lead, self.encoder_widths[-1])
 
     # ---- rollout -----------------------------------------------------------------------------
     def rollout(self, coefs, z0, T: int, dt: float) -> torch.Tensor:
@@ -248,6 +279,22 @@ class Engine:
                                                   order, coefs.data_ptr(), ls.data_ptr(), lc.data_ptr(),
                                                   info.data_ptr(), _stream_ptr()))
         return coefs, ls, lc, info
+
+    def sindy_fit_backward(self, Z, coefs, grad_ls, grad_lc, dt: float, fd_type: str = "sbp12", norm_order=1):
+        """Gradient of sum_b grad_ls[b] loss_sindy[b] + grad_lc[b] loss_coef[b] with respect to Z [B,T,n]."""
+        Z = self._dev(Z, torch.float32)
+        coefs = self._dev(coefs, torch.float32)
+        B, T, n = Z.shape
+        order = 2 if norm_order in (2, "fro") else 1
+        gs = None if grad_ls is None else self._dev(grad_ls, torch.float32).expand(B).contiguous()
+        gc = None if grad_lc is None else self._dev(grad_lc, torch.float32).expand(B).contiguous()
+        out = torch.empty_like(Z)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_sindy_fit_backward(
+                self.h, Z.data_ptr(), coefs.data_ptr(), None if gs is None else gs.data_ptr(),
+                None if gc is None else gc.data_ptr(), B, T, n, _lib.FD_IDS[fd_type], float(dt), order,
+                out.data_ptr(), _stream_ptr()))
+        return out
 
 
 _DEFAULT = {}

@@ -6,9 +6,11 @@
   sample    -> glasdi_rollout over the whole batch in one launch
 
 Signatures, return types and the coefficient layout (row-major flatten of the (dim+1, dim)
-least-squares solution, row 0 = constant term) are the reference's.  The losses returned by
-`calibrate` are detached: differentiating through the fit (used by the reference's training loop,
-gplasdi.py:186-197) is not part of the greedy-sampling path.
+least-squares solution, row 0 = constant term) are the reference's.  When `Z` carries an autograd
+graph (the reference's training loop backpropagates both losses into the encoder, gplasdi.py:186-197)
+the two losses returned by `calibrate` are differentiable: `_SindyFit` pairs the forward kernel with
+the analytic backward kernel `glasdi_sindy_fit_backward`; the coefficients are returned detached,
+as in the reference (sindy.py:80).
 """
 from __future__ import annotations
 
@@ -30,6 +32,27 @@ def _uniform_dt(t_grid) -> float:
     if not np.allclose(d, d[0], rtol=1e-9, atol=1e-14):
         raise ValueError("the CUDA rollout needs a uniform time grid (the reference's physics grids are uniform)")
     return float(d[0])
+
+
+class _SindyFit(torch.autograd.Function):
+    """(loss_sindy[B], loss_coef[B], coefs[B, n(n+1)], info[B]) of a batch of series on the CUDA kernels; the
+    backward is one launch of the analytic gradient kernel (no autograd graph through the solve)."""
+
+    @staticmethod
+    def forward(ctx, Z, engine, dt, fd_type, norm_order):
+        Zc = Z.detach().to(device=engine.tdev, dtype=torch.float32).contiguous()
+        coefs, ls, lc, info = engine.sindy_fit(Zc, dt, fd_type, norm_order)
+        ctx.save_for_backward(Zc, coefs)
+        ctx.engine, ctx.dt, ctx.fd_type, ctx.norm_order = engine, dt, fd_type, norm_order
+        ctx.in_device, ctx.in_dtype = Z.device, Z.dtype
+        ctx.mark_non_differentiable(coefs, info)
+        return ls, lc, coefs, info
+
+    @staticmethod
+    def backward(ctx, g_ls, g_lc, _g_coefs, _g_info):
+        Zc, coefs = ctx.saved_tensors
+        gZ = ctx.engine.sindy_fit_backward(Zc, coefs, g_ls, g_lc, ctx.dt, ctx.fd_type, ctx.norm_order)
+        return gZ.to(device=ctx.in_device, dtype=ctx.in_dtype), None, None, None, None
 
 
 class SINDy(LatentDynamics):
@@ -72,17 +95,20 @@ class SINDy(LatentDynamics):
         batched = Zt.dim() == 3
         if not batched:
             assert Zt.dim() == 2
-        Zb = Zt.detach() if batched else Zt.detach().unsqueeze(0)
-        assert Zb.shape[1] == self.nt or True   # the reference does not check nt either
-        assert Zb.shape[2] == self.dim
-        coefs, ls, lc, info = self.engine.sindy_fit(Zb, dt, self.fd_type, self.coef_norm_order)
+        Zb = Zt if batched else Zt.unsqueeze(0)
+        assert Zb.shape[2] == self.dim          # (the reference does not check nt either)
+        if compute_loss and torch.is_grad_enabled() and Zb.requires_grad:
+            ls, lc, coefs, info = _SindyFit.apply(Zb, self.engine, float(dt), self.fd_type, self.coef_norm_order)
+        else:
+            coefs, ls, lc, info = self.engine.sindy_fit(Zb.detach(), dt, self.fd_type, self.coef_norm_order)
         if batched:
             out = coefs.double().cpu().numpy() if numpy else coefs.cpu()
         else:
             out = coefs[0].cpu().numpy() if numpy else coefs[0].cpu()
         if not compute_loss:
             return out
-        return out, ls.sum().cpu(), lc.sum().cpu()
+        # losses live where Z lives (the reference computes them on the CPU copy of Z, gplasdi.py:183)
+        return out, ls.sum().to(Zt.device), lc.sum().to(Zt.device)
 
     def simulate(self, coefs, z0, t_grid):
         """One trajectory; returns np.ndarray fp64 [nt, dim] like scipy odeint does in the reference."""

@@ -123,6 +123,14 @@ def make_inputs(wl: Workload, p_slice: slice | None = None):
     return dict(coefs=coefs, z0=z0[idx], t_grid=t_grid, params=params[idx], mean=mean[idx], index=idx)
 
 
+def make_noisy_series(B: int, T: int, n: int, dt: float, seed: int = 0, noise: float = 0.02) -> np.ndarray:
+    """`make_latent_series` plus seeded white noise: the SINDy residual is then well above fp32 round-off, which
+    the gradient tests of the calibration losses need (an exactly affine series has a pure-noise residual)."""
+    Z = make_latent_series(B, T, n, dt, seed)
+    rs = np.random.RandomState(9000 + seed)
+    return (Z + noise * rs.normal(size=Z.shape)).astype(np.float32)
+
+
 def make_latent_series(B: int, T: int, n: int, dt: float, seed: int = 0) -> np.ndarray:
     """Well-conditioned training series for calibration tests: trajectories of an oscillatory
     affine system (cond([1|Z]) ~ 10-100, SURVEY.md §7 'lstsq semantics').  fp32 [B, T, n]."""

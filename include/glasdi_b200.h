@@ -188,6 +188,25 @@ int glasdi_sindy_fit(glasdi_handle* h, const float* Z, int B, int T, int n, int 
                      int norm_order, float* coefs_out, float* loss_sindy_out, float* loss_coef_out,
                      int32_t* info_out, void* stream);
 
+/* Encoder ----------------------------------------------------------------------------------------
+ * Replaces: autoencoder.encoder(X) forward (latent_space.py:135-171 with reshape_index = 0, built at :220-222), as
+ * called once per test parameter by initial_condition_latent (latent_space.py:30-63) -- here all
+ * parameters in one batch.  Weights in nn.Linear layout like glasdi_set_decoder; widths[0] = number of dofs,
+ * widths[n_linear] = n_z; any width.  U fp32 [rows, widths[0]] -> Z fp32 [rows, n_z]. */
+int glasdi_set_encoder(glasdi_handle* h, int n_linear, const int* widths, const float* const* W_host,
+                       const float* const* b_host, int act_id);
+int glasdi_encode(glasdi_handle* h, const float* U, int64_t rows, float* Z_out, void* stream);
+
+/* Backward of glasdi_sindy_fit.  Replaces: what torch autograd records through sparse.mm, linalg.lstsq, MSELoss and
+ * norm when the reference's training loop differentiates the two losses (gplasdi.py:186-197 -> sindy.py:66-77; the
+ * coefficients themselves are returned detached, sindy.py:80).
+ * Z [B, T, n] and coefs [B, n(n+1)] as passed to / returned by the forward; grad_loss_sindy / grad_loss_coef fp32 [B]
+ * upstream gradients of the per-series losses (NULL = 0); grad_Z_out fp32 [B, T, n] (NaN for a rank-deficient
+ * series).  Needs 2 * T * n * 4 bytes <= 200 KB of shared memory. */
+int glasdi_sindy_fit_backward(glasdi_handle* h, const float* Z, const float* coefs, const float* grad_loss_sindy,
+                              const float* grad_loss_coef, int B, int T, int n, int fd_id, double dt, int norm_order,
+                              float* grad_Z_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,27 @@ def calibrate(Z: torch.Tensor, dt: float, fd_type: str = "sbp12", coef_norm_orde
     return coefs, ls, lc
 
 
+def calibrate_grad(Z: torch.Tensor, dt: float, fd_type: str = "sbp12", coef_norm_order=1, w_sindy: float = 1.0,
+                   w_coef: float = 1.0, dtype=torch.float32) -> np.ndarray:
+    """d(w_sindy * loss_sindy + w_coef * loss_coef)/dZ by torch autograd through the reference's op sequence
+    (sparse.mm -> cat -> linalg.lstsq -> MSELoss / norm; reference sindy.py:66-77), losses summed over the
+    batch as the reference's training loop consumes them (gplasdi.py:186-190).  `dtype=torch.float64` gives the
+    round-off-free gradient used to judge fp32 results."""
+    Zb = Z if Z.dim() == 3 else Z.unsqueeze(0)
+    Zl = Zb.detach().to(dtype).clone().requires_grad_(True)
+    total = 0.0
+    for i in range(Zl.shape[0]):
+        nt = Zl.shape[1]
+        D = torch.from_numpy(fd_operator_dense(nt, fd_type)).to(dtype).to_sparse_coo()
+        dZdt = 1.0 / dt * torch.sparse.mm(D, Zl[i])
+        Zi = torch.cat([torch.ones(nt, 1, dtype=dtype), Zl[i]], dim=1)
+        coefs = torch.linalg.lstsq(Zi, dZdt).solution
+        total = total + w_sindy * torch.nn.functional.mse_loss(dZdt, Zi @ coefs) + w_coef * torch.norm(coefs, coef_norm_order)
+    total.backward()
+    g = Zl.grad.numpy()
+    return g if Z.dim() == 3 else g[0]
+
+
 def simulate(coefs: np.ndarray, z0: np.ndarray, t_grid: np.ndarray) -> np.ndarray:
     """One latent trajectory.  Reference sindy.py:104-117: coefficient vector = row-major
     flatten of the (n+1, n) lstsq solution; row 0 is the constant term; LSODA via scipy

@@ -74,6 +74,27 @@ def gen_calibrate():
     np.savez_compressed(os.path.join(HERE, "calibrate.npz"), **out)
 
 
+GRAD_CASES = [("sbp12", 3, 65, 1), ("sbp24", 2, 129, "fro"), ("sbp36", 2, 65, 1), ("sbp48", 2, 1001, "fro"),
+              ("sbp12", 2, 1001, 1)]
+GRAD_W = (0.7, 1.0e-3)          # weights of (loss_sindy, loss_coef): both terms contribute at the same order
+
+
+def gen_calibrate_grad():
+    """Z.grad after backpropagating the reference's own calibrate() losses (what train() does, gplasdi.py:186-197)."""
+    out = {}
+    for (name, B, T, order) in GRAD_CASES:
+        dt = 1.0 / (T - 1)
+        Z = torch.from_numpy(synth.make_noisy_series(B, T, 5, dt, seed=11)).requires_grad_(True)
+        ld = SINDy(5, T, {"sindy": {"fd_type": name, "coef_norm_order": order}})
+        coefs, ls, lc = ld.calibrate(Z, dt, compute_loss=True, numpy=True)
+        (GRAD_W[0] * ls + GRAD_W[1] * lc).backward()
+        key = f"{name}_B{B}_T{T}"
+        out[key + "_grad"] = Z.grad.numpy().copy()
+        out[key + "_loss_sindy"] = np.array([float(ls)])
+        out[key + "_loss_coef"] = np.array([float(lc)])
+    np.savez_compressed(os.path.join(HERE, "calibrate_grad.npz"), **out)
+
+
 def _rollout_ref(ld, coefs, z0, t_grid):
     P, S = coefs.shape[:2]
     Zis = np.zeros([P, S, len(t_grid), z0.shape[1]])
@@ -131,10 +152,16 @@ def gen_gp():
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also run config #1 (burgers1d_shipped, ~1 min)")
+    ap.add_argument("--only", default=None, help="regenerate one fixture family (e.g. calibrate_grad)")
     args = ap.parse_args()
     torch.manual_seed(0)
+    if args.only:
+        globals()["gen_" + args.only]()
+        print("done")
+        sys.exit(0)
     gen_fd()
     gen_calibrate()
+    gen_calibrate_grad()
     gen_gp()
     gen_greedy(["tiny", "small", "small_s200", "small_softplus"], "greedy_small.npz", keep_Z=True)
     if args.full:

@@ -88,6 +88,36 @@ def test_sindy_calibrate_return_contract(golden_dir):
     assert np.max(np.abs(Zsim - Z[0].numpy())) < 5e-2 * np.max(np.abs(Z[0].numpy()))
 
 
+def test_sindy_calibrate_is_differentiable_like_the_reference(golden_dir):
+    """The reference's training loop backpropagates calibrate()'s losses into the encoder (gplasdi.py:186-197):
+    same call, same Z.grad (fixture = the reference's own autograd), through an encoder-like upstream op too."""
+    g = np.load(os.path.join(golden_dir, "calibrate_grad.npz"))
+    T = 65; dt = 1.0 / (T - 1)
+    Z0 = torch.from_numpy(synth.make_noisy_series(3, T, 5, dt, seed=11))
+    ld = SINDy(5, T, {"sindy": {"fd_type": "sbp12", "coef_norm_order": 1}})
+    for dev in ("cpu", "cuda"):
+        Z = Z0.detach().clone().to(dev).requires_grad_(True)
+        coefs, ls, lc = ld.calibrate(Z, dt, compute_loss=True, numpy=True)
+        assert isinstance(coefs, np.ndarray) and coefs.dtype == np.float64          # detached, as in the reference
+        assert ls.requires_grad and lc.requires_grad and ls.device == Z.device
+        (0.7 * ls + 1.0e-3 * lc).backward()
+        ref = g["sbp12_B3_T65_grad"]
+        assert np.max(np.abs(Z.grad.cpu().numpy() - ref)) <= 1e-5 * np.max(np.abs(ref))
+    # chain rule through an upstream op, one series, Frobenius norm
+    ld2 = SINDy(5, T, {"sindy": {"fd_type": "sbp24", "coef_norm_order": "fro"}})
+    w = torch.linspace(0.5, 1.5, 5).requires_grad_(True)
+    out = ld2.calibrate(Z0[1] * w, dt, compute_loss=True)
+    (out[1] + 0.01 * out[2]).backward()
+    from oracle import reference_path as orc
+    gz = orc.calibrate_grad(Z0[1] * w.detach(), dt, "sbp24", "fro", 1.0, 0.01, dtype=torch.float64)
+    gw = (gz * Z0[1].numpy()).sum(0)
+    assert np.max(np.abs(w.grad.numpy() - gw)) <= 1e-4 * np.max(np.abs(gw))
+    # no graph requested -> plain (non-differentiable) losses, no autograd node
+    with torch.no_grad():
+        _, ls, lc = ld.calibrate(Z0.requires_grad_(True), dt)
+    assert not ls.requires_grad
+
+
 def test_autoencoder_decoder_is_cuda_kernel_and_matches_torch():
     phys = Physics()
     ae = _autoencoder(phys)

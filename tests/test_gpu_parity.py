@@ -18,6 +18,7 @@ import pytest
 import torch
 
 from gplasdi_b200 import synth, _lib
+from gplasdi_b200._lib import GlasdiError
 from oracle import reference_path as orc
 
 pytestmark = pytest.mark.gpu
@@ -118,6 +119,59 @@ def test_calibration_matches_reference(engine, golden_dir, name, case):
     # the reference sums both losses over the batch; ~1e-9 losses sit on the fp32 noise floor of dZdt
     np.testing.assert_allclose(float(ls.sum()), g[key + "_loss_sindy"][0], rtol=1e-4, atol=5e-11)
     np.testing.assert_allclose(float(lc.sum()), g[key + "_loss_coef"][0], rtol=1e-5)
+
+
+GRAD_CASES = [("sbp12", 3, 65, 1), ("sbp24", 2, 129, "fro"), ("sbp36", 2, 65, 1), ("sbp48", 2, 1001, "fro"),
+              ("sbp12", 2, 1001, 1)]
+GRAD_RTOL = 1e-5       # x max|grad|; the reference's own fp32 autograd sits 3e-7..7e-7 from the fp64 gradient
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_calibration_backward_matches_reference_autograd(engine, golden_dir, case):
+    """glasdi_sindy_fit_backward vs Z.grad of the reference's calibrate() losses (fixture generated by running the
+    reference, tests/golden/gen_golden.py::gen_calibrate_grad) and vs the oracle's fp64 autograd, term by term."""
+    name, B, T, order = case
+    g = np.load(os.path.join(golden_dir, "calibrate_grad.npz"))
+    dt = 1.0 / (T - 1)
+    Z = synth.make_noisy_series(B, T, 5, dt, seed=11)
+    coefs, ls, lc, info = engine.sindy_fit(Z, dt, name, order)
+    np.testing.assert_allclose(float(ls.sum()), g[f"{name}_B{B}_T{T}_loss_sindy"][0], rtol=1e-5)
+    np.testing.assert_allclose(float(lc.sum()), g[f"{name}_B{B}_T{T}_loss_coef"][0], rtol=1e-5)
+    ref = g[f"{name}_B{B}_T{T}_grad"]
+    scale = np.max(np.abs(ref))
+    ones = torch.ones(B)
+    got = engine.sindy_fit_backward(Z, coefs, 0.7 * ones, 1.0e-3 * ones, dt, name, order).cpu().numpy()
+    assert np.max(np.abs(got - ref)) <= GRAD_RTOL * scale
+    for ws, wc in [(1.0, 0.0), (0.0, 1.0)]:
+        g64 = orc.calibrate_grad(torch.from_numpy(Z), dt, name, order, ws, wc, dtype=torch.float64)
+        got = engine.sindy_fit_backward(Z, coefs, ws * ones, wc * ones, dt, name, order).cpu().numpy()
+        assert np.max(np.abs(got - g64)) <= GRAD_RTOL * np.max(np.abs(g64))
+    # per-series upstream gradients and NULL (= 0) terms
+    w = torch.arange(1, B + 1, dtype=torch.float32)
+    got = engine.sindy_fit_backward(Z, coefs, w, None, dt, name, order).cpu().numpy()
+    g64 = orc.calibrate_grad(torch.from_numpy(Z), dt, name, order, 1.0, 0.0, dtype=torch.float64)
+    assert np.max(np.abs(got - g64 * w.numpy()[:, None, None])) <= GRAD_RTOL * np.max(np.abs(g64)) * B
+
+
+@pytest.mark.parametrize("n", [1, 3, 8])
+def test_calibration_backward_other_latent_dimensions(engine, n):
+    T, dt = 97, 1.0 / 96
+    Z = synth.make_noisy_series(2, T, n, dt, seed=3)
+    coefs, ls, lc, info = engine.sindy_fit(Z, dt, "sbp24", 1)
+    got = engine.sindy_fit_backward(Z, coefs, torch.ones(2), 0.01 * torch.ones(2), dt, "sbp24", 1).cpu().numpy()
+    g64 = orc.calibrate_grad(torch.from_numpy(Z), dt, "sbp24", 1, 1.0, 0.01, dtype=torch.float64)
+    assert np.max(np.abs(got - g64)) <= GRAD_RTOL * np.max(np.abs(g64))
+
+
+def test_calibration_backward_rank_deficient_and_too_long(engine):
+    Z = np.zeros((2, 33, 5), dtype=np.float32)
+    Z[1] = synth.make_noisy_series(1, 33, 5, 1 / 32, seed=1)[0]
+    coefs, ls, lc, info = engine.sindy_fit(Z, 1 / 32, "sbp12", 1)
+    g = engine.sindy_fit_backward(Z, coefs, torch.ones(2), torch.ones(2), 1 / 32, "sbp12", 1).cpu().numpy()
+    assert np.all(np.isnan(g[0])) and np.all(np.isfinite(g[1]))
+    with pytest.raises(GlasdiError):
+        engine.sindy_fit_backward(np.zeros((1, 6000, 5), np.float32), np.zeros((1, 30), np.float32), None, None,
+                                  1e-3, "sbp12", 1)
 
 
 def test_calibration_flags_rank_deficient_series(engine):

@@ -50,6 +50,29 @@ def test_calibrate_matches_reference(golden_dir, name, case):
     np.testing.assert_allclose(lc, g[key + "_loss_coef"][0], rtol=1e-6)
 
 
+GRAD_CASES = [("sbp12", 3, 65, 1), ("sbp24", 2, 129, "fro"), ("sbp36", 2, 65, 1), ("sbp48", 2, 1001, "fro"),
+              ("sbp12", 2, 1001, 1)]
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_calibrate_gradient_matches_reference(golden_dir, case):
+    """Z.grad of the reference's own calibrate() losses (fixture) vs the oracle's autograd restatement, and both
+    against the fp64 evaluation of the same graph."""
+    name, B, T, order = case
+    g = np.load(os.path.join(golden_dir, "calibrate_grad.npz"))
+    dt = 1.0 / (T - 1)
+    Z = torch.from_numpy(synth.make_noisy_series(B, T, 5, dt, seed=11))
+    ref = g[f"{name}_B{B}_T{T}_grad"]
+    got = orc.calibrate_grad(Z, dt, name, order, 0.7, 1.0e-3)
+    g64 = orc.calibrate_grad(Z, dt, name, order, 0.7, 1.0e-3, dtype=torch.float64)
+    scale = np.max(np.abs(g64))
+    assert np.max(np.abs(got - ref)) <= 3e-6 * scale        # fp32 lstsq backward: not bit-reproducible across threads
+    assert np.max(np.abs(ref - g64)) <= 5e-6 * scale
+    # both loss terms are present in the fixture (the GPU tests also check each term on its own)
+    gs = orc.calibrate_grad(Z, dt, name, order, 0.7, 0.0, dtype=torch.float64)
+    assert 0.01 < np.max(np.abs(gs)) / scale and 5e-4 < np.max(np.abs(g64 - gs)) / scale
+
+
 @pytest.mark.parametrize("nm", ["tiny", "small", "small_s200", "small_softplus"])
 def test_greedy_small_matches_reference(golden_dir, nm):
     g = np.load(os.path.join(golden_dir, "greedy_small.npz"))
