@@ -39,6 +39,8 @@ SIGNATURES = {
     "glasdi_decode_max_std": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "glasdi_decode_stat_fields": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "glasdi_decode": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "glasdi_gp_predict": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "glasdi_normal_mt19937": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "glasdi_set_encoder": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_vp), _i]),
     "glasdi_encode": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "glasdi_check_numeric": (_i, [_vp, _vp]),
@@ -71,6 +73,11 @@ def load(build_if_missing: bool = True):
         fn.argtypes = args
     _LIB = lib
     return lib
+
+
+class Mt19937State(C.Structure):
+    """glasdi_mt19937_state of include/glasdi_b200.h = np.random.get_state() of the legacy global generator."""
+    _fields_ = [("key", C.c_uint32 * 624), ("pos", C.c_int32), ("has_gauss", C.c_int32), ("cached_gaussian", C.c_double)]
 
 
 class GlasdiError(RuntimeError):

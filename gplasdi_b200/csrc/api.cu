@@ -582,6 +582,29 @@ int glasdi_sindy_fit(glasdi_handle* h, const float* Z, int B, int T, int n, int 
                           (cudaStream_t)stream);
 }
 
+int glasdi_gp_predict(glasdi_handle* h, const double* X_train, int n_train, int n_param, int n_gp, const double* alpha,
+                      const double* L, const double* amplitude, const double* length_scale, const double* y_mean,
+                      const double* y_std, const double* X_test, int P, double* mean_out, double* std_out,
+                      void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!X_train || !alpha || !L || !amplitude || !length_scale || !X_test || !mean_out || !std_out)
+    return set_error(h, GLASDI_ERR_INVALID, "gp_predict: null pointer");
+  if (n_train < 1 || n_param < 1 || n_gp < 1 || P < 1) return set_error(h, GLASDI_ERR_INVALID, "gp_predict: empty input");
+  GL_CUDA(h, cudaSetDevice(h->device));
+  return launch_gp_predict(h, X_train, n_train, n_param, n_gp, alpha, L, amplitude, length_scale, y_mean, y_std, X_test,
+                           P, mean_out, std_out, (cudaStream_t)stream);
+}
+
+int glasdi_normal_mt19937(glasdi_handle* h, glasdi_mt19937_state* state, const double* mean, const double* std, int P,
+                          int S, int n, double* out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!state || P < 0 || S < 0 || n < 0) return set_error(h, GLASDI_ERR_INVALID, "normal_mt19937: bad arguments");
+  if ((long long)P * S * n > 0 && (!mean || !std || !out))
+    return set_error(h, GLASDI_ERR_INVALID, "normal_mt19937: null pointer");
+  GL_CUDA(h, cudaSetDevice(h->device));
+  return launch_normal_mt19937(h, state, mean, std, P, S, n, out, (cudaStream_t)stream);
+}
+
 int glasdi_set_encoder(glasdi_handle* h, int n_linear, const int* widths, const float* const* W_host,
                        const float* const* b_host, int act_id) {
   if (!h) return GLASDI_ERR_INVALID;

@@ -166,6 +166,13 @@ int launch_sindy_fit_backward(glasdi_handle* h, const float* Z, const float* coe
                               const float* g_coef, int B, int T, int n, int fd_id, double dt, int norm_order,
                               float* Zbar, cudaStream_t st);
 
+// gp.cu : GP posterior moments and numpy-legacy (MT19937 + polar Box-Muller) normal draws
+int launch_gp_predict(glasdi_handle* h, const double* Xtr, int ntr, int d, int n_gp, const double* alpha,
+                      const double* L, const double* amp, const double* len, const double* ymean, const double* ystd,
+                      const double* Xte, int P, double* mean, double* stdv, cudaStream_t st);
+int launch_normal_mt19937(glasdi_handle* h, glasdi_mt19937_state* state, const double* mean, const double* stdv, int P,
+                          int S, int n, double* out, cudaStream_t st);
+
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__
 

@@ -250,6 +250,55 @@ class Engine:
                                                     key.data_ptr(), _stream_ptr()))
         return key
 
+    # ---- GP posterior + coefficient draws ------------------------------------------------------------
+    def gp_predict(self, X_train, alpha, L, amplitude, length_scale, X_test, y_mean=None, y_std=None):
+        """Posterior mean / std [P, n_gp] (CUDA fp64) of n_gp independent ConstantKernel * RBF GPs that share the
+        training inputs X_train [n_train, d]: alpha [n_gp, n_train], L [n_gp, n_train, n_train] (lower Cholesky)."""
+        f64 = torch.float64
+        Xtr = self._dev(X_train, f64); al = self._dev(alpha, f64); Lc = self._dev(L, f64)
+        amp = self._dev(amplitude, f64); ls = self._dev(length_scale, f64); Xte = self._dev(X_test, f64)
+        ym = None if y_mean is None else self._dev(y_mean, f64)
+        ys = None if y_std is None else self._dev(y_std, f64)
+        n_train, d = Xtr.shape
+        n_gp = al.shape[0]
+        P = Xte.shape[0]
+        assert al.shape == (n_gp, n_train) and Lc.shape == (n_gp, n_train, n_train) and Xte.shape[1] == d
+        mean = torch.empty((P, n_gp), dtype=f64, device=self.tdev)
+        std = torch.empty((P, n_gp), dtype=f64, device=self.tdev)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_gp_predict(
+                self.h, Xtr.data_ptr(), n_train, d, n_gp, al.data_ptr(), Lc.data_ptr(), amp.data_ptr(), ls.data_ptr(),
+                None if ym is None else ym.data_ptr(), None if ys is None else ys.data_ptr(), Xte.data_ptr(), P,
+                mean.data_ptr(), std.data_ptr(), _stream_ptr()))
+        return mean, std
+
+    def normal_mt19937(self, mean, std, n_samples: int, state=None):
+        """out[p, s, k] = mean[p, k] + std[p, k] * g with g drawn from numpy's LEGACY generator stream in (p, s, k)
+        order -- the stream `np.random.normal` consumes in the reference's sampling loop.  `state` is a
+        `np.random.get_state()` tuple; None = use AND ADVANCE numpy's global generator (np.random.seed-compatible).
+        Returns (out CUDA fp64 [P, S, n], new_state tuple)."""
+        f64 = torch.float64
+        mean = self._dev(mean, f64); std = self._dev(std, f64)
+        P, n = mean.shape
+        assert std.shape == (P, n)
+        use_global = state is None
+        if use_global:
+            state = np.random.get_state()
+        if state[0] != "MT19937":
+            raise ValueError("normal_mt19937 needs a legacy MT19937 state")
+        cs = _lib.Mt19937State()
+        C.memmove(cs.key, np.ascontiguousarray(state[1], dtype=np.uint32).ctypes.data, 624 * 4)
+        cs.pos, cs.has_gauss, cs.cached_gaussian = int(state[2]), int(state[3]), float(state[4])
+        out = torch.empty((P, int(n_samples), n), dtype=f64, device=self.tdev)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_normal_mt19937(self.h, C.byref(cs), mean.data_ptr(), std.data_ptr(), P,
+                                                       int(n_samples), n, out.data_ptr(), _stream_ptr()))
+        new_state = ("MT19937", np.ctypeslib.as_array(cs.key).astype(np.uint32).copy(), int(cs.pos), int(cs.has_gauss),
+                     float(cs.cached_gaussian))
+        if use_global:
+            np.random.set_state(new_state)
+        return out, new_state
+
     # ---- calibration ---------------------------------------------------------------------------
     def fd_dzdt(self, Z, dt: float, fd_type: str = "sbp12") -> torch.Tensor:
         Z = self._dev(Z, torch.float32)

@@ -15,7 +15,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .gp import eval_gp, fit_gps, sample_coefs, sample_coefs_all
+from .gp import eval_gp, fit_gps, sample_coefs, sample_coefs_all, sample_coefs_all_device
 from .latent_space import initial_condition_latent
 from .engine import default_engine
 from . import sharding
@@ -132,7 +132,9 @@ class BayesianGLaSDI:
 
         Z0 = np.stack(initial_condition_latent(ps.test_space, self.physics, ae))
         gp_dictionnary = fit_gps(ps.train_space, self.best_coefs)
-        coef_samples = sample_coefs_all(gp_dictionnary, ps.test_space, self.n_samples)
+        eng = _engine_for(ae)
+        # posterior moments and the (p, s, k)-ordered legacy-stream draws on the device: [n_test, n_samples, n_coef] fp64
+        coef_samples = sample_coefs_all_device(gp_dictionnary, ps.test_space, self.n_samples, eng)
 
         import torch.distributed as dist
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -140,7 +142,6 @@ class BayesianGLaSDI:
         bounds = sharding.shard_bounds(n_test, world)
         lo, hi = bounds[rank], bounds[rank + 1]
 
-        eng = _engine_for(ae)
         dt = float(self.physics.t_grid[1] - self.physics.t_grid[0]) if len(self.physics.t_grid) > 1 else 0.0
         ms, key = sharding.sharded_greedy_step(eng, coef_samples[lo:hi], Z0[lo:hi], len(self.physics.t_grid), dt,
                                                lo, group)

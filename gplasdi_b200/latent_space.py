@@ -5,12 +5,12 @@ Same constructor signatures, attribute names (`encoder`, `decoder`, `n_z`, `qgri
 `state_dict` keys (`encoder.fcs.{i}.weight/bias`, `decoder.fcs.{i}.weight/bias`) as the reference,
 so checkpoints written by either implementation load in the other.
 
-`MultiLayerPerceptron.forward` runs on the hand-written CUDA decoder kernel (glasdi_decode) when
-it is used for inference -- no autograd graph requested -- which is how the greedy-sampling path
-calls the decoder (reference gplasdi.py:66, postprocess.py:32).  When gradients are required (the
-training loop, outside this package's hot path) it evaluates with ordinary differentiable torch
-ops, because the CUDA kernel has no backward.  The encoder (reshape_index == 0) always uses torch
-ops: it is not on the hot path.
+`MultiLayerPerceptron.forward` runs on the hand-written CUDA kernels (glasdi_decode for the decoder,
+glasdi_encode for the encoder) when it is used for inference -- no autograd graph requested -- which
+is how the greedy-sampling path calls them (reference gplasdi.py:66, postprocess.py:32,
+latent_space.py:57).  When gradients are required (the training loop) it evaluates with ordinary
+differentiable torch ops, because the CUDA kernels have no backward.  `initial_condition_latent`
+encodes all test parameters in ONE batched call instead of the reference's loop.
 """
 from __future__ import annotations
 
@@ -41,8 +41,12 @@ def initial_condition_latent(param_grid, physics, autoencoder):
     sol_shape = [1] + list(physics.qgrid_size)
     U0 = np.stack([np.asarray(physics.initial_condition(param_grid[i])).reshape(sol_shape) for i in range(n_param)])
     with torch.no_grad():
-        dev = next(autoencoder.parameters()).device
-        Z0 = autoencoder.encoder(torch.Tensor(U0).to(dev))
+        enc = autoencoder.encoder
+        if isinstance(enc, MultiLayerPerceptron):
+            Z0 = enc(torch.Tensor(U0))                       # CUDA encoder kernel (glasdi_encode), one batch
+        else:                                                # foreign module (e.g. the reference's own encoder)
+            dev = next(autoencoder.parameters()).device
+            Z0 = enc(torch.Tensor(U0).to(dev))
     Z0 = Z0[:, 0, :].detach().cpu().numpy()
     return [Z0[i] for i in range(n_param)]
 
@@ -90,6 +94,25 @@ class MultiLayerPerceptron(torch.nn.Module):
         if self.n_layers < 3 or self.layer_sizes[0] > 8:
             raise NotImplementedError("CUDA decoder needs >= 1 hidden layer and latent dimension <= 8")
 
+    def _require_cuda_encoder(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("gplasdi_b200 encoder inference needs a B200 GPU (no CPU fallback); "
+                               "enable grad to evaluate with differentiable torch ops for training")
+        if self.act_type not in _lib.ACT_IDS:
+            raise NotImplementedError(f"activation {self.act_type!r} has no CUDA encoder kernel "
+                                      f"(supported: {sorted(_lib.ACT_IDS)})")
+
+    def _engine_with_encoder_weights(self):
+        from .engine import default_engine
+        if self._engine is None:
+            self._engine = default_engine()
+        ver = self._weights_version()
+        if self._packed_version != ver or self._engine.encoder_owner is not self:
+            self._engine.set_encoder([fc.weight for fc in self.fcs], [fc.bias for fc in self.fcs], self.act_type)
+            self._engine.encoder_owner = self
+            self._packed_version = ver
+        return self._engine
+
     def _engine_with_weights(self):
         from .engine import default_engine
         if self._engine is None:
@@ -112,8 +135,13 @@ class MultiLayerPerceptron(torch.nn.Module):
             self._require_cuda_decoder()
             eng = self._engine_with_weights()
             y = eng.decode(x.detach().to(torch.float32)).to(x.device)
+        elif not needs_grad:
+            # encoder inference (initial_condition_latent): CUDA kernel chain through the C ABI, or raise
+            self._require_cuda_encoder()
+            eng = self._engine_with_encoder_weights()
+            y = eng.encode(x.detach().to(torch.float32)).to(x.device)
         else:
-            # encoder, or an autograd graph is being recorded (training): differentiable torch ops
+            # an autograd graph is being recorded (training): differentiable torch ops
             y = x
             for i in range(self.n_layers - 2):
                 y = self.act(self.fcs[i](y))

@@ -188,6 +188,36 @@ int glasdi_sindy_fit(glasdi_handle* h, const float* Z, int B, int T, int n, int 
                      int norm_order, float* coefs_out, float* loss_sindy_out, float* loss_coef_out,
                      int32_t* info_out, void* stream);
 
+/* GP posterior and coefficient draws ---------------------------------------
+ * Replaces: eval_gp (src/lasdi/gp.py:36-53) = GaussianProcessRegressor.predict(X, return_std=True) of every
+ * coefficient's GP, for the kernel fit_gps builds (ConstantKernel * RBF, gp.py:28): k(x, x') = amplitude *
+ * exp(-|x - x'|^2 / (2 length_scale^2)).  All arrays fp64 device pointers: X_train [n_train, n_param]; per GP k:
+ * alpha [n_gp, n_train] (gp.alpha_), L [n_gp, n_train, n_train] (gp.L_, lower Cholesky factor, row-major),
+ * amplitude / length_scale [n_gp], y_mean / y_std [n_gp] (gp._y_train_mean/_std; NULL = 0 / 1);
+ * X_test [P, n_param] -> mean_out, std_out [P, n_gp].  n_train <= 400. */
+int glasdi_gp_predict(glasdi_handle* h, const double* X_train, int n_train, int n_param, int n_gp, const double* alpha,
+                      const double* L, const double* amplitude, const double* length_scale, const double* y_mean,
+                      const double* y_std, const double* X_test, int P, double* mean_out, double* std_out,
+                      void* stream);
+
+/* State of numpy's legacy global generator, np.random.get_state(): ('MT19937', key, pos, has_gauss, cached_gaussian). */
+typedef struct glasdi_mt19937_state {
+  uint32_t key[624];
+  int32_t pos;
+  int32_t has_gauss;
+  double cached_gaussian;
+} glasdi_mt19937_state;
+
+/* Replaces: the double loop `coef_samples[s, k] = np.random.normal(pred_mean[k], pred_std[k])` of sample_coefs
+ * (gp.py:76-78) run for every test parameter in turn (gplasdi.py:260), with the SAME stream: out[p, s, k] =
+ * mean[p, k] + std[p, k] * g, g = the next value of numpy's legacy_gauss (MT19937 -> 53-bit doubles -> polar
+ * Box-Muller with rejection and a cached second value), in (p, s, k) order.  `state` (HOST, in/out) is the generator
+ * state before / after the call, so a seeded run continues on the host exactly where the reference would.
+ * mean, std fp64 device [P, n]; out fp64 device [P, S, n].  Values match numpy up to the rounding of log() (<= 1 ulp).
+ * Synchronises `stream` before returning (the new state is a host result). */
+int glasdi_normal_mt19937(glasdi_handle* h, glasdi_mt19937_state* state, const double* mean, const double* std, int P,
+                          int S, int n, double* out, void* stream);
+
 /* Encoder ----------------------------------------------------------------------------------------
  * Replaces: autoencoder.encoder(X) forward (latent_space.py:135-171 with reshape_index = 0, built at :220-222), as
  * called once per test parameter by initial_condition_latent (latent_space.py:30-63) -- here all

@@ -196,6 +196,24 @@ def decoder_forward(weights, biases, act: str, z: torch.Tensor) -> torch.Tensor:
 # gplasdi.py: get_fom_max_std
 # ----------------------------------------------------------------------------------------
 
+def encode_initial_conditions(weights, biases, act: str, U0: np.ndarray) -> np.ndarray:
+    """Z0[i] = encoder(u0_i), one parameter at a time with a [1, 1, D] input, as the loop of
+    `initial_condition_latent` does (reference src/lasdi/latent_space.py:49-61; encoder forward :157-164).
+    U0 [P, D] -> fp32 [P, n_z]."""
+    a = _activation(act)
+    Ws = [torch.as_tensor(np.asarray(w), dtype=torch.float32) for w in weights]
+    bs = [torch.as_tensor(np.asarray(b), dtype=torch.float32) for b in biases]
+    out = []
+    with torch.no_grad():
+        for u in np.asarray(U0):
+            x = torch.Tensor(np.asarray(u).reshape(1, 1, -1))
+            for l in range(len(Ws) - 1):
+                x = a(torch.nn.functional.linear(x, Ws[l], bs[l]))
+            x = torch.nn.functional.linear(x, Ws[-1], bs[-1])
+            out.append(x[0, 0, :].numpy())
+    return np.stack(out)
+
+
 def fom_max_std(weights, biases, act: str, Zis: np.ndarray, t_chunk: int | None = None):
     """Per-parameter max over (t, dof) of the population std over samples, and the
     first-strict-maximum index.  Reference src/lasdi/gplasdi.py:52-74: fp64 -> fp32 cast of

@@ -95,6 +95,40 @@ def gen_calibrate_grad():
     np.savez_compressed(os.path.join(HERE, "calibrate_grad.npz"), **out)
 
 
+class _Phys:     # what initial_condition_latent reads (reference src/lasdi/physics/__init__.py:4-79)
+    def __init__(self, nx):
+        self.qgrid_size = [nx]
+        self.x_grid = np.linspace(-3.0, 3.0, nx)
+
+    def initial_condition(self, param):
+        a, w = param
+        return a * np.exp(-self.x_grid ** 2 / 2 / w / w)
+
+
+ENC_CASES = [(301, [100], "sigmoid", 3), (257, [64, 32], "softplus", 4), (1001, [100], "tanh", 5)]
+
+
+def gen_encoder():
+    """Z0 of the reference's initial_condition_latent (its per-parameter loop) with the reference's own Autoencoder,
+    initialised under torch.manual_seed; the weights are stored too (the CUDA tests load them verbatim)."""
+    from lasdi.latent_space import Autoencoder, initial_condition_latent
+    out = {}
+    a = np.linspace(0.7, 0.9, 4); w = np.linspace(0.9, 1.1, 3)
+    A, W = np.meshgrid(a, w, indexing="ij")
+    grid = np.stack([A.ravel(), W.ravel()], axis=1)
+    out["param_grid"] = grid
+    for (nx, hidden, act, seed) in ENC_CASES:
+        torch.manual_seed(seed)
+        ae = Autoencoder(_Phys(nx), {"hidden_units": hidden, "latent_dimension": 5, "activation": act})
+        Z0 = np.stack(initial_condition_latent(grid, _Phys(nx), ae))
+        key = f"nx{nx}_{act}"
+        out[key + "_Z0"] = Z0
+        for k, v in ae.state_dict().items():
+            if k.startswith("encoder."):
+                out[key + "_" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "encoder.npz"), **out)
+
+
 def _rollout_ref(ld, coefs, z0, t_grid):
     P, S = coefs.shape[:2]
     Zis = np.zeros([P, S, len(t_grid), z0.shape[1]])
@@ -162,6 +196,7 @@ if __name__ == "__main__":
     gen_fd()
     gen_calibrate()
     gen_calibrate_grad()
+    gen_encoder()
     gen_gp()
     gen_greedy(["tiny", "small", "small_s200", "small_softplus"], "greedy_small.npz", keep_Z=True)
     if args.full:

@@ -140,6 +140,28 @@ def test_autoencoder_decoder_is_cuda_kernel_and_matches_torch():
     assert Xg.requires_grad
 
 
+def test_initial_condition_latent_dropin(golden_dir):
+    """Same call as the reference (latent_space.py:30-63): list of fp32 [n_z] vectors, from ONE batched CUDA encode."""
+    from gplasdi_b200.latent_space import initial_condition_latent
+    g = np.load(os.path.join(golden_dir, "encoder.npz"))
+    phys = Physics(nx=301)
+    ae = Autoencoder(phys, {"hidden_units": [100], "latent_dimension": 5, "activation": "sigmoid"})
+    sd = ae.state_dict()
+    for k in list(sd):
+        if k.startswith("encoder."):
+            sd[k] = torch.from_numpy(g["nx301_sigmoid_" + k])
+    ae.load_state_dict(sd)
+    from gplasdi_b200.engine import default_engine
+    n0 = default_engine().launch_count
+    Z0 = initial_condition_latent(g["param_grid"], phys, ae)
+    assert isinstance(Z0, list) and len(Z0) == 12 and Z0[0].dtype == np.float32 and Z0[0].shape == (5,)
+    ref = g["nx301_sigmoid_Z0"]
+    assert np.max(np.abs(np.stack(Z0) - ref)) <= 1e-5 * np.max(np.abs(ref))
+    assert ae.encoder._engine.launch_count - n0 == 2          # two layers, all 12 parameters at once
+    Zg = ae.encoder(torch.zeros(2, 1, 301, requires_grad=True))      # autograd requested: torch ops
+    assert Zg.requires_grad
+
+
 def test_get_fom_max_std_dropin(golden_dir):
     g = np.load(os.path.join(golden_dir, "greedy_small.npz"))
     wl = synth.WORKLOADS["small"]

@@ -183,6 +183,108 @@ def test_calibration_flags_rank_deficient_series(engine):
     assert np.all(np.isnan(coefs[0].cpu().numpy())) and np.all(np.isfinite(coefs[1].cpu().numpy()))
 
 
+# ---- GP posterior + coefficient draws -------------------------------------------------------------------
+def test_gp_posterior_matches_reference_eval_gp(engine, golden_dir):
+    """glasdi_gp_predict vs the reference's eval_gp (fixture: single-point sklearn predicts, gp.py:36-53) and vs
+    scikit-learn on the whole 21 x 21 grid of the shipped example."""
+    import warnings
+    from gplasdi_b200.gp import fit_gps, eval_gp, eval_gp_device
+    g = np.load(os.path.join(golden_dir, "gp_sampling.npz"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gps = fit_gps(g["X"], g["Y"])
+    mean, std = eval_gp_device(gps, g["test"], engine)
+    mean, std = mean.cpu().numpy(), std.cpu().numpy()
+    assert mean.dtype == np.float64 and mean.shape == (3, 30)
+    assert np.max(np.abs(mean - g["mean"])) <= 1e-12 * np.max(np.abs(g["mean"]))
+    # var = c - |L^-1 k*|^2 cancels to ~1e-10 at the training points: std there is sqrt(rounding noise) in sklearn too
+    assert np.max(np.abs(std - g["std"])) <= 1e-8
+    a = np.linspace(0.7, 0.9, 21); w = np.linspace(0.9, 1.1, 21)
+    A, W = np.meshgrid(a, w, indexing="ij")
+    grid = np.stack([A.ravel(), W.ravel()], axis=1)
+    m_ref, s_ref = eval_gp(gps, grid)
+    mean, std = eval_gp_device(gps, grid, engine)
+    assert np.max(np.abs(mean.cpu().numpy() - m_ref)) <= 1e-12 * np.max(np.abs(m_ref))
+    assert np.max(np.abs(std.cpu().numpy() - s_ref)) <= 1e-8
+
+
+def _numpy_draws(mean, std, S):
+    return np.stack([np.random.normal(mean[i][None, :], std[i][None, :], size=(S, mean.shape[1]))
+                     for i in range(mean.shape[0])])
+
+
+@pytest.mark.parametrize("case", [(3, 6, 30, 0), (1, 1, 1, 0), (2, 5, 3, 1), (7, 33, 30, 1), (5, 1, 7, 3), (40, 257, 30, 0)])
+def test_normal_draws_reproduce_numpy_legacy_stream(engine, case):
+    """glasdi_normal_mt19937 vs np.random.normal on the same seeded legacy stream: same values (to the rounding of
+    log), same generator state afterwards -- including a cached gaussian, odd counts and mid-block positions."""
+    P, S, n, predraw = case
+    rs = np.random.RandomState(100 + P)
+    mean = rs.normal(size=(P, n)); std = rs.uniform(0.1, 2.0, size=(P, n))
+    np.random.seed(1234 + S)
+    if predraw:
+        np.random.normal(size=predraw)               # odd count leaves a cached gaussian; also moves the position
+        np.random.random_sample(predraw)
+    st0 = np.random.get_state()
+    ref = _numpy_draws(mean, std, S)
+    st_ref = np.random.get_state()
+    tail_ref = np.random.normal(size=5)
+    np.random.set_state(st0)
+    out, st_new = engine.normal_mt19937(mean, std, S)              # uses and advances numpy's global generator
+    out = out.cpu().numpy()
+    assert out.shape == (P, S, n)
+    assert np.max(np.abs(out - ref)) <= 1e-14 * np.max(np.abs(ref))
+    assert np.array_equal(st_new[1], st_ref[1]) and st_new[2] == st_ref[2] and st_new[3] == st_ref[3]
+    assert abs(st_new[4] - st_ref[4]) <= 1e-14 * max(1.0, abs(st_ref[4]))
+    np.testing.assert_allclose(np.random.normal(size=5), tail_ref, rtol=1e-13)    # the host stream continues in step
+
+
+def test_normal_draws_match_reference_sample_coefs(engine, golden_dir):
+    """Fixture = the reference's own sample_coefs loop (gp.py:55-80) under np.random.seed(5)."""
+    g = np.load(os.path.join(golden_dir, "gp_sampling.npz"))
+    np.random.seed(int(g["seed"][0]))
+    out, _ = engine.normal_mt19937(g["mean"], g["std"], g["samples"].shape[1])
+    assert np.max(np.abs(out.cpu().numpy() - g["samples"])) <= 1e-13 * np.max(np.abs(g["samples"]))
+
+
+def test_normal_draws_block_boundaries_and_explicit_state(engine):
+    """Every read position of the 624-word block, explicit-state call leaves numpy's global generator untouched."""
+    mean = np.zeros((1, 1)); std = np.ones((1, 1))
+    for skip in [0, 1, 310, 311, 312, 620, 623]:
+        np.random.seed(7)
+        np.random.random_sample(skip)                  # 2 words each
+        st0 = np.random.get_state()
+        ref = np.random.normal(size=317)
+        st_ref = np.random.get_state()
+        np.random.set_state(st0)
+        out, st_new = engine.normal_mt19937(mean, std, 317, state=st0)
+        assert np.array_equal(np.random.get_state()[1], st0[1]) and np.random.get_state()[2] == st0[2]
+        assert np.max(np.abs(out.cpu().numpy().ravel() - ref)) <= 1e-14 * np.max(np.abs(ref))
+        assert np.array_equal(st_new[1], st_ref[1]) and st_new[2:4] == st_ref[2:4]
+
+
+# ---- encoder ---------------------------------------------------------------------------------------
+ENC_CASES = [(301, 2, "sigmoid"), (257, 3, "softplus"), (1001, 2, "tanh")]
+Z0_RTOL = 1e-5
+
+
+@pytest.mark.parametrize("case", ENC_CASES)
+def test_encoder_matches_reference_initial_conditions(engine, golden_dir, case):
+    """glasdi_encode (all parameters in one batch) vs the reference's per-parameter initial_condition_latent."""
+    from test_oracle_golden import encoder_case
+    g = np.load(os.path.join(golden_dir, "encoder.npz"))
+    Ws, bs, U0, Z0 = encoder_case(g, *case)
+    engine.set_encoder(Ws, bs, case[2])
+    got = engine.encode(U0.astype(np.float32)).cpu().numpy()
+    assert got.shape == Z0.shape
+    assert np.max(np.abs(got - Z0)) <= Z0_RTOL * np.max(np.abs(Z0))
+    # ragged row counts (tiles of 64 rows) and a leading batch shape
+    big = np.tile(U0, (11, 1))[:131].astype(np.float32)
+    got = engine.encode(big.reshape(131, 1, -1)).cpu().numpy()
+    assert got.shape == (131, 1, 5)
+    ref = orc.encode_initial_conditions(Ws, bs, case[2], big)
+    assert np.max(np.abs(got[:, 0] - ref)) <= Z0_RTOL * np.max(np.abs(ref))
+
+
 # ---- fused greedy step -------------------------------------------------------------------------
 @pytest.mark.parametrize("nm", ["tiny", "small", "small_s200", "small_softplus"])
 @pytest.mark.parametrize("mode", [_lib.MODE_SCREENED_GRAM, _lib.MODE_SCREENED])

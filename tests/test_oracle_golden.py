@@ -73,6 +73,27 @@ def test_calibrate_gradient_matches_reference(golden_dir, case):
     assert 0.01 < np.max(np.abs(gs)) / scale and 5e-4 < np.max(np.abs(g64 - gs)) / scale
 
 
+ENC_CASES = [(301, 2, "sigmoid"), (257, 3, "softplus"), (1001, 2, "tanh")]
+
+
+def encoder_case(g, nx, n_linear, act):
+    key = f"nx{nx}_{act}"
+    Ws = [g[f"{key}_encoder.fcs.{i}.weight"] for i in range(n_linear)]
+    bs = [g[f"{key}_encoder.fcs.{i}.bias"] for i in range(n_linear)]
+    x = np.linspace(-3.0, 3.0, nx)
+    U0 = np.stack([a * np.exp(-x ** 2 / 2 / w / w) for a, w in g["param_grid"]])
+    return Ws, bs, U0, g[key + "_Z0"]
+
+
+@pytest.mark.parametrize("case", ENC_CASES)
+def test_initial_condition_latent_matches_reference(golden_dir, case):
+    g = np.load(os.path.join(golden_dir, "encoder.npz"))
+    Ws, bs, U0, Z0 = encoder_case(g, *case)
+    got = orc.encode_initial_conditions(Ws, bs, case[2], U0)
+    assert got.dtype == np.float32 and got.shape == Z0.shape
+    assert np.max(np.abs(got - Z0)) <= 2e-6 * np.max(np.abs(Z0))     # same torch ops; MKL blocking may differ by an ulp
+
+
 @pytest.mark.parametrize("nm", ["tiny", "small", "small_s200", "small_softplus"])
 def test_greedy_small_matches_reference(golden_dir, nm):
     g = np.load(os.path.join(golden_dir, "greedy_small.npz"))
