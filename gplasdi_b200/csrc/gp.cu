@@ -67,9 +67,11 @@ __global__ void __launch_bounds__(kPredThreads) gp_predict_kernel(
 }
 
 // ---- MT19937 -------------------------------------------------------------------------------------------------
-constexpr int kMtN = 624, kMtM = 397, kMtLag = kMtN - kMtM;        // 227 new words per step
-constexpr int kMtThreads = 256;
-constexpr unsigned int kRing = 1024;
+constexpr int kMtN = 624, kMtM = 397, kMtLag = kMtN - kMtM;        // lag 227
+constexpr int kMtStep = kMtN - 1;                                  // 623 new words per barrier
+constexpr int kMtThreads = 256;                                    // 227 of them produce (up to three words each)
+constexpr int kMtWinSteps = 12;                                    // steps before the window slides back
+constexpr int kMtWin = kMtN + kMtWinSteps * kMtStep;               // shared-memory window, linear addressing
 
 __device__ __forceinline__ unsigned int mt_twist(unsigned int a, unsigned int b) {
   const unsigned int y = (a & 0x80000000u) | (b & 0x7fffffffu);
@@ -83,28 +85,66 @@ __device__ __forceinline__ unsigned int mt_temper(unsigned int y) {
   return y;
 }
 
-// X[0 .. 624) = the generator's current key block; X[i] = X[i - 227] ^ twist(X[i - 624], X[i - 623]) for i >= 624
+// X[0 .. 624) = the generator's current key block; X[i] = X[i - 227] ^ T(i - 624), T(i) = twist(X[i], X[i + 1])
 // (the in-place block regeneration of mt19937_gen written as one linear recurrence over the untempered stream).
+// The recurrence is XOR-linear, so thread t of a step that starts at word m0 chains three words off one another,
+//   v0 = X[m]       = X[m - 227] ^ T(m - 624)          m = m0 + t, t < 227
+//   v1 = X[m + 227] = v0 ^ T(m - 397)
+//   v2 = X[m + 454] = v1 ^ T(m - 170)                  t < 169
+// reading only words older than m0: 623 consecutive words per CTA barrier.  The kernel is bound by instruction issue
+// and the barrier round trip of ONE CTA, so the loop is kept minimal: a linear shared-memory window (all seven loads
+// and three stores at immediate offsets from one pointer) that slides back every 12 steps, no bounds tests (the
+// stream buffer is padded to whole steps), global stores straight from the registers.
 __global__ void __launch_bounds__(kMtThreads) mt_stream_kernel(const unsigned int* __restrict__ state,
-                                                               unsigned int* __restrict__ X, long long n_total) {
-  __shared__ unsigned int ring[kRing];
+                                                               unsigned int* __restrict__ X, long long n_steps) {
+  __shared__ unsigned int win[kMtWin];
   const int tid = threadIdx.x;
   for (int i = tid; i < kMtN; i += kMtThreads) {
     const unsigned int v = state[i];
-    ring[i] = v;
+    win[i] = v;
     X[i] = v;
   }
   __syncthreads();
-  for (long long base = kMtN; base < n_total; base += kMtLag) {
-    const long long i = base + tid;
-    if (tid < kMtLag && i < n_total) {
-      const unsigned int v = ring[(unsigned int)(i - kMtLag) & (kRing - 1)] ^
-                             mt_twist(ring[(unsigned int)(i - kMtN) & (kRing - 1)],
-                                      ring[(unsigned int)(i - kMtN + 1) & (kRing - 1)]);
-      ring[(unsigned int)i & (kRing - 1)] = v;
-      X[i] = v;
+  const bool produce = tid < kMtLag, third = tid < kMtStep - 2 * kMtLag;
+  unsigned int* xg = X + kMtN + tid;
+  long long step = 0;
+  while (step < n_steps) {
+    unsigned int* p = win + kMtN + tid;
+    const int burst = (int)((n_steps - step < kMtWinSteps) ? n_steps - step : kMtWinSteps);
+    for (int b = 0; b < burst; ++b) {
+      if (produce) {
+        const unsigned int v0 = p[-227] ^ mt_twist(p[-624], p[-623]);
+        const unsigned int v1 = v0 ^ mt_twist(p[-397], p[-396]);
+        p[0] = v0;
+        p[227] = v1;
+        xg[0] = v0;
+        xg[227] = v1;
+        if (third) {
+          const unsigned int v2 = v1 ^ mt_twist(p[-170], p[-169]);
+          p[454] = v2;
+          xg[454] = v2;
+        }
+      }
+      p += kMtStep;
+      xg += kMtStep;
+      __syncthreads();
     }
-    __syncthreads();
+    step += burst;
+    if (step < n_steps) {                              // slide: the last 624 words become the head of the window
+      unsigned int keep[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int i = tid + u * kMtThreads;
+        keep[u] = i < kMtN ? win[burst * kMtStep + i] : 0u;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int i = tid + u * kMtThreads;
+        if (i < kMtN) win[i] = keep[u];
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -307,24 +347,30 @@ int launch_normal_mt19937(glasdi_handle* h, glasdi_mt19937_state* state, const d
   // trials has a standard deviation of 0.41 sqrt(A)); a shortfall is reported (GLASDI_ERR_NUMERIC), never ignored
   const long long n_attempts = (long long)std::ceil((double)n_pairs * 1.2732395447351628 * 1.01) + 4096;
   const long long n_blocks = (n_attempts + gp::kGsBlock - 1) / gp::kGsBlock;
-  const long long n_total = ((gp::kMtN + 4 * n_attempts + gp::kMtN - 1) / gp::kMtN + 1) * gp::kMtN;   // pos <= 624
-  const size_t bytes_x = (size_t)n_total * sizeof(unsigned int);
+  // words to generate: the key block, pos <= 624 words already consumed, 4 per attempt, one more key block (the
+  // final state copies a whole one), in whole steps of 623 words (mt_stream_kernel has no bounds tests)
+  const long long n_need = 2 * gp::kMtN + 4 * n_attempts + gp::kMtN;
+  const long long n_steps = (n_need - gp::kMtN + gp::kMtStep - 1) / gp::kMtStep;
+  const long long n_total = gp::kMtN + n_steps * gp::kMtStep;
+  const size_t bytes_x = ((size_t)n_total * sizeof(unsigned int) + 255) / 256 * 256;
   const size_t bytes_cnt = ((size_t)n_blocks * sizeof(unsigned int) + 15) / 16 * 16;
   const size_t bytes_off = (size_t)(n_blocks + 1 + 4) * sizeof(unsigned long long);
   const size_t bytes_state = 640 * sizeof(unsigned int);
   if (bytes_x > ((size_t)16 << 30)) return set_error(h, GLASDI_ERR_OOM, "normal_mt19937: stream buffer above 16 GB");
-  char* scratch = nullptr;
-  GL_CUDA(h, cudaMallocAsync((void**)&scratch, bytes_x + bytes_cnt + bytes_off + bytes_state, st));
+  // the handle's grow-only workspace (shared with the greedy step; calls on one handle are stream-ordered)
+  int rc = ensure_workspace(h, bytes_x + bytes_cnt + bytes_off + bytes_state);
+  if (rc) return rc;
+  char* scratch = reinterpret_cast<char*>(h->ws);
   unsigned int* X = reinterpret_cast<unsigned int*>(scratch);
   unsigned int* counts = reinterpret_cast<unsigned int*>(scratch + bytes_x);
   unsigned long long* offsets = reinterpret_cast<unsigned long long*>(scratch + bytes_x + bytes_cnt);
   unsigned long long* info = offsets + n_blocks + 1;
   unsigned int* dstate = reinterpret_cast<unsigned int*>(scratch + bytes_x + bytes_cnt + bytes_off);
   unsigned int hstate[632];
-  int rc = check_cuda(h, cudaMemcpyAsync(dstate, state->key, gp::kMtN * sizeof(unsigned int), cudaMemcpyHostToDevice, st),
+  rc = check_cuda(h, cudaMemcpyAsync(dstate, state->key, gp::kMtN * sizeof(unsigned int), cudaMemcpyHostToDevice, st),
                       "normal_mt19937 state upload");
   if (rc == GLASDI_OK) {
-    gp::mt_stream_kernel<<<1, gp::kMtThreads, 0, st>>>(dstate, X, n_total);
+    gp::mt_stream_kernel<<<1, gp::kMtThreads, 0, st>>>(dstate, X, n_steps);
     gp::gauss_count_kernel<<<(unsigned)n_blocks, gp::kGsThreads, 0, st>>>(X, (long long)state->pos, n_attempts, counts);
     gp::scan_blocks_kernel<<<1, 1024, 0, st>>>(counts, n_blocks, offsets);
     gp::gauss_scatter_kernel<<<(unsigned)n_blocks, gp::kGsThreads, 0, st>>>(
@@ -337,7 +383,6 @@ int launch_normal_mt19937(glasdi_handle* h, glasdi_mt19937_state* state, const d
   if (rc == GLASDI_OK)
     rc = check_cuda(h, cudaMemcpyAsync(hstate, dstate, 632 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st),
                     "normal_mt19937 state download");
-  cudaFreeAsync(scratch, st);
   if (rc == GLASDI_OK) rc = check_cuda(h, cudaStreamSynchronize(st), "normal_mt19937 sync");
   if (rc) return rc;
   if (hstate[gp::kMtN + 4]) return set_error(h, GLASDI_ERR_NUMERIC, "normal_mt19937: accepted-attempt shortfall (retry)");

@@ -36,6 +36,7 @@ class Engine:
         self.decoder_owner = None   # module whose weights are currently packed in the handle
         self.encoder_widths = None
         self.encoder_owner = None
+        self.host_pipeline_min_bytes = 8 << 20   # pinned host draws above this size are copied in two overlapped blocks
 
     def close(self):
         if getattr(self, "h", None):
@@ -156,7 +157,7 @@ class Engine:
     # ---- fused greedy step ---------------------------------------------------------------------
     def greedy_step(self, coefs, z0, T: int, dt: float, out=None):
         """-> (max_std fp32 [P], argmax int64 [1] (-1 if none), maxval fp32 [1]); CUDA tensors."""
-        coefs = self._dev(coefs, torch.float64)
+        coefs = torch.as_tensor(coefs)
         z0 = self._dev(z0, torch.float32)
         P, S, nc = coefs.shape
         n = z0.shape[-1]
@@ -166,9 +167,48 @@ class Engine:
                    torch.empty(1, dtype=torch.int64, device=self.tdev),
                    torch.empty(1, dtype=torch.float32, device=self.tdev))
         ms, am, mv = out
+        if (coefs.device.type == "cpu" and coefs.dtype == torch.float64 and coefs.is_contiguous() and coefs.is_pinned()
+                and P >= 16 and coefs.numel() * 8 >= self.host_pipeline_min_bytes):
+            return self._greedy_step_from_host(coefs, z0, T, dt, out)
+        coefs = self._dev(coefs, torch.float64)
         with torch.cuda.device(self.device):
             self._check(self.lib.glasdi_greedy_step(self.h, coefs.data_ptr(), z0.data_ptr(), P, S, n, T, float(dt),
                                                     ms.data_ptr(), am.data_ptr(), mv.data_ptr(), _stream_ptr()))
+        return ms, am, mv
+
+    def _greedy_step_from_host(self, coefs, z0, T, dt, out):
+        """Pinned host draws (the 106 MB input of the bench shape): the first eighth of the parameters is copied, then
+        the rest crosses PCIe on a side stream WHILE the first block is being computed; the per-parameter results of
+        the two blocks land in one vector and one first-strict-maximum pass selects the parameter."""
+        P, S, nc = coefs.shape
+        n = z0.shape[-1]
+        ms, am, mv = out
+        key = (P, S, nc)
+        if getattr(self, "_stage_key", None) != key:
+            self._stage = torch.empty((P, S, nc), dtype=torch.float64, device=self.tdev)
+            self._stage_key = key
+            self._copy_stream = torch.cuda.Stream(device=self.tdev)
+            self._am_scratch = torch.empty(1, dtype=torch.int64, device=self.tdev)
+            self._mv_scratch = torch.empty(1, dtype=torch.float32, device=self.tdev)
+        stage, cs = self._stage, self._copy_stream
+        p1 = max(1, P // 8)
+        cur = torch.cuda.current_stream(self.tdev)
+        cs.wait_stream(cur)                         # the previous step may still be reading the staging buffer
+        events = []
+        with torch.cuda.stream(cs):
+            for lo, hi in ((0, p1), (p1, P)):
+                stage[lo:hi].copy_(coefs[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                events.append(ev)
+        with torch.cuda.device(self.device):
+            for ev, (lo, hi) in zip(events, ((0, p1), (p1, P))):
+                cur.wait_event(ev)
+                self._check(self.lib.glasdi_greedy_step(
+                    self.h, stage[lo:hi].data_ptr(), z0[lo:hi].data_ptr(), hi - lo, S, n, T, float(dt),
+                    ms[lo:hi].data_ptr(), self._am_scratch.data_ptr(), self._mv_scratch.data_ptr(), _stream_ptr()))
+            self._check(self.lib.glasdi_argmax_first(self.h, ms.data_ptr(), P, am.data_ptr(), mv.data_ptr(),
+                                                     _stream_ptr()))
         return ms, am, mv
 
     def checked(self, call):

@@ -342,6 +342,27 @@ def test_flagged_screening_falls_back_to_direct_mode(engine, g_small):
     assert np.array_equal(ms.cpu().numpy(), direct)
 
 
+def test_greedy_step_from_pinned_host_overlaps_copy_and_matches(engine, g_small):
+    """Pinned host draws take the two-block path (copy of block 2 overlapped with the compute of block 1): same
+    per-parameter values bit for bit (results do not depend on how parameters are grouped), same selected index."""
+    wl, Ws, bs = setup_wl(engine, "small_s200")
+    inp = synth.make_inputs(wl)
+    reps = 4                                                     # P = 4 x the fixture's parameters (>= 16)
+    coefs = np.concatenate([inp["coefs"]] * reps); z0 = np.concatenate([inp["z0"]] * reps)
+    ms_d, am_d, mv_d = engine.greedy_step(torch.from_numpy(coefs).cuda(), z0, wl.T, wl.dt)
+    old = engine.host_pipeline_min_bytes
+    engine.host_pipeline_min_bytes = 0
+    try:
+        pinned = torch.from_numpy(coefs).pin_memory()
+        for _ in range(2):                                       # second call reuses the staging buffer
+            ms_h, am_h, mv_h = engine.greedy_step(pinned, z0, wl.T, wl.dt)
+        engine.check_numeric()
+    finally:
+        engine.host_pipeline_min_bytes = old
+    assert torch.equal(ms_d, ms_h) and int(am_d) == int(am_h) and float(mv_d) == float(mv_h)
+    std_close(ms_h.cpu().numpy()[: wl.P], g_small["small_s200_max_std"])
+
+
 @pytest.mark.parametrize("nm", ["tiny", "small", "small_s200", "small_softplus"])
 @pytest.mark.parametrize("passes", [3, 2, 1])
 def test_greedy_step_matches_reference(engine, g_small, nm, passes):
