@@ -6,9 +6,8 @@ reference trainer module (reference src/lasdi/gplasdi.py:9-74, :241-274).
 max -> argmax) instead of the reference's python loops; `get_fom_max_std`, `sample_roms` and
 `average_rom` are the literal drop-ins for callers that pass their own arrays.
 
-Out of scope in this round: the autoencoder training loop (`train`), which is
-where gradients flow through `calibrate`; use the reference trainer for training and this class
-for the greedy step -- checkpoints and `best_coefs` are interchangeable.
+`train` is the reference's training leg with the SINDy calibration and its losses on
+the CUDA kernels (analytic backward) -- checkpoints and `best_coefs` are interchangeable with the reference's.
 """
 from __future__ import annotations
 
@@ -100,6 +99,8 @@ class BayesianGLaSDI:
         self.path_checkpoint = config.get("path_checkpoint", "checkpoint")
         self.path_results = config.get("path_results", "results")
         self.device = config.get("device", "cuda")
+        self.verbose = config.get("verbose", True)
+        self.optimizer = torch.optim.Adam(autoencoder.parameters(), lr=self.lr)
         self.best_loss = np.inf
         self.best_coefs = None
         self.restart_iter = 0
@@ -108,9 +109,57 @@ class BayesianGLaSDI:
         self.last_max_std = None
 
     def train(self):
-        raise NotImplementedError(
-            "autoencoder training is outside the B200 greedy-sampling path in this round; "
-            "train with the reference trainer and load `best_coefs` / checkpoint.pt here")
+        """One training leg (reference gplasdi.py:150-238): `n_iter` Adam steps on
+        loss = MSE(X, decoder(encoder(X))) + ld_weight * loss_sindy / n_train + coef_weight * loss_coef / n_train,
+        best-loss checkpoint + `best_coefs`.  The encoder/decoder passes that record an autograd graph are torch ops
+        (cuBLAS); the SINDy calibration and its two losses are this package's CUDA kernels with an analytic backward
+        (`glasdi_sindy_fit` / `glasdi_sindy_fit_backward`), so the latent series never leaves the GPU -- the
+        reference moves Z to the host every iteration (gplasdi.py:183) and differentiates through `lstsq` there."""
+        import os
+        assert self.X_train.size(0) > 0
+        assert self.X_train.size(0) == self.param_space.n_train()
+        dev = torch.device(self.device)
+        ae = self.autoencoder.to(dev)
+        X = self.X_train.to(dev)
+        os.makedirs(self.path_checkpoint, exist_ok=True)
+        os.makedirs(self.path_results, exist_ok=True)
+        ckpt = os.path.join(self.path_checkpoint, "checkpoint.pt")
+        n_train = self.param_space.n_train()
+        ld = self.latent_dynamics
+        mse = torch.nn.MSELoss()
+        self.training_loss, self.ae_loss, self.ld_loss, self.coef_loss = [], [], [], []
+
+        def save_checkpoint():
+            torch.save({k: v.detach().cpu() for k, v in ae.state_dict().items()}, ckpt)
+
+        coefs = None
+        next_iter = min(self.restart_iter + self.n_iter, self.max_iter)
+        for it in range(self.restart_iter, next_iter):
+            self.optimizer.zero_grad()
+            Z = ae.encoder(X)
+            X_pred = ae.decoder(Z)
+            loss_ae = mse(X, X_pred)
+            coefs, loss_ld, loss_coef = ld.calibrate(Z, self.physics.dt, compute_loss=True, numpy=True)
+            loss = loss_ae + self.ld_weight * loss_ld / n_train + self.coef_weight * loss_coef / n_train
+            loss.backward()
+            self.optimizer.step()
+            # one device->host read per iteration for the four histories and the best-loss test
+            lv, la, ll, lc = torch.stack([loss.detach(), loss_ae.detach(), loss_ld.detach(), loss_coef.detach()]).tolist()
+            self.training_loss.append(lv); self.ae_loss.append(la); self.ld_loss.append(ll); self.coef_loss.append(lc)
+            if lv < self.best_loss:
+                # as in the reference, the checkpoint is written AFTER the optimiser step of the best iteration
+                save_checkpoint()
+                self.best_coefs = coefs
+                self.best_loss = lv
+            if self.verbose:
+                print("Iter: %05d/%d, Loss: %3.10f, Loss AE: %3.10f, Loss LD: %3.10f, Loss COEF: %3.10f, max|c|: %04.1f"
+                      % (it + 1, self.max_iter, lv, la, ll, lc, np.abs(coefs).max()))
+        self.restart_iter += self.n_iter
+        if self.best_coefs is not None and self.best_coefs.shape[0] == n_train:
+            self.autoencoder.load_state_dict(torch.load(ckpt))
+        else:
+            self.best_coefs = coefs
+            save_checkpoint()
 
     def load_checkpoint(self):
         """Best-loss decoder weights written by the training loop (reference gplasdi.py:254)."""

@@ -148,3 +148,17 @@ def make_latent_series(B: int, T: int, n: int, dt: float, seed: int = 0) -> np.n
             out[b, k] = z[:n]
             z = E @ z
     return out
+
+
+def make_train_problem():
+    """Tiny autoencoder-training problem shared by the fixture generator (tests/golden/gen_golden.py::gen_train, which
+    runs the reference's own train()) and the GPU test: 4 training parameters, nt = 33, nx = 64, travelling smooth
+    pulses as the FOM snapshots.  Returns (nt, nx, train_space, X fp32 [4, nt, nx], trainer config)."""
+    nt, nx = 33, 64
+    x = np.linspace(-3.0, 3.0, nx); t = np.linspace(0.0, 1.0, nt)
+    train_space = np.array([[0.7, 0.9], [0.7, 1.1], [0.9, 0.9], [0.9, 1.1]])
+    X = np.stack([a * np.exp(-(x[None, :] - 1.5 * t[:, None]) ** 2 / 2 / w / w) * np.cos(2 * t[:, None])
+                  for a, w in train_space]).astype(np.float32)
+    cfg = {"n_samples": 8, "lr": 1e-3, "n_iter": 6, "max_iter": 6, "max_greedy_iter": 1, "ld_weight": 0.1,
+           "coef_weight": 1e-3}
+    return nt, nx, train_space, X, cfg

@@ -129,6 +129,47 @@ def gen_encoder():
     np.savez_compressed(os.path.join(HERE, "encoder.npz"), **out)
 
 
+def gen_train():
+    """Loss histories / best_coefs of the reference's own BayesianGLaSDI.train() (CPU) on the tiny problem."""
+    import tempfile
+    from lasdi.latent_space import Autoencoder
+    from lasdi.gplasdi import BayesianGLaSDI
+
+    nt, nx, train_space, X, cfg = synth.make_train_problem()
+
+    class Phys:
+        qgrid_size = [nx]; dt = 1.0 / (nt - 1); t_grid = np.linspace(0.0, 1.0, nt)
+
+    class PS:
+        def n_train(self): return train_space.shape[0]
+    PS.train_space = train_space
+    torch.manual_seed(21)
+    ae = Autoencoder(Phys(), {"hidden_units": [32], "latent_dimension": 5, "activation": "sigmoid"})
+    out = {"init_" + k: v.numpy().copy() for k, v in ae.state_dict().items()}
+    ld = SINDy(5, nt, {"sindy": {"fd_type": "sbp12", "coef_norm_order": "fro"}})
+    # parameter gradients of the first iteration, formed exactly as the loop body of train() forms the loss
+    # (gplasdi.py:179-190): the well-conditioned half of the comparison (Adam's first step is lr * sign(grad), which
+    # turns round-off in near-zero gradient entries into O(lr) differences of the trajectory)
+    Xt = torch.from_numpy(X)
+    Z = ae.encoder(Xt)
+    loss_ae = torch.nn.MSELoss()(Xt, ae.decoder(Z))
+    _, l_ld, l_coef = ld.calibrate(Z, Phys.dt, compute_loss=True, numpy=True)
+    (loss_ae + cfg["ld_weight"] * l_ld / 4 + cfg["coef_weight"] * l_coef / 4).backward()
+    for k, v in ae.named_parameters():
+        out["grad_" + k] = v.grad.numpy().copy()
+    ae.zero_grad()
+    tmp = tempfile.mkdtemp()
+    tr = BayesianGLaSDI(Phys(), ae, ld, PS(), dict(cfg, path_checkpoint=tmp + "/ckpt", path_results=tmp + "/res"))
+    tr.X_train = torch.from_numpy(X)
+    tr.train()
+    out["training_loss"] = np.array(tr.training_loss); out["ae_loss"] = np.array(tr.ae_loss)
+    out["ld_loss"] = np.array(tr.ld_loss); out["coef_loss"] = np.array(tr.coef_loss)
+    out["best_coefs"] = np.asarray(tr.best_coefs); out["best_loss"] = np.array([tr.best_loss])
+    for k, v in ae.state_dict().items():
+        out["final_" + k] = v.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "train.npz"), **out)
+
+
 def _rollout_ref(ld, coefs, z0, t_grid):
     P, S = coefs.shape[:2]
     Zis = np.zeros([P, S, len(t_grid), z0.shape[1]])
@@ -197,6 +238,7 @@ if __name__ == "__main__":
     gen_calibrate()
     gen_calibrate_grad()
     gen_encoder()
+    gen_train()
     gen_gp()
     gen_greedy(["tiny", "small", "small_s200", "small_softplus"], "greedy_small.npz", keep_Z=True)
     if args.full:
