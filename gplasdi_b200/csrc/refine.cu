@@ -116,113 +116,29 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// One work unit: the hidden activations of the row's S samples, dotted with NC rows of the last layer.
-template <int ACT, int INW, int NC>
-__device__ __forceinline__ void refine_unit(const RefParams& R, const Group& gr, const float* __restrict__ sWl, int ld,
-                                            int last_in_w, float* sWd, const float* sPil, int lane) {
-  const int nc = (int)gr.count;
-  const int nkg = R.Kpad / 8;
-  const Cand* __restrict__ cd = R.cand + gr.first;
-  const float* __restrict__ zb = R.Zs + ((size_t)gr.p * R.T + gr.t) * R.NZ * R.Spad;
-  // rows of the last layer of the unit's candidates (unused slots: zero rows)
-  for (int idx = lane; idx < NC * R.Kpad; idx += 32) {
-    const int c = idx / R.Kpad, k = idx - c * R.Kpad;
-    sWd[idx] = (c < nc && k < R.K) ? __ldg(R.Wlast + (size_t)cd[c].d * R.K + k) : 0.f;
-  }
-  __syncwarp();
-  // sum_k |w_k| |h_k(pilot)| per candidate: scale of the fp32 rounding noise of a decoded value
-  float xabs[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    float a = 0.f;
-    for (int k = lane; k < R.Kpad; k += 32) a = fmaf(fabsf(sWd[c * R.Kpad + k]), fabsf(sPil[k]), a);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    xabs[c] = a;
-  }
-  double s1[NC], s2[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
-  for (int s = lane; s < R.S; s += 32) {
-    float zz[kMaxLatent];
-#pragma unroll
-    for (int i = 0; i < kMaxLatent; ++i) zz[i] = (i < R.NZ) ? __ldg(zb + (size_t)i * R.Spad + s) : 0.f;
-    float xp[INW > 0 ? 1 : kMaxHid];
-    const float* xin = zz;
-    if constexpr (INW == 0) {
-      front_pre<ACT>(R.front, zz, xp);
-      xin = xp;
-    }
-    float dsum[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) dsum[c] = 0.f;
-    for (int kg = 0; kg < nkg; ++kg) {
-      float hv[8];
-      last_front_units<ACT, INW>(sWl, ld, last_in_w, R.front.act, kg * 8, xin, hv);
-      const float4 p0 = *reinterpret_cast<const float4*>(sPil + kg * 8);
-      const float4 p1 = *reinterpret_cast<const float4*>(sPil + kg * 8 + 4);
-      const float dh[8] = {hv[0] - p0.x, hv[1] - p0.y, hv[2] - p0.z, hv[3] - p0.w,
-                           hv[4] - p1.x, hv[5] - p1.y, hv[6] - p1.z, hv[7] - p1.w};
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const float4 w0 = *reinterpret_cast<const float4*>(sWd + c * R.Kpad + kg * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(sWd + c * R.Kpad + kg * 8 + 4);
-        float d = dsum[c];                          // same FMA order as one chain over k = 0 .. K-1
-        d = fmaf(w0.x, dh[0], d);
-        d = fmaf(w0.y, dh[1], d);
-        d = fmaf(w0.z, dh[2], d);
-        d = fmaf(w0.w, dh[3], d);
-        d = fmaf(w1.x, dh[4], d);
-        d = fmaf(w1.y, dh[5], d);
-        d = fmaf(w1.z, dh[6], d);
-        d = fmaf(w1.w, dh[7], d);
-        dsum[c] = d;
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      s1[c] += (double)dsum[c];
-      s2[c] = fma((double)dsum[c], (double)dsum[c], s2[c]);
-    }
-  }
-  const double inv_S = 1.0 / (double)R.S;
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const double t1 = warp_sum(s1[c]), t2 = warp_sum(s2[c]);
-    if (lane == 0 && c < nc) {
-      const double mean = t1 * inv_S;
-      const float var = (float)fmax(t2 * inv_S - mean * mean, 0.0);
-      atomicMax(R.exact_bits + gr.p, __float_as_uint(var));
-      // Screening check.  Below ~2^-24 * sum|w||h| (half an ulp of the decoded value's terms) a spread is fp32
-      // rounding noise in the reference as much as here (sigma of near-identical samples, e.g. at the GP's
-      // training points, where the activations h(s) - h(pilot) themselves carry 1e-2 relative rounding error):
-      // deviations inside that floor say nothing about the screening and are not counted.
-      const float se = sqrtf(var), sa = sqrtf(fmaxf(cd[c].var, 0.f) * R.unscale);
-      const float excess = fabsf(sa - se) - 6.0e-8f * xabs[c];
-      const float dev = (se > 0.f && excess > 0.f) ? excess / se : 0.f;
-      atomicMax(R.dev_bits, __float_as_uint(dev));
-      if (dev > R.dev_tol) atomicOr(R.flags + 2, 1);
-    }
-  }
-}
-
-// One warp per work unit (<= kNC candidates of one row); lanes stride the samples.  Two instantiations share the unit
-// list: NC = 2 takes the units with one or two candidates (64 registers, four CTAs per SM -- the kernel is bound by
-// the latency of the activation chains, so resident warps are what counts), NC = kNC the fuller ones.
+// One CTA per work unit (<= NC candidates of one (p, t) row): thread <-> sample (stride 256), so a unit costs
+// S / 256 activation sweeps of latency instead of S / 32 -- a slab with few candidates is no longer one warp's serial
+// time.  The hidden activations of a sample are evaluated once and dotted with the NC rows of the last layer; the
+// pilot activations are made by one thread per unit group, sample sums in fp64 (warp shuffle, then a fixed-order sum
+// over the warps: bit-reproducible for any grid).  Two instantiations share the unit list: NC = 2 takes the units
+// with one or two candidates (64 registers, four CTAs per SM -- the kernel is bound by the latency of the libdevice
+// activation chains, so resident warps are what counts), NC = kNC the fuller ones.
 template <int ACT, int INW, int NC>
 __global__ void __launch_bounds__(kRefWarps * 32, NC <= 2 ? 4 : 2) refine_kernel(const __grid_constant__ RefParams R) {
   extern __shared__ __align__(16) float rsm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int last_in_w = R.front.widths[R.front.n_front - 1];
   const int ld = wl_stride(last_in_w);
-  float* sWl = rsm;                                              // [Kpad][ld] rows [w.., bias, 0..] of the last FRONT layer
-  float* sWd = rsm + R.Kpad * ld + warp * (kNC + 1) * R.Kpad;    // this warp's kNC rows of the LAST layer
-  float* sPil = sWd + kNC * R.Kpad;                              // this warp's pilot activations
+  float* sWl = rsm;                                  // [Kpad][ld] rows [w.., bias, 0..] of the last FRONT layer
+  float* sWd = sWl + R.Kpad * ld;                    // [NC][Kpad] rows of the LAST layer of the unit's candidates
+  float* sPil = sWd + NC * R.Kpad;                   // [Kpad] pilot activations of the row
+  float* sXabs = sPil + R.Kpad;                      // [8] sum_k |w_k| |h_k(pilot)| per candidate
+  double* sRed = reinterpret_cast<double*>(sXabs + 8);   // [kRefWarps][NC][2]
   {
     const int l = R.front.n_front - 1;
     const float* __restrict__ W = R.front.W[l];
     const float* __restrict__ b = R.front.b[l];
-    for (int idx = threadIdx.x; idx < R.Kpad * ld; idx += blockDim.x) {
+    for (int idx = tid; idx < R.Kpad * ld; idx += blockDim.x) {
       const int k = idx / ld, i = idx - k * ld;
       float v = 0.f;
       if (k < R.K) {
@@ -235,13 +151,19 @@ __global__ void __launch_bounds__(kRefWarps * 32, NC <= 2 ? 4 : 2) refine_kernel
   __syncthreads();
   const unsigned int nunits = min(R.stats[3], R.gcap);
   const int nkg = R.Kpad / 8;
-  // unit u -> CTA u % gridDim.x: consecutive units (= neighbouring rows of one parameter) spread over the SMs
-  for (unsigned int gi = blockIdx.x + gridDim.x * warp; gi < nunits; gi += gridDim.x * kRefWarps) {
+  const double inv_S = 1.0 / (double)R.S;
+  for (unsigned int gi = blockIdx.x; gi < nunits; gi += gridDim.x) {
     const Group gr = R.groups[gi];
-    if ((gr.count <= 2) != (NC <= 2)) continue;
+    if ((gr.count <= 2) != (NC <= 2)) continue;       // uniform over the CTA
+    const int nc = (int)gr.count;
+    const Cand* __restrict__ cd = R.cand + gr.first;
     const float* __restrict__ zb = R.Zs + ((size_t)gr.p * R.T + gr.t) * R.NZ * R.Spad;
-    __syncwarp();
-    {   // pilot activations of this row (sample 0)
+    // rows of the last layer of the unit's candidates (unused slots: zero rows)
+    for (int idx = tid; idx < NC * R.Kpad; idx += kRefWarps * 32) {
+      const int c = idx / R.Kpad, k = idx - c * R.Kpad;
+      sWd[idx] = (c < nc && k < R.K) ? __ldg(R.Wlast + (size_t)cd[c].d * R.K + k) : 0.f;
+    }
+    if (tid < nkg) {   // pilot activations of this row (sample 0), one unit group per thread
       float zz[kMaxLatent];
 #pragma unroll
       for (int i = 0; i < kMaxLatent; ++i) zz[i] = (i < R.NZ) ? __ldg(zb + (size_t)i * R.Spad) : 0.f;
@@ -251,15 +173,95 @@ __global__ void __launch_bounds__(kRefWarps * 32, NC <= 2 ? 4 : 2) refine_kernel
         front_pre<ACT>(R.front, zz, xp);
         xin = xp;
       }
-      for (int kg = lane; kg < nkg; kg += 32) {
+      float hv[8];
+      last_front_units<ACT, INW>(sWl, ld, last_in_w, R.front.act, tid * 8, xin, hv);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sPil[tid * 8 + u] = hv[u];
+    }
+    __syncthreads();
+    if (warp < NC) {   // scale of the fp32 rounding noise of a decoded value, one candidate per warp
+      float a = 0.f;
+      for (int k = lane; k < R.Kpad; k += 32) a = fmaf(fabsf(sWd[warp * R.Kpad + k]), fabsf(sPil[k]), a);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) sXabs[warp] = a;
+    }
+    double s1[NC], s2[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
+    for (int s = tid; s < R.S; s += kRefWarps * 32) {
+      float zz[kMaxLatent];
+#pragma unroll
+      for (int i = 0; i < kMaxLatent; ++i) zz[i] = (i < R.NZ) ? __ldg(zb + (size_t)i * R.Spad + s) : 0.f;
+      float xp[INW > 0 ? 1 : kMaxHid];
+      const float* xin = zz;
+      if constexpr (INW == 0) {
+        front_pre<ACT>(R.front, zz, xp);
+        xin = xp;
+      }
+      float dsum[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) dsum[c] = 0.f;
+      for (int kg = 0; kg < nkg; ++kg) {
         float hv[8];
         last_front_units<ACT, INW>(sWl, ld, last_in_w, R.front.act, kg * 8, xin, hv);
+        const float4 p0 = *reinterpret_cast<const float4*>(sPil + kg * 8);
+        const float4 p1 = *reinterpret_cast<const float4*>(sPil + kg * 8 + 4);
+        const float dh[8] = {hv[0] - p0.x, hv[1] - p0.y, hv[2] - p0.z, hv[3] - p0.w,
+                             hv[4] - p1.x, hv[5] - p1.y, hv[6] - p1.z, hv[7] - p1.w};
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sPil[kg * 8 + u] = hv[u];
+        for (int c = 0; c < NC; ++c) {
+          const float4 w0 = *reinterpret_cast<const float4*>(sWd + c * R.Kpad + kg * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(sWd + c * R.Kpad + kg * 8 + 4);
+          float d = dsum[c];                          // same FMA order as one chain over k = 0 .. K-1
+          d = fmaf(w0.x, dh[0], d);
+          d = fmaf(w0.y, dh[1], d);
+          d = fmaf(w0.z, dh[2], d);
+          d = fmaf(w0.w, dh[3], d);
+          d = fmaf(w1.x, dh[4], d);
+          d = fmaf(w1.y, dh[5], d);
+          d = fmaf(w1.z, dh[6], d);
+          d = fmaf(w1.w, dh[7], d);
+          dsum[c] = d;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        s1[c] += (double)dsum[c];
+        s2[c] = fma((double)dsum[c], (double)dsum[c], s2[c]);
       }
     }
-    __syncwarp();
-    refine_unit<ACT, INW, NC>(R, gr, sWl, ld, last_in_w, sWd, sPil, lane);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double t1 = warp_sum(s1[c]), t2 = warp_sum(s2[c]);
+      if (lane == 0) {
+        sRed[(warp * NC + c) * 2 + 0] = t1;
+        sRed[(warp * NC + c) * 2 + 1] = t2;
+      }
+    }
+    __syncthreads();
+    if (tid < nc) {
+      const int c = tid;
+      double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+      for (int w = 0; w < kRefWarps; ++w) {
+        t1 += sRed[(w * NC + c) * 2 + 0];
+        t2 += sRed[(w * NC + c) * 2 + 1];
+      }
+      const double mean = t1 * inv_S;
+      const float var = (float)fmax(t2 * inv_S - mean * mean, 0.0);
+      atomicMax(R.exact_bits + gr.p, __float_as_uint(var));
+      // Screening check.  Below ~2^-24 * sum|w||h| (half an ulp of the decoded value's terms) a spread is fp32
+      // rounding noise in the reference as much as here (sigma of near-identical samples, e.g. at the GP's
+      // training points, where the activations h(s) - h(pilot) themselves carry 1e-2 relative rounding error):
+      // deviations inside that floor say nothing about the screening and are not counted.
+      const float se = sqrtf(var), sa = sqrtf(fmaxf(cd[c].var, 0.f) * R.unscale);
+      const float excess = fabsf(sa - se) - 6.0e-8f * sXabs[c];
+      const float dev = (se > 0.f && excess > 0.f) ? excess / se : 0.f;
+      atomicMax(R.dev_bits, __float_as_uint(dev));
+      if (dev > R.dev_tol) atomicOr(R.flags + 2, 1);
+    }
+    __syncthreads();                                   // the unit's shared-memory rows are free again
   }
 }
 
@@ -308,8 +310,8 @@ int launch_refine(glasdi_handle* h, const float* Zs, int Spad, int S, int T, uns
   R.unscale = unscale;              // screened variance -> true units
   R.dev_tol = dev_tol;
   const int last_in_w = d.widths[d.n_linear - 2];
-  const size_t smem =
-      ((size_t)d.Kpad * dv::wl_stride(last_in_w) + (size_t)rf::kRefWarps * (rf::kNC + 1) * d.Kpad) * sizeof(float);
+  const size_t smem = ((size_t)d.Kpad * dv::wl_stride(last_in_w) + (size_t)(rf::kNC + 1) * d.Kpad + 8) * sizeof(float) +
+                      (size_t)rf::kRefWarps * rf::kNC * 2 * sizeof(double);
   int rc;
   // accurate libdevice activations (ACT >= 0 resolves the switch at compile time; -1 = runtime switch)
   if (R.front.n_front == 1 && R.NZ == 5) rc = launch_refine_inst<-1, 5>(h, R, smem, st);
