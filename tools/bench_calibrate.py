@@ -68,6 +68,21 @@ def main():
         med, best = time_ms(lambda: eng.sindy_fit(Zs, 1e-3, "sbp12", 1), 30, None, inner=1)
         out.append({"kernel": f"sindy_fit_kernel<{n}>", "fd": "sbp12", "shape": [b, T, n], "us_per_call": med * 1e3,
                     "us_best": best * 1e3, "note": "training-loop batch size: launch/latency bound"})
+    # backward of the fit (glasdi_sindy_fit_backward): reads Z, coefs, 2 upstream gradients per series, writes Zbar
+    Zb = Z[:4096].contiguous()
+    coefs = eng.sindy_fit(Zb, 1e-3, "sbp12", 1)[0]
+    ones = torch.ones(Zb.shape[0], device="cuda")
+    med, best = time_ms(lambda: eng.sindy_fit_backward(Zb, coefs, ones, ones, 1e-3, "sbp12", 1), 10, None)
+    byt = 2 * Zb.numel() * 4 + Zb.shape[0] * (n * (n + 1) + 2) * 4
+    out.append({"kernel": f"sindy_fit_bwd_kernel<{n}>", "fd": "sbp12", "shape": list(Zb.shape), "ms": med, "ms_best": best,
+                "algorithmic_bytes": byt, "achieved_gbs": byt / med / 1e6, "peak_gbs": peak, "frac": byt / med / 1e6 / peak})
+    for b in [4, 8, 16, 32]:
+        Zs = Z[:b].contiguous()
+        cs = eng.sindy_fit(Zs, 1e-3, "sbp12", 1)[0]
+        o1 = torch.ones(b, device="cuda")
+        med, best = time_ms(lambda: eng.sindy_fit_backward(Zs, cs, o1, o1, 1e-3, "sbp12", 1), 30, None, inner=1)
+        out.append({"kernel": f"sindy_fit_bwd_kernel<{n}>", "fd": "sbp12", "shape": [b, T, n], "us_per_call": med * 1e3,
+                    "us_best": best * 1e3, "note": "training-loop batch size: launch/latency bound"})
     for o in out:
         print(json.dumps(o))
 
