@@ -14,7 +14,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .gp import eval_gp, fit_gps, sample_coefs, sample_coefs_all, sample_coefs_all_device
+from .gp import eval_gp, eval_gp_device, fit_gps, sample_coefs, sample_coefs_all, sample_coefs_all_device
 from .latent_space import initial_condition_latent
 from .engine import default_engine
 from . import sharding
@@ -38,8 +38,8 @@ def average_rom(autoencoder, physics, latent_dynamics, gp_dictionary, param_grid
     if param_grid.ndim == 1:
         param_grid = param_grid.reshape(1, -1)
     Z0 = np.stack(initial_condition_latent(param_grid, physics, autoencoder))
-    pred_mean, _ = eval_gp(gp_dictionary, param_grid)
-    return latent_dynamics.sample(pred_mean, Z0, physics.t_grid)
+    pred_mean, _ = eval_gp_device(gp_dictionary, param_grid, latent_dynamics.engine)
+    return latent_dynamics.sample(pred_mean.cpu().numpy(), Z0, physics.t_grid)
 
 
 def sample_roms(autoencoder, physics, latent_dynamics, gp_dictionary, param_grid, n_samples):
@@ -48,8 +48,9 @@ def sample_roms(autoencoder, physics, latent_dynamics, gp_dictionary, param_grid
     if param_grid.ndim == 1:
         param_grid = param_grid.reshape(1, -1)
     Z0 = np.stack(initial_condition_latent(param_grid, physics, autoencoder))
-    coef_samples = np.stack([sample_coefs(gp_dictionary, param_grid[i], n_samples)
-                             for i in range(param_grid.shape[0])])
+    # posterior moments and the draws on the device, from numpy's global legacy stream in the order of the
+    # reference's loop (parameter, then sample, then coefficient; gplasdi.py:43-44 -> gp.py:76-78)
+    coef_samples = sample_coefs_all_device(gp_dictionary, param_grid, n_samples, latent_dynamics.engine)
     Z = latent_dynamics.rollout_ensemble(coef_samples, Z0, physics.t_grid)
     return Z.cpu().numpy()
 

@@ -137,8 +137,7 @@ def test_train_leg_matches_reference_trainer(golden_dir, tmp_path):
     tr = BayesianGLaSDI(Phys(), ae, ld, PS(), dict(cfg, path_checkpoint=str(tmp_path / "ckpt"),
                                                    path_results=str(tmp_path / "res"), verbose=False))
     tr.X_train = torch.from_numpy(X)
-    # (1) parameter gradients of the first iteration vs the reference's autograd (well conditioned: 1e-4 of the largest
-    #     entry of each tensor)
+    # (1) parameter gradients of the first iteration, formed as the loop body of train() forms the loss
     aed = ae.to("cuda")
     Xd = tr.X_train.to("cuda")
     Z = aed.encoder(Xd)
@@ -309,6 +308,16 @@ def test_sample_roms_and_average_rom_shapes():
     np.random.seed(3)
     Zis = sample_roms(ae, phys, ld, gps, ps.test_space[:5], 6)
     assert Zis.shape == (5, 6, 33, 5) and Zis.dtype == np.float64
+    after = np.random.random_sample(3)
+    # same seeded stream as the reference's loop: host draws (sklearn + np.random) give the same trajectories, and the
+    # global generator is left where the reference would leave it
+    from gplasdi_b200.gp import sample_coefs_all
+    np.random.seed(3)
+    draws = sample_coefs_all(gps, ps.test_space[:5], 6)
+    np.testing.assert_array_equal(np.random.random_sample(3), after)
+    z0h = np.stack(initial_condition_latent(ps.test_space[:5], phys, ae))
+    Zh = ld.rollout_ensemble(draws, z0h, phys.t_grid).cpu().numpy()
+    assert np.max(np.abs(Zis - Zh)) <= 1e-9 * np.max(np.abs(Zh))
     Zavg = average_rom(ae, phys, ld, gps, ps.test_space[:5])
     assert Zavg.shape == (5, 33, 5)
     mean, _ = eval_gp(gps, ps.test_space[:5])
