@@ -97,3 +97,34 @@ def test_sindy_constructor_contract():
         SINDy(5, 7, {"sindy": {"fd_type": "sbp48"}})      # shorter than the boundary closure
     with pytest.raises(ValueError):
         ld.simulate(np.zeros(30), np.zeros(5), np.array([0.0, 0.1, 0.3]))   # non-uniform grid
+
+
+def _build_c_host(tmp_path):
+    """gcc -std=c99 build of tests/c_host/abi_smoke.c against include/glasdi_b200.h and the in-tree library."""
+    import shutil
+    import subprocess
+    from gplasdi_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc / CUDA runtime headers not available")
+    _lib.load()
+    libdir = os.path.dirname(_lib.lib_path())
+    exe = str(tmp_path / "abi_smoke")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", os.path.join(root, "tests", "c_host", "abi_smoke.c"),
+           "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+           "-L", libdir, "-lglasdi_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart",
+           "-Wl,-rpath," + libdir, "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", exe]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """The boundary is usable from a compiled C host: the header parses as C99 (-pedantic) and a C program that uses
+    only the header + the CUDA runtime links against the library (it is RUN by tests/test_gpu_api.py on a B200)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", "-pedantic",
+                           os.path.join(root, "include", "glasdi_b200.h")])
+    exe = _build_c_host(tmp_path)
+    assert os.path.exists(exe)

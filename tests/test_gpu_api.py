@@ -324,3 +324,35 @@ def test_sample_roms_and_average_rom_shapes():
     z0 = initial_condition_latent(ps.test_space[:5], phys, ae)
     ex = orc.simulate_exact(mean[2], z0[2], phys.dt, phys.nt)
     assert np.max(np.abs(Zavg[2] - ex)) <= 1e-9 * max(1.0, np.max(np.abs(ex)))
+
+
+def test_c_host_program_on_the_c_abi(golden_dir, tmp_path):
+    """tests/c_host/abi_smoke.c -- C99, the header and the CUDA runtime only -- runs the fused greedy step on the
+    'small' fixture: same selected parameter and per-parameter values as the reference (through no Python at all)."""
+    import struct
+    import subprocess
+    from test_boundary import _build_c_host
+    from gplasdi_b200 import _lib
+    exe = _build_c_host(tmp_path)
+    g = np.load(os.path.join(golden_dir, "greedy_small.npz"))
+    wl = synth.WORKLOADS["small"]
+    Ws, bs = synth.make_decoder(wl.widths, wl.seed)
+    inp = synth.make_inputs(wl)
+    path = str(tmp_path / "problem.bin")
+    with open(path, "wb") as f:
+        f.write(struct.pack("<6i", len(Ws), _lib.ACT_IDS[wl.act], wl.P, wl.S, wl.n_z, wl.T))
+        f.write(struct.pack("<d", wl.dt))
+        f.write(np.asarray(wl.widths, dtype=np.int32).tobytes())
+        for W, b in zip(Ws, bs):
+            f.write(np.ascontiguousarray(W, dtype=np.float32).tobytes())
+            f.write(np.ascontiguousarray(b, dtype=np.float32).tobytes())
+        f.write(np.ascontiguousarray(inp["coefs"], dtype=np.float64).tobytes())
+        f.write(np.ascontiguousarray(inp["z0"], dtype=np.float32).tobytes())
+    out = subprocess.run([exe, path], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert int(lines[0].split()[1]) == int(g["small_m_index"][0])
+    assert int(lines[0].split()[3]) > 0                                   # kernels were launched by the library
+    per = np.array([float(x) for x in lines[1:]])
+    ref = g["small_max_std"]
+    assert per.shape == ref.shape and np.max(np.abs(per - ref) - 1e-5 * ref) <= 5e-6

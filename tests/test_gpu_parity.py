@@ -262,6 +262,41 @@ def test_normal_draws_block_boundaries_and_explicit_state(engine):
         assert np.array_equal(st_new[1], st_ref[1]) and st_new[2:4] == st_ref[2:4]
 
 
+def test_new_entry_points_edge_cases(engine):
+    """Empty / degenerate inputs of the 8f entry points."""
+    # no draws requested: empty output, generator state untouched (also with a cached gaussian pending)
+    np.random.seed(11)
+    np.random.normal(size=3)
+    st0 = np.random.get_state()
+    out, st1 = engine.normal_mt19937(np.zeros((2, 3)), np.ones((2, 3)), 0)
+    assert out.shape == (2, 0, 3)
+    assert np.array_equal(st1[1], st0[1]) and st1[2:] == st0[2:]
+    # a single draw that is served from the cache consumes no words
+    ref = np.random.normal(2.0, 3.0)
+    st_ref = np.random.get_state()
+    np.random.set_state(st0)
+    out, st1 = engine.normal_mt19937(np.full((1, 1), 2.0), np.full((1, 1), 3.0), 1)
+    assert abs(float(out.cpu().numpy().ravel()[0]) - ref) <= 1e-14 * abs(ref)
+    assert np.array_equal(st1[1], st_ref[1]) and st1[2:4] == st_ref[2:4] and st1[3] == 0
+    # GP with a single training point: mean = k* alpha, var = c - k*^2 / c
+    c, l = 2.0, 0.5
+    mean, std = engine.gp_predict(np.array([[0.3, 0.4]]), np.array([[1.5]]), np.array([[[np.sqrt(c)]]]), np.array([c]),
+                                  np.array([l]), np.array([[0.3, 0.4], [0.8, 0.4]]))
+    ks = c * np.exp(-0.5 * np.array([0.0, 0.25]) / l ** 2)
+    np.testing.assert_allclose(mean.cpu().numpy()[:, 0], ks * 1.5, rtol=1e-14)
+    # at the training point c - (k* / sqrt c)^2 cancels to an ulp of c: std = sqrt(rounding noise) ~ 1e-8, as in sklearn
+    np.testing.assert_allclose(std.cpu().numpy()[:, 0], np.sqrt(np.maximum(c - ks ** 2 / c, 0.0)), rtol=1e-12, atol=1e-7)
+    # backward with no upstream gradient is exactly zero; empty encoder batch
+    Z = synth.make_noisy_series(2, 33, 5, 1 / 32, seed=2)
+    coefs = engine.sindy_fit(Z, 1 / 32, "sbp12", 1)[0]
+    assert float(engine.sindy_fit_backward(Z, coefs, None, None, 1 / 32, "sbp12", 1).abs().max()) == 0.0
+    engine.set_encoder([np.ones((4, 7), np.float32), np.ones((5, 4), np.float32)], [np.zeros(4, np.float32), np.zeros(5, np.float32)],
+                       "tanh")
+    assert engine.encode(np.zeros((0, 7), np.float32)).shape == (0, 5)
+    with pytest.raises(GlasdiError):
+        engine.normal_mt19937(np.zeros((1, 1)), np.ones((1, 1)), 1, state=("MT19937", np.zeros(624, np.uint32), 700, 0, 0.0))
+
+
 # ---- encoder ---------------------------------------------------------------------------------------
 ENC_CASES = [(301, 2, "sigmoid"), (257, 3, "softplus"), (1001, 2, "tanh")]
 Z0_RTOL = 1e-5
