@@ -378,7 +378,7 @@ def test_flagged_screening_falls_back_to_direct_mode(engine, g_small):
 
 
 def test_greedy_step_from_pinned_host_overlaps_copy_and_matches(engine, g_small):
-    """Pinned host draws take the two-block path (copy of block 2 overlapped with the compute of block 1): same
+    """Pinned host draws take the block-pipelined path (copies of later blocks overlapped with the compute of earlier ones): same
     per-parameter values bit for bit (results do not depend on how parameters are grouped), same selected index."""
     wl, Ws, bs = setup_wl(engine, "small_s200")
     inp = synth.make_inputs(wl)
