@@ -154,6 +154,151 @@ __global__ void __launch_bounds__(256) last_var_kernel(const float* __restrict__
   }
 }
 
+// ---- 128 x 128 x 8 tiles, 8 x 8 outputs per thread, double-buffered shared memory ---------------------------------
+// The 64 x 64 kernels above reach ~20 % of the fp32 FMA rate (scalar shared-memory reads, no prefetch); the layers
+// that carry the FLOPs of the wide decoders (200 -> 1000, 1000 -> D) go through this main loop instead: float4 global
+// loads prefetched one k-step ahead, operands stored k-major so that the inner loop reads two float4 per operand and
+// issues 64 FMAs per 4 shared-memory loads.  Needs K % 4 == 0 (16-byte rows); other layers keep the small kernel.
+constexpr int GM = 128, GN = 128, GK = 8, GP = 4;          // GP: row padding of the k-major tiles (keeps 16-B alignment)
+
+struct Tiles {
+  float A[2][GK][GM + GP];
+  float B[2][GK][GN + GP];
+};
+
+// acc[i][j] += sum_k Arow[m(i)][k] * Brow[n(j)][k];  m(i) = (i < 4 ? ty*4 + i : 64 + ty*4 + i - 4), n(j) alike with tx
+__device__ __forceinline__ void gemm128_mainloop(const float* __restrict__ A, long long m_valid, const float* __restrict__ B,
+                                                 int n_valid, int K, Tiles& T, float (&acc)[8][8]) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lr = tid >> 1, lk = (tid & 1) * 4;             // this thread's row / k-quad of both operand tiles
+  const bool a_ok = lr < m_valid, b_ok = lr < n_valid;
+  const float* __restrict__ ap = A + (size_t)lr * K + lk;
+  const float* __restrict__ bp = B + (size_t)lr * K + lk;
+  float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+  auto fetch = [&](int k0) {
+    ra = (a_ok && k0 + lk < K) ? __ldg(reinterpret_cast<const float4*>(ap + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = (b_ok && k0 + lk < K) ? __ldg(reinterpret_cast<const float4*>(bp + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto stash = [&](int buf) {
+    T.A[buf][lk + 0][lr] = ra.x; T.A[buf][lk + 1][lr] = ra.y; T.A[buf][lk + 2][lr] = ra.z; T.A[buf][lk + 3][lr] = ra.w;
+    T.B[buf][lk + 0][lr] = rb.x; T.B[buf][lk + 1][lr] = rb.y; T.B[buf][lk + 2][lr] = rb.z; T.B[buf][lk + 3][lr] = rb.w;
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    const bool more = k0 + GK < K;
+    if (more) fetch(k0 + GK);
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&T.A[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&T.A[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&T.B[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&T.B[buf][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+}
+
+__device__ __forceinline__ int sub_index(int t4, int i) { return i < 4 ? t4 * 4 + i : 64 + t4 * 4 + (i - 4); }
+
+__global__ void __launch_bounds__(256, 2) linear_act_kernel128(const float* __restrict__ X, const float* __restrict__ W,
+                                                            const float* __restrict__ b, float* __restrict__ Y,
+                                                            long long R, int in, int out, int act) {
+  __shared__ __align__(16) Tiles T;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const long long r0 = (long long)blockIdx.x * GM;
+  const int o0 = blockIdx.y * GN;
+  float acc[8][8] = {};
+  gemm128_mainloop(X + (size_t)r0 * in, R - r0, W + (size_t)o0 * in, out - o0, in, T, acc);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long r = r0 + sub_index(ty, i);
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = o0 + sub_index(tx, j);
+      if (o < out) Y[r * out + o] = act_apply(act, acc[i][j] + b[o]);
+    }
+  }
+}
+
+// last layer + variance, 128-dof tiles: block = (dof tile, group g); loops over sample tiles of 128.
+__global__ void __launch_bounds__(256, 2) last_var_kernel128(const float* __restrict__ H, const float* __restrict__ W, int S,
+                                                          int K, int D, int T_steps, long long g0,
+                                                          unsigned int* __restrict__ maxvar_bits) {
+  __shared__ __align__(16) Tiles T;
+  __shared__ float shift[GN];
+  __shared__ float reds[16][GN], redq[16][GN];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const long long g = blockIdx.x;
+  const int d0 = blockIdx.y * GN;
+  const float* __restrict__ Hg = H + g * (long long)S * K;
+  float ssum[8] = {}, qsum[8] = {};
+  for (int s0 = 0; s0 < S; s0 += GM) {
+    float acc[8][8] = {};
+    gemm128_mainloop(Hg + (size_t)s0 * K, S - s0, W + (size_t)d0 * K, D - d0, K, T, acc);
+    if (s0 == 0) {
+      if (ty == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) shift[sub_index(tx, j)] = acc[0][j];   // sample 0 = the pilot of the shifted sums
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (s0 + sub_index(ty, i) < S) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dlt = acc[i][j] - shift[sub_index(tx, j)];
+          ssum[j] += dlt;
+          qsum[j] = fmaf(dlt, dlt, qsum[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { reds[ty][sub_index(tx, j)] = ssum[j]; redq[ty][sub_index(tx, j)] = qsum[j]; }
+  __syncthreads();
+  float vmax = 0.f;
+  if (threadIdx.x < GN) {
+    float s = 0.f, q = 0.f;
+    for (int r = 0; r < 16; ++r) { s += reds[r][threadIdx.x]; q += redq[r][threadIdx.x]; }
+    const float inv = 1.0f / (float)S;
+    const float mean = s * inv;
+    if (d0 + (int)threadIdx.x < D) vmax = fmaxf(0.f, fmaf(-mean, mean, q * inv));
+  }
+  if (threadIdx.x < GN) {
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0 && vmax > 0.f) {
+      const long long p = (g0 + g) / T_steps;
+      atomicMax(maxvar_bits + p, __float_as_uint(vmax));
+    }
+  }
+}
+
+// layer launcher: the 128-tile kernel where it pays (16-byte rows, enough rows and outputs), else the small one
+static inline void launch_linear(const float* X, const float* W, const float* b, float* Y, long long R, int in, int out,
+                                 int act, cudaStream_t st) {
+  if (in % 4 == 0 && in >= 32 && out >= 64 && R >= 256 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+    dim3 grid((unsigned)((R + GM - 1) / GM), (out + GN - 1) / GN);
+    linear_act_kernel128<<<grid, 256, 0, st>>>(X, W, b, Y, R, in, out, act);
+  } else {
+    dim3 grid((unsigned)((R + BM - 1) / BM), (out + BN - 1) / BN);
+    linear_act_kernel<<<grid, 256, 0, st>>>(X, W, b, Y, R, in, out, act);
+  }
+}
+
 }  // namespace simt
 
 static int run_chain(glasdi_handle* h, const float* X0, long long R, int upto_layer, float* bufA, float* bufB,
@@ -164,8 +309,7 @@ static int run_chain(glasdi_handle* h, const float* X0, long long R, int upto_la
   float* bufs[2] = {bufA, bufB};
   for (int l = 0; l < upto_layer; ++l) {
     float* dst = bufs[l & 1];
-    dim3 grid((unsigned)((R + simt::BM - 1) / simt::BM), (d.widths[l + 1] + simt::BN - 1) / simt::BN);
-    simt::linear_act_kernel<<<grid, 256, 0, st>>>(cur, d.dW[l], d.db[l], dst, R, d.widths[l], d.widths[l + 1], d.act);
+    simt::launch_linear(cur, d.dW[l], d.db[l], dst, R, d.widths[l], d.widths[l + 1], d.act, st);
     h->launches++;
     int rc = check_cuda(h, cudaGetLastError(), "linear_act launch");
     if (rc) return rc;
@@ -202,8 +346,13 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
     const float* Hlast = nullptr;
     rc = run_chain(h, Xrow, R, d.n_linear - 1, bufA, bufB, &Hlast, st);
     if (rc) break;
-    dim3 grid((unsigned)gn, (d.D + simt::BN - 1) / simt::BN);
-    simt::last_var_kernel<<<grid, 256, 0, st>>>(Hlast, d.dW[d.n_linear - 1], S, d.K, d.D, T, g0, maxvar_bits);
+    if (d.K % 4 == 0 && d.K >= 32 && d.D >= 64 && S >= 64 && (reinterpret_cast<uintptr_t>(Hlast) & 15) == 0) {
+      dim3 grid((unsigned)gn, (d.D + simt::GN - 1) / simt::GN);
+      simt::last_var_kernel128<<<grid, 256, 0, st>>>(Hlast, d.dW[d.n_linear - 1], S, d.K, d.D, T, g0, maxvar_bits);
+    } else {
+      dim3 grid((unsigned)gn, (d.D + simt::BN - 1) / simt::BN);
+      simt::last_var_kernel<<<grid, 256, 0, st>>>(Hlast, d.dW[d.n_linear - 1], S, d.K, d.D, T, g0, maxvar_bits);
+    }
     h->launches++;
     rc = check_cuda(h, cudaGetLastError(), "last_var launch");
   }
@@ -227,9 +376,7 @@ int launch_decode_store_simt(glasdi_handle* h, const float* Z, int64_t rows, flo
     rc = run_chain(h, Z + (size_t)r0 * d.widths[0], R, d.n_linear - 1, bufA, bufB, &Hlast, st);
     if (rc) break;
     const int l = d.n_linear - 1;
-    dim3 grid((unsigned)((R + simt::BM - 1) / simt::BM), (d.D + simt::BN - 1) / simt::BN);
-    simt::linear_act_kernel<<<grid, 256, 0, st>>>(Hlast, d.dW[l], d.db[l], X + (size_t)r0 * d.D, R, d.K, d.D,
-                                                  GLASDI_ACT_IDENTITY);
+    simt::launch_linear(Hlast, d.dW[l], d.db[l], X + (size_t)r0 * d.D, R, d.K, d.D, GLASDI_ACT_IDENTITY, st);
     h->launches++;
     rc = check_cuda(h, cudaGetLastError(), "linear (last) launch");
   }
@@ -252,9 +399,8 @@ int launch_encode_simt(glasdi_handle* h, const float* U, int64_t rows, float* Z,
   for (int l = 0; l < e.n_linear && rc == GLASDI_OK; ++l) {
     const bool last = l == e.n_linear - 1;
     float* dst = last ? Z : bufs[l & 1];
-    dim3 grid((unsigned)((rows + simt::BM - 1) / simt::BM), (e.widths[l + 1] + simt::BN - 1) / simt::BN);
-    simt::linear_act_kernel<<<grid, 256, 0, st>>>(cur, e.dW[l], e.db[l], dst, rows, e.widths[l], e.widths[l + 1],
-                                                  last ? GLASDI_ACT_IDENTITY : e.act);
+    simt::launch_linear(cur, e.dW[l], e.db[l], dst, rows, e.widths[l], e.widths[l + 1], last ? GLASDI_ACT_IDENTITY : e.act,
+                        st);
     h->launches++;
     rc = check_cuda(h, cudaGetLastError(), "encoder linear_act launch");
     cur = dst;

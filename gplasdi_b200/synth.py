@@ -57,6 +57,8 @@ WORKLOADS = {
     "ragged": Workload("ragged", (3, 2), 130, 9, [5, 24, 1300], "tanh", 1.0 / 8),
     # decoder the fused tcgen05 kernel does not cover (K_last > 112) -> CUDA-core path
     "wide_k": Workload("wide_k", (3, 2), 24, 7, [5, 16, 160, 200], "softplus", 1.0 / 6),
+    # same path through its 128 x 128 tiles (rows % 4 == 0, >= 64 samples): ragged sample / dof / k tails
+    "wide_k128": Workload("wide_k128", (3, 2), 130, 5, [5, 40, 164, 300], "softplus", 1.0 / 4),
 }
 
 

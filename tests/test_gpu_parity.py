@@ -439,7 +439,7 @@ def test_decode_max_std_on_reference_trajectories(engine, g_small, nm):
     std_close(ms.cpu().numpy(), g_small[nm + "_max_std"])
 
 
-@pytest.mark.parametrize("nm", ["ragged", "wide_k"])
+@pytest.mark.parametrize("nm", ["ragged", "wide_k", "wide_k128"])
 @pytest.mark.parametrize("mode", [_lib.MODE_SCREENED_GRAM, _lib.MODE_SCREENED, _lib.MODE_DIRECT])
 def test_ragged_and_wide_shapes_against_oracle(engine, nm, mode):
     wl, Ws, bs = setup_wl(engine, nm)
@@ -452,6 +452,12 @@ def test_ragged_and_wide_shapes_against_oracle(engine, nm, mode):
     std_close(ms.cpu().numpy(), per)
     Z = engine.rollout(inp["coefs"], inp["z0"], wl.T, wl.dt).cpu().numpy()
     assert np.max(np.abs(Z - Zis)) <= TRAJ_RTOL * np.max(np.abs(Zis))
+    if nm.startswith("wide_k") and mode == _lib.MODE_DIRECT:
+        # decoder forward of the CUDA-core path (both tile sizes) against torch on the oracle's trajectories
+        Zf = torch.from_numpy(Zis[:, :, :, :].reshape(-1, wl.n_z).astype(np.float32))
+        X = engine.decode(Zf).cpu().numpy()
+        ref = orc.decoder_forward([torch.from_numpy(w) for w in Ws], [torch.from_numpy(b) for b in bs], wl.act, Zf).numpy()
+        assert np.max(np.abs(X - ref)) <= FIELD_RTOL * np.max(np.abs(ref))
 
 
 @pytest.mark.parametrize("K,S,D,T,act", [
