@@ -359,6 +359,7 @@ __device__ __forceinline__ float sbp_entry(const SbpF& sc, int r, int c, int T) 
 }
 
 constexpr int kBwdThreads = 128;
+constexpr int kFitCtaMaxBatch = 296;         // up to two series per SM go to the CTA-cooperative fit kernel
 
 // Gradient of  L = sum_b gs[b] * loss_sindy[b] + gc[b] * loss_coef[b]  with respect to Z, where (reference
 // sindy.py:66-77, differentiated by torch autograd through sparse.mm / lstsq / MSELoss / norm in gplasdi.py:186-197)
@@ -611,6 +612,163 @@ int launch_sindy_fit_backward(glasdi_handle* h, const float* Z, const float* coe
 }
 
 
+// ---- CTA-cooperative fit for the training loop's batch sizes --------------------------------------------------------
+// The warp-per-series kernel above is a throughput design (8192 series in 0.33 ms); at n_train <= ~100 series a call is
+// the serial time of ONE warp walking its series (58 us at T = 1001).  Here 128 threads share a series: 8 rows per
+// thread instead of 32, fp64 partial sums reduced by shuffles and a fixed-order sum over the warps, the same Cholesky
+// solve, the same second pass.  Same arithmetic per row; the fp64 sums are taken in a different order, so coefficients
+// may differ from the warp kernel's in the last fp32 bit (both are within 1e-6 of LAPACK on the fixtures).
+template <int N, int HW>
+__global__ void __launch_bounds__(kBwdThreads) sindy_fit_cta_kernel(const float* __restrict__ Z, int T, int fd_id,
+                                                                    float inv_dt, int norm_order,
+                                                                    float* __restrict__ coefs_out,
+                                                                    float* __restrict__ loss_sindy_out,
+                                                                    float* __restrict__ loss_coef_out,
+                                                                    int32_t* __restrict__ info_out) {
+  constexpr int NA = N + 1;
+  constexpr int NG = NA * (NA + 1) / 2;
+  constexpr int NR = NA * N;
+  constexpr int NS = NG + NR;
+  constexpr int NW = kBwdThreads / 32;
+  __shared__ double sRed[NW][NS];
+  __shared__ double sG[NA][NA];
+  __shared__ double sR[NA][N];
+  __shared__ double sSe[NW];
+  __shared__ int sInfo;
+  extern __shared__ float s_fit[];                    // [T][N] the series
+  const SbpF& sc = c_sbp[fd_id];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const float* __restrict__ zg = Z + (size_t)b * T * N;
+  for (int f = tid; f < T * N; f += kBwdThreads) s_fit[f] = __ldg(zg + f);
+  __syncthreads();
+  const float* z = s_fit;
+
+  double acc[NS];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) acc[q] = 0.0;
+  for (int t = tid; t < T; t += kBwdThreads) {
+    double xd[NA], dd[N];
+    xd[0] = 1.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      xd[1 + i] = (double)z[t * N + i];
+      dd[i] = (double)(inv_dt * sbp_row<HW>(sc, t, T, [&](int row) { return z[row * N + i]; }));
+    }
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int c = a; c < NA; ++c) { acc[q] = fma(xd[a], xd[c], acc[q]); ++q; }
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int i = 0; i < N; ++i) { acc[q] = fma(xd[a], dd[i], acc[q]); ++q; }
+  }
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    double v = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sRed[warp][q] = v;
+  }
+  __syncthreads();
+  if (tid < NS) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += sRed[w][tid];
+    sRed[0][tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int q = 0;
+    for (int a = 0; a < NA; ++a)
+      for (int c = a; c < NA; ++c) { sG[a][c] = sRed[0][q]; sG[c][a] = sRed[0][q]; ++q; }
+    for (int a = 0; a < NA; ++a)
+      for (int i = 0; i < N; ++i) sR[a][i] = sRed[0][q++];
+    int info = 0;
+    double dmax = 0.0;
+    for (int a = 0; a < NA; ++a) dmax = fmax(dmax, sG[a][a]);
+#pragma unroll 1
+    for (int j = 0; j < NA; ++j) {
+      double sdiag = sG[j][j];
+      for (int k = 0; k < j; ++k) sdiag -= sG[j][k] * sG[j][k];
+      if (!(sdiag > 1e-13 * dmax)) { info = j + 1; break; }
+      const double ljj = sqrt(sdiag);
+      sG[j][j] = ljj;
+      const double rl = 1.0 / ljj;
+#pragma unroll 1
+      for (int i = j + 1; i < NA; ++i) {
+        double v = sG[i][j];
+        for (int k = 0; k < j; ++k) v -= sG[i][k] * sG[j][k];
+        sG[i][j] = v * rl;
+      }
+    }
+    sInfo = info;
+  }
+  __syncthreads();
+  const int info = sInfo;
+  if (tid < N && info == 0) {
+#pragma unroll 1
+    for (int i = 0; i < NA; ++i) {
+      double v = sR[i][tid];
+      for (int k = 0; k < i; ++k) v -= sG[i][k] * sR[k][tid];
+      sR[i][tid] = v / sG[i][i];
+    }
+#pragma unroll 1
+    for (int i = NA - 1; i >= 0; --i) {
+      double v = sR[i][tid];
+      for (int k = i + 1; k < NA; ++k) v -= sG[k][i] * sR[k][tid];
+      sR[i][tid] = v / sG[i][i];
+    }
+  }
+  __syncthreads();
+  float Rf[NA][N];
+  double nrm = 0.0;
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      const float cf = info == 0 ? (float)sR[a][c] : nanf("");
+      Rf[a][c] = cf;
+      nrm += (norm_order == 1) ? fabs((double)cf) : (double)cf * (double)cf;
+    }
+  if (tid == 0) {
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int c = 0; c < N; ++c) coefs_out[(size_t)b * NR + a * N + c] = Rf[a][c];
+    if (loss_coef_out) loss_coef_out[b] = (float)((norm_order == 1) ? nrm : sqrt(nrm));
+    if (info_out) info_out[b] = info;
+  }
+  if (!loss_sindy_out) return;
+  double se = 0.0;
+  for (int t = tid; t < T; t += kBwdThreads) {
+    float zr[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) zr[j] = z[t * N + j];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float d = inv_dt * sbp_row<HW>(sc, t, T, [&](int row) { return z[row * N + i]; });
+      float pred = Rf[0][i];
+#pragma unroll
+      for (int j = 0; j < N; ++j) pred = fmaf(zr[j], Rf[1 + j][i], pred);
+      const float e = d - pred;
+      se += (double)e * (double)e;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+  if (lane == 0) sSe[warp] = se;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) tot += sSe[w];
+    loss_sindy_out[b] = (float)(tot / ((double)T * N));
+  }
+}
+
 template <int HW>
 static void launch_fd_hw(const float* Z, int B, int T, int n, int fd_id, float inv_dt, float* dZ, cudaStream_t st) {
   const int per_block = kFdThreads * kFdPerThread;
@@ -651,6 +809,13 @@ int launch_fd_dzdt(glasdi_handle* h, const float* Z, int B, int T, int n, int fd
 template <int N, int HW>
 static void launch_fit_nh(const float* Z, int B, int T, int fd_id, float inv_dt, int norm_order, float* coefs,
                           float* ls, float* lc, int32_t* info, cudaStream_t st) {
+  const size_t smem_cta = (size_t)T * N * sizeof(float);
+  if (B <= kFitCtaMaxBatch && smem_cta <= 200 * 1024) {   // training-loop batch sizes: latency, not throughput
+    if (smem_cta > 40 * 1024)
+      cudaFuncSetAttribute(sindy_fit_cta_kernel<N, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta);
+    sindy_fit_cta_kernel<N, HW><<<B, kBwdThreads, smem_cta, st>>>(Z, T, fd_id, inv_dt, norm_order, coefs, ls, lc, info);
+    return;
+  }
   const int per_cta = kFitThreads / 32;
   size_t smem = (size_t)per_cta * T * N * sizeof(float);
   const int use_smem = smem <= 100 * 1024;            // 2 CTAs per SM keep their series resident (reading through
