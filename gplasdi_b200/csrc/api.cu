@@ -70,6 +70,8 @@ static void free_decoder(Decoder& d) {
   d.w_packed = nullptr;
   if (d.v_packed) cudaFree(d.v_packed);
   d.v_packed = nullptr;
+  if (d.wide_packed) cudaFree(d.wide_packed);
+  d.wide_packed = nullptr;
   d.gram_ok = false;
   d.ready = false;
   d.tc_ok = false;
@@ -197,6 +199,10 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
       if (value < 4 || value > 16) return set_error(h, GLASDI_ERR_INVALID, "screen margin must be 4..16 (delta = 2^-value)");
       h->opt_margin_log2 = value;
       return GLASDI_OK;
+    case GLASDI_OPT_WIDE_TENSOR:
+      if (value != 0 && value != 1) return set_error(h, GLASDI_ERR_INVALID, "wide-tensor option must be 0 or 1");
+      h->opt_wide = value;
+      return GLASDI_OK;
     default: return set_error(h, GLASDI_ERR_INVALID, "unknown option");
   }
 }
@@ -212,6 +218,7 @@ int glasdi_get_option(const glasdi_handle* h, int option, int* value) {
     case GLASDI_OPT_DECODE_KERNEL: *value = h->opt_kernel; return GLASDI_OK;
     case GLASDI_OPT_MODE: *value = h->opt_mode; return GLASDI_OK;
     case GLASDI_OPT_SCREEN_MARGIN: *value = h->opt_margin_log2; return GLASDI_OK;
+    case GLASDI_OPT_WIDE_TENSOR: *value = h->opt_wide; return GLASDI_OK;
     default: return GLASDI_ERR_INVALID;
   }
 }
@@ -283,6 +290,10 @@ int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths, const 
     }
     GL_CUDA(h, cudaMalloc(&d.w_packed, packed.size() * sizeof(__half)));
     GL_CUDA(h, cudaMemcpy(d.w_packed, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
+  if (!ok) {   // wide decoders: the last layer goes through decode_wide.cu
+    int rcw = wide_pack_w(h, WL);
+    if (rcw) return rcw;
   }
   // covariance-form screening: the constant unit must fit the 128-row tile, shared memory must hold the ring
   int xw = 0;

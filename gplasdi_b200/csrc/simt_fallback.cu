@@ -328,14 +328,19 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
   const long long groups = (long long)P * T;
   // slab of (p,t) groups: rows = ng * S, two ping-pong activations + gathered input
   const size_t row_bytes = (size_t)(2 * maxw + n) * sizeof(float);
-  long long ng = std::max<long long>(1, std::min<long long>(groups, ((size_t)1 << 30) / (row_bytes * (size_t)S)));
+  const bool wide = h->opt_wide && d.wide_packed != nullptr;        // last layer + variance on tcgen05 (decode_wide.cu)
+  const size_t bt_group = wide ? wide_b_bytes(d.K, S, 1) : 0;       // packed hidden layer of one (p, t) group
+  long long ng = std::max<long long>(
+      1, std::min<long long>(groups, ((size_t)1 << 30) / (row_bytes * (size_t)S + bt_group)));
   ng = std::min<long long>(ng, 32768);
   // scratch lives behind the trajectory buffer in the workspace: allocate separately here
   float* scratch = nullptr;
-  GL_CUDA(h, cudaMallocAsync((void**)&scratch, (size_t)ng * S * row_bytes, st));
+  const size_t chain_bytes = ((size_t)ng * S * row_bytes + 1023) / 1024 * 1024;
+  GL_CUDA(h, cudaMallocAsync((void**)&scratch, chain_bytes + bt_group * ng, st));
   float* Xrow = scratch;
   float* bufA = Xrow + (size_t)ng * S * n;
   float* bufB = bufA + (size_t)ng * S * maxw;
+  void* bt_ws = reinterpret_cast<uint8_t*>(scratch) + chain_bytes;
   int rc = GLASDI_OK;
   for (long long g0 = 0; g0 < groups && rc == GLASDI_OK; g0 += ng) {
     const long long gn = std::min(ng, groups - g0);
@@ -346,6 +351,10 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
     const float* Hlast = nullptr;
     rc = run_chain(h, Xrow, R, d.n_linear - 1, bufA, bufB, &Hlast, st);
     if (rc) break;
+    if (wide) {
+      rc = launch_wide_last_var(h, Hlast, g0, gn, S, T, bt_ws, maxvar_bits, st);
+      continue;
+    }
     if (d.K % 4 == 0 && d.K >= 32 && d.D >= 64 && S >= 64 && (reinterpret_cast<uintptr_t>(Hlast) & 15) == 0) {
       dim3 grid((unsigned)gn, (d.D + simt::GN - 1) / simt::GN);
       simt::last_var_kernel128<<<grid, 256, 0, st>>>(Hlast, d.dW[d.n_linear - 1], S, d.K, d.D, T, g0, maxvar_bits);

@@ -58,6 +58,8 @@ WORKLOADS = {
     # decoder the fused tcgen05 kernel does not cover (K_last > 112) -> CUDA-core path
     "wide_k": Workload("wide_k", (3, 2), 24, 7, [5, 16, 160, 200], "softplus", 1.0 / 6),
     # same path through its 128 x 128 tiles (rows % 4 == 0, >= 64 samples): ragged sample / dof / k tails
+    # the Vlasov-shaped decoder's tail at full width (K_last = 1000, D = 4096), few rows: 16 k-chunks x 3 split passes
+    "wide_k1000": Workload("wide_k1000", (3, 2), 300, 4, [5, 50, 200, 1000, 4096], "softplus", 1.0 / 3),
     "wide_k128": Workload("wide_k128", (3, 2), 130, 5, [5, 40, 164, 300], "softplus", 1.0 / 4),
 }
 

@@ -48,7 +48,8 @@ def main():
         K = wl.widths[-2]
         path = ("gram_kernel fast path (one front layer) + quad_kernel + refine" if K <= 111 and len(wl.widths) == 3 else
                 "gram_kernel generic producers (deeper front MLP on the CUDA cores) + quad_kernel + refine" if K <= 111 else
-                "CUDA-core fp32 path (simt_fallback.cu: K_last > 112 is not covered by the tcgen05 kernels yet)")
+                "front layers on the CUDA cores (simt_fallback.cu) + last layer and variance as a three-pass fp16-split "
+                "tcgen05 GEMM (decode_wide.cu: xvar_kernel)")
         print(json.dumps({
             "workload": f"{nm}-shaped synthetic (BASELINE.json configs[{list(BLOCKS).index(nm) + 1}]): P={wl.P} x S={wl.S}, T={wl.T}, "
                         f"D={wl.D}, decoder {wl.widths} {wl.act}", "params_in_block": Pb, "rollouts_per_s": Pb * wl.S / t,
