@@ -72,6 +72,9 @@ static void free_decoder(Decoder& d) {
   d.v_packed = nullptr;
   if (d.wide_packed) cudaFree(d.wide_packed);
   d.wide_packed = nullptr;
+  if (d.wide_front) cudaFree(d.wide_front);
+  d.wide_front = nullptr;
+  d.wide_k1 = 0;
   d.gram_ok = false;
   d.ready = false;
   d.tc_ok = false;
@@ -200,7 +203,7 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
       h->opt_margin_log2 = value;
       return GLASDI_OK;
     case GLASDI_OPT_WIDE_TENSOR:
-      if (value != 0 && value != 1) return set_error(h, GLASDI_ERR_INVALID, "wide-tensor option must be 0 or 1");
+      if (value < 0 || value > 2) return set_error(h, GLASDI_ERR_INVALID, "wide-tensor option must be 0, 1 or 2");
       h->opt_wide = value;
       return GLASDI_OK;
     default: return set_error(h, GLASDI_ERR_INVALID, "unknown option");
@@ -292,7 +295,7 @@ int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths, const 
     GL_CUDA(h, cudaMemcpy(d.w_packed, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
   if (!ok) {   // wide decoders: the last layer goes through decode_wide.cu
-    int rcw = wide_pack_w(h, WL);
+    int rcw = wide_pack_w(h, WL, n_linear >= 3 ? W_host[n_linear - 2] : nullptr, n_linear >= 3 ? widths[n_linear - 2] : 0);
     if (rcw) return rcw;
   }
   // covariance-form screening: the constant unit must fit the 128-row tile, shared memory must hold the ring

@@ -44,6 +44,8 @@ struct Decoder {
   int eV = 0;
   bool gram_ok = false;
   __half* wide_packed = nullptr;    // decode_wide.cu: [W_hi | W_hi | W_lo] tiles of the last layer (decoders with !tc_ok)
+  __half* wide_front = nullptr;     // ... of the last FRONT layer (input width wide_k1 >= 16), scale 2^eW1
+  int wide_k1 = 0, eW1 = 0;
   std::vector<float> h_front_last_W, h_front_last_b;   // host copy of the last FRONT layer (kernel-parameter weights)
 };
 
@@ -82,7 +84,7 @@ struct glasdi_handle {
   int* d_flags = nullptr;             // [4] device error flags: [0] fp16 range, [1] candidate overflow, [2] screening deviation
   // screened mode (GLASDI_OPT_MODE = 1): candidates of the last greedy call
   int opt_mode = 2;                   // 0: direct (split passes), 1: x-space screening + refinement, 2: covariance-form screening + refinement
-  int opt_wide = 1;                   // wide decoders: last layer on tcgen05 (decode_wide.cu) instead of the CUDA cores
+  int opt_wide = 2;                   // wide decoders: 0 CUDA cores only, 1 last layer on tcgen05 (decode_wide.cu), 2 + last front layer
   int opt_margin_log2 = 8;            // candidates = variance within (1 - 2^-margin)^2 of the screened maximum
   void* d_cand = nullptr;             // [cand_cap] {p, t, d, approx variance}
   size_t cand_cap = 0;
@@ -149,8 +151,11 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
 int launch_decode_store_simt(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
 int launch_encode_simt(glasdi_handle* h, const float* U, int64_t rows, float* Z, cudaStream_t st);
 // decode_wide.cu : last layer + variance of wide decoders (K_last > 112) as a K-looped three-pass tcgen05 GEMM
-int wide_pack_w(glasdi_handle* h, const float* WL_host);
+int wide_pack_w(glasdi_handle* h, const float* WL_host, const float* W1_host, int K1);
 size_t wide_b_bytes(int K, int S, long long n_groups);
+size_t wide_x_bytes(int K1, int S, long long n_groups);
+int launch_wide_front(glasdi_handle* h, const float* X, long long n_groups, int S, void* xt_ws, void* bt_ws,
+                      cudaStream_t st);
 int launch_wide_last_var(glasdi_handle* h, const float* Hlast, long long g0, long long n_groups, int S, int T, void* bt_ws,
                          unsigned int* maxvar_bits, cudaStream_t st);
 // reduce.cu

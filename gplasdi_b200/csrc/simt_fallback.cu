@@ -329,7 +329,9 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
   // slab of (p,t) groups: rows = ng * S, two ping-pong activations + gathered input
   const size_t row_bytes = (size_t)(2 * maxw + n) * sizeof(float);
   const bool wide = h->opt_wide && d.wide_packed != nullptr;        // last layer + variance on tcgen05 (decode_wide.cu)
-  const size_t bt_group = wide ? wide_b_bytes(d.K, S, 1) : 0;       // packed hidden layer of one (p, t) group
+  const bool wide_front = wide && h->opt_wide >= 2 && d.wide_front != nullptr;   // ... and the last front layer too (xact_kernel)
+  const size_t xt_group = wide_front ? wide_x_bytes(d.wide_k1, S, 1) : 0;
+  const size_t bt_group = wide ? wide_b_bytes(d.K, S, 1) + xt_group : 0;   // packed hidden layer (+ packed input) of one (p, t) group
   long long ng = std::max<long long>(
       1, std::min<long long>(groups, ((size_t)1 << 30) / (row_bytes * (size_t)S + bt_group)));
   ng = std::min<long long>(ng, 32768);
@@ -349,6 +351,16 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
                                                                                                      gn, Xrow);
     h->launches++;
     const float* Hlast = nullptr;
+    if (wide_front) {
+      // layers before the last front layer on the CUDA cores, then both wide layers on tcgen05
+      void* xt_ws = reinterpret_cast<uint8_t*>(bt_ws) + wide_b_bytes(d.K, S, ng);
+      rc = run_chain(h, Xrow, R, d.n_linear - 2, bufA, bufB, &Hlast, st);
+      if (rc) break;
+      rc = launch_wide_front(h, Hlast, gn, S, xt_ws, bt_ws, st);
+      if (rc) break;
+      rc = launch_wide_last_var(h, nullptr, g0, gn, S, T, bt_ws, maxvar_bits, st);
+      continue;
+    }
     rc = run_chain(h, Xrow, R, d.n_linear - 1, bufA, bufB, &Hlast, st);
     if (rc) break;
     if (wide) {

@@ -67,9 +67,10 @@ enum glasdi_option {
   GLASDI_OPT_MODE = 6,          /* enum glasdi_mode (default SCREENED_GRAM) */
   GLASDI_OPT_SCREEN_MARGIN = 7, /* m in 4..16 (default 8): screened mode re-evaluates every (t, dof) whose
                                    single-pass std is within delta = 2^-m of the parameter's screened maximum */
-  GLASDI_OPT_WIDE_TENSOR = 8    /* decoders outside the fused tcgen05 kernels (last-layer input width > 112): 1 (default)
-                                   last layer + variance as a three-pass fp16-split tcgen05 GEMM (decode_wide.cu), 0: the
-                                   fp32 CUDA-core GEMM.  The layers before it run on the CUDA cores either way. */
+  GLASDI_OPT_WIDE_TENSOR = 8    /* decoders outside the fused tcgen05 kernels (last-layer input width > 112): 2 (default)
+                                   last front layer AND last layer + variance as three-pass fp16-split tcgen05 GEMMs
+                                   (decode_wide.cu), 1: only the last layer, 0: fp32 CUDA-core GEMMs throughout.  Earlier
+                                   front layers run on the CUDA cores in every case.  Same results (fp32-faithful). */
 };
 
 /* how glasdi_greedy_step / glasdi_decode_max_std obtain max_std[p] (same result within the fp32 tolerance) */

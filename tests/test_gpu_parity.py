@@ -463,13 +463,16 @@ def test_ragged_and_wide_shapes_against_oracle(engine, nm, mode):
         assert big.any() and np.max(np.abs(got[big] - per[big]) / per[big]) <= 1e-4
     if nm.startswith("wide_k") and mode == _lib.MODE_DIRECT:
         # the same decoders with the last layer on the CUDA cores instead of the three-pass tcgen05 GEMM
-        engine.set_option(_lib.OPT_WIDE_TENSOR, 0)
-        try:
-            ms0, am0, _ = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
-        finally:
-            engine.set_option(_lib.OPT_WIDE_TENSOR, 1)
-        assert int(am0) == idx
-        std_close(ms0.cpu().numpy(), per, atol=atol)
+        # (0), and with only the last layer on tcgen05 (1); the default (2) also runs the last front layer there
+        for wide_mode in (0, 1):
+            engine.set_option(_lib.OPT_WIDE_TENSOR, wide_mode)
+            try:
+                ms0, am0, _ = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
+                engine.check_numeric()
+            finally:
+                engine.set_option(_lib.OPT_WIDE_TENSOR, 2)
+            assert int(am0) == idx
+            std_close(ms0.cpu().numpy(), per, atol=atol)
         # decoder forward of the CUDA-core path (both tile sizes) against torch on the oracle's trajectories
         Zf = torch.from_numpy(Zis[:, :, :, :].reshape(-1, wl.n_z).astype(np.float32))
         X = engine.decode(Zf).cpu().numpy()

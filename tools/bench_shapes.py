@@ -33,7 +33,7 @@ def main():
         lo = (wl.P - Pb) // 2
         inp = synth.make_inputs(wl, slice(lo, lo + Pb))
         coefs = torch.from_numpy(inp["coefs"]).cuda(); z0 = torch.from_numpy(inp["z0"]).cuda()
-        reps = 3 if nm in ("burgers1d", "burgers2d") else 1
+        reps = 3
         eng.greedy_step(coefs, z0, wl.T, wl.dt)              # warm-up
         eng.check_numeric()
         torch.cuda.synchronize()
@@ -48,8 +48,8 @@ def main():
         K = wl.widths[-2]
         path = ("gram_kernel fast path (one front layer) + quad_kernel + refine" if K <= 111 and len(wl.widths) == 3 else
                 "gram_kernel generic producers (deeper front MLP on the CUDA cores) + quad_kernel + refine" if K <= 111 else
-                "front layers on the CUDA cores (simt_fallback.cu) + last layer and variance as a three-pass fp16-split "
-                "tcgen05 GEMM (decode_wide.cu: xvar_kernel)")
+                "early front layers on the CUDA cores (simt_fallback.cu) + last front layer (xact_kernel) and last layer + "
+                "variance (xvar_kernel) as three-pass fp16-split tcgen05 GEMMs (decode_wide.cu)")
         print(json.dumps({
             "workload": f"{nm}-shaped synthetic (BASELINE.json configs[{list(BLOCKS).index(nm) + 1}]): P={wl.P} x S={wl.S}, T={wl.T}, "
                         f"D={wl.D}, decoder {wl.widths} {wl.act}", "params_in_block": Pb, "rollouts_per_s": Pb * wl.S / t,
