@@ -8,15 +8,21 @@ Workload = BASELINE.json configs[1], the Burgers1D-shaped synthetic ensemble: 21
 parameters x 1000 GP samples, nt = 501, nx = 1001, latent dim 5, decoder [5,100,1001] sigmoid.
 A "step" is one pass of the whole greedy-sampling hot path over that ensemble:
 rollout -> decode -> std over samples -> max over (t, x) -> argmax (-> max-loc all-reduce at N > 1).
-Weak scaling: every rank owns its own 441-parameter block of a (441 N)-point grid, no data-path
+Weak scaling (the headline line): every rank owns its own 441-parameter block of a (441 N)-point grid, no data-path
 collective, one 8-byte max-loc all-reduce (NCCL) per step.
 
-Printed JSON (rank 0, one line): metric/value = rollouts/s with inputs resident in HBM, device-timed
-with CUDA events, max over ranks; `e2e` = the same metric through the public Python API from pinned
-HOST buffers (H2D of the coefficient draws and D2H of max_std + index inside the timed region);
-`roofline` = the decode+variance kernel's algorithmic FLOP rate against the measured dense bf16
-tensor peak of MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle (port of the reference's own
-scipy/torch/numpy path) timed on a bounded sample on this box's host cores.
+Printed JSON (rank 0, one line):
+  value      rollouts/s with inputs resident in HBM, device-timed with CUDA events, max over ranks
+  e2e        the same metric through the public Python API (Engine.checked = step + numeric check) from pinned HOST
+             buffers, H2D of the draws and D2H of max_std + key inside the timed region
+  roofline   the dominant kernel: tensor FLOP it ISSUES / its own device time / the measured dense tensor peak of
+             MEASURED_PEAKS.json (burst figure for a sub-second timed region) -- a physical fraction; the algebraic gain of
+             the covariance form over decoding every sample is a separate key, never a roofline fraction
+  strong     ONE fixed grid (this workload's 441 parameters, the grid of the reference-run golden) split over the N ranks
+             through sharding.sharded_greedy_step: ms/step, the selected global index and whether it equals the golden's
+  configs    the other named shapes of BASELINE.json (configs[2..4]) at their named decoder / S / T on a fixed global block
+             of test parameters split over the ranks, >= 1 s of timed work each at N = 1, with their own clock record
+  cpu_baseline  the CPU oracle (port of the reference's own scipy/torch/numpy path) on a bounded sample on the host cores
 
 --impl reference times that CPU path alone (the reference is pure Python + torch/scipy/numpy CPU
 calls and cannot travel to the GPU box; oracle/reference_path.py restates it call for call and is
@@ -82,14 +88,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self, t0: float, t1: float):
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def window(self, t0: float, t1: float):
+        """clocks / throttle reasons of the samples taken inside [t0, t1] (the sampler keeps running)"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
-        self.proc.terminate()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.lines:
+        for ts, line in list(self.lines):
             if ts < t0 - 0.05 or ts > t1 + 0.05:
                 continue
             f = [x.strip() for x in line.split(",")]
@@ -159,6 +169,36 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# Blocks of test parameters the OTHER named shapes (BASELINE.json configs[2..4]) are timed on: a fixed GLOBAL block, split
+# over the ranks like the real grid would be (strong scaling), sized for >= 1 s of timed device work at N = 1.
+NAMED_BLOCKS = {"burgers2d": (None, 10), "vlasov1d1v": (64, 1), "rising_bubble": (48, 1)}     # (params or None = whole grid, steps)
+
+
+def issued_tensor_flop(eng_widths, P, S, T, mode_gram: bool, passes: int):
+    """Tensor-core FLOP the kernels ISSUE for P parameters (padding included): the physical numerator of a tensor-pipe
+    fraction.  Covariance form (last-layer input width K <= 111): Gram MMAs (M = 128, N = ceil16(K + 1), K = 16 samples)
+    + tf32 pre-activation MMAs (one front layer) in gram_kernel, the [P T x Q] x [Q x D] GEMM in quad_kernel.  Wide
+    decoders: three-pass fp16-split GEMMs of the last front layer (xact_kernel) and of the last layer (xvar_kernel)."""
+    L = eng_widths
+    K, D = L[-2], L[-1]
+    n_items = P * T
+    if K + 1 <= 112 and mode_gram:
+        n16 = -(-(K + 1) // 16) * 16
+        gram = n_items * (-(-S // 16)) * 2.0 * 128 * n16 * 16
+        if len(L) == 3:
+            gram += n_items * (-(-S // 128)) * 3 * 2.0 * 128 * n16 * 8
+        q_pad = -(-(K * (K + 1) // 2) // 64) * 64
+        quad = -(-n_items // 128) * 128 * 2.0 * (-(-D // 256) * 256) * q_pad
+        return gram, quad
+    if K + 1 <= 112:
+        return n_items * 2.0 * (-(-S // 128) * 128) * (-(-D // 128) * 128) * (-(-K // 16) * 16) * passes, 0.0
+    Spad = -(-S // 256) * 256
+    K1 = L[-3]
+    xact = n_items * 2.0 * Spad * (-(-K // 128) * 128) * 3 * (-(-K1 // 64) * 64)
+    xvar = n_items * 2.0 * Spad * (-(-D // 128) * 128) * 3 * (-(-K // 64) * 64)
+    return xvar, xact
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -178,7 +218,7 @@ def run_ours(args):
 
     wl = synth.WORKLOADS[WORKLOAD]
     Ws, bs = synth.make_decoder(wl.widths, wl.seed)
-    # weak scaling: rank r owns block r of a (441 * world)-point grid -> its own seeded draws
+    # weak scaling: rank r owns block r of a (441 * world)-point grid -> its own seeded draws (rank 0 = the golden grid)
     from dataclasses import replace
     wl_r = replace(wl, seed=wl.seed + 17 * rank)
     inp = synth.make_inputs(wl_r)
@@ -188,8 +228,8 @@ def run_ours(args):
     eng = Engine(local_rank)
     eng.set_decoder(Ws, bs, wl.act)
     screened = args.mode != "direct"
-    eng.set_option(_lib.OPT_MODE, {"gram": _lib.MODE_SCREENED_GRAM, "screened": _lib.MODE_SCREENED,
-                                   "direct": _lib.MODE_DIRECT}[args.mode])
+    mode_id = {"gram": _lib.MODE_SCREENED_GRAM, "screened": _lib.MODE_SCREENED, "direct": _lib.MODE_DIRECT}[args.mode]
+    eng.set_option(_lib.OPT_MODE, mode_id)
     eng.set_option(_lib.OPT_SPLIT_PASSES, args.passes)
     eng.set_option(_lib.OPT_STAGE_TIMING, 1)
     issued_passes = 1 if screened else args.passes
@@ -212,6 +252,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(max(args.warmup, 3)):
         key = step()
@@ -243,24 +289,23 @@ def run_ours(args):
     barrier()
     t_wall1 = time.perf_counter()
     launches = eng.launch_count - launches0
-    total_ms = float(sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)))
-    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms = float(tt.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    total_ms = max_over_ranks(float(sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))))
+    clocks = sampler.window(t_wall0, t_wall1) if rank == 0 else None
     val_key, sel_idx = sharding.unpack_maxloc(int(key.item()))
+    local_sel = int(out[1].item())                                        # this rank's own selection (rank 0: the golden grid)
 
     # ---- end to end through the public API from pinned host buffers -----------------------------
+    # Engine.checked = greedy step + glasdi_check_numeric (+ the direct-mode repeat if the screening flag is up): the
+    # call get_new_sample_point / sharded_greedy_step make, numeric check inside the timed region
     h2d = coefs_host.numel() * 8 + z0_host.numel() * 4
-    d2h = P * 4 + 8 + 4
+    d2h = P * 4 + 8 + 4 + 16
     host_ms = torch.empty(P, dtype=torch.float32).pin_memory()
     e2e_times = []
     barrier()
     for k in range(args.steps + 1):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ms, am, mv = eng.greedy_step(coefs_host, z0_host, T, wl.dt)      # H2D inside (non_blocking, pinned)
+        ms, am, mv = eng.checked(lambda: eng.greedy_step(coefs_host, z0_host, T, wl.dt))   # H2D inside (pinned, overlapped)
         k2 = eng.pack_maxloc(mv, am, index_offset)
         sharding.allreduce_maxloc(k2)
         host_ms.copy_(ms, non_blocking=True)
@@ -268,10 +313,41 @@ def run_ours(args):
         torch.cuda.synchronize()
         if k > 0:
             e2e_times.append(time.perf_counter() - t0)
-    te = torch.tensor([float(np.sum(e2e_times))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_total = float(te.item())
+    e2e_total = max_over_ranks(float(np.sum(e2e_times)))
+
+    # ---- strong scaling of THIS grid: the 441 parameters of rank 0's (golden) grid split over the ranks ----------
+    gold_path = os.path.join(ROOT, "tests", "golden", "greedy_named_burgers1d.npz")
+    gold_idx = int(np.load(gold_path)["m_index"][0]) if os.path.exists(gold_path) else None
+    bnd = sharding.shard_bounds(P, world)
+    lo, hi = bnd[rank], bnd[rank + 1]
+    inp0 = synth.make_inputs(wl, slice(lo, hi))                           # this rank's block of the UNSHIFTED (golden) grid
+    c_s = torch.from_numpy(inp0["coefs"]).to(dev); z_s = torch.from_numpy(inp0["z0"]).to(dev)
+    strong_ms = []
+    skey = None
+    for k in range(3 + args.steps):
+        barrier()
+        flush.fill_(k & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, skey = sharding.sharded_greedy_step(eng, c_s, z_s, T, wl.dt, lo)
+        e1.record()
+        e1.synchronize()
+        if k >= 3:
+            strong_ms.append(e0.elapsed_time(e1))
+    strong_total = max_over_ranks(float(np.sum(strong_ms)))
+    s_val, s_idx = sharding.unpack_maxloc(int(skey.item()))
+    del c_s, z_s
+
+    # ---- the other named shapes, each on its fixed global block split over the ranks -----------------------------
+    named = []
+    if not args.no_named:
+        for nm, (blk, nsteps) in NAMED_BLOCKS.items():
+            named.append(time_named_shape(eng, nm, blk, nsteps, world, rank, dev, sampler if rank == 0 else None,
+                                          barrier, max_over_ranks, flush, mode_id))
+        eng.set_decoder(Ws, bs, wl.act)
+        eng.set_option(_lib.OPT_MODE, mode_id)
+    if rank == 0:
+        sampler.stop()
 
     if rank == 0:
         pk = peaks()
@@ -279,43 +355,30 @@ def run_ours(args):
         value = rollouts_per_step * args.steps / (total_ms * 1e-3)
         flops_launch = wl.decoder_flops_per_rollout() * P * S          # algorithmic FLOP of one decode launch
         dec_avg_ms = float(np.mean(dec_ms)) / max(1, dec_launches / args.steps)
-        achieved = flops_launch / (dec_avg_ms * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "decode_kernel_traffic.json")
-        if os.path.exists(tpath) and args.mode == "gram":
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        K = wl.widths[-2]
-        pad = 1.12 * 1024.0 / 1001.0 * 1024.0 / 1000.0
+        step_ms = total_ms / args.steps
+        # sub-second timed region -> the burst figure of MEASURED_PEAKS.json is the fair denominator
+        peak = pk["burst"] if step_ms * args.steps < 1000.0 else pk["sustained"]
+        peak_kind = "burst" if peak == pk["burst"] else "sustained"
+        traffic, traffic_src = measured_traffic()
+        issued, issued_2nd = issued_tensor_flop(wl.widths, P, S, T, args.mode == "gram", issued_passes)
+        achieved = issued / (dec_avg_ms * 1e-3) / 1e12                 # ISSUED tensor FLOP of the dominant kernel / its time
         if args.mode == "gram":
-            n_items = P * T
-            nmma = -(-S // 16)
-            q_pad = -(-(K * (K + 1) // 2) // 64) * 64
-            issued = n_items * nmma * 2.0 * 128 * (-(-(K + 1) // 16) * 16) * 16          # gram_kernel: Gram MMAs
-            issued += n_items * (-(-S // 128)) * 3 * 2.0 * 128 * (-(-(K + 1) // 16) * 16) * 8   # + tf32 pre-activation MMAs
-            issued_quad = -(-n_items // 128) * 128 * 2.0 * (-(-wl.D // 256) * 256) * q_pad   # quad_kernel MMAs
             kernel = ("glasdi::gr::gram_kernel<sigmoid, 5, fast> (tcgen05 cta_group::1: tf32 pre-activation MMAs + f16 Gram MMAs on "
                       "MN-major SW128 tiles, M=128 N=112 K=16)")
-            note = ("frac is on the ALGORITHMIC decoder FLOP of the reference formulation (decode every sample, then std). "
-                    "The covariance form reaches the same variances with 5x fewer FLOP (K^2 S + K(K+1)/2 D instead of K S D per "
-                    "(parameter, time step)), so frac > 1 is algebra, not a faster tensor pipe: gram_kernel issues "
-                    f"{issued:.3e} tensor FLOP (+ {issued_quad:.3e} in quad_kernel) and is bound by the CUDA-core work that "
-                    "feeds it -- P*S*T*K = 2.2e10 sigmoid evaluations (MUFU ex2 + rcp: XU pipe 50 %, issue slots 55 % busy in "
-                    "profiles/r01_gram_quad_kernels_bench_full_ncu.json).  kernel_ms is gram_kernel alone; quad_kernel_ms "
-                    "is the second GEMM (80 % tensor-pipe active)")
+            note = ("frac = tensor FLOP gram_kernel ISSUES (padding included) / its own device time / peak: a physical "
+                    "tensor-pipe fraction.  The kernel is bound by the CUDA-core work that feeds the tensor pipe -- P*S*T*K = "
+                    "2.2e10 sigmoid evaluations (MUFU) -- not by the pipe itself; quad_kernel (second GEMM) is tensor-bound. "
+                    "The covariance form needs 5x fewer FLOP than decoding every sample (K^2 S + K(K+1)/2 D instead of K S D "
+                    "per (parameter, time step)): that algebraic gain is reported separately as "
+                    "algorithmic_speedup_vs_single_pass_roofline, never as a roofline fraction")
         else:
-            issued = flops_launch * issued_passes * pad
-            issued_quad = 0.0
             kernel = "glasdi::dv2::decode_pair_kernel<VarT1, sigmoid, 5> (tcgen05 cta_group::2)"
-            note = ("frac is on ALGORITHMIC decoder FLOP (single pass); the kernel issues "
-                    f"{issued_passes} fp16 pass(es) per product and pads K 100->112, D 1001->1024, S 1000->1024: "
-                    "issued_frac is the tensor-pipe view of the same launch.  Decoding the ensemble into TMEM is bound by "
-                    "the accumulator drain (tcgen05.ld, 64 B/clk/SM): K/256 = 44 % of the tensor peak per pass")
+            note = (f"frac = issued tensor FLOP ({issued_passes} fp16 pass(es), K 100->112, D 1001->1024, S 1000->1024 padding) / "
+                    "kernel time / peak.  Decoding the ensemble into TMEM is bound by the accumulator drain (tcgen05.ld, "
+                    "64 B/clk/SM): K/256 = 44 % of the tensor peak per pass")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": ("f32 (fp16 tensor-core screening pass over the ensemble, fp32 TMEM accumulate; exact fp32 decode + "
                       "fp64 sample sums at the near-maximum candidates; fp64 rollout)" if screened else
@@ -325,23 +388,38 @@ def run_ours(args):
                        "mode": args.mode, "split_passes": issued_passes,
                        "parallelism": f"test-grid sharding x{world} + 1 max-loc all-reduce",
                        "l2": "256 MB buffer written between timed iterations; per-step working set 7.7 GB >> 126 MB L2",
-                       "selected_global_index": sel_idx},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["sustained"], "traffic": traffic, "kernel": kernel,
-                         "issued_frac": issued / (dec_avg_ms * 1e-3) / 1e12 / pk["sustained"],
-                         "kernel_ms": dec_avg_ms, "rollout_kernel_ms": float(np.mean(roll_ms)),
-                         "algorithmic_flop_per_launch": flops_launch, "issued_flop_per_launch": issued,
-                         "peak_source": pk["source"] + " bf16 dense, sustained figure (kernel timed inside a long step); "
+                       "selected_global_index": sel_idx, "selected_index_rank0_grid": local_sel,
+                       "golden_index": gold_idx,
+                       "selected_index_matches_golden": (None if gold_idx is None else bool(local_sel == gold_idx))},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel,
+                         "kernel_ms": dec_avg_ms, "kernel_share_of_step": dec_avg_ms / step_ms,
+                         "rollout_kernel_ms": float(np.mean(roll_ms)),
+                         "issued_flop_per_launch": issued,
+                         "whole_step_issued_tflops": (issued + issued_2nd) / (step_ms * 1e-3) / 1e12,
+                         "whole_step_issued_frac": (issued + issued_2nd) / (step_ms * 1e-3) / 1e12 / peak,
+                         "algorithmic_flop_per_launch": flops_launch,
+                         "algorithmic_speedup_vs_single_pass_roofline": flops_launch / (dec_avg_ms * 1e-3) / 1e12 / peak,
+                         "peak_source": pk["source"] + f" bf16 dense, {peak_kind} figure ({'timed region < 1 s' if peak_kind == 'burst' else 'timed region >= 1 s'}); "
                                         "fp16 and bf16 share the tcgen05 kind::f16 rate",
                          "note": note},
             "e2e": {"value": rollouts_per_step * args.steps / e2e_total, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
+                    "d2h_bytes_per_step": d2h,
+                    "call": "Engine.checked(greedy_step(pinned host draws)) + pack_maxloc + all-reduce + D2H of max_std and the key"},
+            "strong": {"workload": workload_desc(wl) + " -- ONE fixed grid split over the ranks", "n_gpus": world,
+                       "shard_bounds": bnd, "ms_per_step": strong_total / args.steps,
+                       "rollouts_per_s": P * S * args.steps / (strong_total * 1e-3),
+                       "selected_global_index": s_idx, "max_std": s_val, "golden_index": gold_idx,
+                       "selected_index_matches_golden": (None if gold_idx is None else bool(s_idx == gold_idx)),
+                       "call": "sharding.sharded_greedy_step (Engine.checked + pack_maxloc + NCCL max-loc all-reduce), device-timed, max over ranks"},
+            "configs": named,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if args.mode == "gram":
             line["roofline"]["quad_kernel_ms"] = float(np.mean(quad_ms))
-            line["roofline"]["quad_issued_flop_per_launch"] = issued_quad
+            line["roofline"]["quad_issued_flop_per_launch"] = issued_2nd
+            line["roofline"]["quad_frac"] = issued_2nd / (float(np.mean(quad_ms)) * 1e-3) / 1e12 / peak
         if screened:
             line["roofline"]["refine"] = {
                 "select_plus_refine_ms": float(np.mean(ref_ms)), "candidates": int(n_cand),
@@ -354,7 +432,7 @@ def run_ours(args):
             except Exception as e:                                   # context only: never lose the headline line
                 line["aux"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
-            ncpu = 8
+            ncpu = 4
             v, dt_cpu, threads = cpu_reference_rate(wl, Ws, bs, ncpu, seed_shift=216)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{ncpu} of 441 test parameters x {S} samples ({ncpu * S} rollouts, {dt_cpu:.1f} s): "
@@ -362,6 +440,81 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from this round's `ncu --set full` capture of
+    this same command (profiles/r02_gram_kernel_traffic.json, written by tools/ncu_summary.py).  The capture records the
+    sha1 of the kernel's source file: a capture of an older kernel reads as null, never as a stale number."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "r02_gram_kernel_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    try:
+        d = json.load(open(path))
+        src = os.path.join(ROOT, "gplasdi_b200", "csrc", "decode_gram.cu")
+        if d.get("source_sha1") != hashlib.sha1(open(src, "rb").read()).hexdigest():
+            return None, "profiles/r02_gram_kernel_traffic.json is of an older decode_gram.cu: ignored"
+        return float(d["dram_bytes_per_launch"]), "profiles/r02_gram_kernel_traffic.json (" + d.get("how", "ncu --set full") + ")"
+    except Exception:
+        return None, None
+
+
+def time_named_shape(eng, nm, blk, nsteps, world, rank, dev, sampler, barrier, max_over_ranks, flush, mode_id):
+    """One named shape of BASELINE.json (configs[2..4]) on a fixed global block of its test grid, split over the ranks
+    (strong scaling), through sharding.sharded_greedy_step; device-timed, max over ranks, clocks sampled in the window."""
+    import torch
+    from gplasdi_b200 import synth, _lib, sharding
+    wl = synth.WORKLOADS[nm]
+    Ws, bs = synth.make_decoder(wl.widths, wl.seed)
+    eng.set_decoder(Ws, bs, wl.act)
+    eng.set_option(_lib.OPT_MODE, mode_id)
+    Pb = wl.P if blk is None else min(blk, wl.P)
+    first = (wl.P - Pb) // 2
+    bnd = sharding.shard_bounds(Pb, world)
+    lo, hi = first + bnd[rank], first + bnd[rank + 1]
+    inp = synth.make_inputs(wl, slice(lo, hi))
+    coefs = torch.from_numpy(inp["coefs"]).to(dev); z0 = torch.from_numpy(inp["z0"]).to(dev)
+    key = None
+    for _ in range(2):
+        _, key = sharding.sharded_greedy_step(eng, coefs, z0, wl.T, wl.dt, lo)
+    barrier()
+    l0 = eng.launch_count
+    t0 = time.perf_counter()
+    ms_list = []
+    for k in range(nsteps):
+        flush.fill_(k & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, key = sharding.sharded_greedy_step(eng, coefs, z0, wl.T, wl.dt, lo)
+        e1.record()
+        e1.synchronize()
+        ms_list.append(e0.elapsed_time(e1))
+    barrier()
+    t1 = time.perf_counter()
+    total = max_over_ranks(float(np.sum(ms_list)))
+    val, idx = sharding.unpack_maxloc(int(key.item()))
+    pk = peaks()
+    peak = pk["burst"] if total < 1000.0 else pk["sustained"]
+    sec = total * 1e-3 / nsteps
+    alg = wl.decoder_flops_per_rollout() * Pb * wl.S
+    a, b = issued_tensor_flop(wl.widths, Pb, wl.S, wl.T, mode_id == _lib.MODE_SCREENED_GRAM, 3)
+    K = wl.widths[-2]
+    path = ("gram_kernel (front MLP producers + tcgen05 Gram MMAs) + quad_kernel + select/refine" if K <= 111 else
+            "front layers + xact_kernel / xvar_kernel (tcgen05 GEMMs of the last front layer and of the last layer + variance "
+            "epilogue, decode_wide.cu)")
+    rec = {"workload": f"{nm}-shaped synthetic (BASELINE.json configs[{list(NAMED_BLOCKS).index(nm) + 2}]): P={wl.P} x S={wl.S}, "
+                       f"T={wl.T}, D={wl.D}, decoder {wl.widths} {wl.act}",
+           "params_timed": Pb, "first_param": first, "shard_bounds": bnd, "n_gpus": world, "steps": nsteps, "ms_per_step": sec * 1e3,
+           "timed_ms_total": total, "rollouts_per_s": Pb * wl.S / sec, "seconds_per_full_grid_at_this_rate": sec * wl.P / Pb,
+           "issued_tensor_tflops": (a + b) / sec / 1e12, "frac": (a + b) / sec / 1e12 / peak,
+           "algorithmic_tflops": alg / sec / 1e12, "frac_algorithmic": alg / sec / 1e12 / peak, "peak": peak,
+           "frac_definition": "frac = tensor FLOP the kernels issue (padding and split passes included) / whole-step device time / "
+                              "peak; frac_algorithmic = 2*sum(L_i L_i+1) decoder FLOP per rollout and time step / the same time / peak",
+           "path": path, "selected_global_index": idx, "max_std": val, "gpu_launches": int(eng.launch_count - l0),
+           "clocks": sampler.window(t0, t1) if sampler is not None else None}
+    del coefs, z0
+    return rec
 
 
 def aux_timings(eng, wl):
@@ -433,6 +586,7 @@ def main():
                          "decoded-ensemble fp16 screening + the same re-evaluation; direct: --passes split passes")
     ap.add_argument("--passes", type=int, default=3, help="direct mode: fp16 split-product passes of the last layer (1..3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-named", action="store_true", help="skip the per-config records of the other named shapes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)       # each step = 1 test parameter (~6 s of host work)

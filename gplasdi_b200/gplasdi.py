@@ -102,6 +102,8 @@ class BayesianGLaSDI:
         self.device = config.get("device", "cuda")
         self.verbose = config.get("verbose", True)
         self.optimizer = torch.optim.Adam(autoencoder.parameters(), lr=self.lr)
+        self.training_loss, self.ae_loss, self.ld_loss, self.coef_loss = [], [], [], []
+        self.timer = _TimerStub()
         self.best_loss = np.inf
         self.best_coefs = None
         self.restart_iter = 0
@@ -128,7 +130,8 @@ class BayesianGLaSDI:
         n_train = self.param_space.n_train()
         ld = self.latent_dynamics
         mse = torch.nn.MSELoss()
-        self.training_loss, self.ae_loss, self.ld_loss, self.coef_loss = [], [], [], []
+        _optimizer_to(self.optimizer, dev)
+        self.training_loss, self.ae_loss, self.ld_loss, self.coef_loss = [], [], [], []      # per leg (reference :166-169)
 
         def save_checkpoint():
             torch.save({k: v.detach().cpu() for k, v in ae.state_dict().items()}, ckpt)
@@ -142,10 +145,13 @@ class BayesianGLaSDI:
             loss_ae = mse(X, X_pred)
             coefs, loss_ld, loss_coef = ld.calibrate(Z, self.physics.dt, compute_loss=True, numpy=True)
             loss = loss_ae + self.ld_weight * loss_ld / n_train + self.coef_weight * loss_coef / n_train
-            loss.backward()
-            self.optimizer.step()
             # one device->host read per iteration for the four histories and the best-loss test
             lv, la, ll, lc = torch.stack([loss.detach(), loss_ae.detach(), loss_ld.detach(), loss_coef.detach()]).tolist()
+            if not np.isfinite(lv):
+                # never let a non-finite loss reach the optimiser: one step would poison every autoencoder weight
+                raise FloatingPointError(f"non-finite training loss at iteration {it + 1} (AE {la}, LD {ll}, COEF {lc})")
+            loss.backward()
+            self.optimizer.step()
             self.training_loss.append(lv); self.ae_loss.append(la); self.ld_loss.append(ll); self.coef_loss.append(lc)
             if lv < self.best_loss:
                 # as in the reference, the checkpoint is written AFTER the optimiser step of the best iteration
@@ -204,12 +210,51 @@ class BayesianGLaSDI:
         return new_sample
 
     def export(self):
+        """Same keys as the reference trainer's dict (reference gplasdi.py:276-287), so that a restart file written here
+        loads there and vice versa: optimiser state (Adam moments), timer dict and the four loss histories included."""
         return {"X_train": self.X_train, "X_test": self.X_test, "lr": self.lr, "n_iter": self.n_iter,
                 "n_samples": self.n_samples, "best_coefs": self.best_coefs, "max_iter": self.max_iter,
-                "ld_weight": self.ld_weight, "coef_weight": self.coef_weight, "restart_iter": self.restart_iter}
+                "max_greedy_iter": self.max_greedy_iter, "ld_weight": self.ld_weight, "coef_weight": self.coef_weight,
+                "restart_iter": self.restart_iter, "timer": self.timer.export(),
+                "optimizer": self.optimizer.state_dict(), "training_loss": self.training_loss, "ae_loss": self.ae_loss,
+                "ld_loss": self.ld_loss, "coeff_loss": self.coef_loss}    # 'coeff_loss': the reference's spelling
 
     def load(self, dict_):
+        """Reference gplasdi.py:289-300: restores the data, `best_coefs`, the restart counter, the timer and the optimiser
+        state (moved to the training device); the loss histories when the dict carries them."""
         self.X_train = dict_["X_train"]
         self.X_test = dict_["X_test"]
         self.best_coefs = dict_["best_coefs"]
         self.restart_iter = dict_["restart_iter"]
+        if "timer" in dict_:
+            self.timer.load(dict_["timer"])
+        if "optimizer" in dict_:
+            self.optimizer.load_state_dict(dict_["optimizer"])
+            if self.device != "cpu" and torch.cuda.is_available():
+                _optimizer_to(self.optimizer, torch.device(self.device))
+        for k, attr in (("training_loss", "training_loss"), ("ae_loss", "ae_loss"), ("ld_loss", "ld_loss"),
+                        ("coeff_loss", "coef_loss")):
+            if k in dict_:
+                setattr(self, attr, list(dict_[k]))
+
+
+def _optimizer_to(optim, device):
+    """Moves the optimiser's state tensors (Adam moments) to `device` (reference gplasdi.py:77-89)."""
+    for state in optim.state.values():
+        for k, v in state.items():
+            if isinstance(v, torch.Tensor):
+                state[k] = v.to(device)
+
+
+class _TimerStub:
+    """Carries the reference's timer dict through export()/load() (reference src/lasdi/timing.py: `export` returns
+    {'names': {name: index}, 'calls': [...], 'times': [...]}); timing itself is out of scope."""
+
+    def __init__(self):
+        self.state = {"names": {}, "calls": [], "times": []}
+
+    def export(self):
+        return self.state
+
+    def load(self, d):
+        self.state = dict(d)

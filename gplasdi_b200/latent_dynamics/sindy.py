@@ -101,6 +101,14 @@ class SINDy(LatentDynamics):
             ls, lc, coefs, info = _SindyFit.apply(Zb, self.engine, float(dt), self.fd_type, self.coef_norm_order)
         else:
             coefs, ls, lc, info = self.engine.sindy_fit(Zb.detach(), dt, self.fd_type, self.coef_norm_order)
+        # The fit reports per series whether the library matrix [1 | Z] had full numerical rank (`info`).  The host copy of
+        # the coefficients below synchronises anyway: read the status with it and never hand NaN coefficients / losses to
+        # the caller (the reference's torch.linalg.lstsq returns a finite minimum-norm answer there, sindy.py:72).
+        bad = torch.nonzero(info.cpu()).flatten().tolist()
+        if bad:
+            raise RuntimeError(
+                f"SINDy.calibrate: the library matrix [1 | Z] of training series {bad} is numerically rank deficient "
+                f"(a constant or collinear latent column); no coefficients were produced for them")
         if batched:
             out = coefs.double().cpu().numpy() if numpy else coefs.cpu()
         else:

@@ -78,7 +78,7 @@ def make_decoder(widths, seed=0):
     return Ws, bs
 
 
-def make_inputs(wl: Workload, p_slice: slice | None = None):
+def make_inputs(wl: Workload, p_slice=None):
     """Returns dict(coefs fp64 [P,S,n(n+1)], z0 fp32 [P,n], t_grid fp64 [T], params fp64 [P,2]).
 
     Mean coefficients: A(p) = 3 (G - G^T) - 0.3 I + smooth variation over the grid, b ~ N(0,1);
@@ -116,7 +116,8 @@ def make_inputs(wl: Workload, p_slice: slice | None = None):
     bump = 1.0 + 0.25 * np.exp(-((params[:, 0] - 0.55) ** 2 + (params[:, 1] - 0.40) ** 2) / 0.02)
     sigma = 0.04 * dist * bump                           # relative spread of each coefficient
 
-    sel = range(P) if p_slice is None else range(*p_slice.indices(P))
+    # p_slice: None (whole grid), a slice, or an explicit list of test-parameter indices
+    sel = range(P) if p_slice is None else (range(*p_slice.indices(P)) if isinstance(p_slice, slice) else [int(p) for p in p_slice])
     coefs = np.zeros((len(sel), wl.S, n * (n + 1)))
     for o, p in enumerate(sel):
         rp = np.random.RandomState((3000 + wl.seed) * 100003 + p)

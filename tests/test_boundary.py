@@ -128,3 +128,52 @@ def test_header_is_plain_c_and_a_c_host_links(tmp_path):
                            os.path.join(root, "include", "glasdi_b200.h")])
     exe = _build_c_host(tmp_path)
     assert os.path.exists(exe)
+
+
+def test_trainer_export_load_round_trip_with_reference_keys(tmp_path):
+    """export() carries every key of the reference trainer's dict (reference src/lasdi/gplasdi.py:276-283) -- optimiser
+    state, timer dict and the four loss histories included -- and load() restores them, so a restart file written by
+    either implementation loads in the other."""
+    import torch
+    from gplasdi_b200.latent_space import Autoencoder
+    from gplasdi_b200.latent_dynamics.sindy import SINDy
+    from gplasdi_b200.gplasdi import BayesianGLaSDI
+
+    class Phys:
+        qgrid_size = [33]; dt = 0.1; t_grid = np.linspace(0, 1, 11)
+
+    class PS:
+        train_space = np.zeros((2, 2)); test_space = np.zeros((3, 2))
+        def n_train(self): return 2
+        def n_test(self): return 3
+
+    cfg = {"n_samples": 4, "lr": 1e-3, "n_iter": 2, "max_iter": 4, "max_greedy_iter": 1, "ld_weight": 0.1, "coef_weight": 1e-3,
+           "path_checkpoint": str(tmp_path / "c"), "path_results": str(tmp_path / "r"), "device": "cpu"}
+
+    def make():
+        torch.manual_seed(3)
+        ae = Autoencoder(Phys(), {"hidden_units": [12], "latent_dimension": 5})
+        return BayesianGLaSDI(Phys(), ae, SINDy(5, 11, {"sindy": {"fd_type": "sbp12"}}), PS(), cfg), ae
+
+    tr, ae = make()
+    # two Adam steps on a plain torch loss populate the optimiser state (the GPU-only calibration is not needed for this)
+    for _ in range(2):
+        tr.optimizer.zero_grad()
+        sum((p ** 2).sum() for p in ae.parameters()).backward()
+        tr.optimizer.step()
+    tr.X_train = torch.ones(2, 11, 33); tr.X_test = torch.ones(3, 11, 33)
+    tr.best_coefs = np.arange(60.0).reshape(2, 30); tr.restart_iter = 2
+    tr.training_loss, tr.ae_loss, tr.ld_loss, tr.coef_loss = [3.0, 2.0], [1.0, 0.9], [0.5, 0.4], [7.0, 6.0]
+    d = tr.export()
+    reference_keys = {"X_train", "X_test", "lr", "n_iter", "n_samples", "best_coefs", "max_iter", "ld_weight", "coef_weight",
+                      "restart_iter", "timer", "optimizer", "training_loss", "ae_loss", "ld_loss", "coeff_loss"}
+    assert reference_keys <= set(d)
+    assert set(d["timer"]) == {"names", "calls", "times"}
+    tr2, ae2 = make()
+    tr2.load(d)
+    assert tr2.restart_iter == 2 and np.array_equal(tr2.best_coefs, tr.best_coefs) and tr2.coef_loss == [7.0, 6.0]
+    s1, s2 = tr.optimizer.state_dict()["state"], tr2.optimizer.state_dict()["state"]
+    assert s1.keys() == s2.keys() and len(s1) > 0
+    for k in s1:
+        assert torch.equal(s1[k]["exp_avg"], s2[k]["exp_avg"]) and torch.equal(s1[k]["exp_avg_sq"], s2[k]["exp_avg_sq"])
+        assert float(s1[k]["step"]) == float(s2[k]["step"]) == 2.0

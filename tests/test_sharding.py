@@ -74,3 +74,46 @@ def test_gloo_world2_selects_reference_index(case):
     assert keys[0][1] == keys[1][1]
     _, idx = sharding.unpack_maxloc(keys[0][1])
     assert idx == expect
+
+
+def _worker_fail(rank, world, port, fail_rank, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    err = ValueError("numeric flag on this rank") if rank == fail_rank else None
+    try:
+        key = sharding.reduce_keys(sharding.pack_maxloc_host(0.25 + rank, 3 + rank), err)
+        q.put((rank, "ok", int(key.item())))
+    except Exception as e:                                     # noqa: BLE001
+        q.put((rank, type(e).__name__, str(e)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 0, 1])
+def test_gloo_world2_failed_rank_reaches_every_rank(fail_rank):
+    """A rank whose step raised must not leave the others waiting in the all-reduce: the error rides in the same
+    collective (sentinel key) and EVERY rank raises afterwards -- the failed one its own exception."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_fail, args=(r, 2, port, fail_rank, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict((r, (kind, msg)) for r, kind, msg in [q.get(timeout=120) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if fail_rank < 0:
+        assert res[0] == res[1] and res[0][0] == "ok"
+        assert sharding.unpack_maxloc(res[0][1]) == (1.25, 4)
+    else:
+        assert res[fail_rank][0] == "ValueError"
+        assert res[1 - fail_rank][0] == "RuntimeError" and "another rank failed" in res[1 - fail_rank][1]
+
+
+def test_more_ranks_than_parameters_gives_empty_blocks():
+    b = sharding.shard_bounds(3, 8)
+    assert b == [0, 1, 2, 3, 3, 3, 3, 3, 3]
+    with pytest.raises(RuntimeError):
+        sharding.unpack_maxloc(sharding.ERROR_KEY)
+    assert sharding.ERROR_KEY > sharding.pack_maxloc_host(3.4e38, 0)
