@@ -17,7 +17,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_READY, ERR_NUMERIC, ERR_OOM = 
 ACT_IDS = {"sigmoid": 0, "tanh": 1, "softplus": 2, "ReLU": 3, "ELU": 4, "SiLU": 5, "GELU": 6, "identity": 7}
 FD_IDS = {"sbp12": 0, "sbp24": 1, "sbp36": 2, "sbp48": 3}
 OPT_SPLIT_PASSES, OPT_INTEGRATOR, OPT_RK4_SUBSTEPS, OPT_MAX_CTAS, OPT_STAGE_TIMING, OPT_DECODE_KERNEL = 0, 1, 2, 3, 4, 5
-OPT_MODE, OPT_SCREEN_MARGIN, OPT_WIDE_TENSOR = 6, 7, 8
+OPT_MODE, OPT_SCREEN_MARGIN, OPT_WIDE_TENSOR, OPT_GRAM_KERNEL, OPT_TAYLOR_RADIUS = 6, 7, 8, 9, 10
 MODE_DIRECT, MODE_SCREENED, MODE_SCREENED_GRAM = 0, 1, 2
 INT_EXPM, INT_RK4 = 0, 1
 

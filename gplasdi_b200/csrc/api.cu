@@ -206,6 +206,14 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
       if (value < 0 || value > 2) return set_error(h, GLASDI_ERR_INVALID, "wide-tensor option must be 0, 1 or 2");
       h->opt_wide = value;
       return GLASDI_OK;
+    case GLASDI_OPT_GRAM_KERNEL:
+      if (value != 0 && value != 1) return set_error(h, GLASDI_ERR_INVALID, "gram kernel variant must be 0 or 1");
+      h->opt_gram_kernel = value;
+      return GLASDI_OK;
+    case GLASDI_OPT_TAYLOR_RADIUS:
+      if (value < 0 || value > 1024) return set_error(h, GLASDI_ERR_INVALID, "Taylor radius must be 0..1024 (units of 1/256)");
+      h->opt_taylor_radius_q8 = value;
+      return GLASDI_OK;
     default: return set_error(h, GLASDI_ERR_INVALID, "unknown option");
   }
 }
@@ -222,6 +230,8 @@ int glasdi_get_option(const glasdi_handle* h, int option, int* value) {
     case GLASDI_OPT_MODE: *value = h->opt_mode; return GLASDI_OK;
     case GLASDI_OPT_SCREEN_MARGIN: *value = h->opt_margin_log2; return GLASDI_OK;
     case GLASDI_OPT_WIDE_TENSOR: *value = h->opt_wide; return GLASDI_OK;
+    case GLASDI_OPT_GRAM_KERNEL: *value = h->opt_gram_kernel; return GLASDI_OK;
+    case GLASDI_OPT_TAYLOR_RADIUS: *value = h->opt_taylor_radius_q8; return GLASDI_OK;
     default: return GLASDI_ERR_INVALID;
   }
 }

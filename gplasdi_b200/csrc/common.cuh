@@ -85,6 +85,8 @@ struct glasdi_handle {
   // screened mode (GLASDI_OPT_MODE = 1): candidates of the last greedy call
   int opt_mode = 2;                   // 0: direct (split passes), 1: x-space screening + refinement, 2: covariance-form screening + refinement
   int opt_wide = 2;                   // wide decoders: 0 CUDA cores only, 1 last layer on tcgen05 (decode_wide.cu), 2 + last front layer
+  int opt_gram_kernel = 1;            // covariance GEMM of one-front-layer decoders: 1 gram2_kernel (Taylor producers), 0 gram_kernel
+  int opt_taylor_radius_q8 = 256;     // gram2_kernel: radius of the polynomial in |da|, in 1/256 (0: exact form everywhere)
   int opt_margin_log2 = 8;            // candidates = variance within (1 - 2^-margin)^2 of the screened maximum
   void* d_cand = nullptr;             // [cand_cap] {p, t, d, approx variance}
   size_t cand_cap = 0;
@@ -135,6 +137,8 @@ size_t gram_a_bytes(int K, long long n_items);
 size_t gram_fscale_bytes(long long n_items);
 size_t decode_gram_smem_bytes(int K, int last_in_w, int xw /* widest intermediate front layer, rounded up to 4; 0 if none */);
 int gram_pack_v(glasdi_handle* h, const float* WL_host);
+size_t decode_gram2_smem_bytes(int K);
+bool gram2_supported(const Decoder& d);
 int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T, void* a_ws, float* fscale_ws,
                        cudaStream_t st);
 int launch_decode_quad(glasdi_handle* h, int P, int T, unsigned int* maxvar_bits, float* var_field, const void* a_ws,

@@ -67,10 +67,15 @@ enum glasdi_option {
   GLASDI_OPT_MODE = 6,          /* enum glasdi_mode (default SCREENED_GRAM) */
   GLASDI_OPT_SCREEN_MARGIN = 7, /* m in 4..16 (default 8): screened mode re-evaluates every (t, dof) whose
                                    single-pass std is within delta = 2^-m of the parameter's screened maximum */
-  GLASDI_OPT_WIDE_TENSOR = 8    /* decoders outside the fused tcgen05 kernels (last-layer input width > 112): 2 (default)
+  GLASDI_OPT_WIDE_TENSOR = 8,   /* decoders outside the fused tcgen05 kernels (last-layer input width > 112): 2 (default)
                                    last front layer AND last layer + variance as three-pass fp16-split tcgen05 GEMMs
                                    (decode_wide.cu), 1: only the last layer, 0: fp32 CUDA-core GEMMs throughout.  Earlier
                                    front layers run on the CUDA cores in every case.  Same results (fp32-faithful). */
+  GLASDI_OPT_GRAM_KERNEL = 9,   /* covariance GEMM of decoders with ONE front layer and sigmoid / tanh / softplus: 1 (default)
+                                   gram2_kernel -- thread = hidden unit, centred activations h(a_pilot + da) - h(a_pilot) from a
+                                   5th-order Taylor polynomial in da (no MUFU), exact form for sample blocks outside the radius;
+                                   0: gram_kernel (round-1 producers).  Screening only: results are the exact re-evaluation's */
+  GLASDI_OPT_TAYLOR_RADIUS = 10 /* radius of that polynomial: bound on |da| in units of 1/256 (default 256 = 1.0; 0 = never) */
 };
 
 /* how glasdi_greedy_step / glasdi_decode_max_std obtain max_std[p] (same result within the fp32 tolerance) */

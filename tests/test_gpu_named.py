@@ -30,7 +30,7 @@ def named_close(got, ref, coefs, rtol=RTOL):
     1e-5 .. 5e-5 in these goldens), which is noise, not a value to reproduce."""
     got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
     zero_spread = np.all(coefs == coefs[:, :1, :], axis=(1, 2))
-    assert np.all(got[zero_spread] == 0.0) and np.all(ref[zero_spread] <= 1e-2 * ref.max())
+    assert np.all(got[zero_spread] == 0.0) and np.all(ref[zero_spread] <= 5e-2 * ref.max())
     rel = np.abs(got - ref)[~zero_spread] / ref[~zero_spread]
     assert rel.size and rel.max() <= rtol, f"max_std: worst relative deviation {rel.max():.3e} (rtol {rtol:g}): {rel}"
     return float(rel.max())

@@ -4,11 +4,13 @@ the CPU oracle on the same seeded inputs.
 
 Stated tolerances (north star: exact selected index; ~1e-5 fp32 relative elsewhere):
   trajectories   |Z - Z_ref|        <= 1e-5 * max|Z_ref|      (reference = LSODA at rtol=atol~1.5e-8)
-  max std        |s - s_ref|        <= 1e-5 * s_ref           wherever s_ref > 1e-4 max(s_ref); elsewhere (the
-                                                               zero-spread corner parameters) <= 5e-6 = the
-                                                               reference's own fp32 noise floor: numpy's
-                                                               two-pass fp32 std of S identical values
-                                                               returns ~1e-8*S*|X|, the CUDA path exactly 0
+  max std        |s - s_ref|        <= 1e-5 * s_ref           no absolute term.  Zero-spread parameters (identical
+                                                               draws at the grid corners): the CUDA path returns
+                                                               exactly 0, accepted against s_ref <= 5e-6 = numpy's
+                                                               fp32 two-pass residue on S identical values.  Where
+                                                               a fixture stores the fp64 value of the same function
+                                                               (config #1), |s_ref - s_fp64| is added: the
+                                                               reference's own fp32 error
   coefficients   |c - c_ref|_max    <= 1e-5 * max|c_ref|
   decoded fields |X - X_ref|_max    <= 5e-6 * max|X_ref|
 """
@@ -32,17 +34,20 @@ FIELD_RTOL = 5e-6
 PASS_RTOL = {3: STD_RTOL, 2: 1e-4, 1: 3e-3}
 
 
-def std_close(got, ref, rtol=STD_RTOL, atol=STD_ATOL):
-    """rtol ONLY wherever the reference value is resolved (ref > 1e-4 max(ref)); the absolute floor applies only to the
-    zero-spread parameters (identical draws at the grid corners), where numpy's fp32 std returns rounding noise."""
+def std_close(got, ref, rtol=STD_RTOL, atol=STD_ATOL, ref_noise=None):
+    """rtol ONLY, with two stated exceptions.  (1) A parameter whose S draws are identical has a true std of exactly 0; the
+    CUDA path returns exactly 0 there, numpy's fp32 two-pass std its own rounding residue: got == 0 is accepted against
+    ref <= atol.  (2) `ref_noise` = |ref - fp64 evaluation of the same function| per parameter, where the fixture
+    carries it: the reference's own fp32 error is added to the allowance (it is what the 1e-5 cannot be held against)."""
     got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
-    resolved = ref > 1e-4 * np.max(ref)
-    tol = np.where(resolved, rtol * np.abs(ref), atol)
+    tol = rtol * np.abs(ref) + (0.0 if ref_noise is None else np.asarray(ref_noise, dtype=np.float64))
+    tol = np.where(got == 0.0, np.maximum(tol, atol), tol)
     err = np.abs(got - ref) - tol
     assert np.all(err <= 0), f"max std mismatch: worst excess {err.max():.3e} at {int(err.argmax())} " \
                              f"(got {got[err.argmax()]:.8e}, ref {ref[err.argmax()]:.8e})"
-    worst = float(np.max(np.abs(got - ref)[resolved] / ref[resolved])) if resolved.any() else 0.0
-    print(f"[std_close] worst relative deviation {worst:.2e} over {int(resolved.sum())} resolved values (rtol {rtol:g})")
+    nz = got != 0.0
+    worst = float(np.max(np.abs(got - ref)[nz] / ref[nz])) if nz.any() else 0.0
+    print(f"[std_close] worst relative deviation {worst:.2e} over {int(nz.sum())} non-zero values (rtol {rtol:g})")
     return worst
 
 
@@ -56,6 +61,8 @@ def setup_wl(engine, nm):
     engine.set_option(_lib.OPT_MAX_CTAS, 0)
     engine.set_option(_lib.OPT_MODE, _lib.MODE_SCREENED_GRAM)  # library default
     engine.set_option(_lib.OPT_SCREEN_MARGIN, 8)
+    engine.set_option(_lib.OPT_GRAM_KERNEL, 1)
+    engine.set_option(_lib.OPT_TAYLOR_RADIUS, 256)
     return wl, Ws, bs
 
 
@@ -460,8 +467,7 @@ def test_ragged_and_wide_shapes_against_oracle(engine, nm, mode):
     # wide_k1000: where the true spread is exactly 0 (identical draws at the corner parameters) numpy's fp32 std of the
     # reference returns 7e-6 of noise (~1e-8 S |x|, |x| = sums over K = 1000 units); the CUDA path returns exactly 0
     atol = 2e-5 if nm == "wide_k1000" else STD_ATOL
-    # wide_k*: spreads of 1e-3..1e-2 on |x| ~ 1: the reference's own fp32 std carries ~6e-8 |x| / sigma ~ 3e-5 there
-    wrtol = 1e-4 if nm.startswith("wide_k") else STD_RTOL
+    wrtol = STD_RTOL                                             # measured on B200: 3e-7 .. 1.1e-6 on the wide decoders
     std_close(ms.cpu().numpy(), per, rtol=wrtol, atol=atol)
     Z = engine.rollout(inp["coefs"], inp["z0"], wl.T, wl.dt).cpu().numpy()
     assert np.max(np.abs(Z - Zis)) <= TRAJ_RTOL * np.max(np.abs(Zis))
@@ -470,7 +476,7 @@ def test_ragged_and_wide_shapes_against_oracle(engine, nm, mode):
         # where the spread is resolved (the reference's own fp32 std carries ~6e-8 |x| / sigma ~ 3e-5 here)
         got = ms.cpu().numpy().astype(np.float64)
         big = per > 1e-4
-        assert big.any() and np.max(np.abs(got[big] - per[big]) / per[big]) <= 1e-4
+        assert big.any() and np.max(np.abs(got[big] - per[big]) / per[big]) <= STD_RTOL
     if nm.startswith("wide_k") and mode == _lib.MODE_DIRECT:
         # the same decoders with the last layer on the CUDA cores instead of the three-pass tcgen05 GEMM
         # (0), and with only the last layer on tcgen05 (1); the default (2) also runs the last front layer there
@@ -519,14 +525,25 @@ def test_covariance_form_shape_sweep(engine, K, S, D, T, act):
 
 
 def test_saturated_units_raise_the_numeric_flag(engine):
-    """Sigmoid pre-activations below -88 make the fast producers' 2^x overflow: the Gram diagonal turns non-finite
-    and glasdi_check_numeric must report it (Engine.checked then repeats the step in direct mode)."""
+    """Sigmoid pre-activations below -88: gram2_kernel (default) evaluates dead units as what they are (all Taylor
+    coefficients 0, exact form 1 / (1 + inf) = 0) and needs no flag; the round-1 producers' pairwise 2^x product overflows,
+    the Gram diagonal turns non-finite and glasdi_check_numeric must report it (Engine.checked then repeats the step in
+    direct mode)."""
     from gplasdi_b200.engine import GlasdiError
     wl, Ws, bs = setup_wl(engine, "tiny")
     Ws = [w.copy() for w in Ws]; bs = [b.copy() for b in bs]
     bs[0][:4] = -3000.0                                          # four dead units: sigmoid(-3000) = 0 exactly
     engine.set_decoder(Ws, bs, wl.act)
     inp = synth.make_inputs(wl)
+    idx0, per0, _ = orc.greedy_step(Ws, bs, wl.act, inp["coefs"], inp["z0"], inp["t_grid"])
+    for radius in (256, 0):
+        engine.set_option(_lib.OPT_TAYLOR_RADIUS, radius)
+        ms0, am0, _ = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
+        engine.check_numeric()
+        assert int(am0) == idx0
+        std_close(ms0.cpu().numpy(), per0)
+    engine.set_option(_lib.OPT_TAYLOR_RADIUS, 256)
+    engine.set_option(_lib.OPT_GRAM_KERNEL, 0)
     engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
     with pytest.raises(GlasdiError) as e:
         engine.check_numeric()
@@ -559,7 +576,16 @@ def test_config1_burgers1d_shipped_full(engine, golden_dir):
     engine.check_numeric()
     ref = g["burgers1d_shipped_max_std"]
     assert int(am) == int(g["burgers1d_shipped_m_index"][0]) == 237
-    std_close(ms.cpu().numpy(), ref)
+    # S = 20 samples of |x| ~ 1 with sigma ~ 2e-3: the reference's fp32 decode + fp32 two-pass std is itself up to ~2e-5 off
+    # the fp64 value of the same function (stored by the generator); the CUDA path must be within 1e-5 + that noise of the
+    # reference AND within 1e-5 of the fp64 value
+    f64 = g["burgers1d_shipped_max_std_f64"]
+    std_close(ms.cpu().numpy(), ref, ref_noise=np.abs(ref.astype(np.float64) - f64))
+    got64 = ms.cpu().numpy().astype(np.float64)
+    nz = f64 > 0
+    print(f"config #1: CUDA vs fp64 {np.max(np.abs(got64 - f64)[nz] / f64[nz]):.2e}, reference vs fp64 "
+          f"{np.max(np.abs(ref - f64)[nz] / f64[nz]):.2e}")
+    assert np.max(np.abs(got64 - f64)[nz] / f64[nz]) <= STD_RTOL
     top2 = np.sort(ref)[-2:]
     assert (top2[1] - top2[0]) / top2[1] > 0.01                # visible top-1 margin of the fixture
 
@@ -704,3 +730,55 @@ def test_bench_shape_properties(engine):
         Zis = engine.rollout(coefs[j:j + 1], z0[j:j + 1], wl.T, wl.dt).cpu().numpy()
         _, per = orc.fom_max_std(Ws, bs, wl.act, Zis, t_chunk=16)
         std_close(a[j:j + 1], per)
+
+
+# ---- gram2_kernel: Taylor-polynomial producers vs the exact form vs the round-1 kernel -----------------------------------
+@pytest.mark.parametrize("nm,act", [("small", "sigmoid"), ("small_s200", "sigmoid"), ("small", "tanh"), ("small", "softplus"),
+                                    ("ragged", "tanh")])
+def test_gram2_polynomial_exact_and_round1_kernels_agree(engine, nm, act):
+    """Three screening kernels, one result: the exact re-evaluation makes max_std independent of which one screened (bit for
+    bit as long as every near-maximum candidate is found), and the screening deviation each reports stays inside a quarter
+    of the margin."""
+    from dataclasses import replace
+    wl, _, _ = setup_wl(engine, nm)
+    wl = replace(wl, act=act)
+    Ws, bs = synth.make_decoder(wl.widths, wl.seed)
+    engine.set_decoder(Ws, bs, act)
+    inp = synth.make_inputs(wl)
+    res = {}
+    for name, kern, radius in (("poly", 1, 256), ("exact", 1, 0), ("round1", 0, 256)):
+        engine.set_option(_lib.OPT_GRAM_KERNEL, kern)
+        engine.set_option(_lib.OPT_TAYLOR_RADIUS, radius)
+        ms, am, _ = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
+        engine.check_numeric()
+        _, ncand, dev = engine.screen_stats()
+        assert dev <= 0.25 * 2.0 ** -8
+        res[name] = (ms.cpu().numpy(), int(am), ncand, dev)
+        print(f"{nm}/{act} {name}: candidates {ncand}, max screening deviation {dev:.2e}")
+    engine.set_option(_lib.OPT_GRAM_KERNEL, 1)
+    engine.set_option(_lib.OPT_TAYLOR_RADIUS, 256)
+    assert res["poly"][1] == res["exact"][1] == res["round1"][1]
+    assert np.array_equal(res["poly"][0], res["exact"][0]) and np.array_equal(res["poly"][0], res["round1"][0])
+    idx, per, _ = orc.greedy_step(Ws, bs, act, inp["coefs"], inp["z0"], inp["t_grid"])
+    assert res["poly"][1] == idx
+    std_close(res["poly"][0], per)
+
+
+def test_gram2_wide_ensemble_mixes_polynomial_and_exact_blocks(engine):
+    """An ensemble whose spread leaves the polynomial's radius at later times (draw spread x 25): sample blocks inside the radius
+    take the polynomial, the others the exact form, in the same launch; a tiny radius (1/256) sends almost every block to the
+    exact form.  All three agree with the oracle."""
+    wl, Ws, bs = setup_wl(engine, "small_s200")
+    inp = synth.make_inputs(wl)
+    mean = inp["coefs"].mean(axis=1, keepdims=True)
+    coefs = mean + 25.0 * (inp["coefs"] - mean)
+    idx, per, _ = orc.greedy_step(Ws, bs, wl.act, coefs, inp["z0"], inp["t_grid"])
+    out = []
+    for radius in (256, 1, 0):
+        engine.set_option(_lib.OPT_TAYLOR_RADIUS, radius)
+        ms, am, _ = engine.checked(lambda: engine.greedy_step(coefs, inp["z0"], wl.T, wl.dt))
+        assert int(am) == idx
+        std_close(ms.cpu().numpy(), per)
+        out.append(ms.cpu().numpy())
+    engine.set_option(_lib.OPT_TAYLOR_RADIUS, 256)
+    assert np.array_equal(out[0], out[2]) and np.array_equal(out[1], out[2])
