@@ -14,7 +14,6 @@
 //    16-byte store into a K-major SWIZZLE_128B tile -- the layout both operands of G += H^T H read natively.
 //    2.9 instead of 8 issue slots per (unit, sample).
 //
-// Warp roles, barriers and the epilogue are those of gram_kernel's fast path (decode_gram.cu).
 #include "decode_gram.cuh"
 
 #include <algorithm>
@@ -95,8 +94,28 @@ __device__ __forceinline__ float act_scaled(int act_rt, float a_scaled) {
   else return act_apply_t<ACT>(act_rt, a_scaled);
 }
 
+// Warp roles (24 warps; the register file gives 80 registers per thread to 21..24 warps alike):
+//   warp 0          MMA issuer, an event loop over two independent queues: pre-activation MMAs (as soon as the dz tile is
+//                   there and the TMEM buffer has been read) and Gram MMAs (as soon as an operand tile is full)
+//   warps 1,2,3,20  epilogue of TMEM lane quadrants 1,2,3,0 (thread = row of the covariance) + the coefficient tables, two
+//                   items ahead
+//   warps 4..19     converters (phase B): thread = unit row, 32 samples per chunk
+//   warps 21..23    phase A: latent differences dz of 32-sample blocks, dealt round-robin over the CTA's stream of chunks
+// TMEM: two Gram accumulators (the epilogue of item n overlaps the MMAs of item n + 1) + two pre-activation buffers, each
+// released as soon as the converters have LOADED it (not when they are done with it).  The first version (roles of
+// gram_kernel, buffers released through the operand-full barrier) spent 2.4 k of its 2.5 k cycles per chunk in that
+// dependency loop whatever the converters cost (profiles/r02_gram2_v1_*).
+constexpr int kG2Threads = 24 * 32;
+constexpr int kG2PhaseAWarp0 = 21, kG2PhaseAWarps = 3;
+constexpr uint32_t kAccCol0 = 0, kD1Col0 = 256;
+
+struct G2Bars {
+  uint64_t h_full[kRing], h_empty[kRing], a1_full[kRing], a1_empty[kRing], d1_full[2], d1_empty[2], tab_full[4],
+      acc_full[2], acc_empty[2];
+};
+
 template <int ACT, int INW>
-__global__ void __launch_bounds__(kGThreads, 1) gram2_kernel(const __grid_constant__ GramParams P) {
+__global__ void __launch_bounds__(kG2Threads, 1) gram2_kernel(const __grid_constant__ GramParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,9 +129,14 @@ __global__ void __launch_bounds__(kGThreads, 1) gram2_kernel(const __grid_consta
   float* sM = reinterpret_cast<float*>(smem + L.m);
   float* sMax = reinterpret_cast<float*>(smem + L.mx);
   __half* sC = reinterpret_cast<__half*>(smem + L.c);
-  GBars* B = reinterpret_cast<GBars*>(smem + L.bars);
+  G2Bars* B = reinterpret_cast<G2Bars*>(smem + L.bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem);
   const int nchunks = (P.S + kCols - 1) / kCols;
+  constexpr int NL = INW > 0 ? INW : kMaxLatent;
+  const int NZ = P.NZ;
+  const uint32_t n_my_items = (long long)blockIdx.x < P.n_items
+                                  ? (uint32_t)((P.n_items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+  const uint32_t n_elems = n_my_items * (uint32_t)nchunks;      // this CTA's stream of chunks
 
   // ---- one-time setup -------------------------------------------------------------------------
   if (threadIdx.x == 0) {
@@ -122,12 +146,13 @@ __global__ void __launch_bounds__(kGThreads, 1) gram2_kernel(const __grid_consta
       mbar_init(&B->a1_full[i], 4);
       mbar_init(&B->a1_empty[i], 1);
     }
-    mbar_init(&B->d1_full[0], 1);
-    mbar_init(&B->d1_full[1], 1);
-    mbar_init(&B->d1_full[2], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&B->tab_full[i], 4);
-    mbar_init(&B->acc_full, 1);
-    mbar_init(&B->acc_empty, kGEpiWarps - 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&B->d1_full[i], 1);
+      mbar_init(&B->d1_empty[i], kGProdWarps);
+      mbar_init(&B->acc_full[i], 1);
+      mbar_init(&B->acc_empty[i], kGEpiWarps);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&B->tab_full[i], kGEpiWarps);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -161,15 +186,64 @@ __global__ void __launch_bounds__(kGThreads, 1) gram2_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= kGProdWarp0) {
-    // ---- producers ---------------------------------------------------------------------------------
+  if (warp >= kG2PhaseAWarp0) {
+    // ---- phase A: dz = z - z_pilot of 32-sample blocks as the tf32 B operand (hi in K 0..7, lo in K 8..15) of the
+    // pre-activation MMA, and whether |da| of the block is inside the polynomial's radius for every unit (Cauchy-Schwarz
+    // bound through the largest row norm of W0).  Block ids 4 e + b (stream element e, block b) are dealt round-robin to
+    // the three warps; the latent states of a warp's next two blocks are in flight while it writes the current one. ----
+    const uint32_t n_blocks = n_elems * 4u;
+    const uint32_t w = (uint32_t)(warp - kG2PhaseAWarp0);
+    float zq[2][NL], zp[2][NL];
+    auto load_block = [&](uint32_t id, float (&z)[NL], float (&zpil)[NL]) {
+      if (id >= n_blocks) return;
+      const uint32_t e = id >> 2, bk = id & 3u;
+      const long long it = (long long)blockIdx.x + (long long)(e / (uint32_t)nchunks) * gridDim.x;
+      const int c = (int)(e % (uint32_t)nchunks);
+      const float* __restrict__ base = P.Zs + (size_t)it * NZ * P.Spad;
+      const float* __restrict__ src = base + c * kCols + bk * 32 + lane;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        z[i] = (INW > 0 || i < NZ) ? __ldg(src + (size_t)i * P.Spad) : 0.f;
+        zpil[i] = (INW > 0 || i < NZ) ? __ldg(base + (size_t)i * P.Spad) : 0.f;      // sample 0 = the pilot
+      }
+    };
+    load_block(w, zq[0], zp[0]);
+    load_block(w + kG2PhaseAWarps, zq[1], zp[1]);
+    uint32_t k = 0;
+    for (uint32_t id = w; id < n_blocks; id += kG2PhaseAWarps, ++k) {
+      const uint32_t e = id >> 2, bk = id & 3u;
+      const uint32_t slot = e % kRing;
+      float hi[NL], lo[NL];
+      float n2 = 0.f;
+      if (k & 1u) {
+#pragma unroll
+        for (int i = 0; i < NL; ++i) { const float dz = zq[1][i] - zp[1][i]; n2 = fmaf(dz, dz, n2); hi[i] = round_tf32(dz); lo[i] = dz - hi[i]; }
+        load_block(id + 2 * kG2PhaseAWarps, zq[1], zp[1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NL; ++i) { const float dz = zq[0][i] - zp[0][i]; n2 = fmaf(dz, dz, n2); hi[i] = round_tf32(dz); lo[i] = dz - hi[i]; }
+        load_block(id + 2 * kG2PhaseAWarps, zq[0], zp[0]);
+      }
+      const int all_ok = __all_sync(0xffffffffu, n2 <= P.poly_thr2);
+      mbar_wait(&B->a1_empty[slot], ((e / kRing) & 1u) ^ 1u);
+      const int col = (int)bk * 32 + lane;
+      uint8_t* dst = sA1 + slot * kA1Bytes + (col >> 3) * 128 + (col & 7) * 16;
+      auto comp = [&](const float (&v)[NL], int i) { return i < NL ? v[i < NL ? i : 0] : 0.f; };
+      *reinterpret_cast<float4*>(dst) = make_float4(comp(hi, 0), comp(hi, 1), comp(hi, 2), comp(hi, 3));
+      *reinterpret_cast<float4*>(dst + 2048) = make_float4(comp(hi, 4), comp(hi, 5), comp(hi, 6), comp(hi, 7));
+      *reinterpret_cast<float4*>(dst + 4096) = make_float4(comp(lo, 0), comp(lo, 1), comp(lo, 2), comp(lo, 3));
+      *reinterpret_cast<float4*>(dst + 6144) = make_float4(comp(lo, 4), comp(lo, 5), comp(lo, 6), comp(lo, 7));
+      if (lane == 0) sFlag[(e & (kFlagRing - 1)) * 4 + bk] = all_ok;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B->a1_full[slot]);
+    }
+  } else if (warp >= kGProdWarp0 && warp < kGProdWarp0 + kGProdWarps) {
+    // ---- converters (phase B) --------------------------------------------------------------------------------
     const float hscale = P.h_scale;
     const int q = warp & 3;                                 // TMEM lane quadrant = unit rows 32 q .. 32 q + 31
     const int j = (warp - kGProdWarp0) >> 2;                // 32-sample block of the chunk this warp converts
-    const int u = q * 32 + lane;                            // this thread's unit row (phase B / tables)
-    const int col = q * 32 + lane;                          // this thread's sample column (phase A)
-    const bool phase_a = j == 0;                            // warps 4..7 also write the latent differences
-    const bool tab_warp = j == 1;                           // warps 8..11 make the coefficient tables, one item ahead
+    const int u = q * 32 + lane;                            // this thread's unit row
     const bool warp_active = q * 32 <= P.K;                 // the quadrant holds at least one real (or the constant) unit
     const bool row_active = u <= P.K;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
@@ -180,130 +254,30 @@ __global__ void __launch_bounds__(kGThreads, 1) gram2_kernel(const __grid_consta
     for (int m = 0; m < 4; ++m)
       st_off[m] = (uint32_t)(j >> 1) * 16384u + (uint32_t)(u >> 3) * 1024u + (uint32_t)(u & 7) * 128u +
                   ((((uint32_t)((j & 1) * 4 + m)) ^ (uint32_t)(u & 7)) << 4);
-    uint32_t g = 0, n_it = 0;                               // chunk counter over the whole kernel, item counter
-    long long item = blockIdx.x;
-    // Phase A (warps 4..7) walks the CTA's stream of chunks TWO AHEAD of phase B (see gram_kernel).
-    constexpr int NL = INW > 0 ? INW : kMaxLatent;
-    const int NZ = P.NZ;
-    float zq[2][NL], zpa[NL], zpn[NL], zpt[NL];
-    long long item_l = item;
-    int c_l = 0;
-    uint32_t ga = 0;
-    int c_a = 0;
-    long long item_a = item;
-    const uint32_t n_elems = item < P.n_items
-                                 ? (uint32_t)((P.n_items - item + gridDim.x - 1) / gridDim.x) * (uint32_t)nchunks : 0u;
-    auto load_col = [&](long long it, int c, float (&z)[NL]) {
-      const float* __restrict__ src = P.Zs + (size_t)it * NZ * P.Spad + c * kCols + col;
-#pragma unroll
-      for (int i = 0; i < NL; ++i) z[i] = (INW > 0 || i < NZ) ? __ldg(src + (size_t)i * P.Spad) : 0.f;
-    };
-    auto load_zp = [&](long long it, float (&z)[NL]) {     // sample 0 = the pilot
-      const float* __restrict__ src = P.Zs + (size_t)it * NZ * P.Spad;
-#pragma unroll
-      for (int i = 0; i < NL; ++i) z[i] = (INW > 0 || i < NZ) ? __ldg(src + (size_t)i * P.Spad) : 0.f;
-    };
-    auto load_next = [&](float (&z)[NL]) {
-      if (item_l < P.n_items) {
-        load_col(item_l, c_l, z);
-        if (++c_l == nchunks) { c_l = 0; item_l += gridDim.x; }
-      }
-    };
-    if (phase_a && item < P.n_items) {
-      load_next(zq[0]);
-      load_next(zq[1]);
-      load_zp(item, zpa);
-      if (item + gridDim.x < P.n_items) load_zp(item + gridDim.x, zpn);
-    }
-    // Coefficient table of an item, row u: c0 (1 for the constant unit K, else 0), c1..c5 of the polynomial in the MMA's
-    // pre-activation difference, and for the exact form a(pilot) and n = c0 - h(pilot) 2^eH (same arithmetic as the samples:
-    // padding columns, copies of sample 0, cancel to exactly 0 / 1 in either form).
-    auto make_tables = [&](uint32_t nseq) {
-      float* T0 = sTab + (nseq & 3u) * (kTabArrays * kTabStride);
-      float a = sBias[u];
-      const uint8_t* w = sB1 + (u >> 3) * 128 + (u & 7) * 16;
-#pragma unroll
-      for (int i = 0; i < NL; ++i) {
-        const uint8_t* wi = w + (i >> 2) * 2048 + (i & 3) * 4;
-        a = fmaf(*reinterpret_cast<const float*>(wi) + *reinterpret_cast<const float*>(wi + 4096), zpt[i], a);
-      }
-      float c[6];
-      taylor_coefs<ACT>(a, hscale, c);
-      c[0] = (u == P.K) ? 1.0f : 0.0f;
-      const float hp = act_scaled<ACT>(P.front.act, a);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) T0[k * kTabStride + u] = (u < P.K || k == 0) ? c[k] : 0.f;
-      T0[6 * kTabStride + u] = a;
-      T0[7 * kTabStride + u] = c[0] - hp * hscale;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&B->tab_full[nseq & 3u]);
-    };
-    if (tab_warp && item < P.n_items) {
-      load_zp(item, zpt);
-      make_tables(0);
-      if (item + gridDim.x < P.n_items) load_zp(item + gridDim.x, zpt);
-    }
-    // dz = z - z_pilot of this thread's sample as the tf32 B operand (hi in K 0..7, lo in K 8..15) of stream element ga,
-    // and whether |da| of its 32-sample block is inside the polynomial's radius for every unit (Cauchy-Schwarz bound)
-    auto phase_a_step = [&]() {
-      const uint32_t slot = ga % kRing;
-      float hi[NL], lo[NL];
-      float n2 = 0.f;
-      if (ga & 1u) {
-#pragma unroll
-        for (int i = 0; i < NL; ++i) { const float dz = zq[1][i] - zpa[i]; n2 = fmaf(dz, dz, n2); hi[i] = round_tf32(dz); lo[i] = dz - hi[i]; }
-        load_next(zq[1]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < NL; ++i) { const float dz = zq[0][i] - zpa[i]; n2 = fmaf(dz, dz, n2); hi[i] = round_tf32(dz); lo[i] = dz - hi[i]; }
-        load_next(zq[0]);
-      }
-      const int all_ok = __all_sync(0xffffffffu, n2 <= P.poly_thr2);
-      mbar_wait_relaxed(&B->a1_empty[slot], ((ga / kRing) & 1u) ^ 1u);
-      uint8_t* dst = sA1 + slot * kA1Bytes + (col >> 3) * 128 + (col & 7) * 16;
-      auto comp = [&](const float (&v)[NL], int i) { return i < NL ? v[i < NL ? i : 0] : 0.f; };
-      *reinterpret_cast<float4*>(dst) = make_float4(comp(hi, 0), comp(hi, 1), comp(hi, 2), comp(hi, 3));
-      *reinterpret_cast<float4*>(dst + 2048) = make_float4(comp(hi, 4), comp(hi, 5), comp(hi, 6), comp(hi, 7));
-      *reinterpret_cast<float4*>(dst + 4096) = make_float4(comp(lo, 0), comp(lo, 1), comp(lo, 2), comp(lo, 3));
-      *reinterpret_cast<float4*>(dst + 6144) = make_float4(comp(lo, 4), comp(lo, 5), comp(lo, 6), comp(lo, 7));
-      if (lane == 0) sFlag[(ga & (kFlagRing - 1)) * 4 + q] = all_ok;
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&B->a1_full[slot]);
-      ++ga;
-      if (++c_a == nchunks) {
-        c_a = 0;
-        item_a += gridDim.x;
-#pragma unroll
-        for (int i = 0; i < NL; ++i) zpa[i] = zpn[i];
-        if (item_a + gridDim.x < P.n_items) load_zp(item_a + gridDim.x, zpn);
-      }
-    };
-    if (phase_a && n_elems > 0) phase_a_step();
-    if (phase_a && n_elems > 1) phase_a_step();
+    uint32_t g = 0;                                         // chunk counter over the whole kernel
     float amax = 0.f;
-    for (; item < P.n_items; item += gridDim.x, ++n_it) {
-      if (tab_warp && item + gridDim.x < P.n_items) {
-        make_tables(n_it + 1u);
-        if (item + 2 * (long long)gridDim.x < P.n_items) load_zp(item + 2 * (long long)gridDim.x, zpt);
-      }
-      while (!mbar_try_wait(&B->tab_full[n_it & 3u], (n_it >> 2) & 1u)) __nanosleep(32);
+    for (uint32_t n_it = 0; n_it < n_my_items; ++n_it) {
+      mbar_wait(&B->tab_full[n_it & 3u], (n_it >> 2) & 1u);
       const float* T0 = sTab + (n_it & 3u) * (kTabArrays * kTabStride) + u;
       unsigned long long c2[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) { const float v = T0[k * kTabStride]; c2[k] = pack_f32x2(v, v); }
       const float a_p = T0[6 * kTabStride], n_p = T0[7 * kTabStride];
       for (int c = 0; c < nchunks; ++c, ++g) {
-        if (phase_a && ga < n_elems) phase_a_step();        // stream element g + 2
-        const uint32_t db = g % 3u, hb = g % kRing;
-        while (!mbar_try_wait(&B->d1_full[db], (g / 3u) & 1u)) __nanosleep(32);
+        const uint32_t db = g & 1u, hb = g % kRing;
+        mbar_wait(&B->d1_full[db], (g >> 1) & 1u);
         tc_fence_after();
-        mbar_wait_relaxed(&B->h_empty[hb], ((g / kRing) & 1u) ^ 1u);
+        const int poly = sFlag[(g & (kFlagRing - 1)) * 4 + j];
+        uint32_t d[32];
         if (warp_active) {
-          const int poly = sFlag[(g & (kFlagRing - 1)) * 4 + j];
-          uint32_t d[32];
-          tmem_ld_32x32(tmem_base + lane_addr + 128u + db * 128u + (uint32_t)(j * 32), d);
+          tmem_ld_32x32(tmem_base + lane_addr + kD1Col0 + db * 128u + (uint32_t)(j * 32), d);
           tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B->d1_empty[db]);       // the buffer is in registers: the next pre-activation MMA may overwrite it
+        mbar_wait(&B->h_empty[hb], ((g / kRing) & 1u) ^ 1u);
+        if (warp_active) {
           uint8_t* Hb = sH + hb * kBufBytes;
           if (poly) {
 #pragma unroll
@@ -340,84 +314,123 @@ __global__ void __launch_bounds__(kGThreads, 1) gram2_kernel(const __grid_consta
             }
           }
         }
-        tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&B->h_full[hb]);
       }
     }
     if (P.check_overflow && !(amax < 60000.f)) atomicOr(P.flags, 1);
-  } else {
-    // ---- consumer warps 0..3 (as gram_kernel's fast path; operands: see the header comment) --------------------
-    const int i = warp * 32 + lane;
-    const int K = P.K;
-    const float inv_S = P.inv_S;
-    const int off_i = (i * (i + 1)) / 2;
+  } else if (warp == 0) {
+    // ---- MMA issuer: whichever of the two queues can move -----------------------------------------------------------
     const uint32_t idesc = umma_idesc_f16_m128((uint32_t)P.Nmma);               // both operands K-major
     // K-major SWIZZLE_128B: LBO field = 1 (ignored), SBO = 1 KB between 8-row groups; a K = 16 slice = 32 bytes inside the
     // 128-byte swizzle row, the second 64-sample block 16 KB further
     const uint64_t desc0 = umma_desc_kmajor(smem_u32(sH), 16u, 1024u) | (2ull << 61);
-    const uint32_t taddr = tmem_base + (((uint32_t)(warp * 32)) << 16);
-    uint32_t h_it = 0, n_it = 0, g1 = 0;
-    for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x, ++n_it) {
-      if (warp == 0) {
+    const uint32_t idesc1 = umma_idesc_tf32_m128(128u);
+    const uint64_t wdesc1 = umma_desc_kmajor(smem_u32(sB1), 2048u, 128u);       // A: units x k
+    const uint64_t zdesc1 = umma_desc_kmajor(smem_u32(sA1), 2048u, 128u);       // B: samples x k
+    uint32_t g1 = 0;                                        // next pre-activation element
+    uint32_t h_it = 0, n_it = 0;                            // next Gram element, its item
+    int c = 0;                                              // ... and its chunk inside the item
+    while (h_it < n_elems) {
+      bool moved = false;
+      if (g1 < n_elems && mbar_test(&B->a1_full[g1 % kRing], (g1 / kRing) & 1u) &&
+          (g1 < 2u || mbar_test(&B->d1_empty[g1 & 1u], ((g1 >> 1) - 1u) & 1u))) {
+        // D1[g1 & 1] = (cf W0) dz^T of stream element g1
+        const uint32_t slot = g1 % kRing;
         tc_fence_after();
-        const uint32_t idesc1 = umma_idesc_tf32_m128(128u);
-        const uint64_t wdesc1 = umma_desc_kmajor(smem_u32(sB1), 2048u, 128u);       // A: units x k
-        const uint64_t zdesc1 = umma_desc_kmajor(smem_u32(sA1), 2048u, 128u);       // B: samples x k
-        const uint32_t n_elems = (uint32_t)((P.n_items - blockIdx.x + gridDim.x - 1) / gridDim.x) * (uint32_t)nchunks;
-        auto issue_mma1 = [&]() {
-          const uint32_t slot = g1 % kRing;
-          while (!mbar_try_wait(&B->a1_full[slot], (g1 / kRing) & 1u)) __nanosleep(32);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t d1 = tmem_base + 128u + (g1 % 3u) * 128u;
-            const uint64_t zd = zdesc1 + (uint64_t)(slot * (kA1Bytes >> 4));
-            tc_mma_tf32(d1, wdesc1, zd, idesc1, 0u);                                         // W_hi dz_hi
-            tc_mma_tf32(d1, wdesc1, zd + (uint64_t)(4096 >> 4), idesc1, 1u);                 // W_hi dz_lo
-            tc_mma_tf32(d1, wdesc1 + (uint64_t)(4096 >> 4), zd, idesc1, 1u);                 // W_lo dz_hi
-            tc_commit(&B->a1_empty[slot]);
-            tc_commit(&B->d1_full[g1 % 3u]);
-          }
-          __syncwarp();
-          ++g1;
-        };
-        if (g1 == 0) {
-          issue_mma1();
-          if (g1 < n_elems) issue_mma1();
+        if (elect_one()) {
+          const uint32_t d1 = tmem_base + kD1Col0 + (g1 & 1u) * 128u;
+          const uint64_t zd = zdesc1 + (uint64_t)(slot * (kA1Bytes >> 4));
+          tc_mma_tf32(d1, wdesc1, zd, idesc1, 0u);                                         // W_hi dz_hi
+          tc_mma_tf32(d1, wdesc1, zd + (uint64_t)(4096 >> 4), idesc1, 1u);                 // W_hi dz_lo
+          tc_mma_tf32(d1, wdesc1 + (uint64_t)(4096 >> 4), zd, idesc1, 1u);                 // W_lo dz_hi
+          tc_commit(&B->a1_empty[slot]);
+          tc_commit(&B->d1_full[g1 & 1u]);
         }
-        for (int c = 0; c < nchunks; ++c) {
-          if (g1 < n_elems && g1 <= h_it + 2u) issue_mma1();
-          const uint32_t buf = h_it % kRing;
-          while (!mbar_try_wait(&B->h_full[buf], (h_it / kRing) & 1u)) __nanosleep(64);
-          if (c == 0 && n_it > 0) mbar_wait(&B->acc_empty, (n_it - 1u) & 1u);
-          tc_fence_after();
-          const int ncols = min(kCols, P.S - c * kCols);       // padding columns beyond hold exact zeros (ones in row K)
-          const int nk = (ncols + 15) >> 4;
-          const uint64_t d0 = desc0 + (uint64_t)(buf * (kBufBytes >> 4));
-          if (elect_one()) {
-#pragma unroll 1
-            for (int k = 0; k < nk; ++k) {
-              const uint64_t dk = d0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4);
-              tc_mma_f16(tmem_base, dk, dk, idesc, (c | k) != 0 ? 1u : 0u);
-            }
-            tc_commit(&B->h_empty[buf]);
-          }
-          __syncwarp();
-          ++h_it;
-        }
-        if (elect_one()) tc_commit(&B->acc_full);
         __syncwarp();
-        if (g1 < n_elems && g1 <= h_it + 2u) issue_mma1();
+        ++g1;
+        moved = true;
       }
-      while (!mbar_try_wait(&B->acc_full, n_it & 1u)) __nanosleep(warp == 0 ? 64 : 1024);
+      const uint32_t ab = n_it & 1u;
+      if (mbar_test(&B->h_full[h_it % kRing], (h_it / kRing) & 1u) &&
+          (c != 0 || n_it < 2u || mbar_test(&B->acc_empty[ab], ((n_it >> 1) - 1u) & 1u))) {
+        const uint32_t buf = h_it % kRing;
+        tc_fence_after();
+        const uint32_t acc = tmem_base + kAccCol0 + ab * 128u;
+        const int ncols = min(kCols, P.S - c * kCols);       // padding columns beyond hold exact zeros (ones in row K)
+        const int nk = (ncols + 15) >> 4;
+        const uint64_t d0 = desc0 + (uint64_t)(buf * (kBufBytes >> 4));
+        if (elect_one()) {
+#pragma unroll 1
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t dk = d0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4);
+            tc_mma_f16(acc, dk, dk, idesc, (c | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&B->h_empty[buf]);
+          if (c == nchunks - 1) tc_commit(&B->acc_full[ab]);
+        }
+        __syncwarp();
+        ++h_it;
+        if (++c == nchunks) { c = 0; ++n_it; }
+        moved = true;
+      }
+      if (!moved) __nanosleep(20);
+    }
+  } else {
+    // ---- epilogue warps 1, 2, 3, 20: thread <-> row i of the Gram matrix (TMEM lane quadrant = warp mod 4); the same
+    // thread makes row i of the coefficient tables, two items ahead ---------------------------------------------------
+    const int qd = warp & 3;
+    const int i = qd * 32 + lane;
+    const int K = P.K;
+    const float inv_S = P.inv_S;
+    const float hscale = P.h_scale;
+    const int off_i = (i * (i + 1)) / 2;                    // packed LOWER triangle, row-major: q(i, j <= i) = i (i + 1) / 2 + j
+    // Coefficient table of an item, row i: c0 (1 for the constant unit K, else 0), c1..c5 of the polynomial in the MMA's
+    // pre-activation difference, and for the exact form a(pilot) and n = c0 - h(pilot) 2^eH (same arithmetic as the samples:
+    // padding columns, copies of sample 0, cancel to exactly 0 / 1 in either form).
+    auto make_tables = [&](uint32_t nseq) {
+      if (nseq >= n_my_items) return;
+      if (nseq >= 4u) {
+        // slot reuse: the converters loaded item nseq - 4's table at its start, and its epilogue (ours) is long done
+      }
+      const long long it = (long long)blockIdx.x + (long long)nseq * gridDim.x;
+      const float* __restrict__ base = P.Zs + (size_t)it * NZ * P.Spad;
+      float* T0 = sTab + (nseq & 3u) * (kTabArrays * kTabStride);
+      float a = sBias[i];
+      const uint8_t* w = sB1 + (i >> 3) * 128 + (i & 7) * 16;
+#pragma unroll
+      for (int k = 0; k < NL; ++k) {
+        const float zk = (INW > 0 || k < NZ) ? __ldg(base + (size_t)k * P.Spad) : 0.f;     // the pilot = sample 0
+        const uint8_t* wi = w + (k >> 2) * 2048 + (k & 3) * 4;
+        a = fmaf(*reinterpret_cast<const float*>(wi) + *reinterpret_cast<const float*>(wi + 4096), zk, a);
+      }
+      float cc[6];
+      taylor_coefs<ACT>(a, hscale, cc);
+      cc[0] = (i == K) ? 1.0f : 0.0f;
+      const float hp = act_scaled<ACT>(P.front.act, a);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) T0[k * kTabStride + i] = (i < K || k == 0) ? cc[k] : 0.f;
+      T0[6 * kTabStride + i] = a;
+      T0[7 * kTabStride + i] = cc[0] - hp * hscale;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B->tab_full[nseq & 3u]);
+    };
+    make_tables(0);
+    make_tables(1);
+    uint32_t n_it = 0;
+    for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x, ++n_it) {
+      make_tables(n_it + 2u);
+      const uint32_t ab = n_it & 1u;
+      while (!mbar_try_wait(&B->acc_full[ab], (n_it >> 1) & 1u)) __nanosleep(256);      // an item takes several us
       tc_fence_after();
+      const uint32_t taddr = tmem_base + kAccCol0 + ab * 128u + (((uint32_t)(qd * 32)) << 16);
       float* sMb = sM + (n_it & 1u) * 128;
       float* sMaxb = sMax + (n_it & 1u) * 4;
       __half* sCb = sC + (size_t)(n_it & 1u) * P.nkgQ * 8;
       uint32_t r[32];
       // step 1: own diagonal entry, own column sum, the row of column sums (from the constant unit's row)
-      tmem_ld_32x32(taddr + warp * 32, r);
+      tmem_ld_32x32(taddr + qd * 32, r);
       uint32_t mi_bits;
       tmem_ld_32x1(taddr + K, mi_bits);
       tmem_ld_wait();
@@ -427,9 +440,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gram2_kernel(const __grid_consta
       const float mi = __uint_as_float(mi_bits);
       const float cii = (i < K) ? (gii - mi * mi * inv_S) * inv_S : 0.f;
       const float wm = warp_max(fmaxf(cii, 0.f));
-      if (lane == 0) sMaxb[warp] = wm;
-      if (__any_sync(0xffffffffu, i < K && !(fabsf(gii) < 3.0e38f)) && lane == 0) atomicOr(P.flags, 1);
-      if (warp == (K >> 5)) {
+      if (lane == 0) sMaxb[qd] = wm;
+      if (__any_sync(0xffffffffu, i < K && !(fabsf(gii) < 3.0e38f)) && lane == 0) atomicOr(P.flags, 1);   // NaN / inf activations
+      if (qd == (K >> 5)) {
         for (int b = 0; b < 4; ++b) {
           tmem_ld_32x32(taddr + b * 32, r);
           tmem_ld_wait();
@@ -449,7 +462,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram2_kernel(const __grid_consta
       }
       // step 2: lower-triangle entries j <= i of row i, scaled, fp16, packed at off(i) + j
       const float mis = mi * inv_S;
-      for (int b = 0; b <= warp; ++b) {
+      for (int b = 0; b <= qd; ++b) {                   // blocks right of the diagonal block hold only j > i
         if (b * 32 >= K) break;
         tmem_ld_32x32(taddr + b * 32, r);
         tmem_ld_wait();
@@ -470,20 +483,17 @@ __global__ void __launch_bounds__(kGThreads, 1) gram2_kernel(const __grid_consta
           }
         }
       }
-      tc_fence_before();
-      if (warp == 0) {
-        asm volatile("bar.arrive 4, 128;" ::: "memory");
-      } else {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&B->acc_empty);
-        asm volatile("bar.sync 4, 128;" ::: "memory");
-        const long long ib = item >> 7;
-        const int row = (int)(item & 127);
-        uint4* dst = reinterpret_cast<uint4*>(P.A) + ((size_t)ib * P.nkgQ) * 128 + row;
-        const uint4* src = reinterpret_cast<const uint4*>(sCb);
-        for (int kg = threadIdx.x - 32; kg < P.nkgQ; kg += (kGEpiWarps - 1) * 32) dst[(size_t)kg * 128] = src[kg];
-        if (threadIdx.x == 32) P.fscale[item] = (f > 0.f) ? ldexpf(1.0f, -(P.exp_base + e)) : 0.f;
-      }
+      tc_fence_before();                                // this warp's TMEM reads of the item are done
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B->acc_empty[ab]);    // the MMA warp may reuse this accumulator (item n_it + 2)
+      asm volatile("bar.sync 4, 128;" ::: "memory");
+      // copy-out: 16-byte pieces of the packed row into the quad kernel's A tiles
+      const long long ib = item >> 7;
+      const int row = (int)(item & 127);
+      uint4* dst = reinterpret_cast<uint4*>(P.A) + ((size_t)ib * P.nkgQ) * 128 + row;
+      const uint4* src = reinterpret_cast<const uint4*>(sCb);
+      for (int kg = i; kg < P.nkgQ; kg += 128) dst[(size_t)kg * 128] = src[kg];
+      if (i == 0) P.fscale[item] = (f > 0.f) ? ldexpf(1.0f, -(P.exp_base + e)) : 0.f;
     }
   }
 
@@ -499,7 +509,7 @@ size_t decode_gram2_smem_bytes(int K) { return gr::gcarve2(gram_nkgQ(K)).total; 
 template <int ACT, int INW>
 static int launch_gram2_inst(glasdi_handle* h, const gr::GramParams& G, int ctas, size_t smem, cudaStream_t st) {
   GL_CUDA(h, cudaFuncSetAttribute(gr::gram2_kernel<ACT, INW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gr::gram2_kernel<ACT, INW><<<ctas, gr::kGThreads, smem, st>>>(G);
+  gr::gram2_kernel<ACT, INW><<<ctas, gr::kG2Threads, smem, st>>>(G);
   return GLASDI_OK;
 }
 

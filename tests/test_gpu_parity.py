@@ -582,7 +582,7 @@ def test_config1_burgers1d_shipped_full(engine, golden_dir):
     f64 = g["burgers1d_shipped_max_std_f64"]
     std_close(ms.cpu().numpy(), ref, ref_noise=np.abs(ref.astype(np.float64) - f64))
     got64 = ms.cpu().numpy().astype(np.float64)
-    nz = f64 > 0
+    nz = f64 > 1e-9                                              # zero-spread corner parameters: fp64 residue ~4e-16
     print(f"config #1: CUDA vs fp64 {np.max(np.abs(got64 - f64)[nz] / f64[nz]):.2e}, reference vs fp64 "
           f"{np.max(np.abs(ref - f64)[nz] / f64[nz]):.2e}")
     assert np.max(np.abs(got64 - f64)[nz] / f64[nz]) <= STD_RTOL
