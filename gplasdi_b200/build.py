@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+LIBDIR = os.environ.get("GLASDI_LIBDIR") or os.path.join(HERE, "lib")   # GLASDI_LIBDIR: a second (instrumented) build beside the product
 LIB = os.path.join(LIBDIR, "libglasdi_b200.so")
 SOURCES = ["api.cu", "rollout.cu", "decode_var.cu", "decode_var2.cu", "decode_gram.cu", "decode_gram2.cu", "simt_fallback.cu", "refine.cu", "reduce.cu", "calibrate.cu", "gp.cu", "decode_wide.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -29,7 +29,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def _stale(src: str, obj: str) -> bool:
+    """An object is stale when its source or any header in csrc/ / include/ is newer."""
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(HERE, "..", "include", "glasdi_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles the stale objects (all with force) in parallel and links the library.  GLASDI_NVCC_EXTRA adds flags
+    (an instrumented build: pair it with force, the objects are shared)."""
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
@@ -37,16 +49,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
+        if not force and not _stale(src, obj):
+            continue
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("GLASDI_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
         log.append(f"== {src}\n{out}")
         failed |= p.returncode != 0
-    with open(os.path.join(LIBDIR, "build.log"), "w") as f:
+    with open(os.path.join(LIBDIR, "build.log"), "a" if not force else "w") as f:
         f.write("\n".join(log))
     if verbose or failed:
         print("\n".join(log))
