@@ -137,6 +137,20 @@ int glasdi_create(glasdi_handle** out, int device) {
   cudaSetDevice(device);
   cudaError_t e = cudaMalloc(&h->d_flags, 4 * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(h->d_flags, 0, 4 * sizeof(int));
+  if (e == cudaSuccess) {
+    // stream-ordered scratch of the CUDA-core / wide-decoder paths comes from the handle's own pool, which keeps its memory
+    // across synchronisations (the default pool returns it to the driver at every sync: 10-40 ms per GB-sized slab)
+    cudaMemPoolProps pp{};
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    e = cudaMemPoolCreate(&h->pool, &pp);
+    if (e == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      e = cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   cudaSetDevice(prev);
   if (e != cudaSuccess) { delete h; return GLASDI_ERR_CUDA; }
   *out = h;
@@ -158,6 +172,10 @@ int glasdi_destroy(glasdi_handle* h) {
   if (h->d_cand_stats) cudaFree(h->d_cand_stats);
   if (h->d_exact) cudaFree(h->d_exact);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->pool) {
+    cudaDeviceSynchronize();
+    cudaMemPoolDestroy(h->pool);
+  }
   cudaSetDevice(prev);
   delete h;
   return GLASDI_OK;
@@ -371,8 +389,11 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
   // screened mode: one fp16 pass on the tensor cores writes the variance field, refine.cu re-evaluates
   // the near-maximum candidates exactly.  Only the CTA-pair tcgen05 kernel has the field epilogue.
   const bool gram = h->opt_mode == GLASDI_MODE_SCREENED_GRAM && d.gram_ok;
-  const bool screened = gram || (h->opt_mode != GLASDI_MODE_DIRECT && d.tc_ok && h->opt_kernel == 1);
-  const int field_ld = decode_field_ld(d.n_tiles);
+  // wide decoders (K_last > 112, decode_wide.cu): one fp16 screening pass of the K-looped GEMMs + the exact CUDA-core chain
+  // at the candidates' rows, instead of three fp32-faithful split passes
+  const bool wide_screen = !d.tc_ok && d.wide_packed != nullptr && h->opt_wide >= 1 && h->opt_mode != GLASDI_MODE_DIRECT;
+  const bool screened = gram || wide_screen || (h->opt_mode != GLASDI_MODE_DIRECT && d.tc_ok && h->opt_kernel == 1);
+  const int field_ld = wide_screen ? (d.D + 255) / 256 * 256 : decode_field_ld(d.n_tiles);
   const size_t traj_bytes = (size_t)T * n * Spad * sizeof(float);
   const size_t field_bytes = screened ? (size_t)T * field_ld * sizeof(float) : 0;
   const size_t gram_bytes = gram ? (size_t)T * (gram_nkgQ(d.K) * 16 + sizeof(float)) : 0;   // packed covariances + scales
@@ -395,7 +416,10 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
   }
   float* Zs = reinterpret_cast<float*>(h->ws);
   float* field = screened ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->ws) + traj_bytes * slab) : nullptr;
-  const float delta = ldexpf(1.0f, -h->opt_margin_log2);
+  // the one-pass x-space screening of the wide decoders carries the fp16 rounding of the last layer's WEIGHTS, an error
+  // common to all samples of a dof that does not average out over the ensemble (measured 1e-3 on sigma at S = 24, 3.5e-4 at
+  // S = 300, against 5e-5 for the covariance form): its candidate margin is one bit wider
+  const float delta = ldexpf(1.0f, -(h->opt_margin_log2 - (wide_screen ? 1 : 0)));
   h->ev_rollout.clear();
   h->ev_decode.clear();
   h->ev_refine.clear();
@@ -418,10 +442,11 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
     if ((rc = t_dec.start())) return rc;
     if (gram) rc = launch_decode_gram(h, Zs, Spad, pn, S, T, reinterpret_cast<uint8_t*>(h->ws) + a_off,
                                       reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->ws) + a_off + a_bytes), st);
+    else if (wide_screen) rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, field, field_ld, st);
     else if (screened) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, field, 1, st);
     else if (d.tc_ok && h->opt_kernel == 1) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, nullptr, 0, st);
     else if (d.tc_ok) rc = launch_decode_var(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
-    else rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
+    else rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, nullptr, 0, st);
     if (rc) return rc;
     if ((rc = t_dec.stop())) return rc;
     if (gram) {
@@ -437,8 +462,9 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
       GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats + 3, 0, sizeof(unsigned int), st));  // per-slab row-group count
       rc = launch_select_candidates(h, field, field_ld, h->d_maxvar + p0, pn, T, d.D, (1.f - delta) * (1.f - delta), st);
       if (rc) return rc;
-      rc = launch_refine(h, Zs, Spad, S, T, h->d_exact + p0, 0.25f * delta,
-                         gram ? 1.0f : ldexpf(1.0f, -2 * (d.eW + d.eH)), st);
+      if (wide_screen) rc = launch_refine_wide(h, Zs, Spad, S, T, h->d_exact + p0, 0.25f * delta, st);
+      else rc = launch_refine(h, Zs, Spad, S, T, h->d_exact + p0, 0.25f * delta,
+                              gram ? 1.0f : ldexpf(1.0f, -2 * (d.eW + d.eH)), st);
       if (rc) return rc;
       if ((rc = t_ref.stop())) return rc;
     }

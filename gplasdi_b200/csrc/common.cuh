@@ -81,6 +81,7 @@ struct glasdi_handle {
   size_t ws_bytes = 0;
   unsigned int* d_maxvar = nullptr;   // [P] float bits
   size_t maxvar_cap = 0;
+  cudaMemPool_t pool = nullptr;       // stream-ordered scratch (release threshold = keep everything)
   int* d_flags = nullptr;             // [4] device error flags: [0] fp16 range, [1] candidate overflow, [2] screening deviation
   // screened mode (GLASDI_OPT_MODE = 1): candidates of the last greedy call
   int opt_mode = 2;                   // 0: direct (split passes), 1: x-space screening + refinement, 2: covariance-form screening + refinement
@@ -150,18 +151,38 @@ int launch_refine(glasdi_handle* h, const float* Zs, int Spad, int S, int T, uns
                   float dev_tol, float unscale, cudaStream_t st);
 int launch_decode_store_pair(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
 // simt_fallback.cu : fp32 CUDA-core path for decoder shapes the tcgen05 kernel does not cover
+// field != nullptr: screening launch (ONE fp16 pass on the tensor cores, variance field [P * T][field_ld] in true units)
 int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
-                           unsigned int* maxvar_bits, cudaStream_t st);
+                           unsigned int* maxvar_bits, float* field, int field_ld, cudaStream_t st);
+// exact re-evaluation of the screened candidates of a wide decoder: fp32 CUDA-core chain + fp64 sample sums
+int launch_refine_wide(glasdi_handle* h, const float* Zs, int Spad, int S, int T, unsigned int* exact_bits, float dev_tol,
+                       cudaStream_t st);
 int launch_decode_store_simt(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
 int launch_encode_simt(glasdi_handle* h, const float* U, int64_t rows, float* Z, cudaStream_t st);
 // decode_wide.cu : last layer + variance of wide decoders (K_last > 112) as a K-looped three-pass tcgen05 GEMM
 int wide_pack_w(glasdi_handle* h, const float* WL_host, const float* W1_host, int K1);
-size_t wide_b_bytes(int K, int S, long long n_groups);
-size_t wide_x_bytes(int K1, int S, long long n_groups);
-int launch_wide_front(glasdi_handle* h, const float* X, long long n_groups, int S, void* xt_ws, void* bt_ws,
+// parts = 3: fp32-faithful [hi | lo | hi] split passes, parts = 1: one fp16 screening pass
+size_t wide_b_bytes(int K, int S, long long n_groups, int parts);
+size_t wide_x_bytes(int K1, int S, long long n_groups, int parts);
+int launch_wide_front(glasdi_handle* h, const float* X, long long n_groups, int S, void* xt_ws, void* bt_ws, int parts,
                       cudaStream_t st);
+bool wide_pre_supported(const Decoder& d);
+int launch_wide_pre(glasdi_handle* h, const float* Zs, int Spad, long long g0, long long n_groups, int S, void* xt_ws,
+                    cudaStream_t st);
 int launch_wide_last_var(glasdi_handle* h, const float* Hlast, long long g0, long long n_groups, int S, int T, void* bt_ws,
-                         unsigned int* maxvar_bits, cudaStream_t st);
+                         unsigned int* maxvar_bits, int parts, float* field, int field_ld, cudaStream_t st);
+// candidate records of the screened modes (refine.cu, simt_fallback.cu)
+namespace rf {
+struct Cand {
+  int p, t, d;
+  float var;       // screened variance (field units)
+};
+struct Group {     // work unit: up to 8 candidates of one (p, t) row
+  int p, t;
+  unsigned int first;      // candidates [first, first + (count & 0xff)) of cand[]
+  unsigned int count;      // low byte: candidates of this unit; bits 8..31: candidates of the whole row in the row's FIRST unit, else 0
+};
+}  // namespace rf
 // reduce.cu
 int launch_finalize(glasdi_handle* h, const unsigned int* maxvar_bits, int P, int scale_exp2,
                     float* max_std, int64_t* argmax, float* maxval, cudaStream_t st);
@@ -219,6 +240,14 @@ __device__ __forceinline__ float act_apply_t(int act_rt, float x) {
     return __fdividef(x, 1.0f + __expf(-x));
   } else if constexpr (ACT >= 0) {
     return act_apply(ACT, x);
+  } else if constexpr (ACT == -2) {      // runtime activation, MUFU forms where they exist (screening passes)
+    switch (act_rt) {
+      case GLASDI_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-x));
+      case GLASDI_ACT_SOFTPLUS: return x > 20.0f ? x : __logf(1.0f + __expf(x));
+      case GLASDI_ACT_SILU: return __fdividef(x, 1.0f + __expf(-x));
+      case GLASDI_ACT_TANH: return fmaf(2.0f, __fdividef(1.0f, 1.0f + __expf(-2.0f * x)), -1.0f);
+      default: return act_apply(act_rt, x);
+    }
   } else {
     return act_apply(act_rt, x);
   }

@@ -15,7 +15,7 @@
 // 128 x 256 tiles (M = dofs on the TMEM lanes, N = samples on the columns), double-buffered 256-column accumulators, four
 // epilogue warps.  The hidden activations come from the exact fp32 CUDA-core chain (simt_fallback.cu) and are centred,
 // scaled, split and packed by pack_hidden_kernel; padding samples are exact zeros.
-#include "common.cuh"
+#include "decode_common.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -38,12 +38,66 @@ struct WideParams {
   unsigned int* maxvar_bits;   // [P] float bits of the scaled variance maximum
   long long g0;           // first (p, t) group of this slab
   int n_groups, n_dofb, n_sb, nkg, T, S;
+  int a_blk_kg;           // 16-byte k groups per dof block of A (3 Kp / 8); the first nkg of them are read: [W_hi] of a
+                          // one-pass screening launch, [W_hi | W_hi | W_lo] of a three-pass one
+  float* field;           // screening launch: [n_groups][field_ld] variance of every dof in true units (else null)
+  int field_ld;
   float unscale;          // 2^(-2 (eW + eH)): scaled variance -> true units
 };
 
 struct Bars {
   uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
 };
+
+// Activations of the SCREENING pass: MUFU ex2 / lg2 / rcp forms (relative error ~2^-21) instead of the libdevice ones the
+// fp32-faithful passes and the exact re-evaluation use -- ~6 instead of ~40 instructions per value in epilogues that
+// are bound by exactly that.  The same function is applied to the pilot, so sample 0 still cancels to exactly 0.
+__device__ __forceinline__ float act_fast(int act, float x) { return act_apply_t<-2>(act, x); }
+
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// bare MUFU forms, activation resolved at compile time: 3-6 instructions per value (the runtime switch + __expf / __logf
+// range handling of act_fast cost ~25 in xact_kernel's epilogue: 40 instructions per value, profiles/r02_xact_*)
+template <int ACT>
+__device__ __forceinline__ float act_mufu(float a) {
+  constexpr float kL2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  if constexpr (ACT == GLASDI_ACT_SIGMOID) return mufu_rcp(1.0f + mufu_ex2(-kL2e * a));
+  else if constexpr (ACT == GLASDI_ACT_TANH) return fmaf(2.0f, mufu_rcp(1.0f + mufu_ex2(-2.0f * kL2e * a)), -1.0f);
+  else if constexpr (ACT == GLASDI_ACT_SOFTPLUS) return fmaf(kLn2, mufu_lg2(1.0f + mufu_ex2(-kL2e * fabsf(a))), fmaxf(a, 0.0f));
+  else if constexpr (ACT == GLASDI_ACT_SILU) return a * mufu_rcp(1.0f + mufu_ex2(-kL2e * a));
+  else if constexpr (ACT == GLASDI_ACT_RELU) return fmaxf(a, 0.0f);
+  else if constexpr (ACT == GLASDI_ACT_IDENTITY) return a;
+  else return act_apply(ACT, a);
+}
+// 32 accumulator columns of one unit row -> (act(a) - pilot) 2^eH as fp16 into the [hi] part of xvar_kernel's B tile
+template <int ACT>
+__device__ __forceinline__ void xact_emit_screen(const uint32_t (&r)[32], float unscale, float bias, float pilot_s, float scale,
+                                                 int valid_cols, bool unit_ok, bool store_ok, __half* dst, float& amax,
+                                                 float& nanacc) {
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const float a = fmaf(__uint_as_float(r[q]), unscale, bias);
+    float dvv = fmaf(act_mufu<ACT>(a), scale, -pilot_s);
+    dvv = (unit_ok && q < valid_cols) ? dvv : 0.f;
+    amax = fmaxf(amax, fabsf(dvv));
+    nanacc = fmaf(dvv, 0.f, nanacc);                    // NaN / inf leave a NaN behind
+    if (store_ok) dst[q * 8] = __float2half_rn(dvv);
+  }
+}
+template <int ACT>
+__device__ __forceinline__ float xact_pilot_screen(float a) { return act_mufu<ACT>(a); }
+#define GLASDI_ACT_DISPATCH(act, CALL)                                            \
+  switch (act) {                                                                  \
+    case GLASDI_ACT_SIGMOID: { constexpr int A_ = GLASDI_ACT_SIGMOID; CALL; } break;   \
+    case GLASDI_ACT_TANH: { constexpr int A_ = GLASDI_ACT_TANH; CALL; } break;         \
+    case GLASDI_ACT_SOFTPLUS: { constexpr int A_ = GLASDI_ACT_SOFTPLUS; CALL; } break; \
+    case GLASDI_ACT_RELU: { constexpr int A_ = GLASDI_ACT_RELU; CALL; } break;         \
+    case GLASDI_ACT_ELU: { constexpr int A_ = GLASDI_ACT_ELU; CALL; } break;           \
+    case GLASDI_ACT_SILU: { constexpr int A_ = GLASDI_ACT_SILU; CALL; } break;         \
+    case GLASDI_ACT_GELU: { constexpr int A_ = GLASDI_ACT_GELU; CALL; } break;         \
+    default: { constexpr int A_ = GLASDI_ACT_IDENTITY; CALL; } break;                  \
+  }
 
 __global__ void __launch_bounds__(kThreads, 1) xvar_kernel(const __grid_constant__ WideParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -81,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) xvar_kernel(const __grid_constant
       for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
         const long long g = u / P.n_dofb;
         const int dofb = (int)(u - g * P.n_dofb);
-        const uint8_t* a0 = reinterpret_cast<const uint8_t*>(P.A) + (size_t)dofb * P.nkg * 128 * 16;
+        const uint8_t* a0 = reinterpret_cast<const uint8_t*>(P.A) + (size_t)dofb * P.a_blk_kg * 128 * 16;
         for (int sb = 0; sb < P.n_sb; ++sb) {
           const uint8_t* b0 = reinterpret_cast<const uint8_t*>(P.Bt) + ((size_t)g * P.n_sb + sb) * P.nkg * 256 * 16;
           for (int kc = 0; kc < nchunks; ++kc) {
@@ -136,6 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) xvar_kernel(const __grid_constant
     const float inv_S = 1.0f / (float)P.S;
     for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
       const long long g = u / P.n_dofb;
+      const int dofb = (int)(u - g * P.n_dofb);
       float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};     // four independent chains
       for (int sb = 0; sb < P.n_sb; ++sb) {
         const uint32_t ab = a_it & 1u;
@@ -173,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) xvar_kernel(const __grid_constant
       const float sq = (s2[0] + s2[1]) + (s2[2] + s2[3]);
       const float mean = sum * inv_S;
       const float var = fmaxf(0.f, fmaf(-mean, mean, sq * inv_S)) * P.unscale;  // rows >= D have zero weights: var = 0
+      if (P.field) P.field[(size_t)(P.g0 + g) * P.field_ld + dofb * 128 + warp * 32 + lane] = var;   // field_ld >= 128 n_dofb
       const float wm = warp_max(var);
       if (lane == 0 && wm > 0.f) atomicMax(P.maxvar_bits + (P.g0 + g) / P.T, __float_as_uint(wm));
     }
@@ -201,10 +257,13 @@ struct ActParams {
   __half* Bt;             // [n_groups][n_sb][3 Kp / 8][256][8]   output = xvar_kernel's B'
   int* flags;
   int n_groups, n_ub, n_sb, nkg, S, K, Kp, act;
+  int a_blk_kg;           // k groups per unit block of A (3 K1p / 8); the first nkg are read (one or three passes)
+  int parts_out;          // 3: [hi | lo | hi] for a three-pass xvar_kernel, 1: [hi] for the screening pass
   float unscale_in;       // 2^-(eW1 + eX)
   float scale_out;        // 2^eH
 };
 
+template <bool SCREEN>
 __global__ void __launch_bounds__(kActThreads, 1) xact_kernel(const __grid_constant__ ActParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -240,7 +299,7 @@ __global__ void __launch_bounds__(kActThreads, 1) xact_kernel(const __grid_const
       for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
         const long long g = u / P.n_ub;
         const int ub = (int)(u - g * P.n_ub);
-        const uint8_t* a0 = reinterpret_cast<const uint8_t*>(P.A) + (size_t)ub * P.nkg * 128 * 16;
+        const uint8_t* a0 = reinterpret_cast<const uint8_t*>(P.A) + (size_t)ub * P.a_blk_kg * 128 * 16;
         for (int sb = 0; sb < P.n_sb; ++sb) {
           const uint8_t* b0 = reinterpret_cast<const uint8_t*>(P.Xt) + ((size_t)g * P.n_sb + sb) * P.nkg * 256 * 16;
           for (int kc = 0; kc < nchunks; ++kc) {
@@ -295,6 +354,7 @@ __global__ void __launch_bounds__(kActThreads, 1) xact_kernel(const __grid_const
     const int nkgK = P.Kp / 8;
     const size_t part = (size_t)nkgK * 256 * 8;                      // halfs per [hi] / [lo] / [hi] part of one tile
     bool over = false;
+    float amax = 0.f, nanacc = 0.f;
     for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
       const long long g = u / P.n_ub;
       const int ub = (int)(u - g * P.n_ub);
@@ -307,12 +367,14 @@ __global__ void __launch_bounds__(kActThreads, 1) xact_kernel(const __grid_const
         mbar_wait_relaxed(&B->acc_full[ab], (a_it >> 1) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (((uint32_t)(quad * 32)) << 16) + ab * 256u;
-        __half* tile = P.Bt + ((size_t)g * P.n_sb + sb) * 3 * part + ((size_t)(k2 >> 3) * 256) * 8 + (k2 & 7);
+        __half* tile = P.Bt + ((size_t)g * P.n_sb + sb) * (SCREEN ? 1 : 3) * part + ((size_t)(k2 >> 3) * 256) * 8 + (k2 & 7);
         uint32_t ra[32], rb[32];
         if (sb == 0) {                                  // every warp makes its own copy of the pilot (sample 0 = column 0)
           tmem_ld_32x32(taddr, ra);
           tmem_ld_wait();
-          pilot = act_apply(P.act, fmaf(__uint_as_float(ra[0]), P.unscale_in, bias));
+          const float ap = fmaf(__uint_as_float(ra[0]), P.unscale_in, bias);
+          if constexpr (SCREEN) { GLASDI_ACT_DISPATCH(P.act, pilot = xact_pilot_screen<A_>(ap)) }
+          else pilot = act_apply(P.act, ap);
         }
         auto emit = [&](const uint32_t (&r)[32], int c0) {
 #pragma unroll
@@ -324,12 +386,14 @@ __global__ void __launch_bounds__(kActThreads, 1) xact_kernel(const __grid_const
             const float dv = (unit_ok && s < P.S) ? (hval - pilot) * P.scale_out : 0.f;
             over |= !(fabsf(dv) <= 65000.f);
             const __half vh = __float2half_rn(dv);
-            const __half vl = __float2half_rn(dv - __half2float(vh));
             if (store_ok) {
               __half* dst = tile + (size_t)col * 8;
               dst[0] = vh;
-              dst[part] = vl;
-              dst[2 * part] = vh;
+              if constexpr (!SCREEN) {
+                const __half vl = __float2half_rn(dv - __half2float(vh));
+                dst[part] = vl;
+                dst[2 * part] = vh;
+              }
             }
           }
         };
@@ -337,16 +401,26 @@ __global__ void __launch_bounds__(kActThreads, 1) xact_kernel(const __grid_const
         tmem_ld_32x32(taddr + c_lo, ra);
         tmem_ld_wait();
         tmem_ld_32x32(taddr + c_lo + 32, rb);
-        emit(ra, c_lo);
-        tmem_ld_wait();
-        emit(rb, c_lo + 32);
+        if constexpr (SCREEN) {
+          const float pilot_s = pilot * P.scale_out;
+          const int v0 = P.S - (sb * 256 + c_lo);          // valid columns from c_lo on
+          GLASDI_ACT_DISPATCH(P.act, xact_emit_screen<A_>(ra, P.unscale_in, bias, pilot_s, P.scale_out, v0, unit_ok, store_ok,
+                                                          tile + (size_t)c_lo * 8, amax, nanacc))
+          tmem_ld_wait();
+          GLASDI_ACT_DISPATCH(P.act, xact_emit_screen<A_>(rb, P.unscale_in, bias, pilot_s, P.scale_out, v0 - 32, unit_ok, store_ok,
+                                                          tile + (size_t)(c_lo + 32) * 8, amax, nanacc))
+        } else {
+          emit(ra, c_lo);
+          tmem_ld_wait();
+          emit(rb, c_lo + 32);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&B->acc_empty[ab]);
         ++a_it;
       }
     }
-    if (over) atomicOr(P.flags + 0, 1);
+    if (over || !(amax <= 65000.f) || nanacc != 0.f) atomicOr(P.flags + 0, 1);
   }
 
   tc_fence_before();
@@ -358,8 +432,8 @@ __global__ void __launch_bounds__(kActThreads, 1) xact_kernel(const __grid_const
 // split hi + lo, laid out [group][sample block of 256][kg over 3 Kp / 8][256][8] with kg blocks [hi | lo | hi].
 // One thread per (group, sample column incl. padding, group of 8 k).
 __global__ void __launch_bounds__(256) pack_hidden_kernel(const float* __restrict__ H, int n_groups, int S, int K, int Kp,
-                                                          int n_sb, float scale, int centre, __half* __restrict__ Bt,
-                                                          int* __restrict__ flags) {
+                                                          int n_sb, float scale, int centre, int parts,
+                                                          __half* __restrict__ Bt, int* __restrict__ flags) {
   const int nkgK = Kp / 8;
   const long long total = (long long)n_groups * n_sb * 256 * nkgK;
   bool over = false;
@@ -385,23 +459,158 @@ __global__ void __launch_bounds__(256) pack_hidden_kernel(const float* __restric
       hi[u] = __float2half_rn(v);
       lo[u] = __float2half_rn(v - __half2float(hi[u]));
     }
-    __half* base = Bt + (((size_t)g * n_sb + sb) * (size_t)(3 * nkgK)) * 256 * 8;
+    __half* base = Bt + (((size_t)g * n_sb + sb) * (size_t)(parts * nkgK)) * 256 * 8;
     const size_t o = ((size_t)kg * 256 + col) * 8;
     const size_t part = (size_t)nkgK * 256 * 8;
     *reinterpret_cast<uint4*>(base + o) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(base + part + o) = *reinterpret_cast<const uint4*>(lo);
-    *reinterpret_cast<uint4*>(base + 2 * part + o) = *reinterpret_cast<const uint4*>(hi);
+    if (parts == 3) {
+      *reinterpret_cast<uint4*>(base + part + o) = *reinterpret_cast<const uint4*>(lo);
+      *reinterpret_cast<uint4*>(base + 2 * part + o) = *reinterpret_cast<const uint4*>(hi);
+    }
   }
   if (over) atomicOr(flags + 0, 1);                     // activation differences beyond the fp16 range of the split
+}
+
+// Screening pass: everything in front of xact_kernel in ONE kernel -- thread <-> sample of a (p, t) group: the latent state
+// from the trajectory scratch, the narrow front layers in registers (front_pre), the layer that feeds xact_kernel from
+// shared-memory weight rows, scaled fp16 written straight into xact_kernel's B tiles [group][sample block][kg][256][8]
+// (16 bytes per thread and k group, coalesced over the sample columns).  Replaces gather_rows + one CUDA-core GEMM launch
+// per layer (activations through HBM in fp32) + pack_hidden: 23 % of the Vlasov-shaped step.
+struct PreParams {
+  FrontMlp f;             // layers 0 .. n_front-1; the last one produces xact_kernel's input (width K1)
+  const float* Zs;        // [P][T][n][Spad]
+  __half* Xt;             // [n_groups][n_sb][K1p / 8][256][8]
+  int* flags;
+  long long g0;
+  int n_groups, n_sb, S, Spad, K1, K1p;
+  float scale;            // 2^eX
+};
+
+// shared-memory image of the pre-chain: narrow layers l < n_front - 1 as transposed, zero-padded [64 in][64 out] blocks + a
+// bias row of 64, the last layer as [K1p / 8][64 in][8 units] + K1p biases.  Inputs and outputs of a layer live in REGISTERS
+// (arrays indexed by fully unrolled loops; the first version kept them in local memory: 343 us per slab against 364 us for
+// the five launches it replaced), widths are honoured in blocks of 8 inputs / 4 outputs.
+constexpr int kPreW = 64;                              // = dv::kMaxHid
+__host__ __device__ inline size_t wide_pre_smem_floats(int n_front, int K1p) {
+  return (size_t)(n_front - 1) * (kPreW * kPreW + kPreW) + (size_t)K1p * kPreW + (size_t)K1p;
+}
+
+__global__ void __launch_bounds__(256) wide_pre_kernel(const __grid_constant__ PreParams P) {
+  extern __shared__ __align__(16) float psm[];
+  const int nf = P.f.n_front;
+  float* sLast = psm + (size_t)(nf - 1) * (kPreW * kPreW + kPreW);       // [K1p / 8][64][8]
+  float* sLastB = sLast + (size_t)P.K1p * kPreW;                          // [K1p]
+  for (int l = 0; l + 1 < nf; ++l) {
+    const int wi = P.f.widths[l], wo = P.f.widths[l + 1];
+    float* Wt = psm + (size_t)l * (kPreW * kPreW + kPreW);
+    for (int idx = threadIdx.x; idx < kPreW * kPreW; idx += blockDim.x) {
+      const int i = idx / kPreW, o = idx - i * kPreW;
+      Wt[idx] = (i < wi && o < wo) ? P.f.W[l][(size_t)o * wi + i] : 0.f;
+    }
+    for (int o = threadIdx.x; o < kPreW; o += blockDim.x) Wt[kPreW * kPreW + o] = o < wo ? P.f.b[l][o] : 0.f;
+  }
+  {
+    const int l = nf - 1, wi = P.f.widths[l];
+    for (int idx = threadIdx.x; idx < P.K1p * kPreW; idx += blockDim.x) {
+      const int u = idx & 7, i = (idx >> 3) % kPreW, kg = idx / (8 * kPreW);
+      const int k = kg * 8 + u;
+      sLast[idx] = (k < P.K1 && i < wi) ? P.f.W[l][(size_t)k * wi + i] : 0.f;
+    }
+    for (int k = threadIdx.x; k < P.K1p; k += blockDim.x) sLastB[k] = k < P.K1 ? P.f.b[l][k] : 0.f;
+  }
+  __syncthreads();
+  const int n = P.f.widths[0];
+  const int nkg = P.K1p / 8;
+  const int w_last_in = P.f.widths[nf - 1];
+  float amax = 0.f, nanacc = 0.f;
+  const long long total = (long long)P.n_groups * P.n_sb * 256;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(idx & 255);
+    const long long r = idx >> 8;
+    const int sb = (int)(r % P.n_sb);
+    const long long g = r / P.n_sb;
+    const int s = sb * 256 + col;
+    uint4* dst = reinterpret_cast<uint4*>(P.Xt) + (((size_t)g * P.n_sb + sb) * nkg) * 256 + col;
+    if (s >= P.S) {                                            // padding samples: exact zeros
+      for (int kg = 0; kg < nkg; ++kg) dst[(size_t)kg * 256] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    float x[kPreW], y[kPreW];
+    const float* __restrict__ zb = P.Zs + ((P.g0 + g) * n) * P.Spad + s;
+#pragma unroll
+    for (int i = 0; i < kPreW; ++i) x[i] = (i < kMaxLatent && i < n) ? __ldg(zb + (size_t)i * P.Spad) : 0.f;
+    for (int l = 0; l + 1 < nf; ++l) {
+      const int wi = P.f.widths[l], wo = P.f.widths[l + 1];
+      const float* __restrict__ Wt = psm + (size_t)l * (kPreW * kPreW + kPreW);
+#pragma unroll
+      for (int o4 = 0; o4 < kPreW / 4; ++o4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(Wt + kPreW * kPreW + o4 * 4);
+        y[o4 * 4 + 0] = b4.x; y[o4 * 4 + 1] = b4.y; y[o4 * 4 + 2] = b4.z; y[o4 * 4 + 3] = b4.w;
+      }
+#pragma unroll
+      for (int i8 = 0; i8 < kPreW / 8; ++i8) {
+        if (i8 * 8 < wi) {
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) {
+            const float xi = x[i8 * 8 + ii];
+#pragma unroll
+            for (int o4 = 0; o4 < kPreW / 4; ++o4) {
+              if (o4 * 4 < wo) {
+                const float4 w4 = *reinterpret_cast<const float4*>(Wt + (i8 * 8 + ii) * kPreW + o4 * 4);
+                y[o4 * 4 + 0] = fmaf(w4.x, xi, y[o4 * 4 + 0]);
+                y[o4 * 4 + 1] = fmaf(w4.y, xi, y[o4 * 4 + 1]);
+                y[o4 * 4 + 2] = fmaf(w4.z, xi, y[o4 * 4 + 2]);
+                y[o4 * 4 + 3] = fmaf(w4.w, xi, y[o4 * 4 + 3]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < kPreW; ++o) x[o] = (o < wo) ? act_fast(P.f.act, y[o]) : 0.f;
+    }
+    for (int kg = 0; kg < nkg; ++kg) {
+      float acc[8];
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(sLastB + kg * 8), b1 = *reinterpret_cast<const float4*>(sLastB + kg * 8 + 4);
+        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+      }
+      const float* __restrict__ Wk = sLast + (size_t)kg * kPreW * 8;
+#pragma unroll
+      for (int i8 = 0; i8 < kPreW / 8; ++i8) {
+        if (i8 * 8 < w_last_in) {
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) {
+            const float xi = x[i8 * 8 + ii];
+            const float4 w0 = *reinterpret_cast<const float4*>(Wk + (i8 * 8 + ii) * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(Wk + (i8 * 8 + ii) * 8 + 4);
+            acc[0] = fmaf(w0.x, xi, acc[0]); acc[1] = fmaf(w0.y, xi, acc[1]); acc[2] = fmaf(w0.z, xi, acc[2]); acc[3] = fmaf(w0.w, xi, acc[3]);
+            acc[4] = fmaf(w1.x, xi, acc[4]); acc[5] = fmaf(w1.y, xi, acc[5]); acc[6] = fmaf(w1.z, xi, acc[6]); acc[7] = fmaf(w1.w, xi, acc[7]);
+          }
+        }
+      }
+      uint32_t out[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float v0 = (kg * 8 + 2 * u < P.K1) ? act_fast(P.f.act, acc[2 * u]) * P.scale : 0.f;
+        const float v1 = (kg * 8 + 2 * u + 1 < P.K1) ? act_fast(P.f.act, acc[2 * u + 1]) * P.scale : 0.f;
+        amax = fmaxf(amax, fmaxf(fabsf(v0), fabsf(v1)));
+        nanacc = fmaf(v0 + v1, 0.f, nanacc);
+        out[u] = dv::h2_as_u32(__floats2half2_rn(v0, v1));
+      }
+      dst[(size_t)kg * 256] = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+  }
+  if (!(amax <= 65000.f) || nanacc != 0.f) atomicOr(P.flags + 0, 1);
 }
 
 }  // namespace wd
 
 int wide_kp(int K) { return (K + 63) / 64 * 64; }
 
-size_t wide_b_bytes(int K, int S, long long n_groups) {
+size_t wide_b_bytes(int K, int S, long long n_groups, int parts) {
   const size_t n_sb = (size_t)(S + 255) / 256;
-  return (size_t)n_groups * n_sb * (size_t)(3 * wide_kp(K) / 8) * 256 * 16;
+  return (size_t)n_groups * n_sb * (size_t)(parts * wide_kp(K) / 8) * 256 * 16;
 }
 
 // [W_hi | W_hi | W_lo] 2^e of a layer W [out][in] as fp16 canonical K-major tiles [row block of 128][3 inp / 8][128][8]
@@ -450,11 +659,11 @@ int wide_pack_w(glasdi_handle* h, const float* WL /*[D][K] host*/, const float* 
   return GLASDI_OK;
 }
 
-size_t wide_x_bytes(int K1, int S, long long n_groups) { return wide_b_bytes(K1, S, n_groups); }
+size_t wide_x_bytes(int K1, int S, long long n_groups, int parts) { return wide_b_bytes(K1, S, n_groups, parts); }
 
 // X fp32 [n_groups * S][K1] (input of the last front layer, from the CUDA-core chain) -> the packed, pilot-centred hidden
 // layer tiles that xvar_kernel consumes (bt_ws); xt_ws = scratch for the packed input
-int launch_wide_front(glasdi_handle* h, const float* X, long long n_groups, int S, void* xt_ws, void* bt_ws,
+int launch_wide_front(glasdi_handle* h, const float* X, long long n_groups, int S, void* xt_ws, void* bt_ws, int parts,
                       cudaStream_t st) {
   const Decoder& d = h->dec;
   const int K1 = d.wide_k1, K1p = wide_kp(K1), Kp = wide_kp(d.K);
@@ -462,11 +671,14 @@ int launch_wide_front(glasdi_handle* h, const float* X, long long n_groups, int 
   const int eX = d.eH;                                   // same range argument as the hidden layer (unbounded act: 2^4)
   const long long total = n_groups * n_sb * 256 * (K1p / 8);
   const unsigned int blocks = (unsigned int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 32);
-  wd::pack_hidden_kernel<<<blocks, 256, 0, st>>>(X, (int)n_groups, S, K1, K1p, n_sb, std::ldexp(1.0f, eX), 0,
-                                                 reinterpret_cast<__half*>(xt_ws), h->d_flags);
-  h->launches++;
-  int rc = check_cuda(h, cudaGetLastError(), "pack_hidden_kernel (input) launch");
-  if (rc) return rc;
+  int rc = GLASDI_OK;
+  if (X) {                                               // X == nullptr: xt_ws was written by launch_wide_pre
+    wd::pack_hidden_kernel<<<blocks, 256, 0, st>>>(X, (int)n_groups, S, K1, K1p, n_sb, std::ldexp(1.0f, eX), 0, parts,
+                                                   reinterpret_cast<__half*>(xt_ws), h->d_flags);
+    h->launches++;
+    rc = check_cuda(h, cudaGetLastError(), "pack_hidden_kernel (input) launch");
+    if (rc) return rc;
+  }
   wd::ActParams A{};
   A.A = d.wide_front;
   A.Xt = reinterpret_cast<const __half*>(xt_ws);
@@ -476,7 +688,9 @@ int launch_wide_front(glasdi_handle* h, const float* X, long long n_groups, int 
   A.n_groups = (int)n_groups;
   A.n_ub = (Kp + 127) / 128;
   A.n_sb = n_sb;
-  A.nkg = 3 * K1p / 8;
+  A.nkg = parts * K1p / 8;
+  A.a_blk_kg = 3 * K1p / 8;
+  A.parts_out = parts;
   A.S = S;
   A.K = d.K;
   A.Kp = Kp;
@@ -484,26 +698,69 @@ int launch_wide_front(glasdi_handle* h, const float* X, long long n_groups, int 
   A.unscale_in = std::ldexp(1.0f, -(d.eW1 + eX));
   A.scale_out = std::ldexp(1.0f, d.eH);
   const size_t smem = wd::kStages * wd::kStageBytes + sizeof(wd::Bars) + 16;
-  GL_CUDA(h, cudaFuncSetAttribute(wd::xact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long ctas = h->num_sms;
   if (h->opt_max_ctas > 0) ctas = std::max<long long>(1, std::min<long long>(ctas, h->opt_max_ctas));
   ctas = std::min<long long>(ctas, n_groups * A.n_ub);
-  wd::xact_kernel<<<(unsigned)ctas, wd::kActThreads, smem, st>>>(A);
+  if (parts == 1) {
+    GL_CUDA(h, cudaFuncSetAttribute(wd::xact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wd::xact_kernel<true><<<(unsigned)ctas, wd::kActThreads, smem, st>>>(A);
+  } else {
+    GL_CUDA(h, cudaFuncSetAttribute(wd::xact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wd::xact_kernel<false><<<(unsigned)ctas, wd::kActThreads, smem, st>>>(A);
+  }
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "xact_kernel launch");
+}
+
+// can the layers in front of xact_kernel run in wide_pre_kernel?  (narrow front: registers of one thread per sample)
+bool wide_pre_supported(const Decoder& d) {
+  if (d.wide_front == nullptr || d.n_linear < 3 || d.widths[0] > kMaxLatent) return false;
+  for (int l = 1; l + 2 < d.n_linear; ++l)
+    if (d.widths[l] > dv::kMaxHid) return false;
+  const int nf = d.n_linear - 2;                          // layers of the pre-chain
+  return wd::wide_pre_smem_floats(nf, wide_kp(d.widths[nf])) * sizeof(float) <= 200 * 1024;
+}
+
+int launch_wide_pre(glasdi_handle* h, const float* Zs, int Spad, long long g0, long long n_groups, int S, void* xt_ws,
+                    cudaStream_t st) {
+  const Decoder& d = h->dec;
+  wd::PreParams P{};
+  const int nf = d.n_linear - 2;
+  P.f.n_front = nf;
+  P.f.act = d.act;
+  for (int l = 0; l <= nf; ++l) P.f.widths[l] = d.widths[l];
+  for (int l = 0; l < nf; ++l) { P.f.W[l] = d.dW[l]; P.f.b[l] = d.db[l]; }
+  P.Zs = Zs;
+  P.Xt = reinterpret_cast<__half*>(xt_ws);
+  P.flags = h->d_flags;
+  P.g0 = g0;
+  P.n_groups = (int)n_groups;
+  P.n_sb = (S + 255) / 256;
+  P.S = S;
+  P.Spad = Spad;
+  P.K1 = d.wide_k1;
+  P.K1p = wide_kp(d.wide_k1);
+  P.scale = std::ldexp(1.0f, d.eH);
+  const size_t smem = wd::wide_pre_smem_floats(nf, P.K1p) * sizeof(float);
+  GL_CUDA(h, cudaFuncSetAttribute(wd::wide_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long total = n_groups * P.n_sb * 256;
+  const unsigned int blocks = (unsigned int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 8);
+  wd::wide_pre_kernel<<<blocks, 256, smem, st>>>(P);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "wide_pre_kernel launch");
 }
 
 // Hlast fp32 [n_groups * S][K] (the exact CUDA-core chain's output for a slab of (p, t) groups) -> scaled variance maxima
 // (Hlast = nullptr: bt_ws already holds the packed hidden layer, written by launch_wide_front)
 int launch_wide_last_var(glasdi_handle* h, const float* Hlast, long long g0, long long n_groups, int S, int T, void* bt_ws,
-                         unsigned int* maxvar_bits, cudaStream_t st) {
+                         unsigned int* maxvar_bits, int parts, float* field, int field_ld, cudaStream_t st) {
   const Decoder& d = h->dec;
   const int Kp = wide_kp(d.K);
   const int n_sb = (S + 255) / 256;
   if (Hlast) {
     const long long total = n_groups * n_sb * 256 * (Kp / 8);
     const unsigned int blocks = (unsigned int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 32);
-    wd::pack_hidden_kernel<<<blocks, 256, 0, st>>>(Hlast, (int)n_groups, S, d.K, Kp, n_sb, std::ldexp(1.0f, d.eH), 1,
+    wd::pack_hidden_kernel<<<blocks, 256, 0, st>>>(Hlast, (int)n_groups, S, d.K, Kp, n_sb, std::ldexp(1.0f, d.eH), 1, parts,
                                                    reinterpret_cast<__half*>(bt_ws), h->d_flags);
     h->launches++;
     int rcp = check_cuda(h, cudaGetLastError(), "pack_hidden_kernel launch");
@@ -517,7 +774,10 @@ int launch_wide_last_var(glasdi_handle* h, const float* Hlast, long long g0, lon
   W.n_groups = (int)n_groups;
   W.n_dofb = (d.D + 127) / 128;
   W.n_sb = n_sb;
-  W.nkg = 3 * Kp / 8;
+  W.nkg = parts * Kp / 8;
+  W.a_blk_kg = 3 * Kp / 8;
+  W.field = field;
+  W.field_ld = field_ld;
   W.T = T;
   W.S = S;
   W.unscale = std::ldexp(1.0f, -2 * (d.eW + d.eH));

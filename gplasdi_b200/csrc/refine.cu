@@ -24,15 +24,6 @@ namespace rf {
 
 using namespace dv;
 
-struct Cand {
-  int p, t, d;
-  float var;       // screened variance (field units)
-};
-struct Group {
-  int p, t;
-  unsigned int first, count;      // candidates [first, first + count) of cand[]
-};
-
 constexpr int kSelWarps = 8;          // rows per block of select_rows_kernel
 constexpr int kRefWarps = 8;
 constexpr int kNC = 8;                // candidates a warp evaluates per pass over the samples
@@ -82,7 +73,8 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_rows_kernel(const float
   gslot = __shfl_sync(0xffffffffu, gslot, 0);
   if (base + (unsigned int)total > cap || gslot + nunits > gcap) return;
   for (unsigned int u = lane; u < nunits; u += 32)
-    groups[gslot + u] = Group{p, t, base + u * kNC, min((unsigned int)kNC, (unsigned int)total - u * kNC)};
+    groups[gslot + u] = Group{p, t, base + u * kNC,
+                              min((unsigned int)kNC, (unsigned int)total - u * kNC) | (u == 0 ? (unsigned int)total << 8 : 0u)};
   // pass 2: write (the row is in L1/L2); lanes own interleaved float4s, so the order inside a row is by lane
   unsigned int w = base + (unsigned int)(incl - mine);
   for (int i4 = lane; i4 < n4; i4 += 32) {
@@ -154,8 +146,8 @@ __global__ void __launch_bounds__(kRefWarps * 32, NC <= 2 ? 4 : 2) refine_kernel
   const double inv_S = 1.0 / (double)R.S;
   for (unsigned int gi = blockIdx.x; gi < nunits; gi += gridDim.x) {
     const Group gr = R.groups[gi];
-    if ((gr.count <= 2) != (NC <= 2)) continue;       // uniform over the CTA
-    const int nc = (int)gr.count;
+    const int nc = (int)(gr.count & 0xffu);
+    if ((nc <= 2) != (NC <= 2)) continue;              // uniform over the CTA
     const Cand* __restrict__ cd = R.cand + gr.first;
     const float* __restrict__ zb = R.Zs + ((size_t)gr.p * R.T + gr.t) * R.NZ * R.Spad;
     // rows of the last layer of the unit's candidates (unused slots: zero rows)

@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <vector>
 
 namespace glasdi {
 namespace simt {
@@ -299,6 +300,138 @@ static inline void launch_linear(const float* X, const float* W, const float* b,
   }
 }
 
+// ---- exact re-evaluation of screened candidates, wide decoders (launch_refine_wide) ----------------------------------
+struct WRow {
+  int p, t;
+  unsigned int first, total;        // candidates [first, first + total) of cand[] lie in this (p, t) row of the field
+};
+
+// rows (r, s) of a batch of listed (p, t) rows: Xrow[(r*S + s)][i] = Zs[p][t][i][s]
+__global__ void gather_listed_rows_kernel(const float* __restrict__ Zs, int Spad, int S, int n, int T,
+                                          const WRow* __restrict__ rows, long long nb, float* __restrict__ Xrow) {
+  const long long total = nb * S;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < total;
+       r += (long long)gridDim.x * blockDim.x) {
+    const long long g = r / S;
+    const int s = (int)(r - g * S);
+    const float* src = Zs + (((long long)rows[g].p * T + rows[g].t) * n) * Spad + s;
+    for (int i = 0; i < n; ++i) Xrow[r * n + i] = src[(size_t)i * Spad];
+  }
+}
+
+constexpr int kWNC = 8;               // candidates per pass over the samples
+constexpr int kWThreads = 256;
+
+__device__ __forceinline__ double wr_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// CTA = (row of the batch, unit of <= 8 candidates; blockIdx.y strides the units).  H = exact fp32 activations of the last
+// hidden layer of the row's S samples (the CUDA-core chain), thread <-> sample: the decoded value of a candidate dof is the
+// fp32 FMA chain over k = 0 .. K-1 on the pilot-centred activations (sample 0 = the pilot) that refine_kernel evaluates for
+// the narrow decoders, the sample sums are fp64 (warp shuffle, then a fixed-order sum over the warps).
+__global__ void __launch_bounds__(kWThreads) wide_cand_kernel(const float* __restrict__ H, const float* __restrict__ Wlast,
+                                                              const WRow* __restrict__ rows, const rf::Cand* __restrict__ cand,
+                                                              int S, int K, unsigned int* __restrict__ exact_bits,
+                                                              unsigned int* __restrict__ dev_bits, int* __restrict__ flags,
+                                                              float dev_tol) {
+  extern __shared__ __align__(16) float wsm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Kp = (K + 3) / 4 * 4;
+  float* sW = wsm;                                   // [kWNC][Kp]
+  float* sPil = sW + kWNC * Kp;                      // [Kp]
+  float* sXabs = sPil + Kp;                          // [8]
+  double* sRed = reinterpret_cast<double*>(sXabs + 8);   // [8 warps][kWNC][2]
+  const WRow row = rows[blockIdx.x];
+  const float* __restrict__ Hr = H + (size_t)blockIdx.x * S * K;
+  const double inv_S = 1.0 / (double)S;
+  const bool vec = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(Hr) & 15) == 0);
+  for (int k = tid; k < Kp; k += kWThreads) sPil[k] = k < K ? Hr[k] : 0.f;
+  for (unsigned int unit = blockIdx.y; unit * kWNC < row.total; unit += gridDim.y) {
+    const int nc = (int)min((unsigned int)kWNC, row.total - unit * kWNC);
+    const rf::Cand* __restrict__ cd = cand + row.first + unit * kWNC;
+    __syncthreads();                                 // the previous unit's rows are free (and sPil is there)
+    for (int idx = tid; idx < kWNC * Kp; idx += kWThreads) {
+      const int c = idx / Kp, k = idx - c * Kp;
+      sW[idx] = (c < nc && k < K) ? __ldg(Wlast + (size_t)cd[c].d * K + k) : 0.f;
+    }
+    __syncthreads();
+    if (warp < kWNC) {   // scale of the fp32 rounding noise of a decoded value, one candidate per warp
+      float a = 0.f;
+      for (int k = lane; k < Kp; k += 32) a = fmaf(fabsf(sW[warp * Kp + k]), fabsf(sPil[k]), a);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) sXabs[warp] = a;
+    }
+    double s1[kWNC], s2[kWNC];
+#pragma unroll
+    for (int c = 0; c < kWNC; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
+    for (int s = tid; s < S; s += kWThreads) {
+      const float* __restrict__ hs = Hr + (size_t)s * K;
+      float dsum[kWNC];
+#pragma unroll
+      for (int c = 0; c < kWNC; ++c) dsum[c] = 0.f;
+      if (vec) {
+        for (int k = 0; k < K; k += 4) {
+          const float4 hv = __ldg(reinterpret_cast<const float4*>(hs + k));
+          const float4 pv = *reinterpret_cast<const float4*>(sPil + k);
+          const float dh0 = hv.x - pv.x, dh1 = hv.y - pv.y, dh2 = hv.z - pv.z, dh3 = hv.w - pv.w;
+#pragma unroll
+          for (int c = 0; c < kWNC; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(sW + c * Kp + k);
+            float d = dsum[c];                        // one chain over k = 0 .. K-1
+            d = fmaf(w.x, dh0, d);
+            d = fmaf(w.y, dh1, d);
+            d = fmaf(w.z, dh2, d);
+            d = fmaf(w.w, dh3, d);
+            dsum[c] = d;
+          }
+        }
+      } else {
+        for (int k = 0; k < K; ++k) {
+          const float dh = __ldg(hs + k) - sPil[k];
+#pragma unroll
+          for (int c = 0; c < kWNC; ++c) dsum[c] = fmaf(sW[c * Kp + k], dh, dsum[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kWNC; ++c) {
+        s1[c] += (double)dsum[c];
+        s2[c] = fma((double)dsum[c], (double)dsum[c], s2[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kWNC; ++c) {
+      const double t1 = wr_warp_sum(s1[c]), t2 = wr_warp_sum(s2[c]);
+      if (lane == 0) {
+        sRed[(warp * kWNC + c) * 2 + 0] = t1;
+        sRed[(warp * kWNC + c) * 2 + 1] = t2;
+      }
+    }
+    __syncthreads();
+    if (tid < nc) {
+      const int c = tid;
+      double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWThreads / 32; ++w) {
+        t1 += sRed[(w * kWNC + c) * 2 + 0];
+        t2 += sRed[(w * kWNC + c) * 2 + 1];
+      }
+      const double mean = t1 * inv_S;
+      const float var = (float)fmax(t2 * inv_S - mean * mean, 0.0);
+      atomicMax(exact_bits + row.p, __float_as_uint(var));
+      // screening check, as in refine_kernel: deviations inside the fp32 rounding noise of the decoded value are not counted
+      const float se = sqrtf(var), sa = sqrtf(fmaxf(cd[c].var, 0.f));
+      const float excess = fabsf(sa - se) - 6.0e-8f * sXabs[c];
+      const float dev = (se > 0.f && excess > 0.f) ? excess / se : 0.f;
+      atomicMax(dev_bits, __float_as_uint(dev));
+      if (dev > dev_tol) atomicOr(flags + 2, 1);
+    }
+  }
+}
+
 }  // namespace simt
 
 static int run_chain(glasdi_handle* h, const float* X0, long long R, int upto_layer, float* bufA, float* bufB,
@@ -320,7 +453,7 @@ static int run_chain(glasdi_handle* h, const float* X0, long long R, int upto_la
 }
 
 int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
-                           unsigned int* maxvar_bits, cudaStream_t st) {
+                           unsigned int* maxvar_bits, float* field, int field_ld, cudaStream_t st) {
   const Decoder& d = h->dec;
   const int n = d.widths[0];
   int maxw = n;
@@ -330,15 +463,17 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
   const size_t row_bytes = (size_t)(2 * maxw + n) * sizeof(float);
   const bool wide = h->opt_wide && d.wide_packed != nullptr;        // last layer + variance on tcgen05 (decode_wide.cu)
   const bool wide_front = wide && h->opt_wide >= 2 && d.wide_front != nullptr;   // ... and the last front layer too (xact_kernel)
-  const size_t xt_group = wide_front ? wide_x_bytes(d.wide_k1, S, 1) : 0;
-  const size_t bt_group = wide ? wide_b_bytes(d.K, S, 1) + xt_group : 0;   // packed hidden layer (+ packed input) of one (p, t) group
+  if (field && !wide) return set_error(h, GLASDI_ERR_INVALID, "screening pass of a wide decoder needs GLASDI_OPT_WIDE_TENSOR >= 1");
+  const int parts = field ? 1 : 3;                                   // screening: one fp16 pass; direct: fp32-faithful split passes
+  const size_t xt_group = wide_front ? wide_x_bytes(d.wide_k1, S, 1, parts) : 0;
+  const size_t bt_group = wide ? wide_b_bytes(d.K, S, 1, parts) + xt_group : 0;   // packed hidden layer (+ packed input) of one (p, t) group
   long long ng = std::max<long long>(
       1, std::min<long long>(groups, ((size_t)1 << 30) / (row_bytes * (size_t)S + bt_group)));
   ng = std::min<long long>(ng, 32768);
   // scratch lives behind the trajectory buffer in the workspace: allocate separately here
   float* scratch = nullptr;
   const size_t chain_bytes = ((size_t)ng * S * row_bytes + 1023) / 1024 * 1024;
-  GL_CUDA(h, cudaMallocAsync((void**)&scratch, chain_bytes + bt_group * ng, st));
+  GL_CUDA(h, cudaMallocFromPoolAsync((void**)&scratch, chain_bytes + bt_group * ng, h->pool, st));
   float* Xrow = scratch;
   float* bufA = Xrow + (size_t)ng * S * n;
   float* bufB = bufA + (size_t)ng * S * maxw;
@@ -347,24 +482,34 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
   for (long long g0 = 0; g0 < groups && rc == GLASDI_OK; g0 += ng) {
     const long long gn = std::min(ng, groups - g0);
     const long long R = gn * S;
+    const float* Hlast = nullptr;
+    if (wide_front && field && wide_pre_supported(d)) {
+      // screening pass: narrow front layers fused (wide_pre_kernel), then both wide layers on tcgen05, one fp16 pass each
+      void* xt_ws = reinterpret_cast<uint8_t*>(bt_ws) + wide_b_bytes(d.K, S, ng, parts);
+      rc = launch_wide_pre(h, Zs, Spad, g0, gn, S, xt_ws, st);
+      if (rc) break;
+      rc = launch_wide_front(h, nullptr, gn, S, xt_ws, bt_ws, parts, st);
+      if (rc) break;
+      rc = launch_wide_last_var(h, nullptr, g0, gn, S, T, bt_ws, maxvar_bits, parts, field, field_ld, st);
+      continue;
+    }
     simt::gather_rows_kernel<<<(unsigned)std::min<long long>((R + 255) / 256, 65535), 256, 0, st>>>(Zs, Spad, S, n, g0,
                                                                                                      gn, Xrow);
     h->launches++;
-    const float* Hlast = nullptr;
     if (wide_front) {
       // layers before the last front layer on the CUDA cores, then both wide layers on tcgen05
-      void* xt_ws = reinterpret_cast<uint8_t*>(bt_ws) + wide_b_bytes(d.K, S, ng);
+      void* xt_ws = reinterpret_cast<uint8_t*>(bt_ws) + wide_b_bytes(d.K, S, ng, parts);
       rc = run_chain(h, Xrow, R, d.n_linear - 2, bufA, bufB, &Hlast, st);
       if (rc) break;
-      rc = launch_wide_front(h, Hlast, gn, S, xt_ws, bt_ws, st);
+      rc = launch_wide_front(h, Hlast, gn, S, xt_ws, bt_ws, parts, st);
       if (rc) break;
-      rc = launch_wide_last_var(h, nullptr, g0, gn, S, T, bt_ws, maxvar_bits, st);
+      rc = launch_wide_last_var(h, nullptr, g0, gn, S, T, bt_ws, maxvar_bits, parts, field, field_ld, st);
       continue;
     }
     rc = run_chain(h, Xrow, R, d.n_linear - 1, bufA, bufB, &Hlast, st);
     if (rc) break;
     if (wide) {
-      rc = launch_wide_last_var(h, Hlast, g0, gn, S, T, bt_ws, maxvar_bits, st);
+      rc = launch_wide_last_var(h, Hlast, g0, gn, S, T, bt_ws, maxvar_bits, parts, field, field_ld, st);
       continue;
     }
     if (d.K % 4 == 0 && d.K >= 32 && d.D >= 64 && S >= 64 && (reinterpret_cast<uintptr_t>(Hlast) & 15) == 0) {
@@ -381,13 +526,76 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
   return rc;
 }
 
+// The candidates of the slab (select_rows_kernel: units of <= 8 candidates, a row's units contiguous, the row total in the
+// first unit) are re-evaluated row by row: the exact fp32 chain of ALL front layers for the S samples of each listed (p, t)
+// row, then wide_cand_kernel.  The list is read back to size the batches: one stream synchronisation per slab, on a path
+// whose slabs take hundreds of milliseconds.
+int launch_refine_wide(glasdi_handle* h, const float* Zs, int Spad, int S, int T, unsigned int* exact_bits, float dev_tol,
+                       cudaStream_t st) {
+  const Decoder& d = h->dec;
+  const int n = d.widths[0];
+  unsigned int stats[4] = {0, 0, 0, 0};
+  GL_CUDA(h, cudaMemcpyAsync(stats, h->d_cand_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
+  GL_CUDA(h, cudaStreamSynchronize(st));
+  const unsigned int nunits = std::min<unsigned int>(stats[3], (unsigned int)h->group_cap);
+  if (nunits == 0 || stats[0] > h->cand_cap) return GLASDI_OK;     // nothing to do / overflow already flagged
+  std::vector<rf::Group> groups(nunits);
+  GL_CUDA(h, cudaMemcpyAsync(groups.data(), h->d_groups, (size_t)nunits * sizeof(rf::Group), cudaMemcpyDeviceToHost, st));
+  GL_CUDA(h, cudaStreamSynchronize(st));
+  std::vector<simt::WRow> rows;
+  unsigned int max_total = 0;
+  for (const rf::Group& g : groups) {
+    const unsigned int total = g.count >> 8;
+    if (total) {
+      rows.push_back(simt::WRow{g.p, g.t, g.first, total});
+      max_total = std::max(max_total, total);
+    }
+  }
+  if (rows.empty()) return GLASDI_OK;
+  int maxw = n;
+  for (int l = 1; l < d.n_linear; ++l) maxw = std::max(maxw, d.widths[l]);
+  const size_t row_bytes = (size_t)(2 * maxw + n) * sizeof(float) * (size_t)S;
+  const long long nb_max = std::max<long long>(1, std::min<long long>((long long)rows.size(), ((size_t)1 << 30) / row_bytes));
+  simt::WRow* d_rows = nullptr;
+  float* scratch = nullptr;
+  GL_CUDA(h, cudaMallocFromPoolAsync((void**)&d_rows, rows.size() * sizeof(simt::WRow), h->pool, st));
+  GL_CUDA(h, cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(simt::WRow), cudaMemcpyHostToDevice, st));
+  GL_CUDA(h, cudaMallocFromPoolAsync((void**)&scratch, (size_t)nb_max * row_bytes, h->pool, st));
+  float* Xrow = scratch;
+  float* bufA = Xrow + (size_t)nb_max * S * n;
+  float* bufB = bufA + (size_t)nb_max * S * maxw;
+  const int Kp = (d.K + 3) / 4 * 4;
+  const size_t smem = ((size_t)(simt::kWNC + 1) * Kp + 8) * sizeof(float) + (size_t)(simt::kWThreads / 32) * simt::kWNC * 2 * sizeof(double);
+  GL_CUDA(h, cudaFuncSetAttribute(simt::wide_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned int gy = std::min<unsigned int>((max_total + simt::kWNC - 1) / simt::kWNC, 64u);
+  int rc = GLASDI_OK;
+  for (size_t r0 = 0; r0 < rows.size() && rc == GLASDI_OK; r0 += (size_t)nb_max) {
+    const long long nb = std::min<long long>(nb_max, (long long)(rows.size() - r0));
+    const long long R = nb * S;
+    simt::gather_listed_rows_kernel<<<(unsigned)std::min<long long>((R + 255) / 256, 65535), 256, 0, st>>>(
+        Zs, Spad, S, n, T, d_rows + r0, nb, Xrow);
+    h->launches++;
+    const float* Hlast = nullptr;
+    rc = run_chain(h, Xrow, R, d.n_linear - 1, bufA, bufB, &Hlast, st);
+    if (rc) break;
+    simt::wide_cand_kernel<<<dim3((unsigned)nb, gy), simt::kWThreads, smem, st>>>(
+        Hlast, d.dW[d.n_linear - 1], d_rows + r0, reinterpret_cast<const rf::Cand*>(h->d_cand), S, d.K, exact_bits,
+        h->d_cand_stats + 2, h->d_flags, dev_tol);
+    h->launches++;
+    rc = check_cuda(h, cudaGetLastError(), "wide_cand_kernel launch");
+  }
+  cudaFreeAsync(scratch, st);
+  cudaFreeAsync(d_rows, st);
+  return rc;
+}
+
 int launch_decode_store_simt(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st) {
   const Decoder& d = h->dec;
   int maxw = 1;
   for (int l = 1; l < d.n_linear; ++l) maxw = std::max(maxw, d.widths[l]);
   const long long slab = std::max<long long>(1, std::min<long long>(rows, ((size_t)1 << 29) / ((size_t)maxw * 8)));
   float* scratch = nullptr;
-  GL_CUDA(h, cudaMallocAsync((void**)&scratch, (size_t)slab * maxw * 2 * sizeof(float), st));
+  GL_CUDA(h, cudaMallocFromPoolAsync((void**)&scratch, (size_t)slab * maxw * 2 * sizeof(float), h->pool, st));
   float* bufA = scratch;
   float* bufB = scratch + (size_t)slab * maxw;
   int rc = GLASDI_OK;
@@ -413,7 +621,7 @@ int launch_encode_simt(glasdi_handle* h, const float* U, int64_t rows, float* Z,
   int maxw = 1;
   for (int l = 1; l < e.n_linear; ++l) maxw = std::max(maxw, e.widths[l]);
   float* scratch = nullptr;
-  if (e.n_linear > 1) GL_CUDA(h, cudaMallocAsync((void**)&scratch, (size_t)rows * maxw * 2 * sizeof(float), st));
+  if (e.n_linear > 1) GL_CUDA(h, cudaMallocFromPoolAsync((void**)&scratch, (size_t)rows * maxw * 2 * sizeof(float), h->pool, st));
   float* bufs[2] = {scratch, scratch ? scratch + (size_t)rows * maxw : nullptr};
   const float* cur = U;
   int rc = GLASDI_OK;
