@@ -321,8 +321,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // waiters that run far ahead of the tensor pipe (producers, epilogue, loader, relay): back off instead
 // of polling -- 2.1e9 polling retries per launch showed up in the first profiles and cost power
+// (mbarrier.try_wait with a suspend-time hint compiles to its own loop of SYNCS.PHASECHK.TRYWAIT + NANOSLEEP.SYNCS that comes
+// back every ~40 clocks until the hint expires -- a warp "suspended" in it issued 28-36 % of all instructions of the Gram
+// kernels (profiles/r02_gram_generic_*): long waits poll with the non-blocking test_wait and a real sleep instead)
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+  while (!mbar_test(bar, parity)) __nanosleep(128);
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_test(bar, parity)) __nanosleep(ns);
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -159,6 +159,92 @@ __device__ __forceinline__ void last_front_units(const float* __restrict__ wl, i
   }
 }
 
+// ---- narrow front layers in REGISTERS (widths <= 24) --------------------------------------------------------------
+// Shared-memory image per layer: transposed, zero-padded weights [32 in][32 out] followed by 32 biases.  A thread keeps the
+// activations of its sample in registers (arrays indexed by fully unrolled loops), reads the weights as warp-uniform 16-byte
+// vectors (one broadcast wavefront per 4 FMAs) and honours the widths in blocks of 8 inputs / 4 outputs.  Replaces the
+// cooperative evaluation through shared memory with one named barrier per layer and weights from global memory (87 k
+// instructions per 128-sample chunk at the Burgers2D-shaped decoder, 15 k of them FMAs: profiles/r02_gram_generic_*).
+constexpr int kNarrowW = 24;
+constexpr int kNarrowLayerFloats = kNarrowW * kNarrowW + kNarrowW;
+
+template <int ACT>
+__device__ __forceinline__ void narrow_layers_regs(const float* __restrict__ sNW, int n_pre, const int* __restrict__ widths,
+                                                   int act_rt, float (&x)[kNarrowW]) {
+  for (int l = 0; l < n_pre; ++l) {
+    const int wi = widths[l], wo = widths[l + 1];
+    const float* __restrict__ Wt = sNW + (size_t)l * kNarrowLayerFloats;
+    float y[kNarrowW];
+#pragma unroll
+    for (int o4 = 0; o4 < kNarrowW / 4; ++o4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(Wt + kNarrowW * kNarrowW + o4 * 4);
+      y[o4 * 4 + 0] = b4.x; y[o4 * 4 + 1] = b4.y; y[o4 * 4 + 2] = b4.z; y[o4 * 4 + 3] = b4.w;
+    }
+#pragma unroll
+    for (int i8 = 0; i8 < kNarrowW / 8; ++i8) {
+      if (i8 * 8 < wi) {
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+          const float xi = x[i8 * 8 + ii];
+#pragma unroll
+          for (int o4 = 0; o4 < kNarrowW / 4; ++o4) {
+            if (o4 * 4 < wo) {
+              const float4 w4 = *reinterpret_cast<const float4*>(Wt + (i8 * 8 + ii) * kNarrowW + o4 * 4);
+              y[o4 * 4 + 0] = fmaf(w4.x, xi, y[o4 * 4 + 0]);
+              y[o4 * 4 + 1] = fmaf(w4.y, xi, y[o4 * 4 + 1]);
+              y[o4 * 4 + 2] = fmaf(w4.z, xi, y[o4 * 4 + 2]);
+              y[o4 * 4 + 3] = fmaf(w4.w, xi, y[o4 * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < kNarrowW; ++o) x[o] = (o < wo) ? act_apply_t<ACT>(act_rt, y[o]) : 0.f;
+  }
+}
+
+// writes the shared-memory image above (all `nthreads` threads of the caller's group; the caller synchronises)
+__device__ __forceinline__ void narrow_layers_stage(float* sNW, const FrontMlp& f, int n_pre, int tid, int nthreads) {
+  for (int l = 0; l < n_pre; ++l) {
+    const int wi = f.widths[l], wo = f.widths[l + 1];
+    float* Wt = sNW + (size_t)l * kNarrowLayerFloats;
+    const float* __restrict__ W = f.W[l];
+    const float* __restrict__ b = f.b[l];
+    for (int idx = tid; idx < kNarrowW * kNarrowW; idx += nthreads) {
+      const int i = idx / kNarrowW, o = idx - i * kNarrowW;
+      Wt[idx] = (i < wi && o < wo) ? W[(size_t)o * wi + i] : 0.f;
+    }
+    for (int o = tid; o < kNarrowW; o += nthreads) Wt[kNarrowW * kNarrowW + o] = o < wo ? b[o] : 0.f;
+  }
+}
+
+// last_front_units for an input that lives in registers (x zero beyond the layer's input width)
+template <int ACT>
+__device__ __forceinline__ void last_front_units_regs(const float* __restrict__ wl, int ld, int inw_rt, int act_rt, int k0,
+                                                      const float (&x)[kNarrowW], float (&hv)[8]) {
+  float acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = wl[(k0 + u) * ld + inw_rt];
+#pragma unroll
+  for (int i4 = 0; i4 < kNarrowW / 4; ++i4) {
+    if (i4 * 4 < inw_rt) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wl + (k0 + u) * ld + i4 * 4);     // ld is a multiple of 4
+        float a = acc[u];
+        a = fmaf(w4.x, x[i4 * 4 + 0], a);
+        a = fmaf(w4.y, x[i4 * 4 + 1], a);
+        a = fmaf(w4.z, x[i4 * 4 + 2], a);
+        a = fmaf(w4.w, x[i4 * 4 + 3], a);
+        acc[u] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) hv[u] = act_apply_t<ACT>(act_rt, acc[u]);
+}
+
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
 }  // namespace dv

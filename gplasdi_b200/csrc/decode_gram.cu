@@ -301,12 +301,12 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         }
         const float* tabA = sPilot + (n_it & 3u) * 2 * L.kpu;
         const float* tabN = tabA + L.kpu;
-        while (!mbar_try_wait(&B->tab_full[n_it & 3u], (n_it >> 2) & 1u)) __nanosleep(32);
+        mbar_wait_sleep(&B->tab_full[n_it & 3u], (n_it >> 2) & 1u, 32);
         for (int c = 0; c < nchunks; ++c, ++g) {
           if (phase_a && ga < n_elems) phase_a_step();        // stream element g + 2
           // ---- phase B: sigmoid of (a_pilot + da), pilot-centred, scaled, fp16, into the Gram operand tile
           const uint32_t db = g % 3u, hb = g % kRing;
-          while (!mbar_try_wait(&B->d1_full[db], (g / 3u) & 1u)) __nanosleep(32);
+          mbar_wait_sleep(&B->d1_full[db], (g / 3u) & 1u, 32);
           tc_fence_after();
           mbar_wait_relaxed(&B->h_empty[hb], ((g / kRing) & 1u) ^ 1u);
           uint8_t* Hb = sH + hb * kBufBytes;
@@ -422,6 +422,15 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         }
       };
       const float* xfinal = xbuf + (size_t)((n_pre - 1) & 1) * 129 * xw;       // valid when n_pre >= 1
+      // narrow fronts (every layer before the last front layer at most 24 wide): each thread evaluates them for its own
+      // sample in registers from a transposed shared-memory image of the weights (decode_common.cuh) -- no barrier, no
+      // global-memory weight loads; the four threads of a column repeat the 900 FMAs of [5,20,20,20] rather than share them
+      const bool regs_path = INW == 0 && n_pre > 0 && xw <= kNarrowW && NZ <= kMaxLatent &&
+                             (size_t)n_pre * kNarrowLayerFloats * 4 <= (size_t)(kRing * kA1Bytes + 4u * 2048u);
+      if (regs_path) {
+        narrow_layers_stage(xbuf, P.front, n_pre, ptid, kGProdThreads);
+        asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");
+      }
       for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const float* __restrict__ zb = P.Zs + (size_t)item * NZ * P.Spad;
         float znext[kMaxLatent], zpil[kMaxLatent];
@@ -443,16 +452,24 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
           }
           const float* x = zin;
           if constexpr (INW == 0) {
-            if (n_pre > 0) {
+            if (!regs_path && n_pre > 0) {
               coop_layers(zin, c == 0 && col == 0, zpil);
               x = xfinal + col * xw;
             }
           }
           if (c == 0) {
             // pilot = activations of sample 0 (its front layers were evaluated with chunk 0's, column 128)
+            float xp[kNarrowW];
+            if (INW == 0 && regs_path && ptid < ((P.nkg + 31) & ~31)) {           // the warps that make the pilot table
+#pragma unroll
+              for (int i = 0; i < kNarrowW; ++i) xp[i] = (i < kMaxLatent) ? zpil[i < kMaxLatent ? i : 0] : 0.f;
+              narrow_layers_regs<ACT>(xbuf, n_pre, P.front.widths, P.front.act, xp);
+            }
             for (int kg = ptid; kg < P.nkg; kg += kGProdThreads) {
               float hv[8];
-              if (INW == 0 && n_pre > 0)
+              if (INW == 0 && regs_path)
+                last_front_units_regs<ACT>(sWl, ld, last_in_w, P.front.act, kg * 8, xp, hv);
+              else if (INW == 0 && n_pre > 0)
                 last_front_units<ACT, 0>(sWl, ld, last_in_w, P.front.act, kg * 8, xfinal + 128 * xw, hv);
               else
                 last_front_units<ACT, INW>(sWl, ld, last_in_w, P.front.act, kg * 8, zpil, hv);
@@ -461,6 +478,14 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
           }
+          float xr[kNarrowW];                               // after the pilot block: its registers are free again
+          if constexpr (INW == 0) {
+            if (regs_path) {
+#pragma unroll
+              for (int i = 0; i < kNarrowW; ++i) xr[i] = (i < kMaxLatent) ? zin[i < kMaxLatent ? i : 0] : 0.f;
+              narrow_layers_regs<ACT>(xbuf, n_pre, P.front.widths, P.front.act, xr);
+            }
+          }
           const uint32_t buf = h_it % kRing;
           uint8_t* Hb = sH + buf * kBufBytes;
           mbar_wait_relaxed(&B->h_empty[buf], ((h_it / kRing) & 1u) ^ 1u);
@@ -468,7 +493,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             uint4 v = make_uint4(0, 0, 0, 0);
             if (valid) {
               float hv[8];
-              last_front_units<ACT, INW>(sWl, ld, last_in_w, P.front.act, kg * 8, x, hv);
+              if (INW == 0 && regs_path) last_front_units_regs<ACT>(sWl, ld, last_in_w, P.front.act, kg * 8, xr, hv);
+              else last_front_units<ACT, INW>(sWl, ld, last_in_w, P.front.act, kg * 8, x, hv);
               const float4 p0 = *reinterpret_cast<const float4*>(sPilot + kg * 8);
               const float4 p1 = *reinterpret_cast<const float4*>(sPilot + kg * 8 + 4);
               const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
@@ -524,7 +550,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         const uint32_t n_elems = (uint32_t)((P.n_items - blockIdx.x + gridDim.x - 1) / gridDim.x) * (uint32_t)nchunks;
         auto issue_mma1 = [&]() {
           const uint32_t slot = g1 % kRing;
-          while (!mbar_try_wait(&B->a1_full[slot], (g1 / kRing) & 1u)) __nanosleep(32);
+          mbar_wait_sleep(&B->a1_full[slot], (g1 / kRing) & 1u, 32);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d1 = tmem_base + 128u + (g1 % 3u) * 128u;
@@ -545,7 +571,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         for (int c = 0; c < nchunks; ++c) {
           if (g1 < n_elems && g1 <= h_it + 2u) issue_mma1();      // element h_it + 2 (its buffer: element h_it - 1, drained)
           const uint32_t buf = h_it % kRing;
-          while (!mbar_try_wait(&B->h_full[buf], (h_it / kRing) & 1u)) __nanosleep(64);   // a chunk takes ~1 us
+          mbar_wait_sleep(&B->h_full[buf], (h_it / kRing) & 1u, 64);   // a chunk takes ~1 us
           if (c == 0 && n_it > 0) mbar_wait(&B->acc_empty, (n_it - 1u) & 1u);             // previous accumulator drained
           tc_fence_after();
           const int ncols = min(kCols, P.S - c * kCols);       // padding columns beyond hold exact zeros
@@ -571,7 +597,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         tc_fence_after();                               // the other warps' TMEM reads of the previous item (bar 4)
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t buf = h_it % kRing;
-          while (!mbar_try_wait(&B->h_full[buf], (h_it / kRing) & 1u)) __nanosleep(64);   // a chunk takes ~1.5 us
+          mbar_wait_sleep(&B->h_full[buf], (h_it / kRing) & 1u, 64);   // a chunk takes ~1.5 us
           if (c == 0 && n_it > 0) mbar_wait(&B->acc_empty, (n_it - 1u) & 1u);             // previous accumulator drained
           tc_fence_after();
           const int ncols = min(kCols, P.S - c * kCols);     // fast path: padding columns beyond hold exact zeros
@@ -591,7 +617,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         if (elect_one()) tc_commit(&B->acc_full);
         __syncwarp();
       }
-      while (!mbar_try_wait(&B->acc_full, n_it & 1u)) __nanosleep(warp == 0 ? 64 : 1024);   // an item takes ~10 us
+      mbar_wait_sleep(&B->acc_full, n_it & 1u, warp == 0 ? 64 : 1024);   // an item takes ~10 us
       tc_fence_after();
       // Warp 0 also issues the MMAs, so its share of the epilogue is kept minimal: row i packs the LOWER triangle
       // j <= i (rows 0..31: one 32-column block), it only ARRIVES on the barrier that separates packing from the

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) gram2_kernel(const __grid_const
     for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x, ++n_it) {
       make_tables(n_it + 2u);
       const uint32_t ab = n_it & 1u;
-      while (!mbar_try_wait(&B->acc_full[ab], (n_it >> 1) & 1u)) __nanosleep(256);      // an item takes several us
+      mbar_wait_sleep(&B->acc_full[ab], (n_it >> 1) & 1u, 256);      // an item takes several us
       tc_fence_after();
       const uint32_t taddr = tmem_base + kAccCol0 + ab * 128u + (((uint32_t)(qd * 32)) << 16);
       float* sMb = sM + (n_it & 1u) * 128;
