@@ -171,14 +171,15 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # Blocks of test parameters the OTHER named shapes (BASELINE.json configs[2..4]) are timed on: a fixed GLOBAL block, split
 # over the ranks like the real grid would be (strong scaling), sized for >= 1 s of timed device work at N = 1.
-NAMED_BLOCKS = {"burgers2d": (None, 10), "vlasov1d1v": (64, 1), "rising_bubble": (48, 1)}     # (params or None = whole grid, steps)
+NAMED_BLOCKS = {"burgers2d": (None, 10), "vlasov1d1v": (64, 3), "rising_bubble": (48, 2)}     # (params or None = whole grid, steps)
 
 
 def issued_tensor_flop(eng_widths, P, S, T, mode_gram: bool, passes: int):
     """Tensor-core FLOP the kernels ISSUE for P parameters (padding included): the physical numerator of a tensor-pipe
     fraction.  Covariance form (last-layer input width K <= 111): Gram MMAs (M = 128, N = ceil16(K + 1), K = 16 samples)
     + tf32 pre-activation MMAs (one front layer) in gram_kernel, the [P T x Q] x [Q x D] GEMM in quad_kernel.  Wide
-    decoders: three-pass fp16-split GEMMs of the last front layer (xact_kernel) and of the last layer (xvar_kernel)."""
+    decoders: `passes` fp16 GEMM passes (1 = screening pass of the screened modes, 3 = fp32-faithful split of the direct
+    mode) of the last front layer (xact_kernel) and of the last layer (xvar_kernel)."""
     L = eng_widths
     K, D = L[-2], L[-1]
     n_items = P * T
@@ -194,8 +195,8 @@ def issued_tensor_flop(eng_widths, P, S, T, mode_gram: bool, passes: int):
         return n_items * 2.0 * (-(-S // 128) * 128) * (-(-D // 128) * 128) * (-(-K // 16) * 16) * passes, 0.0
     Spad = -(-S // 256) * 256
     K1 = L[-3]
-    xact = n_items * 2.0 * Spad * (-(-K // 128) * 128) * 3 * (-(-K1 // 64) * 64)
-    xvar = n_items * 2.0 * Spad * (-(-D // 128) * 128) * 3 * (-(-K // 64) * 64)
+    xact = n_items * 2.0 * Spad * (-(-K // 128) * 128) * passes * (-(-K1 // 64) * 64)
+    xvar = n_items * 2.0 * Spad * (-(-D // 128) * 128) * passes * (-(-K // 64) * 64)
     return xvar, xact
 
 
@@ -363,11 +364,13 @@ def run_ours(args):
         issued, issued_2nd = issued_tensor_flop(wl.widths, P, S, T, args.mode == "gram", issued_passes)
         achieved = issued / (dec_avg_ms * 1e-3) / 1e12                 # ISSUED tensor FLOP of the dominant kernel / its time
         if args.mode == "gram":
-            kernel = ("glasdi::gr::gram_kernel<sigmoid, 5, fast> (tcgen05 cta_group::1: tf32 pre-activation MMAs + f16 Gram MMAs on "
-                      "MN-major SW128 tiles, M=128 N=112 K=16)")
-            note = ("frac = tensor FLOP gram_kernel ISSUES (padding included) / its own device time / peak: a physical "
+            kernel = ("glasdi::g2::gram2_kernel<sigmoid, 5> (tcgen05 cta_group::1: tf32 pre-activation MMAs + f16 Gram MMAs on "
+                      "K-major SW128 tiles, M=128 N=112 K=16; thread = hidden unit, Taylor-polynomial producers)")
+            note = ("frac = tensor FLOP gram2_kernel ISSUES (padding included) / its own device time / peak: a physical "
                     "tensor-pipe fraction.  The kernel is bound by the CUDA-core work that feeds the tensor pipe -- P*S*T*K = "
-                    "2.2e10 sigmoid evaluations (MUFU) -- not by the pipe itself; quad_kernel (second GEMM) is tensor-bound. "
+                    "2.2e10 sigmoid evaluations (FMA-pipe polynomial around the pilot, exact MUFU form outside its radius) -- and by "
+                    "the latency of the chain pre-activation MMA -> tcgen05.ld -> convert -> Gram MMA through one in-order tensor "
+                    "pipe (profiles/r02_gram2_experiments.md), not by the pipe's throughput; quad_kernel (second GEMM) is tensor-bound. "
                     "The covariance form needs 5x fewer FLOP than decoding every sample (K^2 S + K(K+1)/2 D instead of K S D "
                     "per (parameter, time step)): that algebraic gain is reported separately as "
                     "algorithmic_speedup_vs_single_pass_roofline, never as a roofline fraction")
@@ -498,11 +501,13 @@ def time_named_shape(eng, nm, blk, nsteps, world, rank, dev, sampler, barrier, m
     peak = pk["burst"] if total < 1000.0 else pk["sustained"]
     sec = total * 1e-3 / nsteps
     alg = wl.decoder_flops_per_rollout() * Pb * wl.S
-    a, b = issued_tensor_flop(wl.widths, Pb, wl.S, wl.T, mode_id == _lib.MODE_SCREENED_GRAM, 3)
+    wide_passes = 3 if mode_id == _lib.MODE_DIRECT else 1
+    a, b = issued_tensor_flop(wl.widths, Pb, wl.S, wl.T, mode_id == _lib.MODE_SCREENED_GRAM, wide_passes)
     K = wl.widths[-2]
     path = ("gram_kernel (front MLP producers + tcgen05 Gram MMAs) + quad_kernel + select/refine" if K <= 111 else
-            "front layers + xact_kernel / xvar_kernel (tcgen05 GEMMs of the last front layer and of the last layer + variance "
-            "epilogue, decode_wide.cu)")
+            f"wide_pre_kernel (narrow front layers in registers) + xact_kernel / xvar_kernel ({wide_passes} fp16 pass(es) of the "
+            "last front layer and of the last layer + variance epilogue on tcgen05, decode_wide.cu) + select + wide_cand_kernel "
+            "(exact CUDA-core re-evaluation of the candidates' rows)")
     rec = {"workload": f"{nm}-shaped synthetic (BASELINE.json configs[{list(NAMED_BLOCKS).index(nm) + 2}]): P={wl.P} x S={wl.S}, "
                        f"T={wl.T}, D={wl.D}, decoder {wl.widths} {wl.act}",
            "params_timed": Pb, "first_param": first, "shard_bounds": bnd, "n_gpus": world, "steps": nsteps, "ms_per_step": sec * 1e3,

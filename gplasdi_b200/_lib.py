@@ -14,10 +14,13 @@ _LIB = None
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_READY, ERR_NUMERIC, ERR_OOM = range(7)
 
-ACT_IDS = {"sigmoid": 0, "tanh": 1, "softplus": 2, "ReLU": 3, "ELU": 4, "SiLU": 5, "GELU": 6, "identity": 7}
+ACT_IDS = {"sigmoid": 0, "tanh": 1, "softplus": 2, "ReLU": 3, "ELU": 4, "SiLU": 5, "GELU": 6, "identity": 7,
+           "hardshrink": 8, "hardsigmoid": 9, "hardtanh": 10, "hardswish": 11, "leakyReLU": 12, "logsigmoid": 13,
+           "ReLU6": 14, "SELU": 15, "CELU": 16, "mish": 17, "softshrink": 18, "tanhshrink": 19}
 FD_IDS = {"sbp12": 0, "sbp24": 1, "sbp36": 2, "sbp48": 3}
 OPT_SPLIT_PASSES, OPT_INTEGRATOR, OPT_RK4_SUBSTEPS, OPT_MAX_CTAS, OPT_STAGE_TIMING, OPT_DECODE_KERNEL = 0, 1, 2, 3, 4, 5
-OPT_MODE, OPT_SCREEN_MARGIN, OPT_WIDE_TENSOR, OPT_GRAM_KERNEL, OPT_TAYLOR_RADIUS = 6, 7, 8, 9, 10
+OPT_MODE, OPT_SCREEN_MARGIN, OPT_WIDE_TENSOR, OPT_GRAM_KERNEL, OPT_TAYLOR_RADIUS, OPT_SINDY_LIBRARY = 6, 7, 8, 9, 10, 11
+LIB_POLY1, LIB_POLY1_SINE, LIB_POLY2, LIB_POLY2_SINE = 0, 1, 2, 3
 MODE_DIRECT, MODE_SCREENED, MODE_SCREENED_GRAM = 0, 1, 2
 INT_EXPM, INT_RK4 = 0, 1
 
@@ -25,6 +28,7 @@ INT_EXPM, INT_RK4 = 0, 1
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 SIGNATURES = {
     "glasdi_abi_version": (_i, []),
+    "glasdi_library_terms": (_i, [_i, _i]),
     "glasdi_create": (_i, [C.POINTER(_vp), _i]),
     "glasdi_destroy": (_i, [_vp]),
     "glasdi_last_error": (C.c_char_p, [_vp]),

@@ -88,15 +88,22 @@ static void free_encoder(Encoder& e) {
   e.ready = false;
 }
 
-static bool bounded_act(int act) { return act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH; }
+// activations with values in [-1, 1]: the fp16 operands of the hidden layer may be scaled by 2^12 instead of 2^4
+static bool bounded_act(int act) {
+  return act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH || act == GLASDI_ACT_HARDSIGMOID || act == GLASDI_ACT_HARDTANH;
+}
 
 // check-and-clear the device-side numeric flags (activation overflow of the fp16 split)
 static int check_flags(glasdi_handle* h, cudaStream_t st) {
   int flags[4] = {0, 0, 0, 0};
   GL_CUDA(h, cudaMemcpyAsync(flags, h->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
   GL_CUDA(h, cudaStreamSynchronize(st));
-  if (flags[0] || flags[1] || flags[2]) {
+  if (flags[0] || flags[1] || flags[2] || flags[3]) {
     GL_CUDA(h, cudaMemsetAsync(h->d_flags, 0, sizeof(flags), st));
+    if (flags[3])
+      return set_error(h, GLASDI_ERR_NUMERIC,
+                       "latent rollout: a trajectory of the polynomial / sine library needs more than 16384 RK4 sub-steps "
+                       "per output step or turned non-finite (finite-time blow-up)");
     if (flags[0])
       return set_error(h, GLASDI_ERR_NUMERIC,
                        "hidden activations overflowed the fp16 split range (|h - h_pilot| * 2^eH > 6e4)");
@@ -232,9 +239,15 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
       if (value < 0 || value > 1024) return set_error(h, GLASDI_ERR_INVALID, "Taylor radius must be 0..1024 (units of 1/256)");
       h->opt_taylor_radius_q8 = value;
       return GLASDI_OK;
+    case GLASDI_OPT_SINDY_LIBRARY:
+      if (library_terms(value, 1) < 0) return set_error(h, GLASDI_ERR_INVALID, "unknown SINDy library id");
+      h->opt_library = value;
+      return GLASDI_OK;
     default: return set_error(h, GLASDI_ERR_INVALID, "unknown option");
   }
 }
+
+int glasdi_library_terms(int library, int n) { return library_terms(library, n); }
 
 int glasdi_get_option(const glasdi_handle* h, int option, int* value) {
   if (!h || !value) return GLASDI_ERR_INVALID;
@@ -250,6 +263,7 @@ int glasdi_get_option(const glasdi_handle* h, int option, int* value) {
     case GLASDI_OPT_WIDE_TENSOR: *value = h->opt_wide; return GLASDI_OK;
     case GLASDI_OPT_GRAM_KERNEL: *value = h->opt_gram_kernel; return GLASDI_OK;
     case GLASDI_OPT_TAYLOR_RADIUS: *value = h->opt_taylor_radius_q8; return GLASDI_OK;
+    case GLASDI_OPT_SINDY_LIBRARY: *value = h->opt_library; return GLASDI_OK;
     default: return GLASDI_ERR_INVALID;
   }
 }
@@ -259,7 +273,7 @@ int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths, const 
   if (!h) return GLASDI_ERR_INVALID;
   if (n_linear < 2 || n_linear > kMaxLinear) return set_error(h, GLASDI_ERR_INVALID, "decoder needs 2..8 linear layers");
   if (!widths || !W_host || !b_host) return set_error(h, GLASDI_ERR_INVALID, "null decoder arrays");
-  if (act_id < 0 || act_id > GLASDI_ACT_IDENTITY) return set_error(h, GLASDI_ERR_INVALID, "unknown activation id");
+  if (act_id < 0 || act_id >= GLASDI_ACT_COUNT) return set_error(h, GLASDI_ERR_INVALID, "unknown activation id");
   if (widths[0] < 1 || widths[0] > kMaxLatent) return set_error(h, GLASDI_ERR_INVALID, "latent dimension must be 1..8");
   for (int l = 0; l <= n_linear; ++l)
     if (widths[l] < 1) return set_error(h, GLASDI_ERR_INVALID, "non-positive layer width");
@@ -348,7 +362,7 @@ int glasdi_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z
   // P may exceed the grid.y limit: slab it
   for (int p0 = 0; p0 < P; p0 += 32768) {
     const int pn = std::min(32768, P - p0);
-    int rc = launch_rollout(h, coefs + (size_t)p0 * S * n * (n + 1),
+    int rc = launch_rollout(h, coefs + (size_t)p0 * S * n * library_terms(h->opt_library, n),
                             z0 + (size_t)p0 * (z0_per_sample ? (size_t)S * n : (size_t)n), z0_per_sample, pn, S, n, T,
                             dt, nullptr, 0, Z_out + (size_t)p0 * S * T * n, (cudaStream_t)stream);
     if (rc) return rc;
@@ -431,7 +445,7 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
         t_ref(h, st, &h->ev_refine, ev_next), t_quad(h, st, &h->ev_quad, ev_next);
     if ((rc = t_roll.start())) return rc;
     if (coefs) {
-      rc = launch_rollout(h, coefs + (size_t)p0 * S * n * (n + 1), z0 + (size_t)p0 * n, 0, pn, S, n, T, dt, Zs, Spad,
+      rc = launch_rollout(h, coefs + (size_t)p0 * S * n * library_terms(h->opt_library, n), z0 + (size_t)p0 * n, 0, pn, S, n, T, dt, Zs, Spad,
                           nullptr, st);
     } else {
       rc = launch_zis_to_soa(h, Zis + (size_t)p0 * S * T * n, pn, S, T, n, Zs, Spad, st);
@@ -660,7 +674,7 @@ int glasdi_set_encoder(glasdi_handle* h, int n_linear, const int* widths, const 
   if (!h) return GLASDI_ERR_INVALID;
   if (n_linear < 1 || n_linear > 16) return set_error(h, GLASDI_ERR_INVALID, "encoder needs 1..16 linear layers");
   if (!widths || !W_host || !b_host) return set_error(h, GLASDI_ERR_INVALID, "null encoder arrays");
-  if (act_id < 0 || act_id > GLASDI_ACT_IDENTITY) return set_error(h, GLASDI_ERR_INVALID, "unknown activation id");
+  if (act_id < 0 || act_id >= GLASDI_ACT_COUNT) return set_error(h, GLASDI_ERR_INVALID, "unknown activation id");
   for (int l = 0; l <= n_linear; ++l)
     if (widths[l] < 1) return set_error(h, GLASDI_ERR_INVALID, "non-positive layer width");
   GL_CUDA(h, cudaSetDevice(h->device));

@@ -40,6 +40,219 @@ static int upload_sbp(glasdi_handle* h) {
   return GLASDI_OK;
 }
 
+// ---- rank-revealing solve of the normal equations = LAPACK xGELSY on [1|Z] --------------------------------------
+// The reference solves `torch.linalg.lstsq(Z_i, dZdt)` (sindy.py:72) = LAPACK sgelsy with rcond = eps_fp32 * max(m, n):
+// QR with column pivoting, effective rank from an incremental condition estimate of the leading triangle (xLAIC1), and
+// the MINIMUM-NORM solution of the rank-truncated problem.  An untrained encoder produces series with cond([1|Z]) of
+// 1e4..1e6, beyond 1/rcond = 8.4e3 at T = 1001: those are truncated by the reference, not solved.
+// Here the same algorithm runs on the fp64 Gram matrix G = X^T X: Cholesky with diagonal pivoting of G IS the R factor
+// of the column-pivoted QR of X (same pivot rule: largest remaining column norm), Q^T Y[:r] = R11^-T (P^T X^T Y)[:r], and
+// the minimum-norm solution of R1 y = c, R1 = [R11 R12], is y = R1^T (R1 R1^T)^-1 c.  fp64 on G resolves R's diagonal to
+// 1e-16 cond(X)^2: exact enough for a decision at 1e-4.
+struct GelsyWork {   // per series, in shared memory; NA <= 9
+  double M[9][9];    // lower Cholesky factor of R1 R1^T (rank < NA only)
+  int perm[9];
+  int rank;
+};
+
+// xLAIC1: one step of incremental condition estimation.  x (length j) estimates the extreme singular vector of the
+// leading j x j triangle with singular value `sest`; [w; gamma] is the next column.  Returns sestpr and the rotation (s, c).
+__host__ __device__ inline void laic1(bool want_max, int j, const double* x, double sest, const double* w, double gamma, double& sestpr,
+                      double& s, double& c) {
+  const double eps = 2.220446049250313e-16;
+  double alpha = 0.0;
+  for (int i = 0; i < j; ++i) alpha += x[i] * w[i];
+  const double absalp = fabs(alpha), absgam = fabs(gamma), absest = fabs(sest);
+  if (want_max) {
+    if (sest == 0.0) {
+      const double s1 = fmax(absgam, absalp);
+      if (s1 == 0.0) { s = 0.0; c = 1.0; sestpr = 0.0; }
+      else { s = alpha / s1; c = gamma / s1; const double tmp = sqrt(s * s + c * c); s /= tmp; c /= tmp; sestpr = s1 * tmp; }
+    } else if (absgam <= eps * absest) {
+      s = 1.0; c = 0.0;
+      const double tmp = fmax(absest, absalp), s1 = absest / tmp, s2 = absalp / tmp;
+      sestpr = tmp * sqrt(s1 * s1 + s2 * s2);
+    } else if (absalp <= eps * absest) {
+      if (absgam <= absest) { s = 1.0; c = 0.0; sestpr = absest; } else { s = 0.0; c = 1.0; sestpr = absgam; }
+    } else if (absest <= eps * absalp || absest <= eps * absgam) {
+      if (absgam <= absalp) {
+        const double tmp = absgam / absalp; s = sqrt(1.0 + tmp * tmp); sestpr = absalp * s;
+        c = (gamma / absalp) / s; s = copysign(1.0, alpha) / s;
+      } else {
+        const double tmp = absalp / absgam; c = sqrt(1.0 + tmp * tmp); sestpr = absgam * c;
+        s = (alpha / absgam) / c; c = copysign(1.0, gamma) / c;
+      }
+    } else {
+      const double z1 = alpha / absest, z2 = gamma / absest;
+      const double bb = (1.0 - z1 * z1 - z2 * z2) * 0.5, cc = z1 * z1;
+      const double t = bb > 0.0 ? cc / (bb + sqrt(bb * bb + cc)) : sqrt(bb * bb + cc) - bb;
+      const double sine = -z1 / t, cosine = -z2 / (1.0 + t), tmp = sqrt(sine * sine + cosine * cosine);
+      s = sine / tmp; c = cosine / tmp; sestpr = sqrt(t + 1.0) * absest;
+    }
+  } else {
+    if (sest == 0.0) {
+      sestpr = 0.0;
+      double sine, cosine;
+      if (fmax(absgam, absalp) == 0.0) { sine = 1.0; cosine = 0.0; } else { sine = -gamma; cosine = alpha; }
+      const double s1 = fmax(fabs(sine), fabs(cosine));
+      s = sine / s1; c = cosine / s1;
+      const double tmp = sqrt(s * s + c * c); s /= tmp; c /= tmp;
+    } else if (absgam <= eps * absest) {
+      s = 0.0; c = 1.0; sestpr = absgam;
+    } else if (absalp <= eps * absest) {
+      if (absgam <= absest) { s = 0.0; c = 1.0; sestpr = absgam; } else { s = 1.0; c = 0.0; sestpr = absest; }
+    } else if (absest <= eps * absalp || absest <= eps * absgam) {
+      if (absgam <= absalp) {
+        const double tmp = absgam / absalp; c = sqrt(1.0 + tmp * tmp); sestpr = absest * (tmp / c);
+        s = -(gamma / absalp) / c; c = copysign(1.0, alpha) / c;
+      } else {
+        const double tmp = absalp / absgam; s = sqrt(1.0 + tmp * tmp); sestpr = absest / s;
+        c = (alpha / absgam) / s; s = -copysign(1.0, gamma) / s;
+      }
+    } else {
+      const double z1 = alpha / absest, z2 = gamma / absest;
+      const double norma = fmax(1.0 + z1 * z1 + fabs(z1 * z2), fabs(z1 * z2) + z2 * z2);
+      const double test = 1.0 + 2.0 * (z1 - z2) * (z1 + z2);
+      double sine, cosine;
+      if (test >= 0.0) {
+        const double bb = (z1 * z1 + z2 * z2 + 1.0) * 0.5, cc = z2 * z2;
+        const double t = cc / (bb + sqrt(fabs(bb * bb - cc)));
+        sine = z1 / (1.0 - t); cosine = -z2 / t;
+        sestpr = sqrt(t + 4.0 * eps * eps * norma) * absest;
+      } else {
+        const double bb = (z2 * z2 + z1 * z1 - 1.0) * 0.5, cc = z1 * z1;
+        const double t = bb >= 0.0 ? -cc / (bb + sqrt(bb * bb + cc)) : bb - sqrt(bb * bb + cc);
+        sine = -z1 / t; cosine = -z2 / (1.0 + t);
+        sestpr = sqrt(1.0 + t + 4.0 * eps * eps * norma) * absest;
+      }
+      const double tmp = sqrt(sine * sine + cosine * cosine);
+      s = sine / tmp; c = cosine / tmp;
+    }
+  }
+}
+
+// In: G symmetric (full storage).  Out: the upper triangle of G holds R (P^T G P = R^T R), W.perm / W.rank / W.M filled.
+// Single thread; rolled loops.  Returns the effective rank (0 if G is not finite).
+template <int NA>
+__host__ __device__ int gelsy_factor(double (*G)[NA], GelsyWork& W, double rcond) {
+  for (int j = 0; j < NA; ++j) W.perm[j] = j;
+  double chk = 0.0;                                // NaN if any entry of G is inf / NaN (comparisons would skip them)
+  for (int i = 0; i < NA; ++i)
+    for (int k = 0; k < NA; ++k) chk = fma(G[i][k], 0.0, chk);
+  if (chk != 0.0) { W.rank = 0; return 0; }
+  int nr = NA;                                     // rows of R that exist (exactly singular remainder stops earlier)
+#pragma unroll 1
+  for (int j = 0; j < NA; ++j) {
+    int pv = j;
+    double dm = G[j][j];
+    for (int k = j + 1; k < NA; ++k) if (G[k][k] > dm) { dm = G[k][k]; pv = k; }
+    if (!(dm > 0.0) || !(dm <= 1.79e308)) { nr = j; break; }
+    if (pv != j) {
+      for (int i = 0; i < NA; ++i) { const double t = G[i][j]; G[i][j] = G[i][pv]; G[i][pv] = t; }
+      for (int k = 0; k < NA; ++k) { const double t = G[j][k]; G[j][k] = G[pv][k]; G[pv][k] = t; }
+      const int t = W.perm[j]; W.perm[j] = W.perm[pv]; W.perm[pv] = t;
+    }
+    const double rjj = sqrt(G[j][j]), inv = 1.0 / rjj;
+    G[j][j] = rjj;
+    for (int k = j + 1; k < NA; ++k) G[j][k] *= inv;
+    for (int i = j + 1; i < NA; ++i)
+      for (int k = i; k < NA; ++k) { const double v = G[i][k] - G[j][i] * G[j][k]; G[i][k] = v; G[k][i] = v; }
+  }
+  // effective rank (xGELSY): grow the leading triangle while smax * rcond <= smin (incremental estimates)
+  int rank = 0;
+  if (nr > 0) {
+    double xmin[NA], xmax[NA], col[NA];
+    xmin[0] = 1.0; xmax[0] = 1.0;
+    double smax = fabs(G[0][0]), smin = smax;
+    rank = 1;
+#pragma unroll 1
+    while (rank < nr) {
+      const int i = rank;
+      for (int k = 0; k < i; ++k) col[k] = G[k][i];
+      double sminpr, s1, c1, smaxpr, s2, c2;
+      laic1(false, i, xmin, smin, col, G[i][i], sminpr, s1, c1);
+      laic1(true, i, xmax, smax, col, G[i][i], smaxpr, s2, c2);
+      if (!(smaxpr * rcond <= sminpr)) break;
+      for (int k = 0; k < i; ++k) { xmin[k] *= s1; xmax[k] *= s2; }
+      xmin[i] = c1; xmax[i] = c2;
+      smin = sminpr; smax = smaxpr;
+      ++rank;
+    }
+  }
+  W.rank = rank;
+  if (rank > 0 && rank < NA) {                     // M = chol(R1 R1^T), R1 = R[:rank, :]
+    for (int i = 0; i < rank; ++i)
+      for (int k = 0; k <= i; ++k) {
+        double v = 0.0;
+        for (int q = i; q < NA; ++q) v += G[i][q] * G[k][q];     // rows i >= k: columns >= i
+        W.M[i][k] = v;
+      }
+    for (int j = 0; j < rank; ++j) {
+      double d = W.M[j][j];
+      for (int k = 0; k < j; ++k) d -= W.M[j][k] * W.M[j][k];
+      const double ljj = sqrt(d);
+      W.M[j][j] = ljj;
+      for (int i = j + 1; i < rank; ++i) {
+        double v = W.M[i][j];
+        for (int k = 0; k < j; ++k) v -= W.M[i][k] * W.M[j][k];
+        W.M[i][j] = v / ljj;
+      }
+    }
+  }
+  return rank;
+}
+
+// w := (R1 R1^T)^-1 w  (in place, length rank)
+__host__ __device__ __forceinline__ void gelsy_msolve(const GelsyWork& W, double* w) {
+  const int r = W.rank;
+  for (int i = 0; i < r; ++i) { double v = w[i]; for (int k = 0; k < i; ++k) v -= W.M[i][k] * w[k]; w[i] = v / W.M[i][i]; }
+  for (int i = r - 1; i >= 0; --i) { double v = w[i]; for (int k = i + 1; k < r; ++k) v -= W.M[k][i] * w[k]; w[i] = v / W.M[i][i]; }
+}
+
+// x := xGELSY solution for the right-hand side v = (X^T y): x = P R1^T (R1 R1^T)^-1 R11^-T (P^T v)[:rank].
+// `v` / `x` are strided columns (element a at [a * stride]); x may alias v.
+template <int NA>
+__host__ __device__ void gelsy_solve(const double (*R)[NA], const GelsyWork& W, const double* v, double* x, int stride) {
+  const int r = W.rank;
+  double c[NA], y[NA];
+  for (int i = 0; i < NA; ++i) c[i] = v[W.perm[i] * stride];
+  for (int i = 0; i < r; ++i) { double t = c[i]; for (int k = 0; k < i; ++k) t -= R[k][i] * c[k]; c[i] = t / R[i][i]; }
+  if (r == NA) {
+    for (int i = NA - 1; i >= 0; --i) { double t = c[i]; for (int k = i + 1; k < NA; ++k) t -= R[i][k] * y[k]; y[i] = t / R[i][i]; }
+  } else {
+    gelsy_msolve(W, c);
+    for (int k = 0; k < NA; ++k) { double t = 0.0; for (int i = 0; i < r && i <= k; ++i) t += R[i][k] * c[i]; y[k] = t; }
+  }
+  for (int k = 0; k < NA; ++k) x[W.perm[k] * stride] = y[k];
+}
+
+// x := G~^+ v with G~ = P R1^T R1 P^T, the Gram matrix of the rank-truncated problem (= G^-1 v at full rank); pass
+// `null_out` to also get N v = v - G~^+ G~ v, the component in the discarded directions.  Strided like gelsy_solve.
+template <int NA>
+__host__ __device__ void gelsy_pinv(const double (*R)[NA], const GelsyWork& W, const double* v, double* x, double* null_out, int stride) {
+  const int r = W.rank;
+  if (r == NA) {
+    gelsy_solve<NA>(R, W, v, x, stride);
+    if (null_out) for (int k = 0; k < NA; ++k) null_out[k * stride] = 0.0;
+    return;
+  }
+  double u[NA], t[NA], w[NA], y[NA];
+  for (int i = 0; i < NA; ++i) u[i] = v[W.perm[i] * stride];
+  for (int i = 0; i < r; ++i) { double a = 0.0; for (int k = i; k < NA; ++k) a += R[i][k] * u[k]; t[i] = a; }    // R1 P^T v
+  for (int i = 0; i < r; ++i) w[i] = t[i];
+  gelsy_msolve(W, w);                                                                                      // (R1 R1^T)^-1 R1 u
+  if (null_out) {
+    for (int k = 0; k < NA; ++k) { double a = 0.0; for (int i = 0; i < r && i <= k; ++i) a += R[i][k] * w[i]; y[k] = a; }
+    for (int k = 0; k < NA; ++k) null_out[W.perm[k] * stride] = u[k] - y[k];
+  }
+  gelsy_msolve(W, w);
+  for (int k = 0; k < NA; ++k) { double a = 0.0; for (int i = 0; i < r && i <= k; ++i) a += R[i][k] * w[i]; y[k] = a; }
+  for (int k = 0; k < NA; ++k) x[W.perm[k] * stride] = y[k];
+}
+
+// rcond of the reference call: torch.linalg.lstsq default = eps(fp32) * max(m, n), m = T rows, n = N + 1 columns
+__host__ __device__ __forceinline__ double gelsy_rcond(int T, int NA) { return 1.1920928955078125e-07 * (double)max(T, NA); }
+
 // derivative of component i at time row t of one series; `ld(row)` returns Z[row][i].
 // Accumulation in ascending column order, fp32 FMA (the reference's sparse.mm is an fp32 row sum).
 // HW = compile-time interior half-width (1..4): the interior path is fully unrolled with its
@@ -202,6 +415,7 @@ __global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __r
   __shared__ double sG[kFitThreads / 32][NA][NA];
   __shared__ double sR[kFitThreads / 32][NA][N];
   __shared__ int sInfo[kFitThreads / 32];
+  __shared__ GelsyWork sW[kFitThreads / 32];
   extern __shared__ float s_series[];          // [warps per CTA][T*N] when the series fit (else global reads)
   const SbpF& sc = c_sbp[fd_id];
   const int lane = threadIdx.x & 31;
@@ -260,47 +474,11 @@ __global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __r
     for (int a = 0; a < NA; ++a)
 #pragma unroll
       for (int i = 0; i < N; ++i) sR[wib][a][i] = acc[q++];
-    // Cholesky G = L L^T in place (lower), relative pivot test; rolled loops (tiny, latency only)
-    double (*G)[NA] = sG[wib];
-    int info = 0;
-    double dmax = 0.0;
-    for (int a = 0; a < NA; ++a) dmax = fmax(dmax, G[a][a]);
-#pragma unroll 1
-    for (int j = 0; j < NA; ++j) {
-      double sdiag = G[j][j];
-      for (int k = 0; k < j; ++k) sdiag -= G[j][k] * G[j][k];
-      if (!(sdiag > 1e-13 * dmax)) { info = j + 1; break; }
-      const double ljj = sqrt(sdiag);
-      G[j][j] = ljj;
-      const double rl = 1.0 / ljj;
-#pragma unroll 1
-      for (int i = j + 1; i < NA; ++i) {
-        double v = G[i][j];
-        for (int k = 0; k < j; ++k) v -= G[i][k] * G[j][k];
-        G[i][j] = v * rl;
-      }
-    }
-    sInfo[wib] = info;
+    sInfo[wib] = NA - gelsy_factor<NA>(sG[wib], sW[wib], gelsy_rcond(T, NA));
   }
   __syncwarp();
-  const int info = sInfo[wib];
-  if (lane < N && info == 0) {
-    // one right-hand-side column per lane: L y = r, L^T x = y, in place in sR[.][lane]
-    double (*G)[NA] = sG[wib];
-    double (*R)[N] = sR[wib];
-#pragma unroll 1
-    for (int i = 0; i < NA; ++i) {
-      double v = R[i][lane];
-      for (int k = 0; k < i; ++k) v -= G[i][k] * R[k][lane];
-      R[i][lane] = v / G[i][i];
-    }
-#pragma unroll 1
-    for (int i = NA - 1; i >= 0; --i) {
-      double v = R[i][lane];
-      for (int k = i + 1; k < NA; ++k) v -= G[k][i] * R[k][lane];
-      R[i][lane] = v / G[i][i];
-    }
-  }
+  const int info = sInfo[wib];                 // number of truncated directions (0 = full rank); NA = not finite
+  if (lane < N && info < NA) gelsy_solve<NA>(sG[wib], sW[wib], &sR[wib][0][lane], &sR[wib][0][lane], N);
   __syncwarp();
   float Rf[NA][N];
   double nrm = 0.0;
@@ -308,7 +486,7 @@ __global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __r
   for (int a = 0; a < NA; ++a)
 #pragma unroll
     for (int c = 0; c < N; ++c) {
-      const float cf = info == 0 ? (float)sR[wib][a][c] : nanf("");
+      const float cf = info < NA ? (float)sR[wib][a][c] : nanf("");
       Rf[a][c] = cf;
       nrm += (norm_order == 1) ? fabs((double)cf) : (double)cf * (double)cf;
     }
@@ -389,6 +567,9 @@ __global__ void __launch_bounds__(kBwdThreads) sindy_fit_bwd_kernel(const float*
   __shared__ float sBm[NA][N];
   __shared__ float sRf[NA][N];
   __shared__ int sInfo;
+  __shared__ GelsyWork sW;
+  __shared__ double sNull[NA][N], sPR[NA][N];
+  __shared__ float sW3[NA][NA];
   extern __shared__ float s_bwd[];
   float* sZ = s_bwd;                    // [T][N] series, later Xbar[:, 1:]
   float* sY = s_bwd + (size_t)T * N;    // [T][N] residual E, later Ybar
@@ -469,46 +650,30 @@ __global__ void __launch_bounds__(kBwdThreads) sindy_fit_bwd_kernel(const float*
         else dn = nrm > 0.0 ? r / nrm : 0.0;
         sB[a][i] = (double)gc * dn - (double)c * sRed[0][NG + a * N + i];
       }
-    int info = 0;
-    double dmax = 0.0;
-    for (int a = 0; a < NA; ++a) dmax = fmax(dmax, sG[a][a]);
-#pragma unroll 1
-    for (int j = 0; j < NA; ++j) {
-      double sdiag = sG[j][j];
-      for (int k = 0; k < j; ++k) sdiag -= sG[j][k] * sG[j][k];
-      if (!(sdiag > 1e-13 * dmax)) { info = j + 1; break; }
-      const double ljj = sqrt(sdiag);
-      sG[j][j] = ljj;
-      const double rl = 1.0 / ljj;
-#pragma unroll 1
-      for (int i = j + 1; i < NA; ++i) {
-        double v = sG[i][j];
-        for (int k = 0; k < j; ++k) v -= sG[i][k] * sG[j][k];
-        sG[i][j] = v * rl;
-      }
-    }
-    sInfo = info;
+    sInfo = NA - gelsy_factor<NA>(sG, sW, gelsy_rcond(T, NA));
   }
   __syncthreads();
-  const int info = sInfo;
-  if (tid < N && info == 0) {
-#pragma unroll 1
-    for (int i = 0; i < NA; ++i) {
-      double v = sB[i][tid];
-      for (int k = 0; k < i; ++k) v -= sG[i][k] * sB[k][tid];
-      sB[i][tid] = v / sG[i][i];
-    }
-#pragma unroll 1
-    for (int i = NA - 1; i >= 0; --i) {
-      double v = sB[i][tid];
-      for (int k = i + 1; k < NA; ++k) v -= sG[k][i] * sB[k][tid];
-      sB[i][tid] = v / sG[i][i];
-    }
+  const int info = sInfo;                      // truncated directions of the forward's rank decision (same G, same rule)
+  if (tid < N && info < NA) {
+    // Bm = G~^+ Rbar; rank-truncated series also need N Rbar (discarded directions) and G~^+ R for the third term of the
+    // pseudo-inverse derivative  dX^+ = -X^+ dX X^+ + G~^+ dX^T (I - X X^+) + (I - X^+ X) dX^T X^+T X^+
+    gelsy_pinv<NA>(sG, sW, &sB[0][tid], &sB[0][tid], info ? &sNull[0][tid] : nullptr, N);
     for (int i = 0; i < NA; ++i) sBm[i][tid] = (float)sB[i][tid];
+    if (info) {
+      for (int a = 0; a < NA; ++a) sPR[a][tid] = (double)sRf[a][tid];
+      gelsy_pinv<NA>(sG, sW, &sPR[0][tid], &sPR[0][tid], nullptr, N);
+    }
+  }
+  __syncthreads();
+  if (info && info < NA && tid < NA * NA) {    // W3 = (G~^+ R) (N Rbar)^T : Xbar += X W3
+    const int a = tid / NA, bb = tid - a * NA;
+    double v = 0.0;
+    for (int i = 0; i < N; ++i) v += sPR[a][i] * sNull[bb][i];
+    sW3[a][bb] = (float)v;
   }
   __syncthreads();
   float* __restrict__ out = Zbar + (size_t)b * T * N;
-  if (info != 0) {                       // rank-deficient series: the forward returned NaN coefficients
+  if (info >= NA) {                      // non-finite series: the forward returned NaN coefficients
     for (int f = tid; f < T * N; f += kBwdThreads) out[f] = nanf("");
     return;
   }
@@ -536,6 +701,12 @@ __global__ void __launch_bounds__(kBwdThreads) sindy_fit_bwd_kernel(const float*
       for (int i = 0; i < N; ++i) v = fmaf(e[i], Bm[1 + j][i], v);
 #pragma unroll
       for (int i = 0; i < N; ++i) v = fmaf(-yb[i], Rf[1 + j][i], v);
+      if (info) {                        // + (X W3)[t, 1 + j]
+        float w = sW3[0][1 + j];
+#pragma unroll
+        for (int a = 0; a < N; ++a) w = fmaf(zr[a], sW3[1 + a][1 + j], w);
+        v += w;
+      }
       sZ[t * N + j] = v;
     }
 #pragma unroll
@@ -635,6 +806,7 @@ __global__ void __launch_bounds__(kBwdThreads) sindy_fit_cta_kernel(const float*
   __shared__ double sR[NA][N];
   __shared__ double sSe[NW];
   __shared__ int sInfo;
+  __shared__ GelsyWork sW;
   extern __shared__ float s_fit[];                    // [T][N] the series
   const SbpF& sc = c_sbp[fd_id];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -686,42 +858,11 @@ __global__ void __launch_bounds__(kBwdThreads) sindy_fit_cta_kernel(const float*
       for (int c = a; c < NA; ++c) { sG[a][c] = sRed[0][q]; sG[c][a] = sRed[0][q]; ++q; }
     for (int a = 0; a < NA; ++a)
       for (int i = 0; i < N; ++i) sR[a][i] = sRed[0][q++];
-    int info = 0;
-    double dmax = 0.0;
-    for (int a = 0; a < NA; ++a) dmax = fmax(dmax, sG[a][a]);
-#pragma unroll 1
-    for (int j = 0; j < NA; ++j) {
-      double sdiag = sG[j][j];
-      for (int k = 0; k < j; ++k) sdiag -= sG[j][k] * sG[j][k];
-      if (!(sdiag > 1e-13 * dmax)) { info = j + 1; break; }
-      const double ljj = sqrt(sdiag);
-      sG[j][j] = ljj;
-      const double rl = 1.0 / ljj;
-#pragma unroll 1
-      for (int i = j + 1; i < NA; ++i) {
-        double v = sG[i][j];
-        for (int k = 0; k < j; ++k) v -= sG[i][k] * sG[j][k];
-        sG[i][j] = v * rl;
-      }
-    }
-    sInfo = info;
+    sInfo = NA - gelsy_factor<NA>(sG, sW, gelsy_rcond(T, NA));
   }
   __syncthreads();
-  const int info = sInfo;
-  if (tid < N && info == 0) {
-#pragma unroll 1
-    for (int i = 0; i < NA; ++i) {
-      double v = sR[i][tid];
-      for (int k = 0; k < i; ++k) v -= sG[i][k] * sR[k][tid];
-      sR[i][tid] = v / sG[i][i];
-    }
-#pragma unroll 1
-    for (int i = NA - 1; i >= 0; --i) {
-      double v = sR[i][tid];
-      for (int k = i + 1; k < NA; ++k) v -= sG[k][i] * sR[k][tid];
-      sR[i][tid] = v / sG[i][i];
-    }
-  }
+  const int info = sInfo;                      // number of truncated directions (0 = full rank); NA = not finite
+  if (tid < N && info < NA) gelsy_solve<NA>(sG, sW, &sR[0][tid], &sR[0][tid], N);
   __syncthreads();
   float Rf[NA][N];
   double nrm = 0.0;
@@ -729,7 +870,7 @@ __global__ void __launch_bounds__(kBwdThreads) sindy_fit_cta_kernel(const float*
   for (int a = 0; a < NA; ++a)
 #pragma unroll
     for (int c = 0; c < N; ++c) {
-      const float cf = info == 0 ? (float)sR[a][c] : nanf("");
+      const float cf = info < NA ? (float)sR[a][c] : nanf("");
       Rf[a][c] = cf;
       nrm += (norm_order == 1) ? fabs((double)cf) : (double)cf * (double)cf;
     }

@@ -69,6 +69,7 @@ struct glasdi_handle {
   int opt_passes = 3;
   int opt_integrator = GLASDI_INT_EXPM;
   int opt_substeps = 1;
+  int opt_library = GLASDI_LIB_POLY1;  // GLASDI_OPT_SINDY_LIBRARY
   int opt_max_ctas = 0;
   int opt_timing = 0;
   int opt_kernel = 1;                 // 0: one CTA per SM (decode_var.cu), 1: CTA pairs (decode_var2.cu)
@@ -82,7 +83,7 @@ struct glasdi_handle {
   unsigned int* d_maxvar = nullptr;   // [P] float bits
   size_t maxvar_cap = 0;
   cudaMemPool_t pool = nullptr;       // stream-ordered scratch (release threshold = keep everything)
-  int* d_flags = nullptr;             // [4] device error flags: [0] fp16 range, [1] candidate overflow, [2] screening deviation
+  int* d_flags = nullptr;             // [4] device error flags: [0] fp16 range, [1] candidate overflow, [2] screening deviation, [3] rollout step bound
   // screened mode (GLASDI_OPT_MODE = 1): candidates of the last greedy call
   int opt_mode = 2;                   // 0: direct (split passes), 1: x-space screening + refinement, 2: covariance-form screening + refinement
   int opt_wide = 2;                   // wide decoders: 0 CUDA cores only, 1 last layer on tcgen05 (decode_wide.cu), 2 + last front layer
@@ -118,6 +119,7 @@ int launch_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z
                    int P, int S, int n, int T, double dt,
                    float* Zs /*[P][T][n][Spad] or null*/, int Spad, double* Zref /*[P,S,T,n] or null*/,
                    cudaStream_t st);
+int library_terms(int lib, int n);   // |Theta| of enum glasdi_library, -1 if unknown
 int launch_zis_to_soa(glasdi_handle* h, const double* Zis, int P, int S, int T, int n, float* Zs, int Spad,
                       cudaStream_t st);
 int launch_pad_columns(glasdi_handle* h, float* Zs, long long rows, int S, int Spad, cudaStream_t st);
@@ -223,6 +225,18 @@ __device__ __forceinline__ float act_apply(int act, float x) {
     case GLASDI_ACT_ELU: return x > 0.0f ? x : expm1f(x);              // alpha=1
     case GLASDI_ACT_SILU: return x / (1.0f + expf(-x));
     case GLASDI_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case GLASDI_ACT_HARDSHRINK: return fabsf(x) > 0.5f ? x : 0.0f;
+    case GLASDI_ACT_HARDSIGMOID: return fminf(fmaxf(x * (1.0f / 6.0f) + 0.5f, 0.0f), 1.0f);
+    case GLASDI_ACT_HARDTANH: return fminf(fmaxf(x, -1.0f), 1.0f);
+    case GLASDI_ACT_HARDSWISH: return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
+    case GLASDI_ACT_LEAKYRELU: return x >= 0.0f ? x : 0.01f * x;
+    case GLASDI_ACT_LOGSIGMOID: return fminf(x, 0.0f) - log1pf(expf(-fabsf(x)));
+    case GLASDI_ACT_RELU6: return fminf(fmaxf(x, 0.0f), 6.0f);
+    case GLASDI_ACT_SELU: return 1.0507009873554805f * (x > 0.0f ? x : 1.6732632423543772f * expm1f(x));
+    case GLASDI_ACT_CELU: return x > 0.0f ? x : expm1f(x);             // alpha=1
+    case GLASDI_ACT_MISH: return x * tanhf(x > 20.0f ? x : log1pf(expf(x)));
+    case GLASDI_ACT_SOFTSHRINK: return x > 0.5f ? x - 0.5f : (x < -0.5f ? x + 0.5f : 0.0f);
+    case GLASDI_ACT_TANHSHRINK: return x - tanhf(x);
     default: return x;
   }
 }

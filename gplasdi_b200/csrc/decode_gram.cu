@@ -915,7 +915,9 @@ int gram_pack_v(glasdi_handle* h, const float* WL /*[D][K] host*/) {
 namespace gr { struct GramParams; }
 int launch_decode_gram2(glasdi_handle* h, gr::GramParams& G, int ctas, cudaStream_t st);
 
-static bool unbounded_act_g(int act) { return !(act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH); }
+static bool unbounded_act_g(int act) {
+  return !(act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH || act == GLASDI_ACT_HARDSIGMOID || act == GLASDI_ACT_HARDTANH);
+}
 
 template <int ACT, int INW, bool FAST>
 static int launch_gram_inst(glasdi_handle* h, const gr::GramParams& G, int ctas, size_t smem, cudaStream_t st) {

@@ -465,7 +465,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
 
 size_t decode_var_smem_bytes(int Kpad, int last_in_w) { return dv::carve(Kpad, last_in_w).total; }
 
-static bool unbounded_act(int act) { return !(act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH); }
+static bool unbounded_act(int act) {
+  return !(act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH || act == GLASDI_ACT_HARDSIGMOID || act == GLASDI_ACT_HARDTANH);
+}
 
 static int fill_common(glasdi_handle* h, dv::Params& P) {
   const Decoder& d = h->dec;

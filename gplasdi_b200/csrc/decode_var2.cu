@@ -500,7 +500,9 @@ decode_pair_kernel(const __grid_constant__ Params P) {
 
 }  // namespace dv2
 
-static bool unbounded_act2(int act) { return !(act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH); }
+static bool unbounded_act2(int act) {
+  return !(act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH || act == GLASDI_ACT_HARDSIGMOID || act == GLASDI_ACT_HARDTANH);
+}
 
 static int fill_common2(glasdi_handle* h, dv::Params& P) {
   const Decoder& d = h->dec;

@@ -60,7 +60,7 @@ __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ft
 // bare MUFU forms, activation resolved at compile time: 3-6 instructions per value (the runtime switch + __expf / __logf
 // range handling of act_fast cost ~25 in xact_kernel's epilogue: 40 instructions per value, profiles/r02_xact_*)
 template <int ACT>
-__device__ __forceinline__ float act_mufu(float a) {
+__device__ __forceinline__ float act_mufu(float a, int act_rt) {   // ACT < 0: runtime switch (the rarely used activations)
   constexpr float kL2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
   if constexpr (ACT == GLASDI_ACT_SIGMOID) return mufu_rcp(1.0f + mufu_ex2(-kL2e * a));
   else if constexpr (ACT == GLASDI_ACT_TANH) return fmaf(2.0f, mufu_rcp(1.0f + mufu_ex2(-2.0f * kL2e * a)), -1.0f);
@@ -68,17 +68,18 @@ __device__ __forceinline__ float act_mufu(float a) {
   else if constexpr (ACT == GLASDI_ACT_SILU) return a * mufu_rcp(1.0f + mufu_ex2(-kL2e * a));
   else if constexpr (ACT == GLASDI_ACT_RELU) return fmaxf(a, 0.0f);
   else if constexpr (ACT == GLASDI_ACT_IDENTITY) return a;
+  else if constexpr (ACT < 0) return act_apply(act_rt, a);
   else return act_apply(ACT, a);
 }
 // 32 accumulator columns of one unit row -> (act(a) - pilot) 2^eH as fp16 into the [hi] part of xvar_kernel's B tile
 template <int ACT>
-__device__ __forceinline__ void xact_emit_screen(const uint32_t (&r)[32], float unscale, float bias, float pilot_s, float scale,
+__device__ __forceinline__ void xact_emit_screen(int act_rt, const uint32_t (&r)[32], float unscale, float bias, float pilot_s, float scale,
                                                  int valid_cols, bool unit_ok, bool store_ok, __half* dst, float& amax,
                                                  float& nanacc) {
 #pragma unroll
   for (int q = 0; q < 32; ++q) {
     const float a = fmaf(__uint_as_float(r[q]), unscale, bias);
-    float dvv = fmaf(act_mufu<ACT>(a), scale, -pilot_s);
+    float dvv = fmaf(act_mufu<ACT>(a, act_rt), scale, -pilot_s);
     dvv = (unit_ok && q < valid_cols) ? dvv : 0.f;
     amax = fmaxf(amax, fabsf(dvv));
     nanacc = fmaf(dvv, 0.f, nanacc);                    // NaN / inf leave a NaN behind
@@ -86,7 +87,7 @@ __device__ __forceinline__ void xact_emit_screen(const uint32_t (&r)[32], float 
   }
 }
 template <int ACT>
-__device__ __forceinline__ float xact_pilot_screen(float a) { return act_mufu<ACT>(a); }
+__device__ __forceinline__ float xact_pilot_screen(float a, int act_rt) { return act_mufu<ACT>(a, act_rt); }
 #define GLASDI_ACT_DISPATCH(act, CALL)                                            \
   switch (act) {                                                                  \
     case GLASDI_ACT_SIGMOID: { constexpr int A_ = GLASDI_ACT_SIGMOID; CALL; } break;   \
@@ -96,7 +97,8 @@ __device__ __forceinline__ float xact_pilot_screen(float a) { return act_mufu<AC
     case GLASDI_ACT_ELU: { constexpr int A_ = GLASDI_ACT_ELU; CALL; } break;           \
     case GLASDI_ACT_SILU: { constexpr int A_ = GLASDI_ACT_SILU; CALL; } break;         \
     case GLASDI_ACT_GELU: { constexpr int A_ = GLASDI_ACT_GELU; CALL; } break;         \
-    default: { constexpr int A_ = GLASDI_ACT_IDENTITY; CALL; } break;                  \
+    case GLASDI_ACT_IDENTITY: { constexpr int A_ = GLASDI_ACT_IDENTITY; CALL; } break; \
+    default: { constexpr int A_ = -1; CALL; } break;                                   \
   }
 
 __global__ void __launch_bounds__(kThreads, 1) xvar_kernel(const __grid_constant__ WideParams P) {
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(kActThreads, 1) xact_kernel(const __grid_const
           tmem_ld_32x32(taddr, ra);
           tmem_ld_wait();
           const float ap = fmaf(__uint_as_float(ra[0]), P.unscale_in, bias);
-          if constexpr (SCREEN) { GLASDI_ACT_DISPATCH(P.act, pilot = xact_pilot_screen<A_>(ap)) }
+          if constexpr (SCREEN) { GLASDI_ACT_DISPATCH(P.act, pilot = xact_pilot_screen<A_>(ap, P.act)) }
           else pilot = act_apply(P.act, ap);
         }
         auto emit = [&](const uint32_t (&r)[32], int c0) {
@@ -404,10 +406,10 @@ __global__ void __launch_bounds__(kActThreads, 1) xact_kernel(const __grid_const
         if constexpr (SCREEN) {
           const float pilot_s = pilot * P.scale_out;
           const int v0 = P.S - (sb * 256 + c_lo);          // valid columns from c_lo on
-          GLASDI_ACT_DISPATCH(P.act, xact_emit_screen<A_>(ra, P.unscale_in, bias, pilot_s, P.scale_out, v0, unit_ok, store_ok,
+          GLASDI_ACT_DISPATCH(P.act, xact_emit_screen<A_>(P.act, ra, P.unscale_in, bias, pilot_s, P.scale_out, v0, unit_ok, store_ok,
                                                           tile + (size_t)c_lo * 8, amax, nanacc))
           tmem_ld_wait();
-          GLASDI_ACT_DISPATCH(P.act, xact_emit_screen<A_>(rb, P.unscale_in, bias, pilot_s, P.scale_out, v0 - 32, unit_ok, store_ok,
+          GLASDI_ACT_DISPATCH(P.act, xact_emit_screen<A_>(P.act, rb, P.unscale_in, bias, pilot_s, P.scale_out, v0 - 32, unit_ok, store_ok,
                                                           tile + (size_t)(c_lo + 32) * 8, amax, nanacc))
         } else {
           emit(ra, c_lo);

@@ -1,4 +1,5 @@
-// rollout.cu -- latent ODE rollout of the affine SINDy system  dz/dt = A z + b.
+// rollout.cu -- latent ODE rollout of the SINDy system: affine  dz/dt = A z + b  (src/lasdi) and the polynomial / sine
+// candidate libraries of the legacy drivers (rollout_lib_kernel below).
 //
 // Replaces the python double loop over SINDy.simulate (reference src/lasdi/gplasdi.py:262-266,
 // src/lasdi/latent_dynamics/sindy.py:104-117: scipy odeint/LSODA, fp64, rtol=atol~1.5e-8).
@@ -209,6 +210,194 @@ rollout_kernel(const double* __restrict__ coefs, const float* __restrict__ z0, i
   }
 }
 
+// ---- non-affine candidate libraries (reference legacy/Vlasov1D1V/utils/utils_sindy.py:91-170) -------------------
+// dz/dt = Theta(z) R with Theta = [1, z, z_i z_j (i <= j) if QUAD, sin z if SINE], R = [|Theta|, N] row-major.  One thread
+// per trajectory; the |Theta| N fp64 coefficients (up to 424 at N = 8) live in shared memory as [coefficient][thread]
+// (conflict-free, read at compile-time offsets), the state and the RK4 stages in registers.  fp64 RK4; the number of
+// sub-steps of every output step comes from a row-sum bound of the Jacobian at the current state:
+//   L(z) = max_i ( sum_j |A_ij| + sum_j |c_sin,ij| + sum_{j<=k} |q_i,jk| (|z_j| + |z_k|) ),   substeps = ceil(16 dt L)
+// so h L <= 1/16: the local truncation error (h L)^5 / 120 per step keeps the trajectory within ~1e-7 L t of LSODA's.
+template <int N, bool QUAD, bool SINE>
+struct Lib {
+  static constexpr int kQ = QUAD ? N * (N + 1) / 2 : 0;
+  static constexpr int kTerms = 1 + N + kQ + (SINE ? N : 0);
+  static constexpr int kCoefs = kTerms * N;
+};
+
+template <int N, bool QUAD, bool SINE>
+__device__ __forceinline__ void rhs_lib(const volatile double* c, int bd, const double (&z)[N], double (&f)[N]) {
+  using L = Lib<N, QUAD, SINE>;
+#pragma unroll
+  for (int i = 0; i < N; ++i) f[i] = c[i * bd];
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int i = 0; i < N; ++i) f[i] = fma(c[((1 + j) * N + i) * bd], z[j], f[i]);
+  if constexpr (QUAD) {
+    int q = 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int k = j; k < N; ++k, ++q) {
+        const double zz = z[j] * z[k];
+#pragma unroll
+        for (int i = 0; i < N; ++i) f[i] = fma(c[((1 + N + q) * N + i) * bd], zz, f[i]);
+      }
+  }
+  if constexpr (SINE) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const double sj = sin(z[j]);
+#pragma unroll
+      for (int i = 0; i < N; ++i) f[i] = fma(c[((1 + N + L::kQ + j) * N + i) * bd], sj, f[i]);
+    }
+  }
+}
+
+template <int N, bool QUAD, bool SINE>
+__global__ void rollout_lib_kernel(const double* __restrict__ coefs, const float* __restrict__ z0, int z0_per_sample,
+                                   int P, int S, int T, double dt, int min_substeps, float* __restrict__ Zs, int Spad,
+                                   double* __restrict__ Zref, unsigned int* __restrict__ flags) {
+  using L = Lib<N, QUAD, SINE>;
+  extern __shared__ double cs[];                         // [kCoefs][blockDim.x]
+  const int bd = blockDim.x;
+  const int p = blockIdx.y;
+  const int s0 = blockIdx.x * bd;
+  const int s = s0 + threadIdx.x;
+  // the block's trajectories are contiguous in `coefs`: coalesced read, transposed store
+  const int nloc = min(bd, S - s0);
+  const double* cblk = coefs + ((size_t)p * S + s0) * L::kCoefs;
+  for (int e = threadIdx.x; e < nloc * L::kCoefs; e += bd) cs[(e % L::kCoefs) * bd + e / L::kCoefs] = cblk[e];
+  __syncthreads();
+  if (s >= S) return;
+  const size_t traj = (size_t)p * S + s;
+  const volatile double* c = cs + threadIdx.x;   // volatile: re-read at every use instead of being hoisted into (spilled) registers
+
+  double z[N];
+  const float* zp = z0_per_sample ? (z0 + traj * N) : (z0 + (size_t)p * N);
+#pragma unroll
+  for (int i = 0; i < N; ++i) z[i] = (double)zp[i];
+  // state-independent part of the Jacobian bound
+  double lin[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double a = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) a += fabs(c[((1 + j) * N + i) * bd]);
+    if constexpr (SINE) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) a += fabs(c[((1 + N + L::kQ + j) * N + i) * bd]);
+    }
+    lin[i] = a;
+  }
+
+  float* zs_base = Zs ? (Zs + ((size_t)p * T * N) * Spad + s) : nullptr;
+  double* zr_base = Zref ? (Zref + traj * (size_t)T * N) : nullptr;
+  auto emit = [&](int k) {
+    if (zs_base) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) zs_base[((size_t)k * N + i) * Spad] = (float)z[i];
+    }
+    if (zr_base) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) zr_base[(size_t)k * N + i] = z[i];
+    }
+  };
+
+  bool bad = false;
+  emit(0);
+  for (int k = 1; k < T; ++k) {
+    double lmax = 0.0;
+    {
+      double li[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) li[i] = lin[i];
+      if constexpr (QUAD) {
+        int q = 0;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+          for (int kk = j; kk < N; ++kk, ++q) {
+            const double w = fabs(z[j]) + fabs(z[kk]);
+#pragma unroll
+            for (int i = 0; i < N; ++i) li[i] = fma(fabs(c[((1 + N + q) * N + i) * bd]), w, li[i]);
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) lmax = fmax(lmax, li[i]);
+    }
+    double chk = 0.0;                                          // NaN as soon as a component is inf / NaN (fmax drops NaNs)
+#pragma unroll
+    for (int i = 0; i < N; ++i) chk = fma(z[i], 0.0, chk);
+    const double want = ceil(16.0 * fabs(dt) * lmax);
+    int sub = min_substeps;
+    if (chk != 0.0) { bad = true; }
+    else if (!(want <= 16384.0)) { bad = true; sub = 16384; }
+    else sub = max(sub, (int)want);
+    const double hstep = dt / (double)sub;
+    for (int q = 0; q < sub; ++q) {
+      double k1[N], k2[N], k3[N], k4[N], zt[N];
+      rhs_lib<N, QUAD, SINE>(c, bd, z, k1);
+#pragma unroll
+      for (int i = 0; i < N; ++i) zt[i] = fma(0.5 * hstep, k1[i], z[i]);
+      rhs_lib<N, QUAD, SINE>(c, bd, zt, k2);
+#pragma unroll
+      for (int i = 0; i < N; ++i) zt[i] = fma(0.5 * hstep, k2[i], z[i]);
+      rhs_lib<N, QUAD, SINE>(c, bd, zt, k3);
+#pragma unroll
+      for (int i = 0; i < N; ++i) zt[i] = fma(hstep, k3[i], z[i]);
+      rhs_lib<N, QUAD, SINE>(c, bd, zt, k4);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        z[i] = fma(hstep / 6.0, (k1[i] + 2.0 * k2[i]) + (2.0 * k3[i] + k4[i]), z[i]);
+    }
+    emit(k);
+  }
+  {
+    double chk = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) chk = fma(z[i], 0.0, chk);
+    bad |= chk != 0.0;
+  }
+  if (bad && flags) atomicOr(flags, 1u);
+}
+
+template <int N, bool QUAD, bool SINE>
+static int launch_rollout_lib_inst(glasdi_handle* h, const double* coefs, const float* z0, int z0ps, int P, int S, int T,
+                                   double dt, float* Zs, int Spad, double* Zref, cudaStream_t st) {
+  using L = Lib<N, QUAD, SINE>;
+  int bd = 128;
+  while (bd > 32 && (size_t)bd * L::kCoefs * sizeof(double) > 100 * 1024) bd >>= 1;
+  const size_t smem = (size_t)bd * L::kCoefs * sizeof(double);
+  auto kern = rollout_lib_kernel<N, QUAD, SINE>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(h, e, "rollout_lib_kernel shared memory");
+  }
+  dim3 block(bd), grid((S + bd - 1) / bd, P);
+  kern<<<grid, block, smem, st>>>(coefs, z0, z0ps, P, S, T, dt, h->opt_substeps, Zs, Spad, Zref,
+                                         reinterpret_cast<unsigned int*>(h->d_flags + 3));
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "rollout_lib_kernel launch");
+}
+
+template <int N>
+static int launch_rollout_lib_n(glasdi_handle* h, int lib, const double* coefs, const float* z0, int z0ps, int P, int S,
+                                int T, double dt, float* Zs, int Spad, double* Zref, cudaStream_t st) {
+  switch (lib) {
+    case GLASDI_LIB_POLY1_SINE: return launch_rollout_lib_inst<N, false, true>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+    case GLASDI_LIB_POLY2: return launch_rollout_lib_inst<N, true, false>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+    default: return launch_rollout_lib_inst<N, true, true>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+  }
+}
+
+int library_terms(int lib, int n) {
+  if (lib < GLASDI_LIB_POLY1 || lib > GLASDI_LIB_POLY2_SINE || n < 1) return -1;
+  const bool quad = lib == GLASDI_LIB_POLY2 || lib == GLASDI_LIB_POLY2_SINE;
+  const bool sine = lib == GLASDI_LIB_POLY1_SINE || lib == GLASDI_LIB_POLY2_SINE;
+  return 1 + n + (quad ? n * (n + 1) / 2 : 0) + (sine ? n : 0);
+}
+
 // caller-supplied trajectories: Zis fp64 [P,S,T,n] -> Zs fp32 [P][T][n][Spad]
 // (the fp64 -> fp32 cast is `torch.Tensor(Zi)` of reference gplasdi.py:65)
 __global__ void zis_to_soa_kernel(const double* __restrict__ Zis, int P, int S, int T, int n,
@@ -245,6 +434,20 @@ int launch_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z
                    double dt, float* Zs, int Spad, double* Zref, cudaStream_t st) {
   if (P <= 0 || S <= 0 || T <= 0) return set_error(h, GLASDI_ERR_INVALID, "rollout: empty shape");
   if (P > 65535) return set_error(h, GLASDI_ERR_INVALID, "rollout: P > 65535 per call (shard the test grid)");
+  if (h->opt_library != GLASDI_LIB_POLY1) {
+    const int lib = h->opt_library;
+    switch (n) {
+      case 1: return launch_rollout_lib_n<1>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+      case 2: return launch_rollout_lib_n<2>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+      case 3: return launch_rollout_lib_n<3>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+      case 4: return launch_rollout_lib_n<4>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+      case 5: return launch_rollout_lib_n<5>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+      case 6: return launch_rollout_lib_n<6>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+      case 7: return launch_rollout_lib_n<7>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+      case 8: return launch_rollout_lib_n<8>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+      default: return set_error(h, GLASDI_ERR_INVALID, "rollout: latent dimension must be 1..8");
+    }
+  }
   switch (n) {
     case 1: return launch_rollout_n<1>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
     case 2: return launch_rollout_n<2>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);

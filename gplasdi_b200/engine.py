@@ -140,13 +140,26 @@ class Engine:
         return Z.reshape(*lead, self.encoder_widths[-1])
 
     # ---- rollout -----------------------------------------------------------------------------
+    def set_library(self, poly_order: int = 1, sine_term: bool = False):
+        """Candidate library of the latent ODE for `rollout` / `greedy_step` (legacy utils_sindy.py:91-170):
+        poly_order 1 or 2, optional sine terms.  Default = the affine library of src/lasdi."""
+        if poly_order not in (1, 2):
+            raise ValueError("poly_order must be 1 or 2 (the reference's simulate_sindy has no other branch)")
+        self.set_option(_lib.OPT_SINDY_LIBRARY, (2 if poly_order == 2 else 0) + (1 if sine_term else 0))
+
+    def library_terms(self, n: int) -> int:
+        """|Theta| of the selected library at latent dimension n; coefficient rows are [|Theta|, n]."""
+        return int(self.lib.glasdi_library_terms(self.get_option(_lib.OPT_SINDY_LIBRARY), int(n)))
+
     def rollout(self, coefs, z0, T: int, dt: float) -> torch.Tensor:
-        """coefs [P,S,n(n+1)] fp64, z0 [P,n] (or [P,S,n]) fp32 -> Z fp64 [P,S,T,n] (CUDA tensor)."""
+        """coefs [P,S,|Theta| n] fp64 (n(n+1) for the default library), z0 [P,n] (or [P,S,n]) fp32 -> Z fp64 [P,S,T,n]
+        (CUDA tensor)."""
         coefs = self._dev(coefs, torch.float64)
         z0 = self._dev(z0, torch.float32)
         P, S, nc = coefs.shape
         n = z0.shape[-1]
-        assert nc == n * (n + 1)
+        if nc != n * self.library_terms(n):
+            raise ValueError(f"coefficient rows of {nc} values do not match the selected library ({self.library_terms(n)} x {n})")
         per_sample = 1 if z0.dim() == 3 else 0
         out = torch.empty((P, S, T, n), dtype=torch.float64, device=self.tdev)
         with torch.cuda.device(self.device):
@@ -161,7 +174,9 @@ class Engine:
         z0 = self._dev(z0, torch.float32)
         P, S, nc = coefs.shape
         n = z0.shape[-1]
-        assert z0.shape == (P, n) and nc == n * (n + 1)
+        assert z0.shape == (P, n)
+        if nc != n * self.library_terms(n):
+            raise ValueError(f"coefficient rows of {nc} values do not match the selected library ({self.library_terms(n)} x {n})")
         if out is None:
             out = (torch.empty(P, dtype=torch.float32, device=self.tdev),
                    torch.empty(1, dtype=torch.int64, device=self.tdev),

@@ -20,6 +20,7 @@ import torch
 from . import LatentDynamics
 from ..fd import FDdict
 from ..engine import default_engine
+from .. import _lib
 
 
 def _uniform_dt(t_grid) -> float:
@@ -32,6 +33,37 @@ def _uniform_dt(t_grid) -> float:
     if not np.allclose(d, d[0], rtol=1e-9, atol=1e-14):
         raise ValueError("the CUDA rollout needs a uniform time grid (the reference's physics grids are uniform)")
     return float(d[0])
+
+
+def lib_size(n_z: int, poly_order: int) -> int:
+    """Number of polynomial terms of order 2..poly_order (legacy/Vlasov1D1V/utils/utils_sindy.py:12-27)."""
+    from math import comb
+    return sum(comb(n_z + k - 1, k) for k in range(poly_order + 1)) - n_z - 1
+
+
+def simulate_sindy(sindy_coef, Z0, t_grid, n_z, poly_order=1, library_size=None, sine_term=False, engine=None):
+    """Drop-in for the legacy drivers' `simulate_sindy` (legacy/Vlasov1D1V/utils/utils_sindy.py:91-170): integrates
+    dz/dt = Theta(z) sindy_coef[i] from Z0[i] for every i, Theta = [1, z, z_i z_j (i <= j) if poly_order == 2, sin z if
+    sine_term].  sindy_coef: sequence of [|Theta|, n_z] matrices; returns np.ndarray fp64 [len(sindy_coef), nt, n_z].
+    All systems run in ONE launch of the CUDA rollout (`rollout_lib_kernel`; the affine case on the exact propagator)."""
+    eng = engine if engine is not None else default_engine()
+    c = np.stack([np.asarray(ci, dtype=np.float64) for ci in sindy_coef])
+    N = c.shape[0]
+    n_q = lib_size(n_z, 2) if poly_order == 2 else 0
+    if library_size is not None and poly_order == 2 and int(library_size) != n_q:
+        raise ValueError(f"library_size {library_size} does not match lib_size({n_z}, 2) = {n_q}")
+    terms = 1 + n_z + n_q + (n_z if sine_term else 0)
+    if c.shape[1:] != (terms, n_z):
+        raise ValueError(f"sindy_coef matrices must be [{terms}, {n_z}] for this library, got {c.shape[1:]}")
+    z = np.asarray(Z0, dtype=np.float32).reshape(N, n_z)
+    prev = eng.get_option(_lib.OPT_SINDY_LIBRARY)
+    eng.set_library(poly_order, sine_term)
+    try:
+        Z = eng.rollout(c.reshape(N, 1, terms * n_z), z, len(t_grid), _uniform_dt(t_grid))
+        eng.check_numeric()          # a blown-up trajectory (RK4 step bound exceeded / non-finite) raises
+    finally:
+        eng.set_option(_lib.OPT_SINDY_LIBRARY, prev)
+    return Z[:, 0].cpu().numpy()
 
 
 class _SindyFit(torch.autograd.Function):
@@ -101,14 +133,16 @@ class SINDy(LatentDynamics):
             ls, lc, coefs, info = _SindyFit.apply(Zb, self.engine, float(dt), self.fd_type, self.coef_norm_order)
         else:
             coefs, ls, lc, info = self.engine.sindy_fit(Zb.detach(), dt, self.fd_type, self.coef_norm_order)
-        # The fit reports per series whether the library matrix [1 | Z] had full numerical rank (`info`).  The host copy of
-        # the coefficients below synchronises anyway: read the status with it and never hand NaN coefficients / losses to
-        # the caller (the reference's torch.linalg.lstsq returns a finite minimum-norm answer there, sindy.py:72).
-        bad = torch.nonzero(info.cpu()).flatten().tolist()
+        # `info` = number of directions of the library matrix [1 | Z] the fit truncated, by LAPACK gelsy's own rank rule
+        # (rcond = eps_fp32 * max(nt, dim + 1), what torch.linalg.lstsq applies at sindy.py:72): 0 = full rank; 1..dim = the
+        # MINIMUM-NORM solution of the rank-truncated problem was returned, finite, as the reference does for the constant /
+        # collinear latent columns of an untrained encoder; dim + 1 = the series is not finite.  The host copy of the
+        # coefficients below synchronises anyway: read the status with it.
+        info_h = info.cpu()
+        self.last_truncated_rank = info_h.numpy().copy()
+        bad = torch.nonzero(info_h > self.dim).flatten().tolist()
         if bad:
-            raise RuntimeError(
-                f"SINDy.calibrate: the library matrix [1 | Z] of training series {bad} is numerically rank deficient "
-                f"(a constant or collinear latent column); no coefficients were produced for them")
+            raise RuntimeError(f"SINDy.calibrate: training series {bad} contain non-finite latent values")
         if batched:
             out = coefs.double().cpu().numpy() if numpy else coefs.cpu()
         else:

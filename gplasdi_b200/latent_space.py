@@ -19,19 +19,16 @@ import torch
 
 from . import _lib
 
-# activations with a CUDA implementation (names of the reference's act_dict, latent_space.py:5-28)
-_TORCH_ACT = {
+# every parameter-free activation of the reference's act_dict (latent_space.py:5-28) has a CUDA implementation
+# (include/glasdi_b200.h: enum glasdi_act); 'threshold' (two parameters) is torch-only: training works, inference raises
+act_dict = {
     "sigmoid": torch.nn.Sigmoid, "tanh": torch.nn.Tanh, "softplus": torch.nn.Softplus, "ReLU": torch.nn.ReLU,
     "ELU": torch.nn.ELU, "SiLU": torch.nn.SiLU, "GELU": torch.nn.GELU,
-}
-# remaining parameter-free activations of the reference: torch-only (no CUDA decode kernel)
-_TORCH_ONLY_ACT = {
     "hardshrink": torch.nn.Hardshrink, "hardsigmoid": torch.nn.Hardsigmoid, "hardtanh": torch.nn.Hardtanh,
     "hardswish": torch.nn.Hardswish, "leakyReLU": torch.nn.LeakyReLU, "logsigmoid": torch.nn.LogSigmoid,
     "ReLU6": torch.nn.ReLU6, "SELU": torch.nn.SELU, "CELU": torch.nn.CELU, "mish": torch.nn.Mish,
     "softshrink": torch.nn.Softshrink, "tanhshrink": torch.nn.Tanhshrink,
 }
-act_dict = {**_TORCH_ACT, **_TORCH_ONLY_ACT}
 
 
 def initial_condition_latent(param_grid, physics, autoencoder):

@@ -41,7 +41,14 @@ enum glasdi_status {
 /* activation ids = names of reference src/lasdi/latent_space.py:5-28 (`act_dict`), torch defaults */
 enum glasdi_act {
   GLASDI_ACT_SIGMOID = 0, GLASDI_ACT_TANH = 1, GLASDI_ACT_SOFTPLUS = 2, GLASDI_ACT_RELU = 3,
-  GLASDI_ACT_ELU = 4, GLASDI_ACT_SILU = 5, GLASDI_ACT_GELU = 6, GLASDI_ACT_IDENTITY = 7
+  GLASDI_ACT_ELU = 4, GLASDI_ACT_SILU = 5, GLASDI_ACT_GELU = 6, GLASDI_ACT_IDENTITY = 7,
+  /* the remaining parameter-free entries of act_dict (torch default arguments): Hardshrink(0.5), Hardsigmoid, Hardtanh(-1, 1),
+     Hardswish, LeakyReLU(0.01), LogSigmoid, ReLU6, SELU, CELU(1), Mish, Softshrink(0.5), Tanhshrink.  Not covered: 'threshold'
+     (two parameters), 'PReLU' (learnable), 'RReLU' (random in training mode), 'multihead' (not an activation) */
+  GLASDI_ACT_HARDSHRINK = 8, GLASDI_ACT_HARDSIGMOID = 9, GLASDI_ACT_HARDTANH = 10, GLASDI_ACT_HARDSWISH = 11,
+  GLASDI_ACT_LEAKYRELU = 12, GLASDI_ACT_LOGSIGMOID = 13, GLASDI_ACT_RELU6 = 14, GLASDI_ACT_SELU = 15,
+  GLASDI_ACT_CELU = 16, GLASDI_ACT_MISH = 17, GLASDI_ACT_SOFTSHRINK = 18, GLASDI_ACT_TANHSHRINK = 19,
+  GLASDI_ACT_COUNT = 20
 };
 
 /* finite-difference scheme ids = keys of reference src/lasdi/fd.py:219-222 (`FDdict`) */
@@ -75,7 +82,9 @@ enum glasdi_option {
                                    gram2_kernel -- thread = hidden unit, centred activations h(a_pilot + da) - h(a_pilot) from a
                                    5th-order Taylor polynomial in da (no MUFU), exact form for sample blocks outside the radius;
                                    0: gram_kernel (round-1 producers).  Screening only: results are the exact re-evaluation's */
-  GLASDI_OPT_TAYLOR_RADIUS = 10 /* radius of that polynomial: bound on |da| in units of 1/256 (default 256 = 1.0; 0 = never) */
+  GLASDI_OPT_TAYLOR_RADIUS = 10, /* radius of that polynomial: bound on |da| in units of 1/256 (default 256 = 1.0; 0 = never) */
+  GLASDI_OPT_SINDY_LIBRARY = 11 /* enum glasdi_library (default POLY1 = the affine library of src/lasdi): which candidate
+                                   functions the coefficient rows of glasdi_rollout / glasdi_greedy_step multiply */
 };
 
 /* how glasdi_greedy_step / glasdi_decode_max_std obtain max_std[p] (same result within the fp32 tolerance) */
@@ -94,6 +103,20 @@ enum glasdi_mode {
                                 candidate-buffer overflow, is reported as GLASDI_ERR_NUMERIC by
                                 glasdi_check_numeric -- never silently accepted. */
 };
+
+/* SINDy candidate library Theta(z) of the latent ODE dz/dt = Theta(z) R, R = coefficients [|Theta|, n] row-major.
+ * Replaces: the four right-hand sides of `simulate_sindy` (reference legacy/Vlasov1D1V/utils/utils_sindy.py:91-170;
+ * library size :12-27, construction order :31-64): Theta = [1, z_0..z_{n-1}, z_i z_j (i <= j, i slowest) if poly_order = 2,
+ * sin z_0..sin z_{n-1} if sine_term].  POLY1 is the library of src/lasdi/latent_dynamics/sindy.py:104-117 (affine: exact
+ * propagator or RK4 by GLASDI_OPT_INTEGRATOR); the other three are always integrated by fp64 RK4 whose sub-step count is
+ * re-chosen at every output step from a row-sum bound L of the Jacobian at the current state (h L <= 1/16, at least
+ * GLASDI_OPT_RK4_SUBSTEPS); a trajectory that needs more than 16384 sub-steps per output step (finite-time blow-up of a
+ * quadratic system) or turns non-finite raises GLASDI_ERR_NUMERIC at the next glasdi_check_numeric. */
+enum glasdi_library {
+  GLASDI_LIB_POLY1 = 0, GLASDI_LIB_POLY1_SINE = 1, GLASDI_LIB_POLY2 = 2, GLASDI_LIB_POLY2_SINE = 3
+};
+/* |Theta| of a library for latent dimension n (= 1 + n + `lib_size(n, 2)` + n sines); -1 for an unknown id */
+int glasdi_library_terms(int library, int n);
 
 int glasdi_abi_version(void);
 
@@ -134,7 +157,7 @@ int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths,
  * Replaces: SINDy.simulate in the loops of gplasdi.py:20-21, :45-48, :262-266 and
  *   LatentDynamics.sample (latent_dynamics/__init__.py:39-54).
  * coefs fp64 [P, S, n(n+1)] (row-major flatten of the (n+1, n) lstsq solution, row 0 = constant,
- * sindy.py:72,80,112-113); z0 fp32 [P, n] (one initial condition per parameter, shared by its S
+ * sindy.py:72,80,112-113; [P, S, |Theta| n] under GLASDI_OPT_SINDY_LIBRARY, here and in glasdi_greedy_step); z0 fp32 [P, n] (one initial condition per parameter, shared by its S
  * samples; pass z0_per_sample != 0 for z0 [P, S, n]); uniform grid t_k = k*dt, k < T.
  * Z_out fp64 [P, S, T, n] in the reference's layout. */
 int glasdi_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z0_per_sample,
@@ -189,10 +212,13 @@ int glasdi_fd_dzdt(glasdi_handle* h, const float* Z, int B, int T, int n, int fd
                    float* dZ_out, void* stream);
 
 /* Replaces: SINDy.calibrate (sindy.py:41-87): per series dZ/dt by the stencil, library [1 | Z],
- * least squares (normal equations accumulated and solved in fp64), MSE(dZdt, [1|Z] R) and
- * ||R||_p (norm_order 1 or 2; 2 = 'fro').  coefs_out fp32 [B, n(n+1)] (row-major (n+1, n));
+ * least squares with LAPACK xGELSY's semantics (what torch.linalg.lstsq runs at sindy.py:72): column-pivoted
+ * factorisation, effective rank from the incremental condition estimate against rcond = eps_fp32 * max(T, n + 1),
+ * minimum-norm solution of the rank-truncated problem -- computed on the fp64 normal equations --, MSE(dZdt, [1|Z] R)
+ * and ||R||_p (norm_order 1 or 2; 2 = 'fro').  coefs_out fp32 [B, n(n+1)] (row-major (n+1, n));
  * loss_sindy_out / loss_coef_out fp32 [B] (per series; the reference SUMS them over the batch);
- * info_out int32 [B]: 0 ok, >0 Gram matrix not positive definite at that pivot (rank deficient). */
+ * info_out int32 [B]: number of truncated directions -- 0 = full rank, 1..n = rank-deficient series (finite
+ * minimum-norm coefficients, as the reference returns), n + 1 = non-finite series (NaN coefficients). */
 int glasdi_sindy_fit(glasdi_handle* h, const float* Z, int B, int T, int n, int fd_id, double dt,
                      int norm_order, float* coefs_out, float* loss_sindy_out, float* loss_coef_out,
                      int32_t* info_out, void* stream);
@@ -240,8 +266,8 @@ int glasdi_encode(glasdi_handle* h, const float* U, int64_t rows, float* Z_out, 
  * norm when the reference's training loop differentiates the two losses (gplasdi.py:186-197 -> sindy.py:66-77; the
  * coefficients themselves are returned detached, sindy.py:80).
  * Z [B, T, n] and coefs [B, n(n+1)] as passed to / returned by the forward; grad_loss_sindy / grad_loss_coef fp32 [B]
- * upstream gradients of the per-series losses (NULL = 0); grad_Z_out fp32 [B, T, n] (NaN for a rank-deficient
- * series).  Needs 2 * T * n * 4 bytes <= 200 KB of shared memory. */
+ * upstream gradients of the per-series losses (NULL = 0); grad_Z_out fp32 [B, T, n] (rank-truncated series: the
+ * derivative of the pseudo-inverse at constant rank, as torch's lstsq backward; NaN for a non-finite series).  Needs 2 * T * n * 4 bytes <= 200 KB of shared memory. */
 int glasdi_sindy_fit_backward(glasdi_handle* h, const float* Z, const float* coefs, const float* grad_loss_sindy,
                               const float* grad_loss_coef, int B, int T, int n, int fd_id, double dt, int norm_order,
                               float* grad_Z_out, void* stream);

@@ -131,6 +131,35 @@ def simulate(coefs: np.ndarray, z0: np.ndarray, t_grid: np.ndarray) -> np.ndarra
     return odeint(dzdt, z0, t_grid)
 
 
+def library_terms(n: int, poly_order: int = 1, sine_term: bool = False) -> int:
+    """|Theta| = 1 + n + lib_size(n, poly_order) + n sines.  Reference legacy/Vlasov1D1V/utils/utils_sindy.py:12-27."""
+    from scipy.special import binom
+    n_poly = sum(int(binom(n + k - 1, k)) for k in range(poly_order + 1)) - n - 1
+    return 1 + n + n_poly + (n if sine_term else 0)
+
+
+def simulate_library(coefs: np.ndarray, z0: np.ndarray, t_grid: np.ndarray, poly_order: int = 1,
+                     sine_term: bool = False) -> np.ndarray:
+    """One latent trajectory of dz/dt = Theta(z) R for the polynomial / sine candidate libraries.
+    Reference legacy/Vlasov1D1V/utils/utils_sindy.py:91-170 (`simulate_sindy`, one iteration of its loop): `c_i = R.T`;
+    Theta = [1, z, z_i z_j for i <= j (i slowest) if poly_order == 2, sin(z) if sine_term]; LSODA via scipy `odeint`
+    with default tolerances.  `coefs` = R [|Theta|, n] (or its row-major flatten).  Returns fp64 [nt, n]."""
+    n = z0.shape[0]
+    c_i = np.asarray(coefs, dtype=np.float64).reshape([library_terms(n, poly_order, sine_term), n]).T
+    n_q = n * (n + 1) // 2 if poly_order == 2 else 0
+
+    def dzdt(z, t):
+        parts = [z]
+        if poly_order == 2:
+            parts.append(np.array([z[i] * z[j] for i in range(n) for j in range(i, n)]))
+        if sine_term:
+            parts.append(np.sin(z))
+        return c_i[:, 1:] @ np.concatenate(parts) + c_i[:, 0]
+
+    assert c_i.shape[1] == 1 + n + n_q + (n if sine_term else 0)
+    return odeint(dzdt, z0, t_grid)
+
+
 def simulate_exact(coefs: np.ndarray, z0: np.ndarray, dt: float, nt: int) -> np.ndarray:
     """Independent fp64 cross-check of `simulate` for the affine ODE: exact propagator
     expm([[A, b], [0, 0]] * dt) applied step by step (not in the reference; used only to
@@ -176,6 +205,11 @@ def _activation(name: str):
         "ELU": torch.nn.functional.elu,
         "SiLU": torch.nn.functional.silu,
         "GELU": torch.nn.functional.gelu,
+        # the remaining parameter-free modules of act_dict, with the default arguments the reference constructs them with
+        "hardshrink": torch.nn.Hardshrink(), "hardsigmoid": torch.nn.Hardsigmoid(), "hardtanh": torch.nn.Hardtanh(),
+        "hardswish": torch.nn.Hardswish(), "leakyReLU": torch.nn.LeakyReLU(), "logsigmoid": torch.nn.LogSigmoid(),
+        "ReLU6": torch.nn.ReLU6(), "SELU": torch.nn.SELU(), "CELU": torch.nn.CELU(), "mish": torch.nn.Mish(),
+        "softshrink": torch.nn.Softshrink(), "tanhshrink": torch.nn.Tanhshrink(),
     }
     return table[name]
 

@@ -95,6 +95,66 @@ def gen_calibrate_grad():
     np.savez_compressed(os.path.join(HERE, "calibrate_grad.npz"), **out)
 
 
+def rankdef_series(kind: str, T: int = 129) -> np.ndarray:
+    """Latent series whose library matrix [1 | Z] is rank deficient the way an untrained / saturated encoder makes it."""
+    dt = 1.0 / (T - 1)
+    Z = synth.make_noisy_series(1, T, 5, dt, seed=21)[0].copy()
+    if kind == "const_col":
+        Z[:, 3] = 0.75                     # a constant latent column: collinear with the library's 1
+    elif kind == "collinear":
+        Z[:, 4] = 2.0 * Z[:, 1]            # two proportional latent columns
+    elif kind == "two_lost":
+        Z[:, 3] = -0.5; Z[:, 2] = Z[:, 0] - Z[:, 1]
+    elif kind == "near":
+        rs = np.random.RandomState(5)
+        Z[:, 4] = Z[:, 1] + 3.0e-6 * rs.normal(size=T).astype(np.float32)      # cond ~ 1e6 >> 1/rcond: truncated by gelsy
+    return np.ascontiguousarray(Z[None], dtype=np.float32)
+
+
+RANKDEF_KINDS = ["const_col", "collinear", "two_lost", "near"]
+
+
+def gen_calibrate_rankdef():
+    """The reference's own calibrate() (torch.linalg.lstsq = LAPACK sgelsy: rank-truncated minimum-norm answer,
+    sindy.py:72) and its autograd gradient on rank-deficient series.
+
+    torch's CPU lstsq is NOT reproducible on these inputs: repeated calls on the same tensor return different
+    solutions (three different losses in three calls were observed here; LAPACK's xGEQP3 treats non-zero entries of its
+    JPVT argument as columns to pin to the front, and the answers look like that array is handed over uninitialised).
+    The rule LAPACK documents -- JPVT zeroed, free pivoting -- is what scipy's sgelsy wrapper runs, deterministically.
+    The fixture therefore stores the reference run (calibrate + backward, repeated up to 200 times) whose coefficients
+    agree with scipy's sgelsy on the same fp32 matrices, together with the losses of the other answers that were seen."""
+    import scipy.linalg as sl
+    out = {}
+    for kind in RANKDEF_KINDS:
+        Zn = rankdef_series(kind)
+        T = Zn.shape[1]; dt = 1.0 / (T - 1)
+        ld = SINDy(5, T, {"sindy": {"fd_type": "sbp12", "coef_norm_order": 1}})
+        dz = ld.compute_time_derivative(torch.from_numpy(Zn[0]), dt).numpy()
+        X = np.concatenate([np.ones((T, 1), dtype=np.float32), Zn[0]], axis=1)
+        x_l, _, rank_l, _ = sl.lstsq(X, dz, cond=float(np.finfo(np.float32).eps) * max(X.shape), lapack_driver="gelsy")
+        seen = []
+        for attempt in range(200):
+            Z = torch.from_numpy(Zn).requires_grad_(True)
+            coefs, ls, lc = ld.calibrate(Z, dt, compute_loss=True, numpy=True)
+            seen.append(float(ls))
+            if np.max(np.abs(coefs.ravel() - x_l.ravel())) <= 1e-4 * np.max(np.abs(x_l)):
+                (GRAD_W[0] * ls + GRAD_W[1] * lc).backward()
+                break
+        else:
+            raise RuntimeError(f"{kind}: no reference run agreed with sgelsy in 200 attempts; losses seen {sorted(set(seen))}")
+        out[kind + "_Z"] = Zn
+        out[kind + "_coefs"] = coefs
+        out[kind + "_coefs_sgelsy"] = x_l.ravel(); out[kind + "_rank_sgelsy"] = np.array([rank_l])
+        out[kind + "_loss_sindy"] = np.array([float(ls)]); out[kind + "_loss_coef"] = np.array([float(lc)])
+        out[kind + "_grad"] = Z.grad.numpy().copy()
+        out[kind + "_losses_seen"] = np.array(sorted(set(seen)))
+        out[kind + "_sv"] = np.linalg.svd(X.astype(np.float64), compute_uv=False)
+        print(kind, "sgelsy rank", rank_l, "accepted after", attempt + 1, "runs; losses seen", sorted(set(seen)),
+              "grad finite", bool(np.isfinite(Z.grad.numpy()).all()))
+    np.savez_compressed(os.path.join(HERE, "calibrate_rankdef.npz"), **out)
+
+
 class _Phys:     # what initial_condition_latent reads (reference src/lasdi/physics/__init__.py:4-79)
     def __init__(self, nx):
         self.qgrid_size = [nx]
@@ -250,6 +310,7 @@ if __name__ == "__main__":
     gen_fd()
     gen_calibrate()
     gen_calibrate_grad()
+    gen_calibrate_rankdef()
     gen_encoder()
     gen_train()
     gen_gp()
