@@ -274,8 +274,9 @@ def test_calibration_rank_deficient_matches_reference_gelsy(engine, golden_dir, 
     produces): the reference's torch.linalg.lstsq (LAPACK gelsy, rcond = eps * max(m, n), sindy.py:72) returns the
     minimum-norm solution of the rank-truncated problem, and autograd the derivative of the pseudo-inverse.  Fixture =
     the reference's own calibrate() + backward on these series.  Tolerances: the kept directions are well conditioned
-    (cond ~ 15), so the usual 1e-5 on coefficients; the gradient is judged against the fp64 graph of the same function.  'near' (cond 5e5, an almost-proportional column) sits where gelsy's fp32 QR and the fp64 normal equations
-    may order the pivots differently: the truncated solutions then differ at the size of the discarded singular value."""
+    (cond ~ 15), so the usual 1e-5 on coefficients; the gradient is judged against the fp64 graph of the same
+    function.  'near' = an almost-proportional column (cond 5e5, far beyond 1/rcond): truncated by gelsy, and by this
+    kernel, exactly like the exactly singular cases."""
     g = np.load(os.path.join(golden_dir, "calibrate_rankdef.npz"))
     Z = g[kind + "_Z"]
     T = Z.shape[1]; dt = 1.0 / (T - 1)
