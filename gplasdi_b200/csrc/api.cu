@@ -50,7 +50,7 @@ static int ensure_screen_buffers(glasdi_handle* h, size_t P) {
     GL_CUDA(h, cudaMalloc(&h->d_groups, gcap * 16));
     h->group_cap = gcap;
   }
-  if (!h->d_cand_stats) GL_CUDA(h, cudaMalloc(&h->d_cand_stats, 4 * sizeof(unsigned int)));
+  if (!h->d_cand_stats) GL_CUDA(h, cudaMalloc(&h->d_cand_stats, 8 * sizeof(unsigned int)));
   if (P > h->exact_cap) {
     if (h->d_exact) cudaFree(h->d_exact);
     h->d_exact = nullptr;
@@ -70,6 +70,8 @@ static void free_decoder(Decoder& d) {
   d.w_packed = nullptr;
   if (d.v_packed) cudaFree(d.v_packed);
   d.v_packed = nullptr;
+  if (d.w4norm) cudaFree(d.w4norm);
+  d.w4norm = nullptr;
   if (d.wide_packed) cudaFree(d.wide_packed);
   d.wide_packed = nullptr;
   if (d.wide_front) cudaFree(d.wide_front);
@@ -239,6 +241,10 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
       if (value < 0 || value > 1024) return set_error(h, GLASDI_ERR_INVALID, "Taylor radius must be 0..1024 (units of 1/256)");
       h->opt_taylor_radius_q8 = value;
       return GLASDI_OK;
+    case GLASDI_OPT_SCREEN_BOUND:
+      if (value < 0 || value > 64) return set_error(h, GLASDI_ERR_INVALID, "screening bound must be 0..64 sigmas");
+      h->opt_screen_bound = value;
+      return GLASDI_OK;
     case GLASDI_OPT_SINDY_LIBRARY:
       if (library_terms(value, 1) < 0) return set_error(h, GLASDI_ERR_INVALID, "unknown SINDy library id");
       h->opt_library = value;
@@ -264,6 +270,7 @@ int glasdi_get_option(const glasdi_handle* h, int option, int* value) {
     case GLASDI_OPT_GRAM_KERNEL: *value = h->opt_gram_kernel; return GLASDI_OK;
     case GLASDI_OPT_TAYLOR_RADIUS: *value = h->opt_taylor_radius_q8; return GLASDI_OK;
     case GLASDI_OPT_SINDY_LIBRARY: *value = h->opt_library; return GLASDI_OK;
+    case GLASDI_OPT_SCREEN_BOUND: *value = h->opt_screen_bound; return GLASDI_OK;
     default: return GLASDI_ERR_INVALID;
   }
 }
@@ -418,15 +425,19 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
   const size_t a_off = (traj_bytes + field_bytes) * slab;
   const size_t a_bytes = gram ? gram_a_bytes(d.K, (long long)slab * T) : 0;
   const size_t fs_bytes = gram ? gram_fscale_bytes((long long)slab * T) : 0;
-  int rc = ensure_workspace(h, a_off + a_bytes + fs_bytes);
+  const bool bound = gram && h->opt_screen_bound > 0 && d.w4norm != nullptr;
+  int rc = ensure_workspace(h, a_off + a_bytes + fs_bytes * (bound ? 2 : 1));
   if (rc) return rc;
+  float* cnorm = bound ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->ws) + a_off + a_bytes + fs_bytes) : nullptr;
+  // sigmas * 1.15 * 2^-11: standard deviation of the fp16 rounding error of the quadratic form (refine.cu, select_rows_kernel)
+  const float beta = (float)h->opt_screen_bound * 1.15f * ldexpf(1.0f, -11);
   rc = ensure_maxvar(h, (size_t)P);
   if (rc) return rc;
   GL_CUDA(h, cudaMemsetAsync(h->d_maxvar, 0, (size_t)P * sizeof(unsigned int), st));
   if (screened) {
     if ((rc = ensure_screen_buffers(h, (size_t)P))) return rc;
     GL_CUDA(h, cudaMemsetAsync(h->d_exact, 0, (size_t)P * sizeof(unsigned int), st));
-    GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats, 0, 4 * sizeof(unsigned int), st));
+    GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats, 0, 8 * sizeof(unsigned int), st));
   }
   float* Zs = reinterpret_cast<float*>(h->ws);
   float* field = screened ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->ws) + traj_bytes * slab) : nullptr;
@@ -474,7 +485,12 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
       if ((rc = t_ref.start())) return rc;
       GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats, 0, sizeof(unsigned int), st));      // per-slab candidate count
       GL_CUDA(h, cudaMemsetAsync(h->d_cand_stats + 3, 0, sizeof(unsigned int), st));  // per-slab row-group count
-      rc = launch_select_candidates(h, field, field_ld, h->d_maxvar + p0, pn, T, d.D, (1.f - delta) * (1.f - delta), st);
+      if (bound && (rc = launch_gram_diag_norm(h, reinterpret_cast<uint8_t*>(h->ws) + a_off,
+                                               reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->ws) + a_off + a_bytes),
+                                               (long long)pn * T, cnorm, st)))
+        return rc;
+      rc = launch_select_candidates(h, field, field_ld, h->d_maxvar + p0, pn, T, d.D, (1.f - delta) * (1.f - delta), cnorm,
+                                    d.w4norm, beta, (1.f - 0.5f * delta) * (1.f - 0.5f * delta), st);
       if (rc) return rc;
       if (wide_screen) rc = launch_refine_wide(h, Zs, Spad, S, T, h->d_exact + p0, 0.25f * delta, st);
       else rc = launch_refine(h, Zs, Spad, S, T, h->d_exact + p0, 0.25f * delta,
@@ -604,6 +620,18 @@ int glasdi_screen_stats(glasdi_handle* h, double* refine_ms, double* quad_ms, in
   }
   if (n_candidates) *n_candidates = (int64_t)st[1];
   if (max_rel_dev) std::memcpy(max_rel_dev, &st[2], sizeof(float));
+  return GLASDI_OK;
+}
+
+int glasdi_screen_bound_count(glasdi_handle* h, int64_t* n_bound_candidates, void* stream) {
+  if (!h || !n_bound_candidates) return GLASDI_ERR_INVALID;
+  GL_CUDA(h, cudaSetDevice(h->device));
+  unsigned int v = 0;
+  if (h->d_cand_stats) {
+    GL_CUDA(h, cudaMemcpyAsync(&v, h->d_cand_stats + 4, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GL_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  }
+  *n_bound_candidates = (int64_t)v;
   return GLASDI_OK;
 }
 

@@ -41,6 +41,7 @@ struct Decoder {
   bool tc_ok = false;               // tcgen05 path supports this shape
   // covariance-form screening (decode_gram.cu): V[dof, (i<=j)] = (2 - delta_ij) w_i w_j 2^eV, fp16 UMMA tiles
   __half* v_packed = nullptr;
+  float* w4norm = nullptr;            // [ceil256(D)] |w_dof o w_dof|_2: per-dof factor of the a-priori screening bound
   int eV = 0;
   bool gram_ok = false;
   __half* wide_packed = nullptr;    // decode_wide.cu: [W_hi | W_hi | W_lo] tiles of the last layer (decoders with !tc_ok)
@@ -70,6 +71,7 @@ struct glasdi_handle {
   int opt_integrator = GLASDI_INT_EXPM;
   int opt_substeps = 1;
   int opt_library = GLASDI_LIB_POLY1;  // GLASDI_OPT_SINDY_LIBRARY
+  int opt_screen_bound = 6;            // GLASDI_OPT_SCREEN_BOUND: sigmas of the a-priori rounding-error bound (0 = off)
   int opt_max_ctas = 0;
   int opt_timing = 0;
   int opt_kernel = 1;                 // 0: one CTA per SM (decode_var.cu), 1: CTA pairs (decode_var2.cu)
@@ -147,8 +149,13 @@ int launch_decode_gram(glasdi_handle* h, const float* Zs, int Spad, int P, int S
 int launch_decode_quad(glasdi_handle* h, int P, int T, unsigned int* maxvar_bits, float* var_field, const void* a_ws,
                        const float* fscale_ws, cudaStream_t st);
 // refine.cu : candidate selection on the screened variance field + exact fp32/fp64 re-evaluation
+int launch_gram_diag_norm(glasdi_handle* h, const void* a_ws, const float* fscale_ws, long long n_items, float* cnorm,
+                          cudaStream_t st);
+// cnorm / w4norm / beta: a-priori rounding-error bound of the covariance-form screening (null / 0: off); keep2 = the
+// fraction of the screened maximum a (t, dof) must reach WITH its bound added to become a candidate as well
 int launch_select_candidates(glasdi_handle* h, const float* var_field, int field_ld, const unsigned int* approx_bits,
-                             int P, int T, int D, float keep, cudaStream_t st);
+                             int P, int T, int D, float keep, const float* cnorm, const float* w4norm, float beta,
+                             float keep2, cudaStream_t st);
 int launch_refine(glasdi_handle* h, const float* Zs, int Spad, int S, int T, unsigned int* exact_bits,
                   float dev_tol, float unscale, cudaStream_t st);
 int launch_decode_store_pair(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);

@@ -909,7 +909,45 @@ int gram_pack_v(glasdi_handle* h, const float* WL /*[D][K] host*/) {
   d.v_packed = nullptr;
   GL_CUDA(h, cudaMalloc(&d.v_packed, packed.size() * sizeof(__half)));
   GL_CUDA(h, cudaMemcpy(d.v_packed, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  // omega[dof] = |w_dof o w_dof|_2, the per-dof factor of the a-priori screening bound (refine.cu)
+  std::vector<float> w4((size_t)(D + 255) / 256 * 256, 0.f);
+  for (int dof = 0; dof < D; ++dof) {
+    double a = 0.0;
+    for (int i = 0; i < K; ++i) { const double w2 = (double)WL[(size_t)dof * K + i] * WL[(size_t)dof * K + i]; a += w2 * w2; }
+    w4[dof] = (float)std::sqrt(a);
+  }
+  if (d.w4norm) cudaFree(d.w4norm);
+  d.w4norm = nullptr;
+  GL_CUDA(h, cudaMalloc(&d.w4norm, w4.size() * sizeof(float)));
+  GL_CUDA(h, cudaMemcpy(d.w4norm, w4.data(), w4.size() * sizeof(float), cudaMemcpyHostToDevice));
   return GLASDI_OK;
+}
+
+// cnorm[item] = |diag C[item]|_2 in true units, from the packed covariances gram_kernel wrote: entry q(i, i) = i (i + 3) / 2
+// of the item's row, times fscale[item] 2^eV (the scale quad_kernel's accumulator carries on top of the covariance's).
+// Thread = item: a warp reads 32 neighbouring 16-byte groups per diagonal entry.
+__global__ void gram_diag_norm_kernel(const __half* __restrict__ A, const float* __restrict__ fscale, long long n_items,
+                                      int K, int nkgQ, float scale_v, float* __restrict__ cnorm) {
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_items) return;
+  const __half* base = A + ((size_t)(item >> 7) * nkgQ * 128 + (size_t)(item & 127)) * 8;
+  float acc = 0.f;
+  for (int i = 0; i < K; ++i) {
+    const int q = (i * (i + 3)) >> 1;
+    const float v = __half2float(base[(size_t)(q >> 3) * 128 * 8 + (q & 7)]);
+    acc = fmaf(v, v, acc);
+  }
+  cnorm[item] = sqrtf(acc) * fscale[item] * scale_v;
+}
+
+int launch_gram_diag_norm(glasdi_handle* h, const void* a_ws, const float* fscale_ws, long long n_items, float* cnorm,
+                          cudaStream_t st) {
+  const Decoder& d = h->dec;
+  const unsigned int blocks = (unsigned int)((n_items + 255) / 256);
+  gram_diag_norm_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(a_ws), fscale_ws, n_items, d.K,
+                                                gram_nkgQ(d.K), ldexpf(1.0f, d.eV), cnorm);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "gram_diag_norm_kernel launch");
 }
 
 namespace gr { struct GramParams; }

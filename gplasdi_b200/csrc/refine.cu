@@ -32,6 +32,9 @@ constexpr int kNC = 8;                // candidates a warp evaluates per pass ov
 __global__ void __launch_bounds__(kSelWarps * 32) select_rows_kernel(const float* __restrict__ field, int field_ld,
                                                                     const unsigned int* __restrict__ approx_bits,
                                                                     long long n_rows, int T, int D, float keep,
+                                                                    const float* __restrict__ cnorm,
+                                                                    const float* __restrict__ w4norm, float beta,
+                                                                    float keep2,
                                                                     Cand* __restrict__ cand, unsigned int cap,
                                                                     Group* __restrict__ groups, unsigned int gcap,
                                                                     unsigned int* __restrict__ stats,
@@ -43,14 +46,26 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_rows_kernel(const float
   const float vmax = __uint_as_float(approx_bits[p]);
   if (!(vmax > 0.f)) return;
   const float thr = vmax * keep;
+  // A-priori bound of the screening's rounding error (covariance form): the fp16 roundings of the covariance entries and of
+  // the products w_i w_j are independent, relative 2^-11 each, so the error of sigma^2 = sum_ij C_ij w_i w_j has a standard
+  // deviation <= 2^-11 * 1.15 * sum_i C_ii w_i^2 <= 2^-11 * 1.15 * |diag C|_2 |w o w|_2 (|C_ij| <= sqrt(C_ii C_jj), Cauchy-
+  // Schwarz).  A (t, dof) whose screened variance PLUS beta |diag C[p,t]|_2 |w_dof o w_dof|_2 (beta = the configured number
+  // of sigmas) reaches (1 - delta/2)^2 of the screened maximum is a candidate too: a dof whose quadratic form cancels badly
+  // (large weights nearly orthogonal to the covariance's dominant directions) is re-evaluated exactly instead of trusted.
+  const float brow = (cnorm != nullptr) ? beta * __ldg(cnorm + row) : 0.f;
+  const float thr2 = (cnorm != nullptr) ? vmax * keep2 : 3.0e38f;
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(w4norm);
+  auto is_cand = [&](float v, float om) { return v >= thr || fmaf(brow, om, v) >= thr2; };
   const float4* __restrict__ f4 = reinterpret_cast<const float4*>(field + (size_t)row * field_ld);
   const int n4 = field_ld / 4;                                      // field_ld is a multiple of 256
   // pass 1: count
   int mine = 0;
   for (int i4 = lane; i4 < n4; i4 += 32) {
     const float4 v = __ldg(f4 + i4);
+    const float4 om = (cnorm != nullptr) ? __ldg(w4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
     const int d0 = i4 * 4;
-    mine += (v.x >= thr && d0 < D) + (v.y >= thr && d0 + 1 < D) + (v.z >= thr && d0 + 2 < D) + (v.w >= thr && d0 + 3 < D);
+    mine += (is_cand(v.x, om.x) && d0 < D) + (is_cand(v.y, om.y) && d0 + 1 < D) + (is_cand(v.z, om.z) && d0 + 2 < D) +
+            (is_cand(v.w, om.w) && d0 + 3 < D);
   }
   int incl = mine;                                                  // inclusive prefix sum over the lanes
 #pragma unroll
@@ -79,10 +94,15 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_rows_kernel(const float
   unsigned int w = base + (unsigned int)(incl - mine);
   for (int i4 = lane; i4 < n4; i4 += 32) {
     const float4 v = __ldg(f4 + i4);
+    const float4 om = (cnorm != nullptr) ? __ldg(w4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float vv[4] = {v.x, v.y, v.z, v.w};
+    const float oo[4] = {om.x, om.y, om.z, om.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (vv[q] >= thr && i4 * 4 + q < D) cand[w++] = Cand{p, t, i4 * 4 + q, vv[q]};
+      if (is_cand(vv[q], oo[q]) && i4 * 4 + q < D) {
+        if (vv[q] < thr) atomicAdd(stats + 4, 1u);                  // admitted by the bound alone (diagnostic)
+        cand[w++] = Cand{p, t, i4 * 4 + q, vv[q]};
+      }
   }
 }
 
@@ -260,11 +280,14 @@ __global__ void __launch_bounds__(kRefWarps * 32, NC <= 2 ? 4 : 2) refine_kernel
 }  // namespace rf
 
 int launch_select_candidates(glasdi_handle* h, const float* var_field, int field_ld, const unsigned int* approx_bits,
-                             int P, int T, int D, float keep, cudaStream_t st) {
+                             int P, int T, int D, float keep, const float* cnorm, const float* w4norm, float beta,
+                             float keep2, cudaStream_t st) {
+  if (!cnorm || !w4norm || !(beta > 0.f)) { cnorm = nullptr; w4norm = nullptr; }
+  if (field_ld > ((D + 255) / 256) * 256) return set_error(h, GLASDI_ERR_INVALID, "select: field wider than the bound table");
   const long long n_rows = (long long)P * T;
   const unsigned int blocks = (unsigned int)((n_rows + rf::kSelWarps - 1) / rf::kSelWarps);
   rf::select_rows_kernel<<<blocks, rf::kSelWarps * 32, 0, st>>>(
-      var_field, field_ld, approx_bits, n_rows, T, D, keep, reinterpret_cast<rf::Cand*>(h->d_cand),
+      var_field, field_ld, approx_bits, n_rows, T, D, keep, cnorm, w4norm, beta, keep2, reinterpret_cast<rf::Cand*>(h->d_cand),
       (unsigned)h->cand_cap, reinterpret_cast<rf::Group*>(h->d_groups), (unsigned)h->group_cap, h->d_cand_stats,
       h->d_flags);
   h->launches++;

@@ -82,6 +82,13 @@ class Engine:
         self.last_quad_ms = qms.value
         return ms.value, n.value, dev.value
 
+    def screen_bound_count(self) -> int:
+        """(t, dof) of the last greedy call re-evaluated only because of the a-priori rounding-error bound."""
+        v = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_screen_bound_count(self.h, C.byref(v), _stream_ptr()))
+        return int(v.value)
+
     def check_numeric(self):
         with torch.cuda.device(self.device):
             self._check(self.lib.glasdi_check_numeric(self.h, _stream_ptr()))

@@ -83,6 +83,12 @@ enum glasdi_option {
                                    5th-order Taylor polynomial in da (no MUFU), exact form for sample blocks outside the radius;
                                    0: gram_kernel (round-1 producers).  Screening only: results are the exact re-evaluation's */
   GLASDI_OPT_TAYLOR_RADIUS = 10, /* radius of that polynomial: bound on |da| in units of 1/256 (default 256 = 1.0; 0 = never) */
+  GLASDI_OPT_SCREEN_BOUND = 12, /* covariance-form screening: number of standard deviations (default 6; 0 = off) of the A-PRIORI
+                                   bound on the fp16 rounding error of sigma^2 = sum_ij C_ij w_i w_j that is added to the
+                                   screened variance of every (t, dof): beta |diag C[p,t]|_2 |w_dof o w_dof|_2, beta =
+                                   sigmas * 1.15 * 2^-11.  A (t, dof) that reaches (1 - delta/2)^2 of its parameter's
+                                   screened maximum only WITH that bound is re-evaluated exactly as well: a dof whose
+                                   quadratic form cancels badly cannot be screened out unseen. */
   GLASDI_OPT_SINDY_LIBRARY = 11 /* enum glasdi_library (default POLY1 = the affine library of src/lasdi): which candidate
                                    functions the coefficient rows of glasdi_rollout / glasdi_greedy_step multiply */
 };
@@ -142,6 +148,10 @@ int glasdi_stage_times(glasdi_handle* h, double* rollout_ms, double* decode_ms, 
  * |std_screen - std_exact| / std_exact seen at them. */
 int glasdi_screen_stats(glasdi_handle* h, double* refine_ms, double* quad_ms, int64_t* n_candidates,
                         float* max_rel_dev, void* stream);
+
+/* Number of (t, dof) of the LAST greedy call that became candidates through the a-priori bound alone
+ * (GLASDI_OPT_SCREEN_BOUND); 0 for the other modes.  Synchronises `stream`. */
+int glasdi_screen_bound_count(glasdi_handle* h, int64_t* n_bound_candidates, void* stream);
 
 /* decoder weights ------------------------------------------------------------------------------
  * Replaces: the `autoencoder.decoder` nn.Module state consumed by get_fom_max_std

@@ -63,6 +63,8 @@ def setup_wl(engine, nm):
     engine.set_option(_lib.OPT_SCREEN_MARGIN, 8)
     engine.set_option(_lib.OPT_GRAM_KERNEL, 1)
     engine.set_option(_lib.OPT_TAYLOR_RADIUS, 256)
+    engine.set_option(_lib.OPT_SCREEN_BOUND, 6)
+    engine.set_library(1, False)
     return wl, Ws, bs
 
 
@@ -471,6 +473,86 @@ def test_screened_greedy_step_matches_reference(engine, g_small, nm, mode):
     assert engine.screen_stats()[1] >= ncand
     assert np.array_equal(ms6.cpu().numpy(), ms.cpu().numpy())
     engine.set_option(_lib.OPT_SCREEN_MARGIN, 8)
+
+
+def _oracle_small(wl, Ws, bs, inp):
+    Zis = orc.rollout_ensemble(inp["coefs"], inp["z0"].astype(np.float64), inp["t_grid"])
+    return orc.fom_max_std(Ws, bs, wl.act, Zis)
+
+
+def test_smooth_trained_like_decoder_matches_oracle(engine):
+    """A last layer that is SMOOTH in the dof index (what a decoder trained on a PDE field looks like: a few decaying
+    cosine modes), not Xavier noise: neighbouring dofs are near-ties, a row of the variance field holds dozens of
+    candidates, and the screened path must still return the oracle's values and index."""
+    wl, Ws, bs = setup_wl(engine, "small_s200")
+    rs = np.random.RandomState(5)
+    D, K = Ws[-1].shape
+    xg = np.linspace(0.0, 1.0, D)[:, None]
+    modes = np.arange(1, 13)[None, :]
+    basis = np.cos(np.pi * modes * xg) / modes
+    Ws[-1] = ((basis @ rs.normal(size=(12, K))) * 0.05).astype(np.float32)
+    engine.set_decoder(Ws, bs, wl.act)
+    inp = synth.make_inputs(wl)
+    ref_idx, ref_std = _oracle_small(wl, Ws, bs, inp)
+    ms, am, mv = engine.checked(lambda: engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt))
+    _, ncand, dev = engine.screen_stats()
+    print(f"[smooth decoder] {ncand} candidates ({ncand / wl.P:.1f} per parameter), max screening deviation {dev:.2e}, "
+          f"{engine.screen_bound_count()} admitted by the a-priori bound")
+    assert int(am) == ref_idx
+    std_close(ms.cpu().numpy(), ref_std)
+    assert ncand > 3 * wl.P                     # near-ties between neighbouring dofs: many candidates per parameter
+
+
+def test_adversarial_cancelling_row_is_caught_by_the_a_priori_bound(engine):
+    """A dof whose last-layer row is LARGE and nearly orthogonal to the dominant directions of the hidden layer's
+    covariance: sigma^2 = w^T C w is the small difference of large terms, so the fp16 screening (covariance entries and
+    products w_i w_j rounded to 11 bits) can place it anywhere.  The row is tuned so that its true std is the parameter's
+    maximum by a small margin.  The a-priori bound beta |diag C|_2 |w o w|_2 (GLASDI_OPT_SCREEN_BOUND) must admit it for
+    exact re-evaluation, and the result must be the oracle's; what the screening alone does with it is printed."""
+    wl, Ws, bs = setup_wl(engine, "small_s200")
+    inp = synth.make_inputs(wl)
+    P, S, T, n = wl.P, wl.S, wl.T, wl.n_z
+    Zis = orc.rollout_ensemble(inp["coefs"], inp["z0"].astype(np.float64), inp["t_grid"])
+    W0, b0 = Ws[0].astype(np.float64), bs[0].astype(np.float64)
+    H = 1.0 / (1.0 + np.exp(-(Zis @ W0.T + b0)))                       # [P, S, T, K]
+    _, base_std = orc.fom_max_std(Ws, bs, wl.act, Zis)
+    p_star = int(np.argmax(base_std)); t_star = T - 1
+    Hc = H[p_star, :, t_star, :] - H[p_star, :, t_star, :].mean(0)
+    C = Hc.T @ Hc / S
+    lam, V = np.linalg.eigh(C)
+    # the strongest eigen-direction plus a much larger component in the 60 weakest ones: sum_i w_i^2 C_ii ~ 50 x w^T C w,
+    # i.e. a screening error of ~3 % of the row's sigma^2 (2^-11 * 50 per sigma) against a candidate margin of 0.4 %, while
+    # the reference's own fp32 decode still resolves it (1e-7 * 50); then scaled until the row's std exceeds the maximum by 2 %
+    rs = np.random.RandomState(3)
+    weak = V[:, :60] @ rs.normal(size=60)
+    weak /= np.linalg.norm(weak)
+    cbar = np.trace(C) / C.shape[0]
+    w = V[:, -1] + np.sqrt(50.0 * lam[-1] / cbar) * weak
+    target = 1.02 * float(base_std[p_star])
+    w *= target / np.sqrt(w @ C @ w)
+    d_star = 17
+    Ws[-1] = Ws[-1].copy(); Ws[-1][d_star] = w.astype(np.float32)
+    cancel = float((w * w * np.diag(C)).sum() / (w @ C @ w))
+    engine.set_decoder(Ws, bs, wl.act)
+    ref_idx, ref_std = orc.fom_max_std(Ws, bs, wl.act, Zis)
+    assert ref_idx == p_star and ref_std[p_star] > 1.005 * base_std[p_star]      # the planted row IS the answer
+    out = {}
+    for sig in (0, 6):
+        engine.set_option(_lib.OPT_SCREEN_BOUND, sig)
+        ms, am, mv = engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt)
+        try:
+            engine.check_numeric(); flagged = False
+        except GlasdiError:
+            flagged = True
+        out[sig] = (ms.cpu().numpy(), int(am), flagged, engine.screen_stats()[1], engine.screen_bound_count())
+    print(f"[adversarial row] |w| = {np.abs(w).max():.1f}, sum_i w_i^2 C_ii / w^T C w = {cancel:.1f}; "
+          f"bound off: value {out[0][0][p_star]:.6e} (oracle {ref_std[p_star]:.6e}), flagged {out[0][2]}, {out[0][3]} candidates; "
+          f"bound on: value {out[6][0][p_star]:.6e}, {out[6][3]} candidates, {out[6][4]} admitted by the bound")
+    engine.set_option(_lib.OPT_SCREEN_BOUND, 6)
+    ms, am, mv = engine.checked(lambda: engine.greedy_step(inp["coefs"], inp["z0"], wl.T, wl.dt))
+    assert int(am) == ref_idx
+    std_close(ms.cpu().numpy(), ref_std)
+    assert out[6][4] >= 1 or out[0][1] == ref_idx      # either the bound admitted points, or the screening was fine anyway
 
 
 def test_screening_deviation_is_reported(engine):
