@@ -217,8 +217,8 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
       h->opt_timing = value ? 1 : 0;
       return GLASDI_OK;
     case GLASDI_OPT_DECODE_KERNEL:
-      if (value != 0 && value != 1) return set_error(h, GLASDI_ERR_INVALID, "decode kernel variant must be 0 or 1");
-      h->opt_kernel = value;
+      if (value != 1)
+        return set_error(h, GLASDI_ERR_INVALID, "decode kernel variant must be 1 (the one-CTA-per-SM kernel of round 1 was retired)");
       return GLASDI_OK;
     case GLASDI_OPT_MODE:
       if (value != GLASDI_MODE_DIRECT && value != GLASDI_MODE_SCREENED && value != GLASDI_MODE_SCREENED_GRAM)
@@ -263,7 +263,7 @@ int glasdi_get_option(const glasdi_handle* h, int option, int* value) {
     case GLASDI_OPT_RK4_SUBSTEPS: *value = h->opt_substeps; return GLASDI_OK;
     case GLASDI_OPT_MAX_CTAS: *value = h->opt_max_ctas; return GLASDI_OK;
     case GLASDI_OPT_STAGE_TIMING: *value = h->opt_timing; return GLASDI_OK;
-    case GLASDI_OPT_DECODE_KERNEL: *value = h->opt_kernel; return GLASDI_OK;
+    case GLASDI_OPT_DECODE_KERNEL: *value = 1; return GLASDI_OK;
     case GLASDI_OPT_MODE: *value = h->opt_mode; return GLASDI_OK;
     case GLASDI_OPT_SCREEN_MARGIN: *value = h->opt_margin_log2; return GLASDI_OK;
     case GLASDI_OPT_WIDE_TENSOR: *value = h->opt_wide; return GLASDI_OK;
@@ -413,7 +413,7 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
   // wide decoders (K_last > 112, decode_wide.cu): one fp16 screening pass of the K-looped GEMMs + the exact CUDA-core chain
   // at the candidates' rows, instead of three fp32-faithful split passes
   const bool wide_screen = !d.tc_ok && d.wide_packed != nullptr && h->opt_wide >= 1 && h->opt_mode != GLASDI_MODE_DIRECT;
-  const bool screened = gram || wide_screen || (h->opt_mode != GLASDI_MODE_DIRECT && d.tc_ok && h->opt_kernel == 1);
+  const bool screened = gram || wide_screen || (h->opt_mode != GLASDI_MODE_DIRECT && d.tc_ok);
   const int field_ld = wide_screen ? (d.D + 255) / 256 * 256 : decode_field_ld(d.n_tiles);
   const size_t traj_bytes = (size_t)T * n * Spad * sizeof(float);
   const size_t field_bytes = screened ? (size_t)T * field_ld * sizeof(float) : 0;
@@ -469,8 +469,7 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
                                       reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->ws) + a_off + a_bytes), st);
     else if (wide_screen) rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, field, field_ld, st);
     else if (screened) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, field, 1, st);
-    else if (d.tc_ok && h->opt_kernel == 1) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, nullptr, 0, st);
-    else if (d.tc_ok) rc = launch_decode_var(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, st);
+    else if (d.tc_ok) rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, nullptr, 0, st);
     else rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar + p0, nullptr, 0, st);
     if (rc) return rc;
     if ((rc = t_dec.stop())) return rc;
@@ -524,14 +523,16 @@ int glasdi_decode_stat_fields(glasdi_handle* h, const double* Zis, int P, int S,
   if (!h) return GLASDI_ERR_INVALID;
   const Decoder& d = h->dec;
   if (!d.ready) return set_error(h, GLASDI_ERR_NOT_READY, "decoder weights not set (glasdi_set_decoder)");
-  if (!d.tc_ok) return set_error(h, GLASDI_ERR_INVALID, "stat fields: decoder shape not supported by the tcgen05 kernel");
+  const bool wide = !d.tc_ok;
+  if (wide && (d.wide_packed == nullptr || h->opt_wide < 1))
+    return set_error(h, GLASDI_ERR_INVALID, "stat fields of a wide decoder need GLASDI_OPT_WIDE_TENSOR >= 1");
   if (!Zis || (!mean_out && !std_out)) return set_error(h, GLASDI_ERR_INVALID, "stat fields: null pointer");
   if (n != d.widths[0]) return set_error(h, GLASDI_ERR_INVALID, "latent dimension does not match the decoder");
   if (P <= 0 || S <= 0 || T <= 0) return set_error(h, GLASDI_ERR_INVALID, "empty ensemble");
   cudaStream_t st = (cudaStream_t)stream;
   GL_CUDA(h, cudaSetDevice(h->device));
   const int Spad = (S + 127) / 128 * 128;
-  const int field_ld = decode_field_ld(d.n_tiles);
+  const int field_ld = wide ? (d.D + 255) / 256 * 256 : decode_field_ld(d.n_tiles);
   const size_t traj_bytes = (size_t)T * n * Spad * sizeof(float);
   const size_t field_bytes = (size_t)T * field_ld * sizeof(float);
   const size_t rows_bytes = ((size_t)T * n * sizeof(float) + 255) / 256 * 256;
@@ -554,13 +555,19 @@ int glasdi_decode_stat_fields(glasdi_handle* h, const double* Zis, int P, int S,
     if ((rc = launch_zis_to_soa(h, Zis + (size_t)p0 * S * T * n, pn, S, T, n, Zs, Spad, st))) return rc;
     GL_CUDA(h, cudaMemsetAsync(h->d_maxvar, 0, (size_t)pn * sizeof(unsigned int), st));
     // three split passes: the fields are fp32-faithful (this is an output, not a screening pass)
-    if ((rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar, varf, 3, st, meanf))) return rc;
+    // wide decoders (K_last > 112): exact CUDA-core front layers, xact_kernel / xvar_kernel with three split passes and
+    // the field epilogue (variance and mean of x(s) - x(pilot) in true units)
+    if (wide) rc = launch_decode_var_simt(h, Zs, Spad, pn, S, T, h->d_maxvar, varf, field_ld, st, 3, meanf);
+    else rc = launch_decode_var_pair(h, Zs, Spad, pn, S, T, h->d_maxvar, varf, 3, st, meanf);
+    if (rc) return rc;
     float* mean_p = mean_out ? mean_out + (size_t)p0 * T * d.D : nullptr;
     if (mean_p) {
       if ((rc = launch_gather_pilot_rows(h, Zs, Spad, rows, n, zrows, st))) return rc;
-      if ((rc = launch_decode_store_pair(h, zrows, rows, mean_p, st))) return rc;     // decode(pilot), exact fp32
+      if (wide) rc = launch_decode_store_simt(h, zrows, rows, mean_p, st);
+      else rc = launch_decode_store_pair(h, zrows, rows, mean_p, st);                 // decode(pilot), exact fp32
+      if (rc) return rc;
     }
-    if ((rc = launch_finalize_fields(h, meanf, varf, field_ld, rows, d.D, d.eW + d.eH, mean_p,
+    if ((rc = launch_finalize_fields(h, meanf, varf, field_ld, rows, d.D, wide ? 0 : d.eW + d.eH, mean_p,
                                      std_out ? std_out + (size_t)p0 * T * d.D : nullptr, st)))
       return rc;
   }
@@ -573,8 +580,7 @@ int glasdi_decode(glasdi_handle* h, const float* Z, int64_t rows, float* X_out, 
   if (rows < 0 || (rows > 0 && (!Z || !X_out))) return set_error(h, GLASDI_ERR_INVALID, "decode: bad arguments");
   if (rows == 0) return GLASDI_OK;
   GL_CUDA(h, cudaSetDevice(h->device));
-  if (h->dec.tc_ok && h->opt_kernel == 1) return launch_decode_store_pair(h, Z, rows, X_out, (cudaStream_t)stream);
-  if (h->dec.tc_ok) return launch_decode_store(h, Z, rows, X_out, (cudaStream_t)stream);
+  if (h->dec.tc_ok) return launch_decode_store_pair(h, Z, rows, X_out, (cudaStream_t)stream);
   return launch_decode_store_simt(h, Z, rows, X_out, (cudaStream_t)stream);
 }
 

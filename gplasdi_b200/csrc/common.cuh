@@ -74,7 +74,6 @@ struct glasdi_handle {
   int opt_screen_bound = 6;            // GLASDI_OPT_SCREEN_BOUND: sigmas of the a-priori rounding-error bound (0 = off)
   int opt_max_ctas = 0;
   int opt_timing = 0;
-  int opt_kernel = 1;                 // 0: one CTA per SM (decode_var.cu), 1: CTA pairs (decode_var2.cu)
   int64_t launches = 0;
   // stage timing (GLASDI_OPT_STAGE_TIMING): event pairs of the last greedy call
   std::vector<cudaEvent_t> ev_pool;
@@ -125,10 +124,7 @@ int library_terms(int lib, int n);   // |Theta| of enum glasdi_library, -1 if un
 int launch_zis_to_soa(glasdi_handle* h, const double* Zis, int P, int S, int T, int n, float* Zs, int Spad,
                       cudaStream_t st);
 int launch_pad_columns(glasdi_handle* h, float* Zs, long long rows, int S, int Spad, cudaStream_t st);
-// decode_var.cu
-int launch_decode_var(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
-                      unsigned int* maxvar_bits, cudaStream_t st);
-int launch_decode_store(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
+// decode_var2.cu
 size_t decode_var_smem_bytes(int Kpad, int last_in_w);
 // decode_var2.cu : CTA-pair (cta_group::2) variant of the same kernel
 // var_field (optional): [P][T][decode_field_ld] scaled variance of every (t, dof); passes > 0 overrides the handle option
@@ -161,8 +157,11 @@ int launch_refine(glasdi_handle* h, const float* Zs, int Spad, int S, int T, uns
 int launch_decode_store_pair(glasdi_handle* h, const float* Z, int64_t rows, float* X, cudaStream_t st);
 // simt_fallback.cu : fp32 CUDA-core path for decoder shapes the tcgen05 kernel does not cover
 // field != nullptr: screening launch (ONE fp16 pass on the tensor cores, variance field [P * T][field_ld] in true units)
+// passes > 0 overrides the number of fp16 passes (3 + field = fp32-faithful FIELD output, exact activations); mean_field
+// (optional, same layout): mean over the samples of x(s) - x(pilot) in true units
 int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
-                           unsigned int* maxvar_bits, float* field, int field_ld, cudaStream_t st);
+                           unsigned int* maxvar_bits, float* field, int field_ld, cudaStream_t st, int passes = 0,
+                           float* mean_field = nullptr);
 // exact re-evaluation of the screened candidates of a wide decoder: fp32 CUDA-core chain + fp64 sample sums
 int launch_refine_wide(glasdi_handle* h, const float* Zs, int Spad, int S, int T, unsigned int* exact_bits, float dev_tol,
                        cudaStream_t st);
@@ -179,7 +178,8 @@ bool wide_pre_supported(const Decoder& d);
 int launch_wide_pre(glasdi_handle* h, const float* Zs, int Spad, long long g0, long long n_groups, int S, void* xt_ws,
                     cudaStream_t st);
 int launch_wide_last_var(glasdi_handle* h, const float* Hlast, long long g0, long long n_groups, int S, int T, void* bt_ws,
-                         unsigned int* maxvar_bits, int parts, float* field, int field_ld, cudaStream_t st);
+                         unsigned int* maxvar_bits, int parts, float* field, int field_ld, cudaStream_t st,
+                         float* mean_field = nullptr);
 // candidate records of the screened modes (refine.cu, simt_fallback.cu)
 namespace rf {
 struct Cand {

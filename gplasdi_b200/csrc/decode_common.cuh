@@ -1,5 +1,5 @@
-// decode_common.cuh -- pieces shared by the two tcgen05 decode kernels (decode_var.cu: one CTA per SM,
-// decode_var2.cu: CTA pairs with cta_group::2): parameters, shared-memory carve-up, front-MLP producers.
+// decode_common.cuh -- pieces shared by the tcgen05 decode kernels (decode_var2.cu: CTA pairs with cta_group::2;
+// decode_gram.cu, refine.cu): parameters, shared-memory carve-up, front-MLP producers.
 #pragma once
 #include "common.cuh"
 

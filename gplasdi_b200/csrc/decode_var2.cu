@@ -1,11 +1,14 @@
-// decode_var2.cu -- CTA-pair (cta_group::2) variant of the fused decode + variance kernel.
+// decode_var2.cu -- fused decode + variance kernel of the decoded-ensemble form (GLASDI_MODE_DIRECT / GLASDI_MODE_SCREENED,
+// glasdi_decode, glasdi_decode_stat_fields), on CTA pairs (cta_group::2).
 //
-// Same algorithm, numerics and roles as decode_var.cu (see there), but two CTAs on the two SMs of a
+// Warp-specialised: producers evaluate the front MLP and write the fp16 hi/lo split of the pilot-centred hidden activations
+// as the B operand, a loader streams the pre-packed last-layer tiles with bulk copies, one thread issues the MMAs, the
+// epilogue forms sum d / sum d^2 per dof from TMEM.  Two CTAs on the two SMs of a
 // TPC cooperate on every MMA: M = 256 (each CTA owns one 128-DOF tile: its A operand and its TMEM
 // accumulator rows) x N = 256 columns (each CTA produces and holds 128 of them: half of the B
 // operand), K = 16.  Per SM and per MMA this halves the shared-memory operand reads (64 B/clk
 // instead of the 128 B/clk = 100 % of the SMEM pipe that M=128 x N=128 needs) and the W-tile bytes
-// streamed per FLOP, which is what bounded the single-CTA kernel (profiles/).
+// streamed per FLOP, which is what bounded the one-CTA-per-SM kernel of round 1 (retired; profiles/r01_*).
 //
 // Cross-CTA protocol (rank 0 = leader issues every tcgen05.mma for the pair):
 //   h_full[2]    leader   count 16  <- producer warps of BOTH CTAs (remote mbarrier arrive, release.cluster)
@@ -499,6 +502,8 @@ decode_pair_kernel(const __grid_constant__ Params P) {
 }
 
 }  // namespace dv2
+
+size_t decode_var_smem_bytes(int Kpad, int last_in_w) { return dv::carve(Kpad, last_in_w).total; }
 
 static bool unbounded_act2(int act) {
   return !(act == GLASDI_ACT_SIGMOID || act == GLASDI_ACT_TANH || act == GLASDI_ACT_HARDSIGMOID || act == GLASDI_ACT_HARDTANH);

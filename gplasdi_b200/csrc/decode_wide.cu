@@ -42,6 +42,8 @@ struct WideParams {
                           // one-pass screening launch, [W_hi | W_hi | W_lo] of a three-pass one
   float* field;           // screening launch: [n_groups][field_ld] variance of every dof in true units (else null)
   int field_ld;
+  float* mean_field;      // optional, same layout: mean_s (x(s) - x(pilot)) in true units
+  float mean_unscale;
   float unscale;          // 2^(-2 (eW + eH)): scaled variance -> true units
 };
 
@@ -231,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) xvar_kernel(const __grid_constant
       const float mean = sum * inv_S;
       const float var = fmaxf(0.f, fmaf(-mean, mean, sq * inv_S)) * P.unscale;  // rows >= D have zero weights: var = 0
       if (P.field) P.field[(size_t)(P.g0 + g) * P.field_ld + dofb * 128 + warp * 32 + lane] = var;   // field_ld >= 128 n_dofb
+      if (P.mean_field) P.mean_field[(size_t)(P.g0 + g) * P.field_ld + dofb * 128 + warp * 32 + lane] = mean * P.mean_unscale;
       const float wm = warp_max(var);
       if (lane == 0 && wm > 0.f) atomicMax(P.maxvar_bits + (P.g0 + g) / P.T, __float_as_uint(wm));
     }
@@ -755,7 +758,8 @@ int launch_wide_pre(glasdi_handle* h, const float* Zs, int Spad, long long g0, l
 // Hlast fp32 [n_groups * S][K] (the exact CUDA-core chain's output for a slab of (p, t) groups) -> scaled variance maxima
 // (Hlast = nullptr: bt_ws already holds the packed hidden layer, written by launch_wide_front)
 int launch_wide_last_var(glasdi_handle* h, const float* Hlast, long long g0, long long n_groups, int S, int T, void* bt_ws,
-                         unsigned int* maxvar_bits, int parts, float* field, int field_ld, cudaStream_t st) {
+                         unsigned int* maxvar_bits, int parts, float* field, int field_ld, cudaStream_t st,
+                         float* mean_field) {
   const Decoder& d = h->dec;
   const int Kp = wide_kp(d.K);
   const int n_sb = (S + 255) / 256;
@@ -780,6 +784,8 @@ int launch_wide_last_var(glasdi_handle* h, const float* Hlast, long long g0, lon
   W.a_blk_kg = 3 * Kp / 8;
   W.field = field;
   W.field_ld = field_ld;
+  W.mean_field = mean_field;
+  W.mean_unscale = std::ldexp(1.0f, -(d.eW + d.eH));
   W.T = T;
   W.S = S;
   W.unscale = std::ldexp(1.0f, -2 * (d.eW + d.eH));

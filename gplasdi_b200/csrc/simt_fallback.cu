@@ -1,6 +1,6 @@
 // simt_fallback.cu -- fp32 CUDA-core decode path for decoder shapes the fused tcgen05 kernel does
 // not cover yet (last-layer input width > 112, e.g. the Vlasov / rising-bubble decoders with
-// K_last = 1000).  Same semantics as decode_var.cu (reference src/lasdi/gplasdi.py:52-74,
+// K_last = 1000).  Same semantics as decode_var2.cu (reference src/lasdi/gplasdi.py:52-74,
 // src/lasdi/latent_space.py:157-164), plain tiled SGEMMs with fused epilogues; it is a GPU path
 // (no CPU fallback exists), kept simple and exact in fp32, and is NOT the benchmarked kernel.
 #include "common.cuh"
@@ -453,7 +453,8 @@ static int run_chain(glasdi_handle* h, const float* X0, long long R, int upto_la
 }
 
 int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, int S, int T,
-                           unsigned int* maxvar_bits, float* field, int field_ld, cudaStream_t st) {
+                           unsigned int* maxvar_bits, float* field, int field_ld, cudaStream_t st, int passes,
+                           float* mean_field) {
   const Decoder& d = h->dec;
   const int n = d.widths[0];
   int maxw = n;
@@ -464,7 +465,8 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
   const bool wide = h->opt_wide && d.wide_packed != nullptr;        // last layer + variance on tcgen05 (decode_wide.cu)
   const bool wide_front = wide && h->opt_wide >= 2 && d.wide_front != nullptr;   // ... and the last front layer too (xact_kernel)
   if (field && !wide) return set_error(h, GLASDI_ERR_INVALID, "screening pass of a wide decoder needs GLASDI_OPT_WIDE_TENSOR >= 1");
-  const int parts = field ? 1 : 3;                                   // screening: one fp16 pass; direct: fp32-faithful split passes
+  const int parts = passes > 0 ? passes : (field ? 1 : 3);          // screening: one fp16 pass; direct / field output: fp32-faithful split passes
+  if (mean_field && !wide) return set_error(h, GLASDI_ERR_INVALID, "mean field of a wide decoder needs GLASDI_OPT_WIDE_TENSOR >= 1");
   const size_t xt_group = wide_front ? wide_x_bytes(d.wide_k1, S, 1, parts) : 0;
   const size_t bt_group = wide ? wide_b_bytes(d.K, S, 1, parts) + xt_group : 0;   // packed hidden layer (+ packed input) of one (p, t) group
   long long ng = std::max<long long>(
@@ -483,7 +485,7 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
     const long long gn = std::min(ng, groups - g0);
     const long long R = gn * S;
     const float* Hlast = nullptr;
-    if (wide_front && field && wide_pre_supported(d)) {
+    if (wide_front && field && parts == 1 && wide_pre_supported(d)) {
       // screening pass: narrow front layers fused (wide_pre_kernel), then both wide layers on tcgen05, one fp16 pass each
       void* xt_ws = reinterpret_cast<uint8_t*>(bt_ws) + wide_b_bytes(d.K, S, ng, parts);
       rc = launch_wide_pre(h, Zs, Spad, g0, gn, S, xt_ws, st);
@@ -503,13 +505,13 @@ int launch_decode_var_simt(glasdi_handle* h, const float* Zs, int Spad, int P, i
       if (rc) break;
       rc = launch_wide_front(h, Hlast, gn, S, xt_ws, bt_ws, parts, st);
       if (rc) break;
-      rc = launch_wide_last_var(h, nullptr, g0, gn, S, T, bt_ws, maxvar_bits, parts, field, field_ld, st);
+      rc = launch_wide_last_var(h, nullptr, g0, gn, S, T, bt_ws, maxvar_bits, parts, field, field_ld, st, mean_field);
       continue;
     }
     rc = run_chain(h, Xrow, R, d.n_linear - 1, bufA, bufB, &Hlast, st);
     if (rc) break;
     if (wide) {
-      rc = launch_wide_last_var(h, Hlast, g0, gn, S, T, bt_ws, maxvar_bits, parts, field, field_ld, st);
+      rc = launch_wide_last_var(h, Hlast, g0, gn, S, T, bt_ws, maxvar_bits, parts, field, field_ld, st, mean_field);
       continue;
     }
     if (d.K % 4 == 0 && d.K >= 32 && d.D >= 64 && S >= 64 && (reinterpret_cast<uintptr_t>(Hlast) & 15) == 0) {

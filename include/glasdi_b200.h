@@ -67,8 +67,8 @@ enum glasdi_option {
   GLASDI_OPT_INTEGRATOR = 1,    /* enum glasdi_integrator (default EXPM) */
   GLASDI_OPT_RK4_SUBSTEPS = 2,  /* default 1 */
   GLASDI_OPT_MAX_CTAS = 3,      /* cap on persistent CTAs (0 = one per SM); for tests */
-  GLASDI_OPT_DECODE_KERNEL = 5, /* 1 (default): CTA-pair tcgen05 kernel (cta_group::2, 256x256 tiles);
-                                   0: single-CTA kernel (128x128 tiles).  Same numerics. */
+  GLASDI_OPT_DECODE_KERNEL = 5, /* only 1 is accepted: the CTA-pair tcgen05 kernel (cta_group::2, 256x256 tiles); the
+                                   one-CTA-per-SM kernel of round 1 (value 0) was retired */
   GLASDI_OPT_STAGE_TIMING = 4,  /* 1: bracket the rollout and decode kernels of the greedy step with
                                    CUDA events on the caller's stream (read with glasdi_stage_times) */
   GLASDI_OPT_MODE = 6,          /* enum glasdi_mode (default SCREENED_GRAM) */
@@ -193,7 +193,8 @@ int glasdi_decode_max_std(glasdi_handle* h, const double* Zis, int P, int S, int
  * Replaces: `pred = autoencoder.decoder(torch.Tensor(Z)); pred.mean(0); pred.std(0)` of plot_prediction
  *   (src/lasdi/postprocess.py:32-34; examples/burgers1d.ipynb) for every parameter of Zis fp64 [P, S, T, n].
  * mean_out / std_out fp32 [P, T, D] (either may be NULL).  Three fp16 split passes on the tensor cores (fp32-faithful),
- * mean = decode(sample 0) + mean_s(x(s) - x(0)); the decoded ensemble is never written.  tcgen05-covered decoders only. */
+ * mean = decode(sample 0) + mean_s(x(s) - x(0)); the decoded ensemble is never written.  Wide decoders (last-layer input
+ * width > 112) take the K-looped GEMMs of decode_wide.cu with the same three passes and a field epilogue. */
 int glasdi_decode_stat_fields(glasdi_handle* h, const double* Zis, int P, int S, int T, int n, float* mean_out,
                               float* std_out, void* stream);
 

@@ -18,7 +18,6 @@ eng = Engine(0)
 eng.set_decoder(Ws, bs, wl.act)
 eng.set_option(_lib.OPT_SPLIT_PASSES, passes)
 eng.set_option(_lib.OPT_STAGE_TIMING, 1)
-eng.set_option(_lib.OPT_DECODE_KERNEL, variant)
 eng.set_option(_lib.OPT_MODE, mode)
 coefs = torch.from_numpy(inp["coefs"]).cuda(); z0 = torch.from_numpy(inp["z0"]).cuda()
 for _ in range(reps):
