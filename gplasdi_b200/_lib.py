@@ -19,7 +19,7 @@ ACT_IDS = {"sigmoid": 0, "tanh": 1, "softplus": 2, "ReLU": 3, "ELU": 4, "SiLU": 
            "ReLU6": 14, "SELU": 15, "CELU": 16, "mish": 17, "softshrink": 18, "tanhshrink": 19}
 FD_IDS = {"sbp12": 0, "sbp24": 1, "sbp36": 2, "sbp48": 3}
 OPT_SPLIT_PASSES, OPT_INTEGRATOR, OPT_RK4_SUBSTEPS, OPT_MAX_CTAS, OPT_STAGE_TIMING, OPT_DECODE_KERNEL = 0, 1, 2, 3, 4, 5
-OPT_MODE, OPT_SCREEN_MARGIN, OPT_WIDE_TENSOR, OPT_GRAM_KERNEL, OPT_TAYLOR_RADIUS, OPT_SINDY_LIBRARY, OPT_SCREEN_BOUND = 6, 7, 8, 9, 10, 11, 12
+OPT_MODE, OPT_SCREEN_MARGIN, OPT_WIDE_TENSOR, OPT_GRAM_KERNEL, OPT_TAYLOR_RADIUS, OPT_SINDY_LIBRARY, OPT_SCREEN_BOUND, OPT_MT_SEGMENT_LOG2 = 6, 7, 8, 9, 10, 11, 12, 13
 LIB_POLY1, LIB_POLY1_SINE, LIB_POLY2, LIB_POLY2_SINE = 0, 1, 2, 3
 MODE_DIRECT, MODE_SCREENED, MODE_SCREENED_GRAM = 0, 1, 2
 INT_EXPM, INT_RK4 = 0, 1

@@ -176,6 +176,8 @@ int glasdi_destroy(glasdi_handle* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->d_maxvar) cudaFree(h->d_maxvar);
   if (h->d_flags) cudaFree(h->d_flags);
+  if (h->d_mt_polys) cudaFree(h->d_mt_polys);
+  if (h->d_mt_pos) cudaFree(h->d_mt_pos);
   if (h->d_cand) cudaFree(h->d_cand);
   if (h->d_groups) cudaFree(h->d_groups);
   if (h->d_cand_stats) cudaFree(h->d_cand_stats);
@@ -241,6 +243,11 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
       if (value < 0 || value > 1024) return set_error(h, GLASDI_ERR_INVALID, "Taylor radius must be 0..1024 (units of 1/256)");
       h->opt_taylor_radius_q8 = value;
       return GLASDI_OK;
+    case GLASDI_OPT_MT_SEGMENT_LOG2:
+      if (value != 0 && (value < 11 || value > 24))
+        return set_error(h, GLASDI_ERR_INVALID, "MT19937 segment size must be 0 (one CTA) or 2^11..2^24 words");
+      h->opt_mt_seg_log2 = value;
+      return GLASDI_OK;
     case GLASDI_OPT_SCREEN_BOUND:
       if (value < 0 || value > 64) return set_error(h, GLASDI_ERR_INVALID, "screening bound must be 0..64 sigmas");
       h->opt_screen_bound = value;
@@ -271,6 +278,7 @@ int glasdi_get_option(const glasdi_handle* h, int option, int* value) {
     case GLASDI_OPT_TAYLOR_RADIUS: *value = h->opt_taylor_radius_q8; return GLASDI_OK;
     case GLASDI_OPT_SINDY_LIBRARY: *value = h->opt_library; return GLASDI_OK;
     case GLASDI_OPT_SCREEN_BOUND: *value = h->opt_screen_bound; return GLASDI_OK;
+    case GLASDI_OPT_MT_SEGMENT_LOG2: *value = h->opt_mt_seg_log2; return GLASDI_OK;
     default: return GLASDI_ERR_INVALID;
   }
 }

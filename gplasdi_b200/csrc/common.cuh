@@ -71,6 +71,10 @@ struct glasdi_handle {
   int opt_integrator = GLASDI_INT_EXPM;
   int opt_substeps = 1;
   int opt_library = GLASDI_LIB_POLY1;  // GLASDI_OPT_SINDY_LIBRARY
+  int opt_mt_seg_log2 = 18;            // GLASDI_OPT_MT_SEGMENT_LOG2: words per MT19937 stream segment (0: one CTA)
+  unsigned int* d_mt_polys = nullptr;  // [mt_poly_cap][624] jump polynomials t^(c 2^L) mod phi
+  unsigned short* d_mt_pos = nullptr;  // exponents of phi, then of mu
+  int mt_poly_cap = 0, mt_poly_count = 0, mt_poly_log2 = -1;
   int opt_screen_bound = 6;            // GLASDI_OPT_SCREEN_BOUND: sigmas of the a-priori rounding-error bound (0 = off)
   int opt_max_ctas = 0;
   int opt_timing = 0;

@@ -16,10 +16,12 @@
 //   (key block, position, cached gaussian) is reconstructed from the number of words consumed.
 //   Values agree with numpy to the last bit except for the rounding of log() (device libm vs glibc: <= 1 ulp).
 #include "common.cuh"
+#include "mt_jump_tables.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace glasdi {
 namespace gp {
@@ -91,22 +93,76 @@ __device__ __forceinline__ unsigned int mt_temper(unsigned int y) {
 //   v0 = X[m]       = X[m - 227] ^ T(m - 624)          m = m0 + t, t < 227
 //   v1 = X[m + 227] = v0 ^ T(m - 397)
 //   v2 = X[m + 454] = v1 ^ T(m - 170)                  t < 169
-// reading only words older than m0: 623 consecutive words per CTA barrier.  The kernel is bound by instruction issue
-// and the barrier round trip of ONE CTA, so the loop is kept minimal: a linear shared-memory window (all seven loads
-// and three stores at immediate offsets from one pointer) that slides back every 12 steps, no bounds tests (the
-// stream buffer is padded to whole steps), global stores straight from the registers.
-__global__ void __launch_bounds__(kMtThreads) mt_stream_kernel(const unsigned int* __restrict__ state,
-                                                               unsigned int* __restrict__ X, long long n_steps) {
-  __shared__ unsigned int win[kMtWin];
+// reading only words older than m0: 623 consecutive words per CTA barrier.  One CTA is bound by instruction issue and
+// the barrier round trip (4.5 words / ns), so the STREAM IS CUT INTO SEGMENTS of J = 2^L words that different CTAs
+// generate at the same time -- MT19937's jump-ahead:
+//   every bit sequence of the generator obeys the recurrence of its characteristic polynomial phi (degree 19937), hence
+//   with g_c(t) = t^(c J) mod phi the words c J places ahead are  X[i + c J] = XOR_{k : g_c[k] = 1} X[i + k]  (i >= 1; the
+//   low 31 bits of X[0] are not part of the 19937-bit state).
+// CTA c > 0 therefore (1) extends the key block to the first 21 183 words of the stream in shared memory (34 steps),
+// (2) forms its window X[c J + 1 .. c J + 625) as 624 GF(2) dot products with g_c (thread = word: ~10^4 shared-memory
+// loads + XORs each, uniform control flow), (3) streams words from there on with the chained recurrence, a linear
+// shared-memory window (all seven loads and three stores at immediate offsets from one pointer) that slides back every
+// 12 steps, no bounds tests, global stores straight from the registers.  A segment runs up to 622 words into the next
+// one: both CTAs write the same values.  The polynomials g_c come from mt_poly_kernel (once per handle and segment size).
+constexpr int kMtBaseSteps = 33;                                   // 624 + 33 * 623 = 21183 >= 19937 + 1 + 624 words
+constexpr int kMtBase = kMtN + kMtBaseSteps * kMtStep;
+static_assert(kMtBase >= 19937 + 1 + kMtN, "base sequence too short for the jump");
+constexpr int kMtSegThreads = 640;                                 // 624 of them own a window word in the jump
+
+__global__ void __launch_bounds__(kMtSegThreads) mt_stream_seg_kernel(const unsigned int* __restrict__ state,
+                                                                      const unsigned int* __restrict__ polys,
+                                                                      unsigned int* __restrict__ X, int seg_log2,
+                                                                      long long n_words) {
+  extern __shared__ unsigned int win[];                            // max(kMtBase, kMtWin) words
   const int tid = threadIdx.x;
-  for (int i = tid; i < kMtN; i += kMtThreads) {
-    const unsigned int v = state[i];
-    win[i] = v;
-    X[i] = v;
-  }
+  const long long c = blockIdx.x;
+  const long long J = 1ll << seg_log2;
+  for (int i = tid; i < kMtN; i += kMtSegThreads) win[i] = state[i];
   __syncthreads();
   const bool produce = tid < kMtLag, third = tid < kMtStep - 2 * kMtLag;
-  unsigned int* xg = X + kMtN + tid;
+  long long w0 = 0;                                                // global index of win[0]
+  if (c > 0) {
+    // (1) the head of the stream
+    {
+      unsigned int* p = win + kMtN + tid;
+      for (int b = 0; b < kMtBaseSteps; ++b) {
+        if (produce) {
+          const unsigned int v0 = p[-227] ^ mt_twist(p[-624], p[-623]);
+          const unsigned int v1 = v0 ^ mt_twist(p[-397], p[-396]);
+          p[0] = v0;
+          p[227] = v1;
+          if (third) p[454] = v1 ^ mt_twist(p[-170], p[-169]);
+        }
+        p += kMtStep;
+        __syncthreads();
+      }
+    }
+    // (2) window word i = X[c J + 1 + i] = XOR over the set bits k of g_c of X[k + 1 + i]
+    unsigned int acc = 0;
+    if (tid < kMtN) {
+      const unsigned int* __restrict__ g = polys + (size_t)c * kMtN;
+      const unsigned int* __restrict__ base = win + 1 + tid;
+      for (int wq = 0; wq < kMtN; ++wq) {
+        unsigned int pw = __ldg(g + wq);                           // uniform over the CTA
+        const unsigned int* __restrict__ bq = base + 32 * wq;
+        while (pw) {
+          const int b = __ffs(pw) - 1;
+          pw &= pw - 1;
+          acc ^= bq[b];
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < kMtN) win[tid] = acc;
+    __syncthreads();
+    w0 = c * J + 1;
+  }
+  // (3) stream: words [w0 + 624, end) with end = the next segment's first window word (or the end of the buffer)
+  const long long end = (c + 1 == gridDim.x) ? n_words : (c + 1) * J + 1;
+  for (int i = tid; i < kMtN; i += kMtSegThreads) X[w0 + i] = win[i];
+  const long long n_steps = (end - (w0 + kMtN) + kMtStep - 1) / kMtStep;
+  unsigned int* xg = X + w0 + kMtN + tid;
   long long step = 0;
   while (step < n_steps) {
     unsigned int* p = win + kMtN + tid;
@@ -131,20 +187,79 @@ __global__ void __launch_bounds__(kMtThreads) mt_stream_kernel(const unsigned in
     }
     step += burst;
     if (step < n_steps) {                              // slide: the last 624 words become the head of the window
-      unsigned int keep[3];
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int i = tid + u * kMtThreads;
-        keep[u] = i < kMtN ? win[burst * kMtStep + i] : 0u;
-      }
+      const int i = tid;
+      const unsigned int keep = i < kMtN ? win[burst * kMtStep + i] : 0u;
       __syncthreads();
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int i = tid + u * kMtThreads;
-        if (i < kMtN) win[i] = keep[u];
-      }
+      if (i < kMtN) win[i] = keep;
       __syncthreads();
     }
+  }
+}
+
+// g_c(t) = t^(c 2^L) mod phi for c = c0 + blockIdx.x, as (t^c)^(2^L): L squarings (bit spread) with a Barrett reduction
+// each.  phi and mu = floor(t^(2n) / phi) are SPARSE (135 and 161 terms, mt_jump_tables.h), so both products of the
+// reduction are a few hundred shifted XORs of a 312-word vector.  Polynomials as 64-bit words, thread = word.
+constexpr int kPolyN = 19937;
+constexpr int kPolyW = 312;                                        // 64-bit words of a reduced polynomial (19968 bits)
+constexpr int kPolyThreads = 640;                                  // >= 624 words of a square
+
+__device__ __forceinline__ unsigned long long spread32(unsigned int x) {
+  unsigned long long v = x;
+  v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+  v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+  v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+  v = (v | (v << 2)) & 0x3333333333333333ull;
+  v = (v | (v << 1)) & 0x5555555555555555ull;
+  return v;
+}
+
+// out[w] = (v * sum_j t^pos[j])[w] for a 312-word v stored at vpad[kPolyW .. 2 kPolyW) with zeros on both sides
+__device__ __forceinline__ unsigned long long sparse_mul_word(const unsigned long long* vpad, const unsigned short* __restrict__ pos,
+                                                              int npos, int w) {
+  unsigned long long acc = 0;
+  for (int j = 0; j < npos; ++j) {
+    const int ps = __ldg(pos + j);
+    const int idx = kPolyW + w - (ps >> 6), sh = ps & 63;
+    if (idx < 1) continue;                                        // entirely below the operand
+    const unsigned long long lo = vpad[idx], lo1 = vpad[idx - 1];
+    acc ^= sh ? ((lo << sh) | (lo1 >> (64 - sh))) : lo;
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kPolyThreads) mt_poly_kernel(int c0, int seg_log2, const unsigned short* __restrict__ phi_pos,
+                                                               int n_phi, const unsigned short* __restrict__ mu_pos, int n_mu,
+                                                               unsigned int* __restrict__ polys) {
+  __shared__ unsigned long long r[kPolyW];
+  __shared__ unsigned long long sq[2 * kPolyW + 2];
+  __shared__ unsigned long long m1[2 * kPolyW + 2];
+  __shared__ unsigned long long vpad[3 * kPolyW + 2];              // operand of the sparse products, zero padded
+  const int w = threadIdx.x;
+  const int c = c0 + blockIdx.x;
+  if (w < kPolyW) r[w] = (w == (c >> 6)) ? (1ull << (c & 63)) : 0ull;          // t^c, c < 19937
+  for (int i = w; i < 3 * kPolyW + 2; i += kPolyThreads) vpad[i] = 0ull;
+  if (w < 2) { sq[2 * kPolyW + w] = 0ull; m1[2 * kPolyW + w] = 0ull; }
+  __syncthreads();
+  constexpr int kWs = kPolyN >> 6, kBs = kPolyN & 63;              // 19937 = 311 * 64 + 33
+  for (int it = 0; it < seg_log2; ++it) {
+    if (w < 2 * kPolyW) sq[w] = spread32((unsigned int)(r[w >> 1] >> (32 * (w & 1))));
+    __syncthreads();
+    if (w < kPolyW) vpad[kPolyW + w] = (sq[w + kWs] >> kBs) | (sq[w + kWs + 1] << (64 - kBs));     // hi = sq >> n
+    __syncthreads();
+    if (w < 2 * kPolyW) m1[w] = sparse_mul_word(vpad, mu_pos, n_mu, w);                            // hi * mu
+    __syncthreads();
+    if (w < kPolyW) vpad[kPolyW + w] = (m1[w + kWs] >> kBs) | (m1[w + kWs + 1] << (64 - kBs));     // q = (hi mu) >> n
+    __syncthreads();
+    if (w < kPolyW) {
+      unsigned long long v = sq[w] ^ sparse_mul_word(vpad, phi_pos, n_phi, w);                     // sq - q phi, low n bits
+      if (w == kWs) v &= (1ull << kBs) - 1ull;
+      r[w] = v;
+    }
+    __syncthreads();
+  }
+  if (w < kPolyW) {
+    polys[(size_t)c * kMtN + 2 * w] = (unsigned int)r[w];
+    polys[(size_t)c * kMtN + 2 * w + 1] = (unsigned int)(r[w] >> 32);
   }
 }
 
@@ -336,6 +451,45 @@ int launch_gp_predict(glasdi_handle* h, const double* Xtr, int ntr, int d, int n
   return check_cuda(h, cudaGetLastError(), "gp_predict launch");
 }
 
+// g_c = t^(c 2^L) mod phi for c < n_seg, cached on the handle (recomputed when L changes or more segments are needed)
+static int ensure_mt_polys(glasdi_handle* h, int seg_log2, int n_seg, cudaStream_t st) {
+  if (!h->d_mt_pos) {
+    std::vector<unsigned short> pos(gp::kMtPhiPosCount + gp::kMtMuPosCount);
+    std::copy(gp::kMtPhiPos, gp::kMtPhiPos + gp::kMtPhiPosCount, pos.begin());
+    std::copy(gp::kMtMuPos, gp::kMtMuPos + gp::kMtMuPosCount, pos.begin() + gp::kMtPhiPosCount);
+    GL_CUDA(h, cudaMalloc(&h->d_mt_pos, pos.size() * sizeof(unsigned short)));
+    GL_CUDA(h, cudaMemcpy(h->d_mt_pos, pos.data(), pos.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+  }
+  if (h->mt_poly_log2 == seg_log2 && h->mt_poly_count >= n_seg) return GLASDI_OK;
+  const int want = std::max(n_seg, 160);
+  if (h->mt_poly_cap < want) {
+    GL_CUDA(h, cudaStreamSynchronize(st));
+    if (h->d_mt_polys) cudaFree(h->d_mt_polys);
+    h->d_mt_polys = nullptr;
+    h->mt_poly_cap = 0;
+    GL_CUDA(h, cudaMalloc(&h->d_mt_polys, (size_t)want * gp::kMtN * sizeof(unsigned int)));
+    h->mt_poly_cap = want;
+    h->mt_poly_count = 0;
+  }
+  if (h->mt_poly_log2 != seg_log2) h->mt_poly_count = 0;
+  const int c0 = h->mt_poly_count;
+  gp::mt_poly_kernel<<<want - c0, gp::kPolyThreads, 0, st>>>(c0, seg_log2, h->d_mt_pos, gp::kMtPhiPosCount,
+                                                            h->d_mt_pos + gp::kMtPhiPosCount, gp::kMtMuPosCount, h->d_mt_polys);
+  h->launches++;
+  int rc = check_cuda(h, cudaGetLastError(), "mt_poly_kernel launch");
+  if (rc) return rc;
+  if (seg_log2 == 18 && c0 <= 1) {                      // known answer of the squaring chain (tools/gen_mt_jump.py)
+    unsigned int chk[4];
+    GL_CUDA(h, cudaMemcpyAsync(chk, h->d_mt_polys + gp::kMtN, sizeof(chk), cudaMemcpyDeviceToHost, st));
+    GL_CUDA(h, cudaStreamSynchronize(st));
+    if (std::memcmp(chk, gp::kMtG18Check, sizeof(chk)) != 0)
+      return set_error(h, GLASDI_ERR_NUMERIC, "MT19937 jump polynomial self-check failed");
+  }
+  h->mt_poly_log2 = seg_log2;
+  h->mt_poly_count = want;
+  return GLASDI_OK;
+}
+
 int launch_normal_mt19937(glasdi_handle* h, glasdi_mt19937_state* state, const double* mean, const double* stdv, int P,
                           int S, int n, double* out, cudaStream_t st) {
   if (state->pos < 0 || state->pos > gp::kMtN)
@@ -352,7 +506,15 @@ int launch_normal_mt19937(glasdi_handle* h, glasdi_mt19937_state* state, const d
   const long long n_need = 2 * gp::kMtN + 4 * n_attempts + gp::kMtN;
   const long long n_steps = (n_need - gp::kMtN + gp::kMtStep - 1) / gp::kMtStep;
   const long long n_total = gp::kMtN + n_steps * gp::kMtStep;
-  const size_t bytes_x = ((size_t)n_total * sizeof(unsigned int) + 255) / 256 * 256;
+  // segments of 2^L words for mt_stream_seg_kernel; the polynomials t^(c 2^L), c < n_seg, need c < 19937: double L
+  // until at most 4096 segments are left (L = 0: one CTA generates the whole stream)
+  int seg_log2 = h->opt_mt_seg_log2;
+  long long n_seg = 1;
+  if (seg_log2 > 0) {
+    while (((n_total - 1) >> seg_log2) + 1 > 4096) ++seg_log2;
+    n_seg = std::max<long long>(1, ((n_total - 1) + (1ll << seg_log2) - 1) >> seg_log2);
+  }
+  const size_t bytes_x = ((size_t)(n_total + 2048) * sizeof(unsigned int) + 255) / 256 * 256;   // a segment runs < 623 words over
   const size_t bytes_cnt = ((size_t)n_blocks * sizeof(unsigned int) + 15) / 16 * 16;
   const size_t bytes_off = (size_t)(n_blocks + 1 + 4) * sizeof(unsigned long long);
   const size_t bytes_state = 640 * sizeof(unsigned int);
@@ -370,7 +532,17 @@ int launch_normal_mt19937(glasdi_handle* h, glasdi_mt19937_state* state, const d
   rc = check_cuda(h, cudaMemcpyAsync(dstate, state->key, gp::kMtN * sizeof(unsigned int), cudaMemcpyHostToDevice, st),
                       "normal_mt19937 state upload");
   if (rc == GLASDI_OK) {
-    gp::mt_stream_kernel<<<1, gp::kMtThreads, 0, st>>>(dstate, X, n_steps);
+    if (n_seg > 1) rc = ensure_mt_polys(h, seg_log2, (int)n_seg, st);
+  }
+  if (rc == GLASDI_OK) {
+    const size_t smem = (size_t)std::max(gp::kMtBase, gp::kMtWin) * sizeof(unsigned int);
+    rc = check_cuda(h, cudaFuncSetAttribute(gp::mt_stream_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "mt_stream_seg_kernel shared memory");
+    if (rc == GLASDI_OK)
+      gp::mt_stream_seg_kernel<<<(unsigned)n_seg, gp::kMtSegThreads, smem, st>>>(dstate, h->d_mt_polys, X, seg_log2 > 0 ? seg_log2 : 62,
+                                                                                n_total);
+  }
+  if (rc == GLASDI_OK) {
     gp::gauss_count_kernel<<<(unsigned)n_blocks, gp::kGsThreads, 0, st>>>(X, (long long)state->pos, n_attempts, counts);
     gp::scan_blocks_kernel<<<1, 1024, 0, st>>>(counts, n_blocks, offsets);
     gp::gauss_scatter_kernel<<<(unsigned)n_blocks, gp::kGsThreads, 0, st>>>(

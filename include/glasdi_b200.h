@@ -89,6 +89,10 @@ enum glasdi_option {
                                    sigmas * 1.15 * 2^-11.  A (t, dof) that reaches (1 - delta/2)^2 of its parameter's
                                    screened maximum only WITH that bound is re-evaluated exactly as well: a dof whose
                                    quadratic form cancels badly cannot be screened out unseen. */
+  GLASDI_OPT_MT_SEGMENT_LOG2 = 13, /* glasdi_normal_mt19937: the MT19937 word stream is cut into segments of 2^value words
+                                   (default 18; 11..24) that different CTAs generate at the same time, each from a state
+                                   reached by jump-ahead (t^(c 2^value) mod the generator's characteristic polynomial,
+                                   computed once per handle); 0 = the whole stream from one CTA.  Same bits either way. */
   GLASDI_OPT_SINDY_LIBRARY = 11 /* enum glasdi_library (default POLY1 = the affine library of src/lasdi): which candidate
                                    functions the coefficient rows of glasdi_rollout / glasdi_greedy_step multiply */
 };

@@ -367,6 +367,31 @@ def test_normal_draws_reproduce_numpy_legacy_stream(engine, case):
     np.testing.assert_allclose(np.random.normal(size=5), tail_ref, rtol=1e-13)    # the host stream continues in step
 
 
+@pytest.mark.parametrize("seg_log2,P,S,n", [(11, 40, 50, 30), (12, 7, 333, 5), (18, 441, 100, 30), (0, 40, 50, 30)])
+def test_normal_draws_segmented_stream_is_bit_identical(engine, seg_log2, P, S, n):
+    """The MT19937 word stream generated by many CTAs at once -- each from a state reached by jump-ahead with
+    t^(c 2^L) mod the generator's characteristic polynomial -- against numpy's sequential generator: same draws, same
+    final state.  L = 11 / 12: hundreds of short segments (every segment boundary, the overlap of a segment's tail with
+    its successor's window, the final state inside a late segment); L = 18: the default; L = 0: one CTA."""
+    rs = np.random.RandomState(7 + seg_log2)
+    mean = rs.normal(size=(P, n)); std = rs.uniform(0.1, 2.0, size=(P, n))
+    np.random.seed(4321 + seg_log2)
+    np.random.normal(size=3)
+    st0 = np.random.get_state()
+    ref = _numpy_draws(mean, std, S)
+    st_ref = np.random.get_state()
+    np.random.set_state(st0)
+    engine.set_option(_lib.OPT_MT_SEGMENT_LOG2, seg_log2)
+    try:
+        out, st_new = engine.normal_mt19937(mean, std, S)
+    finally:
+        engine.set_option(_lib.OPT_MT_SEGMENT_LOG2, 18)
+    out = out.cpu().numpy()
+    assert np.max(np.abs(out - ref)) <= 1e-14 * np.max(np.abs(ref))
+    assert np.array_equal(st_new[1], st_ref[1]) and st_new[2] == st_ref[2] and st_new[3] == st_ref[3]
+    assert abs(st_new[4] - st_ref[4]) <= 1e-14 * max(1.0, abs(st_ref[4]))
+
+
 def test_normal_draws_match_reference_sample_coefs(engine, golden_dir):
     """Fixture = the reference's own sample_coefs loop (gp.py:55-80) under np.random.seed(5)."""
     g = np.load(os.path.join(golden_dir, "gp_sampling.npz"))
