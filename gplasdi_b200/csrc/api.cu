@@ -232,7 +232,7 @@ int glasdi_set_option(glasdi_handle* h, int option, int value) {
       h->opt_margin_log2 = value;
       return GLASDI_OK;
     case GLASDI_OPT_WIDE_TENSOR:
-      if (value < 0 || value > 2) return set_error(h, GLASDI_ERR_INVALID, "wide-tensor option must be 0, 1 or 2");
+      if (value < 0 || value > 3) return set_error(h, GLASDI_ERR_INVALID, "wide-tensor option must be 0..3");
       h->opt_wide = value;
       return GLASDI_OK;
     case GLASDI_OPT_GRAM_KERNEL:

@@ -75,9 +75,12 @@ enum glasdi_option {
   GLASDI_OPT_SCREEN_MARGIN = 7, /* m in 4..16 (default 8): screened mode re-evaluates every (t, dof) whose
                                    single-pass std is within delta = 2^-m of the parameter's screened maximum */
   GLASDI_OPT_WIDE_TENSOR = 8,   /* decoders outside the fused tcgen05 kernels (last-layer input width > 112): 2 (default)
-                                   last front layer AND last layer + variance as three-pass fp16-split tcgen05 GEMMs
-                                   (decode_wide.cu), 1: only the last layer, 0: fp32 CUDA-core GEMMs throughout.  Earlier
-                                   front layers run on the CUDA cores in every case.  Same results (fp32-faithful). */
+                                   last front layer AND last layer + variance as tcgen05 GEMMs (decode_wide.cu: one fp16
+                                   screening pass in the screened modes, three fp16-split passes in the direct mode and
+                                   for field outputs), the narrow layers in front of them as a register-to-register
+                                   mma.sync chain with split operands (screening pass) or fp32 CUDA-core GEMMs (exact
+                                   passes); 3: as 2 with the screening pass's narrow layers on the CUDA cores; 1: only the
+                                   last layer on tcgen05; 0: fp32 CUDA-core GEMMs throughout.  Same results. */
   GLASDI_OPT_GRAM_KERNEL = 9,   /* covariance GEMM of decoders with ONE front layer and sigmoid / tanh / softplus: 1 (default)
                                    gram2_kernel -- thread = hidden unit, centred activations h(a_pilot + da) - h(a_pilot) from a
                                    5th-order Taylor polynomial in da (no MUFU), exact form for sample blocks outside the radius;
