@@ -247,5 +247,135 @@ __device__ __forceinline__ void last_front_units_regs(const float* __restrict__ 
 
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
+// ---- warp-level tensor-core MLP chain (mma.sync m16n8k16, fp16 split operands, fp32 accumulators) ----------------------
+// Shared by the screening pass of the wide decoders (decode_wide.cu, wide_pre_mma_kernel) and the generic producers of
+// gram_kernel (decode_gram.cu): a warp owns 16 samples; the accumulator fragment of two neighbouring n8 tiles of a layer
+// IS the A fragment of one k16 block of the next layer, so narrow front layers chain register to register.
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_h2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 hf = __half22float2(h);
+  hi = h2_as_u32(h);
+  lo = h2_as_u32(__floats2half2_rn(x - hf.x, y - hf.y));
+}
+
+constexpr int kPmMaxKb = kMaxHid / 16;              // k16 blocks of a narrow layer's input (<= 64 wide)
+__host__ __device__ inline int pm_in_pad(int w) { return (w + 15) / 16 * 16; }
+__host__ __device__ inline int pm_out_pad(int w, bool last) { return last ? (w + 7) / 8 * 8 : (w + 15) / 16 * 16; }
+__host__ __device__ inline size_t pm_layer_halfs(int wi, int wo, bool last) {
+  return 2 * (size_t)pm_out_pad(wo, last) * (pm_in_pad(wi) + 8);
+}
+// + biases (fp32) behind each layer's weights
+__host__ inline size_t pm_smem_bytes(const int* widths, int nf) {
+  size_t b = 0;
+  for (int l = 0; l < nf; ++l) {
+    b += pm_layer_halfs(widths[l], widths[l + 1], l == nf - 1) * sizeof(__half);
+    b = (b + 15) / 16 * 16;
+    b += (size_t)pm_out_pad(widths[l + 1], l == nf - 1) * sizeof(float);
+    b = (b + 15) / 16 * 16;
+  }
+  return b;
+}
+
+
+// Writes the image of layers 0 .. nf-1 at `base` (every thread of the calling group, stride nthreads; the caller
+// synchronises): per layer [hi | lo] fp16 weights [out_pad][in_pad + 8] + fp32 biases [out_pad].  `last_exact8`: the
+// last layer's outputs are padded to 8 (its tiles are written out), the others to 16 (they feed the next layer's k blocks).
+struct PmLayer { const __half* wh; const __half* wl; const float* bias; int nkb, op, ld, nt; };   // nt: n8 tiles with real units
+__device__ __forceinline__ void pm_stage(uint8_t* base, const FrontMlp& f, int nf, int tid, int nthreads, PmLayer* out) {
+  size_t off = 0;
+  for (int l = 0; l < nf; ++l) {
+    const bool last = l == nf - 1;
+    const int wi = f.widths[l], wo = f.widths[l + 1];
+    const int ip = pm_in_pad(wi), op = pm_out_pad(wo, last), ld = ip + 8;
+    __half* w = reinterpret_cast<__half*>(base + off);
+    for (int idx = tid; idx < op * ip; idx += nthreads) {
+      const int o = idx / ip, i = idx - o * ip;
+      const float v = (o < wo && i < wi) ? f.W[l][(size_t)o * wi + i] : 0.f;
+      const __half vh = __float2half_rn(v);
+      w[(size_t)o * ld + i] = vh;
+      w[(size_t)op * ld + (size_t)o * ld + i] = __float2half_rn(v - __half2float(vh));
+    }
+    off += pm_layer_halfs(wi, wo, last) * sizeof(__half);
+    off = (off + 15) / 16 * 16;
+    float* b = reinterpret_cast<float*>(base + off);
+    for (int o = tid; o < op; o += nthreads) b[o] = o < wo ? f.b[l][o] : 0.f;
+    out[l] = PmLayer{w, w + (size_t)op * ld, b, ip / 16, op, ld, (wo + 7) / 8};
+    off += (size_t)op * sizeof(float);
+    off = (off + 15) / 16 * 16;
+  }
+}
+// one n8 tile j of a layer for the warp's 16 samples: acc = bias + A W^T, three split MMAs per k block.  The number of k
+// blocks is a template argument behind a warp-uniform switch: a predicated-off HMMA still takes its issue slot (the first
+// version spent 55 % of its HMMA slots on them, profiles/r02_gram_generic_mma_*).
+template <int NKB>
+__device__ __forceinline__ void pm_tile_n(const PmLayer& Ly, int j, int g, int t, const uint32_t (&Ah)[kPmMaxKb][4],
+                                          const uint32_t (&Al)[kPmMaxKb][4], float (&acc)[4]) {
+  const float2 bb = *reinterpret_cast<const float2*>(Ly.bias + 8 * j + 2 * t);
+  acc[0] = bb.x; acc[1] = bb.y; acc[2] = bb.x; acc[3] = bb.y;
+  const __half* rh = Ly.wh + (size_t)(8 * j + g) * Ly.ld + 2 * t;
+  const __half* rl = Ly.wl + (size_t)(8 * j + g) * Ly.ld + 2 * t;
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb) {
+    const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(rh + 16 * kb), bh1 = *reinterpret_cast<const uint32_t*>(rh + 16 * kb + 8);
+    const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(rl + 16 * kb), bl1 = *reinterpret_cast<const uint32_t*>(rl + 16 * kb + 8);
+    mma16816(acc, Ah[kb], bh0, bh1);
+    mma16816(acc, Al[kb], bh0, bh1);
+    mma16816(acc, Ah[kb], bl0, bl1);
+  }
+}
+__device__ __forceinline__ void pm_tile(const PmLayer& Ly, int j, int g, int t, const uint32_t (&Ah)[kPmMaxKb][4],
+                                        const uint32_t (&Al)[kPmMaxKb][4], float (&acc)[4]) {
+  switch (Ly.nkb) {
+    case 1: pm_tile_n<1>(Ly, j, g, t, Ah, Al, acc); break;
+    case 2: pm_tile_n<2>(Ly, j, g, t, Ah, Al, acc); break;
+    case 3: pm_tile_n<3>(Ly, j, g, t, Ah, Al, acc); break;
+    default: pm_tile_n<4>(Ly, j, g, t, Ah, Al, acc); break;
+  }
+}
+// layers 0 .. n_layers-1 (none of them the written-out one): A fragments of layer 0 in, A fragments of layer n_layers out
+template <typename ActF>
+__device__ __forceinline__ void pm_chain(const PmLayer* Ly, int n_layers, int g, int t, uint32_t (&Ah)[kPmMaxKb][4],
+                                         uint32_t (&Al)[kPmMaxKb][4], ActF act) {
+  for (int l = 0; l < n_layers; ++l) {
+    uint32_t Nh[kPmMaxKb][4], Nl[kPmMaxKb][4];
+#pragma unroll
+    for (int jp = 0; jp < kPmMaxKb; ++jp) {
+      if (2 * jp < Ly[l].nt) {
+        float a0[4], a1[4] = {0.f, 0.f, 0.f, 0.f};
+        pm_tile(Ly[l], 2 * jp, g, t, Ah, Al, a0);
+        if (2 * jp + 1 < Ly[l].nt) pm_tile(Ly[l], 2 * jp + 1, g, t, Ah, Al, a1);     // else pure padding: next layer's weights are 0
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { a0[q] = act(a0[q]); a1[q] = act(a1[q]); }
+        split_h2(a0[0], a0[1], Nh[jp][0], Nl[jp][0]);      // row g,     k = 16 jp + 2t, + 1
+        split_h2(a0[2], a0[3], Nh[jp][1], Nl[jp][1]);      // row g + 8
+        split_h2(a1[0], a1[1], Nh[jp][2], Nl[jp][2]);      // row g,     k = 16 jp + 8 + 2t, + 1
+        split_h2(a1[2], a1[3], Nh[jp][3], Nl[jp][3]);      // row g + 8
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { Nh[jp][q] = 0u; Nl[jp][q] = 0u; }
+      }
+    }
+#pragma unroll
+    for (int kb = 0; kb < kPmMaxKb; ++kb)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { Ah[kb][q] = Nh[kb][q]; Al[kb][q] = Nl[kb][q]; }
+  }
+}
+// A fragments of layer 0 from the latent states of rows g and g + 8: this lane's components 2t, 2t + 1 (0 beyond n <= 8)
+__device__ __forceinline__ void pm_latent_frag(float zlo0, float zlo1, float zhi0, float zhi1, uint32_t (&Ah)[kPmMaxKb][4],
+                                               uint32_t (&Al)[kPmMaxKb][4]) {
+#pragma unroll
+  for (int kb = 0; kb < kPmMaxKb; ++kb)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { Ah[kb][q] = 0u; Al[kb][q] = 0u; }
+  split_h2(zlo0, zlo1, Ah[0][0], Al[0][0]);
+  split_h2(zhi0, zhi1, Ah[0][1], Al[0][1]);
+}
+
 }  // namespace dv
 }  // namespace glasdi

@@ -427,6 +427,87 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       // global-memory weight loads; the four threads of a column repeat the 900 FMAs of [5,20,20,20] rather than share them
       const bool regs_path = INW == 0 && n_pre > 0 && xw <= kNarrowW && NZ <= kMaxLatent &&
                              (size_t)n_pre * kNarrowLayerFloats * 4 <= (size_t)(kRing * kA1Bytes + 4u * 2048u);
+      // Deep narrow fronts on the TENSOR CORES (warp-level mma.sync chain, decode_common.cuh): a warp owns 16 sample
+      // columns of the chunk and half of the last front layer's unit groups; the narrow layers chain register to
+      // register with split fp16 operands (fp32-faithful), the pilot goes through the same arithmetic (16 copies of
+      // sample 0), and (act(.) - pilot) 2^eH lands in the operand tile as 4-byte stores.  The per-thread CUDA-core
+      // version below ran the Burgers2D-shaped item in 333 k clocks, 15x its FMA bound.
+      bool mma_path = INW == 0 && n_pre > 0 && NZ <= kMaxLatent && pm_out_pad(P.K, true) / 8 <= P.nkg;
+      {
+        size_t need = 0;
+        for (int l = 0; l < P.front.n_front; ++l) {
+          const bool last = l == P.front.n_front - 1;
+          if (P.front.widths[l] > kMaxHid) mma_path = false;
+          need += (pm_layer_halfs(P.front.widths[l], P.front.widths[l + 1], last) * 2 + 15) / 16 * 16;
+          need += ((size_t)pm_out_pad(P.front.widths[l + 1], last) * 4 + 15) / 16 * 16;
+        }
+        if (need > (size_t)(L.wl - L.xb)) mma_path = false;
+      }
+      if (mma_path) {
+        const int nf = P.front.n_front;
+        PmLayer Ly[kMaxLinear];
+        pm_stage(smem + L.xb, P.front, nf, ptid, kGProdThreads, Ly);
+        asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");
+        const int pw = ptid >> 5;                            // producer warp 0..15
+        const int mt = pw & 7, half = pw >> 3;               // m16 tile of the chunk, half of the unit groups
+        const int g = lane >> 2, t = lane & 3;
+        const int ntl = Ly[nf - 1].op / 8;                   // n8 tiles the last front layer really has (units < K)
+        const int j_begin = half ? (P.nkg + 1) / 2 : 0, j_end = half ? P.nkg : (P.nkg + 1) / 2;
+        const int act_rt = P.front.act;
+        auto act = [&](float x) { return act_apply_t<ACT>(act_rt, x); };
+        const int k0 = 2 * t, k1 = 2 * t + 1;
+        uint32_t Ah[kPmMaxKb][4], Al[kPmMaxKb][4];
+        for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+          const float* __restrict__ zb = P.Zs + (size_t)item * NZ * P.Spad;
+          if (pw == 0) {
+            // pilot table: the chain on 16 copies of sample 0; row 0 (lanes 0..3) holds units 8 j + 2 t, + 1
+            const float zp0 = k0 < NZ ? __ldg(zb + (size_t)k0 * P.Spad) : 0.f, zp1 = k1 < NZ ? __ldg(zb + (size_t)k1 * P.Spad) : 0.f;
+            pm_latent_frag(zp0, zp1, zp0, zp1, Ah, Al);
+            pm_chain(Ly, nf - 1, g, t, Ah, Al, act);
+            for (int j = 0; j < P.nkg; ++j) {
+              float acc[4] = {0.f, 0.f, 0.f, 0.f};
+              if (j < ntl) pm_tile(Ly[nf - 1], j, g, t, Ah, Al, acc);
+              if (g == 0) {
+                sPilot[8 * j + k0] = (8 * j + k0 < P.K) ? act(acc[0]) * hscale : 0.f;
+                sPilot[8 * j + k1] = (8 * j + k1 < P.K) ? act(acc[1]) * hscale : 0.f;
+              }
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
+          for (int c = 0; c < nchunks; ++c) {
+            const int col_lo = mt * 16 + g, col_hi = col_lo + 8;
+            const int s_lo = c * kCols + col_lo, s_hi = s_lo + 8;
+            const int sl = s_lo < P.S ? s_lo : 0, sh = s_hi < P.S ? s_hi : 0;
+            pm_latent_frag(k0 < NZ ? __ldg(zb + (size_t)k0 * P.Spad + sl) : 0.f, k1 < NZ ? __ldg(zb + (size_t)k1 * P.Spad + sl) : 0.f,
+                           k0 < NZ ? __ldg(zb + (size_t)k0 * P.Spad + sh) : 0.f, k1 < NZ ? __ldg(zb + (size_t)k1 * P.Spad + sh) : 0.f,
+                           Ah, Al);
+            pm_chain(Ly, nf - 1, g, t, Ah, Al, act);
+            const uint32_t buf = h_it % kRing;
+            uint8_t* Hb = sH + buf * kBufBytes;
+            mbar_wait_relaxed(&B->h_empty[buf], ((h_it / kRing) & 1u) ^ 1u);
+            for (int j = j_begin; j < j_end; ++j) {
+              float acc[4] = {0.f, 0.f, 0.f, 0.f};
+              if (j < ntl) pm_tile(Ly[nf - 1], j, g, t, Ah, Al, acc);
+              const float2 pv = *reinterpret_cast<const float2*>(sPilot + 8 * j + k0);
+              const int k = 8 * j + k0;
+              float v0 = fmaf(act(acc[0]), hscale, -pv.x), v1 = fmaf(act(acc[1]), hscale, -pv.y);
+              float v2 = fmaf(act(acc[2]), hscale, -pv.x), v3 = fmaf(act(acc[3]), hscale, -pv.y);
+              if (k >= P.K) { v0 = (k == P.K) ? 1.0f : 0.f; v2 = v0; }            // the constant unit, then padding
+              if (k + 1 >= P.K) { v1 = (k + 1 == P.K) ? 1.0f : 0.f; v3 = v1; }
+              if (s_lo >= P.S) { v0 = 0.f; v1 = 0.f; }
+              if (s_hi >= P.S) { v2 = 0.f; v3 = 0.f; }
+              if (P.check_overflow) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3))));
+              *reinterpret_cast<uint32_t*>(Hb + h_offset(j, col_lo) + 4 * t) = h2_as_u32(__floats2half2_rn(v0, v1));
+              *reinterpret_cast<uint32_t*>(Hb + h_offset(j, col_hi) + 4 * t) = h2_as_u32(__floats2half2_rn(v2, v3));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&B->h_full[buf]);
+            ++h_it;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item
+        }
+      } else {
       if (regs_path) {
         narrow_layers_stage(xbuf, P.front, n_pre, ptid, kGProdThreads);
         asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");
@@ -522,6 +603,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item
       }
+      }   // !mma_path
     }
     if (P.check_overflow && !(amax < 60000.f)) atomicOr(P.flags, 1);
   } else {

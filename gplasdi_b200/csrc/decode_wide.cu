@@ -620,72 +620,20 @@ __global__ void __launch_bounds__(256) wide_pre_kernel(const __grid_constant__ P
 // the legacy HMMA path is idle while the CTA-wide GEMM kernels are not running.
 // Shared-memory weight image per layer: [hi | lo][out, padded to 8][in, padded to 16, row stride = in_pad + 8 halfs]:
 // a B fragment (k = 2t, 2t + 1 | 2t + 8, 2t + 9 of column n = g) is two conflict-free 4-byte loads.
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void split_h2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(x, y);
-  const float2 hf = __half22float2(h);
-  hi = dv::h2_as_u32(h);
-  lo = dv::h2_as_u32(__floats2half2_rn(x - hf.x, y - hf.y));
-}
-
-constexpr int kPmMaxKb = dv::kMaxHid / 16;              // k16 blocks of a narrow layer's input (<= 64 wide)
-__host__ __device__ inline int pm_in_pad(int w) { return (w + 15) / 16 * 16; }
-__host__ __device__ inline int pm_out_pad(int w, bool last) { return last ? (w + 7) / 8 * 8 : (w + 15) / 16 * 16; }
-__host__ __device__ inline size_t pm_layer_halfs(int wi, int wo, bool last) {
-  return 2 * (size_t)pm_out_pad(wo, last) * (pm_in_pad(wi) + 8);
-}
-// + biases (fp32) behind each layer's weights
-__host__ inline size_t pm_smem_bytes(const int* widths, int nf) {
-  size_t b = 0;
-  for (int l = 0; l < nf; ++l) {
-    b += pm_layer_halfs(widths[l], widths[l + 1], l == nf - 1) * sizeof(__half);
-    b = (b + 15) / 16 * 16;
-    b += (size_t)pm_out_pad(widths[l + 1], l == nf - 1) * sizeof(float);
-    b = (b + 15) / 16 * 16;
-  }
-  return b;
-}
-
 constexpr int kPmThreads = 512;
 
 template <int ACT>      // compile-time activation (bare MUFU forms); < 0: runtime switch
 __global__ void __launch_bounds__(kPmThreads, 1) wide_pre_mma_kernel(const __grid_constant__ PreParams P) {
   extern __shared__ __align__(16) uint8_t pmsm[];
   const int nf = P.f.n_front;
-  const __half* sW[kMaxLinear];
-  const float* sB[kMaxLinear];
-  {
-    size_t off = 0;
-    for (int l = 0; l < nf; ++l) {
-      const bool last = l == nf - 1;
-      const int wi = P.f.widths[l], wo = P.f.widths[l + 1];
-      const int ip = pm_in_pad(wi), op = pm_out_pad(wo, last), ld = ip + 8;
-      __half* w = reinterpret_cast<__half*>(pmsm + off);
-      sW[l] = w;
-      for (int idx = threadIdx.x; idx < op * ip; idx += blockDim.x) {
-        const int o = idx / ip, i = idx - o * ip;
-        const float v = (o < wo && i < wi) ? P.f.W[l][(size_t)o * wi + i] : 0.f;
-        const __half vh = __float2half_rn(v);
-        w[(size_t)o * ld + i] = vh;
-        w[(size_t)op * ld + (size_t)o * ld + i] = __float2half_rn(v - __half2float(vh));
-      }
-      off += pm_layer_halfs(wi, wo, last) * sizeof(__half);
-      off = (off + 15) / 16 * 16;
-      float* b = reinterpret_cast<float*>(pmsm + off);
-      sB[l] = b;
-      for (int o = threadIdx.x; o < op; o += blockDim.x) b[o] = o < wo ? P.f.b[l][o] : 0.f;
-      off += (size_t)op * sizeof(float);
-      off = (off + 15) / 16 * 16;
-    }
-  }
+  dv::PmLayer Ly[kMaxLinear];
+  dv::pm_stage(pmsm, P.f, nf, threadIdx.x, blockDim.x, Ly);
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int n = P.f.widths[0];
   const int nkg = P.K1p / 8;
+  const int act_rt = P.f.act;
+  auto act = [&](float x) { return act_mufu<ACT>(x, act_rt); };
   float amax = 0.f, nanacc = 0.f;
   const long long n_tiles = (long long)P.n_groups * P.n_sb * 16;          // m16 tiles: 16 per 256-sample block
   const long long warp0 = (long long)blockIdx.x * (kPmThreads / 32) + (threadIdx.x >> 5);
@@ -698,90 +646,36 @@ __global__ void __launch_bounds__(kPmThreads, 1) wide_pre_mma_kernel(const __gri
     const int s_lo = sb * 256 + col0 + g, s_hi = s_lo + 8;
     __half* xt = P.Xt + (((size_t)grp * P.n_sb + sb) * nkg) * 256 * 8;
     // A fragments of the first layer: the latent state (k < n <= 8), rows g and g + 8; padding samples read sample 0
-    uint32_t Ah[kPmMaxKb][4], Al[kPmMaxKb][4];
-#pragma unroll
-    for (int kb = 0; kb < kPmMaxKb; ++kb)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { Ah[kb][q] = 0u; Al[kb][q] = 0u; }
+    uint32_t Ah[dv::kPmMaxKb][4], Al[dv::kPmMaxKb][4];
     {
       const float* __restrict__ zb = P.Zs + ((P.g0 + grp) * n) * P.Spad;
       const int sl = s_lo < P.S ? s_lo : 0, sh = s_hi < P.S ? s_hi : 0;
       const int k0 = 2 * t, k1 = 2 * t + 1;
-      const float z00 = k0 < n ? __ldg(zb + (size_t)k0 * P.Spad + sl) : 0.f, z01 = k1 < n ? __ldg(zb + (size_t)k1 * P.Spad + sl) : 0.f;
-      const float z10 = k0 < n ? __ldg(zb + (size_t)k0 * P.Spad + sh) : 0.f, z11 = k1 < n ? __ldg(zb + (size_t)k1 * P.Spad + sh) : 0.f;
-      split_h2(z00, z01, Ah[0][0], Al[0][0]);
-      split_h2(z10, z11, Ah[0][1], Al[0][1]);
+      dv::pm_latent_frag(k0 < n ? __ldg(zb + (size_t)k0 * P.Spad + sl) : 0.f, k1 < n ? __ldg(zb + (size_t)k1 * P.Spad + sl) : 0.f,
+                         k0 < n ? __ldg(zb + (size_t)k0 * P.Spad + sh) : 0.f, k1 < n ? __ldg(zb + (size_t)k1 * P.Spad + sh) : 0.f,
+                         Ah, Al);
     }
-    for (int l = 0; l < nf; ++l) {
-      const bool last = l == nf - 1;
-      const int wi = P.f.widths[l], wo = P.f.widths[l + 1];
-      const int ip = pm_in_pad(wi), op = pm_out_pad(wo, last), ld = ip + 8;
-      const int nkb = ip / 16;
-      const __half* __restrict__ wh = sW[l];
-      const __half* __restrict__ wl = wh + (size_t)op * ld;
-      const float* __restrict__ bias = sB[l];
-      // one n8 tile: acc = bias + A W^T (three split MMAs per k block)
-      auto tile_acc = [&](int j, float (&acc)[4]) {
-        const float2 bb = *reinterpret_cast<const float2*>(bias + 8 * j + 2 * t);
-        acc[0] = bb.x; acc[1] = bb.y; acc[2] = bb.x; acc[3] = bb.y;
-        const __half* rh = wh + (size_t)(8 * j + g) * ld + 2 * t;
-        const __half* rl = wl + (size_t)(8 * j + g) * ld + 2 * t;
-#pragma unroll
-        for (int kb = 0; kb < kPmMaxKb; ++kb) {
-          if (kb < nkb) {
-            const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(rh + 16 * kb), bh1 = *reinterpret_cast<const uint32_t*>(rh + 16 * kb + 8);
-            const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(rl + 16 * kb), bl1 = *reinterpret_cast<const uint32_t*>(rl + 16 * kb + 8);
-            mma16816(acc, Ah[kb], bh0, bh1);
-            mma16816(acc, Al[kb], bh0, bh1);
-            mma16816(acc, Ah[kb], bl0, bl1);
-          }
-        }
-      };
-      if (!last) {
-        uint32_t Nh[kPmMaxKb][4], Nl[kPmMaxKb][4];
-#pragma unroll
-        for (int jp = 0; jp < kPmMaxKb; ++jp) {
-          if (jp * 16 < op) {
-            float a0[4], a1[4];
-            tile_acc(2 * jp, a0);
-            tile_acc(2 * jp + 1, a1);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { a0[q] = act_mufu<ACT>(a0[q], P.f.act); a1[q] = act_mufu<ACT>(a1[q], P.f.act); }
-            split_h2(a0[0], a0[1], Nh[jp][0], Nl[jp][0]);      // row g,     k = 16 jp + 2t, + 1
-            split_h2(a0[2], a0[3], Nh[jp][1], Nl[jp][1]);      // row g + 8
-            split_h2(a1[0], a1[1], Nh[jp][2], Nl[jp][2]);      // row g,     k = 16 jp + 8 + 2t, + 1
-            split_h2(a1[2], a1[3], Nh[jp][3], Nl[jp][3]);      // row g + 8
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { Nh[jp][q] = 0u; Nl[jp][q] = 0u; }
-          }
-        }
-#pragma unroll
-        for (int kb = 0; kb < kPmMaxKb; ++kb)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) { Ah[kb][q] = Nh[kb][q]; Al[kb][q] = Nl[kb][q]; }
-      } else {
-        // the layer that feeds xact_kernel: (act(.) 2^eX) as fp16 into the B' tiles [kg][256 columns][8]
-        for (int j = 0; j < nkg; ++j) {
-          uint32_t o_lo = 0u, o_hi = 0u;
-          if (8 * j < op) {
-            float acc[4];
-            tile_acc(j, acc);
-            const int k = 8 * j + 2 * t;
-            const float v0 = (k < P.K1 && s_lo < P.S) ? act_mufu<ACT>(acc[0], P.f.act) * P.scale : 0.f;
-            const float v1 = (k + 1 < P.K1 && s_lo < P.S) ? act_mufu<ACT>(acc[1], P.f.act) * P.scale : 0.f;
-            const float v2 = (k < P.K1 && s_hi < P.S) ? act_mufu<ACT>(acc[2], P.f.act) * P.scale : 0.f;
-            const float v3 = (k + 1 < P.K1 && s_hi < P.S) ? act_mufu<ACT>(acc[3], P.f.act) * P.scale : 0.f;
-            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3))));
-            nanacc = fmaf((v0 + v1) + (v2 + v3), 0.f, nanacc);
-            o_lo = dv::h2_as_u32(__floats2half2_rn(v0, v1));
-            o_hi = dv::h2_as_u32(__floats2half2_rn(v2, v3));
-          }
-          uint32_t* dst = reinterpret_cast<uint32_t*>(xt + ((size_t)j * 256 + col0 + g) * 8 + 2 * t);
-          dst[0] = o_lo;
-          dst[8 * 8 / 2] = o_hi;                               // column + 8: 8 columns x 16 bytes further
-        }
+    dv::pm_chain(Ly, nf - 1, g, t, Ah, Al, act);
+    // the layer that feeds xact_kernel: (act(.) 2^eX) as fp16 into the B' tiles [kg][256 columns][8]
+    const dv::PmLayer& LL = Ly[nf - 1];
+    for (int j = 0; j < nkg; ++j) {
+      uint32_t o_lo = 0u, o_hi = 0u;
+      if (8 * j < LL.op) {
+        float acc[4];
+        dv::pm_tile(LL, j, g, t, Ah, Al, acc);
+        const int k = 8 * j + 2 * t;
+        const float v0 = (k < P.K1 && s_lo < P.S) ? act(acc[0]) * P.scale : 0.f;
+        const float v1 = (k + 1 < P.K1 && s_lo < P.S) ? act(acc[1]) * P.scale : 0.f;
+        const float v2 = (k < P.K1 && s_hi < P.S) ? act(acc[2]) * P.scale : 0.f;
+        const float v3 = (k + 1 < P.K1 && s_hi < P.S) ? act(acc[3]) * P.scale : 0.f;
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3))));
+        nanacc = fmaf((v0 + v1) + (v2 + v3), 0.f, nanacc);
+        o_lo = dv::h2_as_u32(__floats2half2_rn(v0, v1));
+        o_hi = dv::h2_as_u32(__floats2half2_rn(v2, v3));
       }
+      uint32_t* dst = reinterpret_cast<uint32_t*>(xt + ((size_t)j * 256 + col0 + g) * 8 + 2 * t);
+      dst[0] = o_lo;
+      dst[8 * 8 / 2] = o_hi;                               // column + 8: 8 columns x 16 bytes further
     }
   }
   if (!(amax <= 65000.f) || nanacc != 0.f) atomicOr(P.flags + 0, 1);
@@ -925,7 +819,7 @@ int launch_wide_pre(glasdi_handle* h, const float* Zs, int Spad, long long g0, l
   P.K1p = wide_kp(d.wide_k1);
   P.scale = std::ldexp(1.0f, d.eH);
   if (h->opt_wide != 3) {                                 // default: the pre-chain on mma.sync (3 = the CUDA-core version)
-    const size_t smem_mma = wd::pm_smem_bytes(P.f.widths, nf);
+    const size_t smem_mma = dv::pm_smem_bytes(P.f.widths, nf);
     if (smem_mma <= 200 * 1024) {
       const long long n_tiles = n_groups * P.n_sb * 16;
       const unsigned int blocks =
