@@ -447,18 +447,18 @@ def run_ours(args):
 
 def measured_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from this round's `ncu --set full` capture of
-    this same command (profiles/r02_gram_kernel_traffic.json, written by tools/ncu_summary.py).  The capture records the
+    this same command (profiles/r02_gram2_kernel_traffic.json, written by tools/ncu_summary.py).  The capture records the
     sha1 of the kernel's source file: a capture of an older kernel reads as null, never as a stale number."""
     import hashlib
-    path = os.path.join(ROOT, "profiles", "r02_gram_kernel_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_gram2_kernel_traffic.json")
     if not os.path.exists(path):
         return None, None
     try:
         d = json.load(open(path))
-        src = os.path.join(ROOT, "gplasdi_b200", "csrc", "decode_gram.cu")
+        src = os.path.join(ROOT, "gplasdi_b200", "csrc", "decode_gram2.cu")
         if d.get("source_sha1") != hashlib.sha1(open(src, "rb").read()).hexdigest():
-            return None, "profiles/r02_gram_kernel_traffic.json is of an older decode_gram.cu: ignored"
-        return float(d["dram_bytes_per_launch"]), "profiles/r02_gram_kernel_traffic.json (" + d.get("how", "ncu --set full") + ")"
+            return None, "profiles/r02_gram2_kernel_traffic.json is of an older decode_gram2.cu: ignored"
+        return float(d["dram_bytes_per_launch"]), "profiles/r02_gram2_kernel_traffic.json (" + d.get("how", "ncu --set full") + ")"
     except Exception:
         return None, None
 
@@ -512,10 +512,10 @@ def time_named_shape(eng, nm, blk, nsteps, world, rank, dev, sampler, barrier, m
                        f"T={wl.T}, D={wl.D}, decoder {wl.widths} {wl.act}",
            "params_timed": Pb, "first_param": first, "shard_bounds": bnd, "n_gpus": world, "steps": nsteps, "ms_per_step": sec * 1e3,
            "timed_ms_total": total, "rollouts_per_s": Pb * wl.S / sec, "seconds_per_full_grid_at_this_rate": sec * wl.P / Pb,
-           "issued_tensor_tflops": (a + b) / sec / 1e12, "frac": (a + b) / sec / 1e12 / peak,
-           "algorithmic_tflops": alg / sec / 1e12, "frac_algorithmic": alg / sec / 1e12 / peak, "peak": peak,
+           "issued_tensor_tflops": (a + b) / sec / 1e12, "frac": (a + b) / sec / 1e12 / peak / world,
+           "algorithmic_tflops": alg / sec / 1e12, "frac_algorithmic": alg / sec / 1e12 / peak / world, "peak": peak,
            "frac_definition": "frac = tensor FLOP the kernels issue (padding and split passes included) / whole-step device time / "
-                              "peak; frac_algorithmic = 2*sum(L_i L_i+1) decoder FLOP per rollout and time step / the same time / peak",
+                              "(peak x n_gpus); frac_algorithmic = 2*sum(L_i L_i+1) decoder FLOP per rollout and time step / the same time / peak",
            "path": path, "selected_global_index": idx, "max_std": val, "gpu_launches": int(eng.launch_count - l0),
            "clocks": sampler.window(t0, t1) if sampler is not None else None}
     del coefs, z0
