@@ -53,6 +53,10 @@ SIGNATURES = {
     "glasdi_pack_maxloc": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "glasdi_fd_dzdt": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp]),
     "glasdi_sindy_fit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp]),
+    "glasdi_mlp_forward_train": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_vp), _i, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "glasdi_mlp_backward": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_vp), _i, _vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(_vp),
+                                 C.POINTER(_vp), _vp]),
+    "glasdi_mse_loss_grad": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "glasdi_sindy_fit_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _i, _vp, _vp]),
 }
 

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.environ.get("GLASDI_LIBDIR") or os.path.join(HERE, "lib")   # GLASDI_LIBDIR: a second (instrumented) build beside the product
 LIB = os.path.join(LIBDIR, "libglasdi_b200.so")
-SOURCES = ["api.cu", "rollout.cu", "decode_var2.cu", "decode_gram.cu", "decode_gram2.cu", "simt_fallback.cu", "refine.cu", "reduce.cu", "calibrate.cu", "gp.cu", "decode_wide.cu"]
+SOURCES = ["api.cu", "rollout.cu", "decode_var2.cu", "decode_gram.cu", "decode_gram2.cu", "simt_fallback.cu", "refine.cu", "reduce.cu", "calibrate.cu", "gp.cu", "decode_wide.cu", "train_mlp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -411,6 +411,55 @@ class Engine:
                 out.data_ptr(), _stream_ptr()))
         return out
 
+    # ---- training-mode MLP + reconstruction loss ---------------------------------------------
+    @staticmethod
+    def _ptr_array(tensors):
+        arr = (C.c_void_p * len(tensors))()
+        for i, t in enumerate(tensors):
+            arr[i] = t.data_ptr()
+        return arr
+
+    def mlp_forward_train(self, x, weights, biases, act: str):
+        """x [rows, w0] fp32 CUDA; weights / biases: the module's own CUDA parameters.  -> (y, pre, post)."""
+        rows = x.shape[0]
+        widths = [weights[0].shape[1]] + [w.shape[0] for w in weights]
+        nl = len(weights)
+        hid = sum(widths[1:nl])
+        pre = torch.empty((max(1, rows * hid),), dtype=torch.float32, device=self.tdev)
+        post = torch.empty_like(pre)
+        y = torch.empty((rows, widths[-1]), dtype=torch.float32, device=self.tdev)
+        wid = (C.c_int * (nl + 1))(*widths)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_mlp_forward_train(self.h, nl, wid, self._ptr_array(weights), self._ptr_array(biases),
+                                                          _lib.ACT_IDS[act], x.data_ptr(), rows, pre.data_ptr(),
+                                                          post.data_ptr(), y.data_ptr(), _stream_ptr()))
+        return y, pre, post
+
+    def mlp_backward(self, x, weights, act: str, pre, post, dy, need_dx: bool):
+        rows = x.shape[0]
+        widths = [weights[0].shape[1]] + [w.shape[0] for w in weights]
+        nl = len(weights)
+        dW = [torch.empty_like(w) for w in weights]
+        db = [torch.empty((w.shape[0],), dtype=torch.float32, device=self.tdev) for w in weights]
+        dx = torch.empty_like(x) if need_dx else None
+        wid = (C.c_int * (nl + 1))(*widths)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_mlp_backward(self.h, nl, wid, self._ptr_array(weights), _lib.ACT_IDS[act], x.data_ptr(),
+                                                     pre.data_ptr(), post.data_ptr(), dy.data_ptr(), rows,
+                                                     None if dx is None else dx.data_ptr(), self._ptr_array(dW),
+                                                     self._ptr_array(db), _stream_ptr()))
+        return dx, dW, db
+
+    def mse_loss_grad(self, a, b, want_grad: bool = True):
+        """-> (loss fp32 [1] = mean((a - b)^2), grad = 2 (a - b) / n or None); one pass over the data."""
+        n = a.numel()
+        loss = torch.empty(1, dtype=torch.float32, device=self.tdev)
+        grad = torch.empty_like(a) if want_grad else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_mse_loss_grad(self.h, a.data_ptr(), b.data_ptr(), n, loss.data_ptr(),
+                                                      None if grad is None else grad.data_ptr(), _stream_ptr()))
+        return loss, grad
+
 
 _DEFAULT = {}
 

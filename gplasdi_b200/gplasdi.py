@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from .gp import eval_gp, eval_gp_device, fit_gps, sample_coefs, sample_coefs_all, sample_coefs_all_device
-from .latent_space import initial_condition_latent
+from .latent_space import initial_condition_latent, mse_loss
 from .engine import default_engine
 from . import sharding
 
@@ -115,7 +115,9 @@ class BayesianGLaSDI:
         """One training leg (reference gplasdi.py:150-238): `n_iter` Adam steps on
         loss = MSE(X, decoder(encoder(X))) + ld_weight * loss_sindy / n_train + coef_weight * loss_coef / n_train,
         best-loss checkpoint + `best_coefs`.  The encoder/decoder passes that record an autograd graph are torch ops
-        (cuBLAS); the SINDy calibration and its two losses are this package's CUDA kernels with an analytic backward
+        (cuBLAS) ONLY on the host; on the GPU the autoencoder's forward / backward and the reconstruction loss are this
+        package's kernels too (glasdi_mlp_forward_train / glasdi_mlp_backward / glasdi_mse_loss_grad, one autograd node per
+        network); the SINDy calibration and its two losses are this package's CUDA kernels with an analytic backward
         (`glasdi_sindy_fit` / `glasdi_sindy_fit_backward`), so the latent series never leaves the GPU -- the
         reference moves Z to the host every iteration (gplasdi.py:183) and differentiates through `lstsq` there."""
         import os
@@ -129,7 +131,6 @@ class BayesianGLaSDI:
         ckpt = os.path.join(self.path_checkpoint, "checkpoint.pt")
         n_train = self.param_space.n_train()
         ld = self.latent_dynamics
-        mse = torch.nn.MSELoss()
         _optimizer_to(self.optimizer, dev)
         self.training_loss, self.ae_loss, self.ld_loss, self.coef_loss = [], [], [], []      # per leg (reference :166-169)
 
@@ -142,7 +143,7 @@ class BayesianGLaSDI:
             self.optimizer.zero_grad()
             Z = ae.encoder(X)
             X_pred = ae.decoder(Z)
-            loss_ae = mse(X, X_pred)
+            loss_ae = mse_loss(X_pred, X)          # loss + gradient in one kernel pass (glasdi_mse_loss_grad)
             coefs, loss_ld, loss_coef = ld.calibrate(Z, self.physics.dt, compute_loss=True, numpy=True)
             loss = loss_ae + self.ld_weight * loss_ld / n_train + self.coef_weight * loss_coef / n_train
             # one device->host read per iteration for the four histories and the best-loss test

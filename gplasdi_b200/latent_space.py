@@ -31,6 +31,52 @@ act_dict = {
 }
 
 
+class _MlpTrain(torch.autograd.Function):
+    """Training-mode MLP on the CUDA kernels: one autograd node instead of the per-layer graph torch records through
+    MultiLayerPerceptron.forward (reference latent_space.py:157-164).  Saves the hidden layers' pre- and post-activations."""
+
+    @staticmethod
+    def forward(ctx, x, engine, act, n_linear, *params):
+        weights = [p.detach().contiguous() for p in params[:n_linear]]
+        biases = [p.detach().contiguous() for p in params[n_linear:]]
+        xc = x.detach().contiguous()
+        y, pre, post = engine.mlp_forward_train(xc, weights, biases, act)
+        ctx.save_for_backward(xc, pre, post, *weights)
+        ctx.engine, ctx.act, ctx.n_linear = engine, act, n_linear
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, pre, post, *weights = ctx.saved_tensors
+        dx, dW, db = ctx.engine.mlp_backward(xc, weights, ctx.act, pre, post, gy.contiguous(), ctx.needs_input_grad[0])
+        return (dx, None, None, None, *dW, *db)
+
+
+class _MseLoss(torch.autograd.Function):
+    """`MSELoss()(a, b)` with the loss and its gradient produced by ONE pass of glasdi_mse_loss_grad (the 'fused AE MSE' of
+    SURVEY 8f rank 3); differentiable in its first argument (the reconstruction)."""
+
+    @staticmethod
+    def forward(ctx, a, b, engine):
+        loss, grad = engine.mse_loss_grad(a.detach().contiguous(), b.detach().contiguous(), True)
+        ctx.save_for_backward(grad)
+        ctx.shape = a.shape
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * g).reshape(ctx.shape), None, None
+
+
+def mse_loss(pred, target, engine=None):
+    """Reconstruction loss of the training step (reference gplasdi.py:157,182): CUDA kernel when both live on the GPU."""
+    if pred.is_cuda and target.is_cuda and pred.dtype == torch.float32 and target.dtype == torch.float32:
+        from .engine import default_engine
+        return _MseLoss.apply(pred, target, engine if engine is not None else default_engine(pred.device.index))
+    return torch.nn.functional.mse_loss(pred, target)
+
+
 def initial_condition_latent(param_grid, physics, autoencoder):
     """Z0[i] = encoder(u0(param_i)) as a list of fp32 numpy vectors (reference latent_space.py:30-63);
     all parameters are encoded in one batched pass instead of a python loop."""
@@ -137,8 +183,18 @@ class MultiLayerPerceptron(torch.nn.Module):
             self._require_cuda_encoder()
             eng = self._engine_with_encoder_weights()
             y = eng.encode(x.detach().to(torch.float32)).to(x.device)
+        elif (x.is_cuda and self.act_type in _lib.ACT_IDS and all(p.is_cuda and p.dtype == torch.float32 for p in self.parameters())
+              and x.dtype == torch.float32):
+            # an autograd graph is being recorded on the GPU (the training step, reference gplasdi.py:180-181,197): this
+            # package's forward / backward kernels behind one autograd node (glasdi_mlp_forward_train / glasdi_mlp_backward)
+            from .engine import default_engine
+            eng = self._engine if self._engine is not None else default_engine(x.device.index)
+            lead = x.shape[:-1]
+            y = _MlpTrain.apply(x.reshape(-1, self.layer_sizes[0]), eng, self.act_type, len(self.fcs),
+                                *[fc.weight for fc in self.fcs], *[fc.bias for fc in self.fcs])
+            y = y.reshape(*lead, self.layer_sizes[-1])
         else:
-            # an autograd graph is being recorded (training): differentiable torch ops
+            # an autograd graph is being recorded on the host (CPU training / tests without a GPU): differentiable torch ops
             y = x
             for i in range(self.n_layers - 2):
                 y = self.act(self.fcs[i](y))

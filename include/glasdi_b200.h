@@ -290,6 +290,27 @@ int glasdi_sindy_fit_backward(glasdi_handle* h, const float* Z, const float* coe
                               const float* grad_loss_coef, int B, int T, int n, int fd_id, double dt, int norm_order,
                               float* grad_Z_out, void* stream);
 
+/* Training-mode autoencoder ---------------------------------------------------
+ * Replaces: the graph torch autograd records through MultiLayerPerceptron.forward (src/lasdi/latent_space.py:157-164) in
+ * the training step `Z = encoder(X); X_pred = decoder(Z)` (src/lasdi/gplasdi.py:180-181) and replays in `loss.backward()`
+ * (:197).  Weights are DEVICE fp32 pointers (the optimiser's own parameters, nn.Linear layout): W[l] [widths[l+1],
+ * widths[l]], b[l] [widths[l+1]]; the activation follows every layer but the last.
+ * forward: X [rows, widths[0]] -> Y [rows, widths[n_linear]]; pre_out / post_out [rows, widths[1] + .. + widths[n_linear-1]]
+ * (layer after layer, each [rows, width]) keep the hidden layers' pre- and post-activations for the backward. */
+int glasdi_mlp_forward_train(glasdi_handle* h, int n_linear, const int* widths, const float* const* W_dev,
+                             const float* const* b_dev, int act_id, const float* X, int64_t rows, float* pre_out,
+                             float* post_out, float* Y_out, void* stream);
+/* backward: dY [rows, widths[n_linear]] -> dX_out [rows, widths[0]] (NULL: not needed), dW_out[l], db_out[l] (device,
+ * overwritten).  The activation derivative is applied to the incoming gradient in the loaders of the two products of a layer
+ * (dW = dA^T in, dIn = dA W); fixed summation orders: bit-reproducible. */
+int glasdi_mlp_backward(glasdi_handle* h, int n_linear, const int* widths, const float* const* W_dev, int act_id,
+                        const float* X, const float* pre, const float* post, const float* dY, int64_t rows, float* dX_out,
+                        float* const* dW_out, float* const* db_out, void* stream);
+/* Replaces: `loss_ae = MSELoss()(X, X_pred)` (gplasdi.py:157,182) and its gradient: loss_out[0] = mean((A - B)^2) over n
+ * elements (fp64 partial sums, fixed order) and, in the same pass, dA_out = 2 (A - B) / n (NULL: loss only). */
+int glasdi_mse_loss_grad(glasdi_handle* h, const float* A, const float* B, int64_t n, float* loss_out, float* dA_out,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

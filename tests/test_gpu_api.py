@@ -118,6 +118,54 @@ def test_sindy_calibrate_is_differentiable_like_the_reference(golden_dir):
     assert not ls.requires_grad
 
 
+@pytest.mark.parametrize("act", ["sigmoid", "tanh", "softplus", "SiLU", "GELU", "ELU", "mish", "leakyReLU"])
+@pytest.mark.parametrize("sizes,rows", [([37, 20, 5], 70), ([5, 100, 1001], 200), ([64, 33, 17, 4], 129)])
+def test_training_mode_mlp_matches_torch_autograd(act, sizes, rows):
+    """glasdi_mlp_forward_train / glasdi_mlp_backward behind one autograd node (MultiLayerPerceptron.forward with grad on
+    the GPU) against the per-layer graph torch records for the same module (reference latent_space.py:157-164): output,
+    input gradient and every parameter gradient.  Tolerance 2e-5 of the largest entry (fp32, different summation orders)."""
+    from gplasdi_b200.latent_space import MultiLayerPerceptron
+    torch.manual_seed(3)
+    mlp = MultiLayerPerceptron(sizes, act).cuda()
+    x = torch.randn(rows, sizes[0], device="cuda", requires_grad=True)
+    gy = torch.randn(rows, sizes[-1], device="cuda")
+    y = mlp(x)
+    node = y.grad_fn
+    while node is not None and not type(node).__name__.startswith("_MlpTrain"):
+        node = node.next_functions[0][0] if node.next_functions else None
+    assert node is not None                                          # the CUDA node, not torch's per-layer graph
+    y.backward(gy)
+    got = [x.grad.clone()] + [p.grad.clone() for p in mlp.parameters()]
+    x.grad = None
+    for p in mlp.parameters():
+        p.grad = None
+    h = x
+    for i in range(len(mlp.fcs) - 1):
+        h = mlp.act(mlp.fcs[i](h))
+    yr = mlp.fcs[-1](h)
+    yr.backward(gy)
+    ref = [x.grad] + [p.grad for p in mlp.parameters()]
+    assert float((y - yr).abs().max()) <= 2e-5 * float(yr.abs().max())
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= 2e-5 * max(float(b.abs().max()), 1e-30)
+
+
+def test_mse_loss_kernel_matches_torch():
+    from gplasdi_b200.latent_space import mse_loss
+    torch.manual_seed(5)
+    a = torch.randn(4, 1001, 257, device="cuda", requires_grad=True)
+    b = torch.randn(4, 1001, 257, device="cuda")
+    loss = mse_loss(a, b)
+    (3.0 * loss).backward()
+    g = a.grad.clone(); a.grad = None
+    ref = torch.nn.functional.mse_loss(a.double(), b.double())
+    (3.0 * ref).backward()
+    assert abs(float(loss) - float(ref)) <= 1e-6 * float(ref)
+    assert float((g - a.grad).abs().max()) <= 1e-6 * float(a.grad.abs().max())
+    assert float(mse_loss(a.detach(), b)) == float(loss)               # bit-reproducible
+
+
 def test_train_leg_matches_reference_trainer(golden_dir, tmp_path):
     """BayesianGLaSDI.train(): same loss histories, best coefficients and checkpoint as the reference's own train()
     (fixture, run on CPU by tests/golden/gen_golden.py::gen_train) from the same initial weights -- with the SINDy
@@ -173,7 +221,10 @@ def test_train_leg_matches_reference_trainer(golden_dir, tmp_path):
     #     coefficient norm and the tiny SINDy residual, 2e-5, feel it at the 1 % level after six steps)
     n0 = ld.engine.launch_count
     tr.train()
-    assert ld.engine.launch_count - n0 == 2 * cfg["n_iter"]           # one fit + one backward kernel per iteration
+    # every kernel of an iteration is this package's: SINDy fit + its backward (2), encoder and decoder forward (2 GEMMs
+    # each), the reconstruction loss (2), decoder backward (dW, db, dIn for both layers: 6), encoder backward (the input
+    # needs no gradient: 5) -- and nothing else launches on the library's handle
+    assert ld.engine.launch_count - n0 == 19 * cfg["n_iter"]
     np.testing.assert_allclose(tr.ld_loss[0], g["ld_loss"][0], rtol=1e-4)
     for name, rtol in (("training_loss", 2e-3), ("ae_loss", 2e-3), ("ld_loss", 3e-2), ("coef_loss", 2e-2)):
         np.testing.assert_allclose(getattr(tr, name), g[name], rtol=rtol, err_msg=name)
