@@ -574,9 +574,35 @@ def aux_timings(eng, wl):
     ones = torch.ones(ntr, device="cuda")
     out["sindy_fit_backward_us"] = 1e3 * timed(lambda: eng.sindy_fit_backward(Zt, coefs, ones, ones, 1e-3, "sbp12", "fro"), 20)
     out["calibration_shape"] = [ntr, 1001, n]
+    # one whole training iteration (reference gplasdi.py:177-199) at the shipped shapes: 25 training series of 1001 snapshots
+    # x 1001 dofs through the [1001, 100, 5] autoencoder, reconstruction + SINDy + coefficient losses, backward -- every
+    # kernel this package's own (forward/backward GEMMs, loss, fit, fit backward); optimiser step excluded
+    try:
+        from gplasdi_b200.latent_space import Autoencoder, mse_loss
+        from gplasdi_b200.latent_dynamics.sindy import SINDy
+
+        class _Phys:
+            qgrid_size = [wl.D]
+        torch.manual_seed(0)
+        ae = Autoencoder(_Phys(), {"hidden_units": [100], "latent_dimension": n, "activation": wl.act}).cuda()
+        ld = SINDy(n, 1001, {"sindy": {"fd_type": "sbp12", "coef_norm_order": "fro"}}, engine=eng)
+        Xtr_t = torch.from_numpy(rs.normal(size=(ntr, 1001, wl.D)).astype(np.float32)).cuda()
+
+        def train_iter():
+            ae.zero_grad(set_to_none=True)
+            Z = ae.encoder(Xtr_t)
+            loss = mse_loss(ae.decoder(Z), Xtr_t, eng)
+            _, l_ld, l_c = ld.calibrate(Z, 1e-3, compute_loss=True, numpy=True)
+            (loss + 0.1 * l_ld / ntr + 1e-3 * l_c / ntr).backward()
+        out["train_iteration_ms"] = timed(train_iter, 5)
+        out["train_iteration_shape"] = [ntr, 1001, wl.D]
+    except Exception as e:                                      # never let a context number break the contract line
+        out["train_iteration_ms"] = None
+        out["train_iteration_error"] = str(e)[:200]
     out["note"] = ("device times (CUDA events) of the SURVEY 8f kernels at this workload's shapes, outside the timed step: "
                    "GP posterior of 30 coefficient GPs at every test parameter, numpy-legacy MT19937/Box-Muller draws "
-                   "reproduced on the GPU, batched encoder of the initial conditions, SINDy fit and its analytic backward")
+                   "reproduced on the GPU, batched encoder of the initial conditions, SINDy fit and its analytic backward, one "
+                   "training iteration (autoencoder forward/backward + losses + calibration) on this package's kernels")
     return out
 
 
