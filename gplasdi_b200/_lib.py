@@ -40,6 +40,7 @@ SIGNATURES = {
     "glasdi_screen_bound_count": (_i, [_vp, C.POINTER(_i64), _vp]),
     "glasdi_set_decoder": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_vp), _i]),
     "glasdi_rollout": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp]),
+    "glasdi_rollout_grid": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_d), _vp, _vp]),
     "glasdi_greedy_step": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp]),
     "glasdi_decode_max_std": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "glasdi_decode_stat_fields": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -292,7 +292,7 @@ int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths, const 
   if (widths[0] < 1 || widths[0] > kMaxLatent) return set_error(h, GLASDI_ERR_INVALID, "latent dimension must be 1..8");
   for (int l = 0; l <= n_linear; ++l)
     if (widths[l] < 1) return set_error(h, GLASDI_ERR_INVALID, "non-positive layer width");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   Decoder& d = h->dec;
   free_decoder(d);
   d.n_linear = n_linear;
@@ -373,7 +373,7 @@ int glasdi_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z
                    int T, double dt, double* Z_out, void* stream) {
   if (!h) return GLASDI_ERR_INVALID;
   if (!coefs || !z0 || !Z_out) return set_error(h, GLASDI_ERR_INVALID, "rollout: null pointer");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   // P may exceed the grid.y limit: slab it
   for (int p0 = 0; p0 < P; p0 += 32768) {
     const int pn = std::min(32768, P - p0);
@@ -383,6 +383,33 @@ int glasdi_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z
     if (rc) return rc;
   }
   return GLASDI_OK;
+}
+
+int glasdi_rollout_grid(glasdi_handle* h, const double* coefs, const float* z0, int z0_per_sample, int P, int S, int n,
+                        int T, const double* t_grid_host, double* Z_out, void* stream) {
+  if (!h) return GLASDI_ERR_INVALID;
+  if (!coefs || !z0 || !Z_out || !t_grid_host) return set_error(h, GLASDI_ERR_INVALID, "rollout_grid: null pointer");
+  if (T < 1) return set_error(h, GLASDI_ERR_INVALID, "rollout_grid: empty time grid");
+  DeviceGuard device_guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<double> dts((size_t)std::max(1, T - 1), 0.0);
+  for (int k = 1; k < T; ++k) {
+    dts[k - 1] = t_grid_host[k] - t_grid_host[k - 1];
+    if (!(std::fabs(dts[k - 1]) < 1e300)) return set_error(h, GLASDI_ERR_INVALID, "rollout_grid: non-finite time grid");
+  }
+  double* d_dts = nullptr;
+  GL_CUDA(h, cudaMallocFromPoolAsync((void**)&d_dts, dts.size() * sizeof(double), h->pool, st));
+  GL_CUDA(h, cudaMemcpyAsync(d_dts, dts.data(), dts.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  GL_CUDA(h, cudaStreamSynchronize(st));                    // `dts` is a host temporary
+  int rc = GLASDI_OK;
+  const size_t cstride = (size_t)S * n * library_terms(h->opt_library, n);
+  for (int p0 = 0; p0 < P && rc == GLASDI_OK; p0 += 32768) {
+    const int pn = std::min(32768, P - p0);
+    rc = launch_rollout(h, coefs + (size_t)p0 * cstride, z0 + (size_t)p0 * (z0_per_sample ? (size_t)S * n : (size_t)n),
+                        z0_per_sample, pn, S, n, T, 0.0, nullptr, 0, Z_out + (size_t)p0 * S * T * n, st, d_dts);
+  }
+  cudaFreeAsync(d_dts, st);
+  return rc;
 }
 
 // event pair helpers for GLASDI_OPT_STAGE_TIMING
@@ -413,7 +440,7 @@ static int greedy_core(glasdi_handle* h, const double* coefs, const float* z0, c
   if (n != d.widths[0]) return set_error(h, GLASDI_ERR_INVALID, "latent dimension does not match the decoder");
   if (P <= 0 || S <= 0 || T <= 0) return set_error(h, GLASDI_ERR_INVALID, "empty ensemble");
   if (!max_std_out) return set_error(h, GLASDI_ERR_INVALID, "null output");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   const int Spad = (S + 127) / 128 * 128;        // whole 128-sample chunks (covariance-form producers)
   // screened mode: one fp16 pass on the tensor cores writes the variance field, refine.cu re-evaluates
   // the near-maximum candidates exactly.  Only the CTA-pair tcgen05 kernel has the field epilogue.
@@ -538,7 +565,7 @@ int glasdi_decode_stat_fields(glasdi_handle* h, const double* Zis, int P, int S,
   if (n != d.widths[0]) return set_error(h, GLASDI_ERR_INVALID, "latent dimension does not match the decoder");
   if (P <= 0 || S <= 0 || T <= 0) return set_error(h, GLASDI_ERR_INVALID, "empty ensemble");
   cudaStream_t st = (cudaStream_t)stream;
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   const int Spad = (S + 127) / 128 * 128;
   const int field_ld = wide ? (d.D + 255) / 256 * 256 : decode_field_ld(d.n_tiles);
   const size_t traj_bytes = (size_t)T * n * Spad * sizeof(float);
@@ -587,7 +614,7 @@ int glasdi_decode(glasdi_handle* h, const float* Z, int64_t rows, float* X_out, 
   if (!h->dec.ready) return set_error(h, GLASDI_ERR_NOT_READY, "decoder weights not set (glasdi_set_decoder)");
   if (rows < 0 || (rows > 0 && (!Z || !X_out))) return set_error(h, GLASDI_ERR_INVALID, "decode: bad arguments");
   if (rows == 0) return GLASDI_OK;
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   if (h->dec.tc_ok) return launch_decode_store_pair(h, Z, rows, X_out, (cudaStream_t)stream);
   return launch_decode_store_simt(h, Z, rows, X_out, (cudaStream_t)stream);
 }
@@ -613,7 +640,7 @@ int glasdi_stage_times(glasdi_handle* h, double* rollout_ms, double* decode_ms, 
 int glasdi_screen_stats(glasdi_handle* h, double* refine_ms, double* quad_ms, int64_t* n_candidates, float* max_rel_dev,
                         void* stream) {
   if (!h) return GLASDI_ERR_INVALID;
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   double* outs[2] = {refine_ms, quad_ms};
   const std::vector<int>* lists[2] = {&h->ev_refine, &h->ev_quad};
   for (int k = 0; k < 2; ++k) {
@@ -639,7 +666,7 @@ int glasdi_screen_stats(glasdi_handle* h, double* refine_ms, double* quad_ms, in
 
 int glasdi_screen_bound_count(glasdi_handle* h, int64_t* n_bound_candidates, void* stream) {
   if (!h || !n_bound_candidates) return GLASDI_ERR_INVALID;
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   unsigned int v = 0;
   if (h->d_cand_stats) {
     GL_CUDA(h, cudaMemcpyAsync(&v, h->d_cand_stats + 4, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -652,14 +679,14 @@ int glasdi_screen_bound_count(glasdi_handle* h, int64_t* n_bound_candidates, voi
 // host-visible check of the numeric flags raised by the last asynchronous calls (synchronises `stream`)
 int glasdi_check_numeric(glasdi_handle* h, void* stream) {
   if (!h) return GLASDI_ERR_INVALID;
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   return check_flags(h, (cudaStream_t)stream);
 }
 
 int glasdi_argmax_first(glasdi_handle* h, const float* vals, int P, int64_t* idx_out, float* val_out, void* stream) {
   if (!h) return GLASDI_ERR_INVALID;
   if (!vals || P <= 0 || !idx_out) return set_error(h, GLASDI_ERR_INVALID, "argmax: bad arguments");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   return launch_argmax_first(h, vals, P, idx_out, val_out, (cudaStream_t)stream);
 }
 
@@ -667,7 +694,7 @@ int glasdi_pack_maxloc(glasdi_handle* h, const float* val, const int64_t* local_
                        int64_t* key_out, void* stream) {
   if (!h) return GLASDI_ERR_INVALID;
   if (!val || !local_idx || !key_out) return set_error(h, GLASDI_ERR_INVALID, "pack_maxloc: null pointer");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   return launch_pack_maxloc(h, val, local_idx, index_offset, key_out, (cudaStream_t)stream);
 }
 
@@ -675,7 +702,7 @@ int glasdi_fd_dzdt(glasdi_handle* h, const float* Z, int B, int T, int n, int fd
                    void* stream) {
   if (!h) return GLASDI_ERR_INVALID;
   if (!Z || !dZ_out) return set_error(h, GLASDI_ERR_INVALID, "fd_dzdt: null pointer");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   return launch_fd_dzdt(h, Z, B, T, n, fd_id, dt, dZ_out, (cudaStream_t)stream);
 }
 
@@ -683,7 +710,7 @@ int glasdi_sindy_fit(glasdi_handle* h, const float* Z, int B, int T, int n, int 
                      float* coefs_out, float* loss_sindy_out, float* loss_coef_out, int32_t* info_out, void* stream) {
   if (!h) return GLASDI_ERR_INVALID;
   if (!Z || !coefs_out) return set_error(h, GLASDI_ERR_INVALID, "sindy_fit: null pointer");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   return launch_sindy_fit(h, Z, B, T, n, fd_id, dt, norm_order, coefs_out, loss_sindy_out, loss_coef_out, info_out,
                           (cudaStream_t)stream);
 }
@@ -696,7 +723,7 @@ int glasdi_gp_predict(glasdi_handle* h, const double* X_train, int n_train, int 
   if (!X_train || !alpha || !L || !amplitude || !length_scale || !X_test || !mean_out || !std_out)
     return set_error(h, GLASDI_ERR_INVALID, "gp_predict: null pointer");
   if (n_train < 1 || n_param < 1 || n_gp < 1 || P < 1) return set_error(h, GLASDI_ERR_INVALID, "gp_predict: empty input");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   return launch_gp_predict(h, X_train, n_train, n_param, n_gp, alpha, L, amplitude, length_scale, y_mean, y_std, X_test,
                            P, mean_out, std_out, (cudaStream_t)stream);
 }
@@ -707,7 +734,7 @@ int glasdi_normal_mt19937(glasdi_handle* h, glasdi_mt19937_state* state, const d
   if (!state || P < 0 || S < 0 || n < 0) return set_error(h, GLASDI_ERR_INVALID, "normal_mt19937: bad arguments");
   if ((long long)P * S * n > 0 && (!mean || !std || !out))
     return set_error(h, GLASDI_ERR_INVALID, "normal_mt19937: null pointer");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   return launch_normal_mt19937(h, state, mean, std, P, S, n, out, (cudaStream_t)stream);
 }
 
@@ -719,7 +746,7 @@ int glasdi_set_encoder(glasdi_handle* h, int n_linear, const int* widths, const 
   if (act_id < 0 || act_id >= GLASDI_ACT_COUNT) return set_error(h, GLASDI_ERR_INVALID, "unknown activation id");
   for (int l = 0; l <= n_linear; ++l)
     if (widths[l] < 1) return set_error(h, GLASDI_ERR_INVALID, "non-positive layer width");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   Encoder& e = h->enc;
   free_encoder(e);
   e.n_linear = n_linear;
@@ -743,7 +770,7 @@ int glasdi_encode(glasdi_handle* h, const float* U, int64_t rows, float* Z_out, 
   if (!h->enc.ready) return set_error(h, GLASDI_ERR_NOT_READY, "encoder weights not set (glasdi_set_encoder)");
   if (rows < 0 || (rows > 0 && (!U || !Z_out))) return set_error(h, GLASDI_ERR_INVALID, "encode: bad arguments");
   if (rows == 0) return GLASDI_OK;
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   return launch_encode_simt(h, U, rows, Z_out, (cudaStream_t)stream);
 }
 
@@ -752,7 +779,7 @@ int glasdi_sindy_fit_backward(glasdi_handle* h, const float* Z, const float* coe
                               float* grad_Z_out, void* stream) {
   if (!h) return GLASDI_ERR_INVALID;
   if (!Z || !coefs || !grad_Z_out) return set_error(h, GLASDI_ERR_INVALID, "sindy_fit_backward: null pointer");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   return launch_sindy_fit_backward(h, Z, coefs, grad_loss_sindy, grad_loss_coef, B, T, n, fd_id, dt, norm_order,
                                    grad_Z_out, (cudaStream_t)stream);
 }

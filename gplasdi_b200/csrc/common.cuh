@@ -112,6 +112,21 @@ int check_cuda(glasdi_handle* h, cudaError_t e, const char* what);
 int ensure_workspace(glasdi_handle* h, size_t bytes);
 int ensure_maxvar(glasdi_handle* h, size_t n);
 
+// Entry points run on the handle's device and put the caller's current device back when they return.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != dev) prev = cur;
+    cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 #define GL_CUDA(h, expr)                                                   \
   do {                                                                     \
     cudaError_t _e = (expr);                                               \
@@ -123,7 +138,7 @@ int ensure_maxvar(glasdi_handle* h, size_t n);
 int launch_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z0_per_sample,
                    int P, int S, int n, int T, double dt,
                    float* Zs /*[P][T][n][Spad] or null*/, int Spad, double* Zref /*[P,S,T,n] or null*/,
-                   cudaStream_t st);
+                   cudaStream_t st, const double* dts = nullptr /* device [T-1] step sizes of a non-uniform grid */);
 int library_terms(int lib, int n);   // |Theta| of enum glasdi_library, -1 if unknown
 int launch_zis_to_soa(glasdi_handle* h, const double* Zis, int P, int S, int T, int n, float* Zs, int Spad,
                       cudaStream_t st);

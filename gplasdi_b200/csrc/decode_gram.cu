@@ -449,10 +449,13 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         pm_stage(smem + L.xb, P.front, nf, ptid, kGProdThreads, Ly);
         asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");
         const int pw = ptid >> 5;                            // producer warp 0..15
-        const int mt = pw & 7, half = pw >> 3;               // m16 tile of the chunk, half of the unit groups
+        // warps 0..7 take the even chunks of the CTA's stream, warps 8..15 the odd ones (the operand ring is four deep), each
+        // warp one m16 tile with ALL unit groups: the narrow chain is evaluated once per sample (two warps sharing a tile
+        // by halves of the unit groups repeated it: 204 instead of 138 MMA triples per pair of chunks)
+        const int mt = pw & 7, grp = pw >> 3;
         const int g = lane >> 2, t = lane & 3;
         const int ntl = Ly[nf - 1].op / 8;                   // n8 tiles the last front layer really has (units < K)
-        const int j_begin = half ? (P.nkg + 1) / 2 : 0, j_end = half ? P.nkg : (P.nkg + 1) / 2;
+        const int j_begin = 0, j_end = P.nkg;
         const int act_rt = P.front.act;
         auto act = [&](float x) { return act_apply_t<ACT>(act_rt, x); };
         const int k0 = 2 * t, k1 = 2 * t + 1;
@@ -475,6 +478,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");
           for (int c = 0; c < nchunks; ++c) {
+            if ((h_it & 1u) != (uint32_t)grp) { ++h_it; continue; }       // the other warp group's chunk
             const int col_lo = mt * 16 + g, col_hi = col_lo + 8;
             const int s_lo = c * kCols + col_lo, s_hi = s_lo + 8;
             const int sl = s_lo < P.S ? s_lo : 0, sh = s_hi < P.S ? s_hi : 0;
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&B->h_full[buf]);
+            if (lane < 2) mbar_arrive(&B->h_full[buf]);                    // eight warps fill a tile: two arrivals each (count 16)
             ++h_it;
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item

@@ -256,8 +256,9 @@ __device__ __forceinline__ void rhs_lib(const volatile double* c, int bd, const 
 
 template <int N, bool QUAD, bool SINE>
 __global__ void rollout_lib_kernel(const double* __restrict__ coefs, const float* __restrict__ z0, int z0_per_sample,
-                                   int P, int S, int T, double dt, int min_substeps, float* __restrict__ Zs, int Spad,
-                                   double* __restrict__ Zref, unsigned int* __restrict__ flags) {
+                                   int P, int S, int T, double dt_uniform, const double* __restrict__ dts, int min_substeps,
+                                   float* __restrict__ Zs, int Spad, double* __restrict__ Zref,
+                                   unsigned int* __restrict__ flags) {
   using L = Lib<N, QUAD, SINE>;
   extern __shared__ double cs[];                         // [kCoefs][blockDim.x]
   const int bd = blockDim.x;
@@ -307,6 +308,7 @@ __global__ void rollout_lib_kernel(const double* __restrict__ coefs, const float
   bool bad = false;
   emit(0);
   for (int k = 1; k < T; ++k) {
+    const double dt = dts ? dts[k - 1] : dt_uniform;           // non-uniform output grids: dts[k-1] = t_k - t_{k-1}
     double lmax = 0.0;
     {
       double li[N];
@@ -364,7 +366,7 @@ __global__ void rollout_lib_kernel(const double* __restrict__ coefs, const float
 
 template <int N, bool QUAD, bool SINE>
 static int launch_rollout_lib_inst(glasdi_handle* h, const double* coefs, const float* z0, int z0ps, int P, int S, int T,
-                                   double dt, float* Zs, int Spad, double* Zref, cudaStream_t st) {
+                                   double dt, float* Zs, int Spad, double* Zref, cudaStream_t st, const double* dts = nullptr) {
   using L = Lib<N, QUAD, SINE>;
   int bd = 128;
   while (bd > 32 && (size_t)bd * L::kCoefs * sizeof(double) > 100 * 1024) bd >>= 1;
@@ -375,7 +377,7 @@ static int launch_rollout_lib_inst(glasdi_handle* h, const double* coefs, const 
     if (e != cudaSuccess) return check_cuda(h, e, "rollout_lib_kernel shared memory");
   }
   dim3 block(bd), grid((S + bd - 1) / bd, P);
-  kern<<<grid, block, smem, st>>>(coefs, z0, z0ps, P, S, T, dt, h->opt_substeps, Zs, Spad, Zref,
+  kern<<<grid, block, smem, st>>>(coefs, z0, z0ps, P, S, T, dt, dts, h->opt_substeps, Zs, Spad, Zref,
                                          reinterpret_cast<unsigned int*>(h->d_flags + 3));
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "rollout_lib_kernel launch");
@@ -383,11 +385,12 @@ static int launch_rollout_lib_inst(glasdi_handle* h, const double* coefs, const 
 
 template <int N>
 static int launch_rollout_lib_n(glasdi_handle* h, int lib, const double* coefs, const float* z0, int z0ps, int P, int S,
-                                int T, double dt, float* Zs, int Spad, double* Zref, cudaStream_t st) {
+                                int T, double dt, float* Zs, int Spad, double* Zref, cudaStream_t st, const double* dts = nullptr) {
   switch (lib) {
-    case GLASDI_LIB_POLY1_SINE: return launch_rollout_lib_inst<N, false, true>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
-    case GLASDI_LIB_POLY2: return launch_rollout_lib_inst<N, true, false>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
-    default: return launch_rollout_lib_inst<N, true, true>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+    case GLASDI_LIB_POLY1: return launch_rollout_lib_inst<N, false, false>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
+    case GLASDI_LIB_POLY1_SINE: return launch_rollout_lib_inst<N, false, true>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
+    case GLASDI_LIB_POLY2: return launch_rollout_lib_inst<N, true, false>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
+    default: return launch_rollout_lib_inst<N, true, true>(h, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
   }
 }
 
@@ -431,20 +434,22 @@ static int launch_rollout_n(glasdi_handle* h, const double* coefs, const float* 
 }
 
 int launch_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z0ps, int P, int S, int n, int T,
-                   double dt, float* Zs, int Spad, double* Zref, cudaStream_t st) {
+                   double dt, float* Zs, int Spad, double* Zref, cudaStream_t st, const double* dts) {
   if (P <= 0 || S <= 0 || T <= 0) return set_error(h, GLASDI_ERR_INVALID, "rollout: empty shape");
   if (P > 65535) return set_error(h, GLASDI_ERR_INVALID, "rollout: P > 65535 per call (shard the test grid)");
-  if (h->opt_library != GLASDI_LIB_POLY1) {
+  // a non-uniform output grid (dts) takes the step-adaptive RK4 kernel for every library, the affine one included: the
+  // exact propagator would have to be rebuilt for every distinct step
+  if (h->opt_library != GLASDI_LIB_POLY1 || dts != nullptr) {
     const int lib = h->opt_library;
     switch (n) {
-      case 1: return launch_rollout_lib_n<1>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
-      case 2: return launch_rollout_lib_n<2>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
-      case 3: return launch_rollout_lib_n<3>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
-      case 4: return launch_rollout_lib_n<4>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
-      case 5: return launch_rollout_lib_n<5>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
-      case 6: return launch_rollout_lib_n<6>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
-      case 7: return launch_rollout_lib_n<7>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
-      case 8: return launch_rollout_lib_n<8>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st);
+      case 1: return launch_rollout_lib_n<1>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
+      case 2: return launch_rollout_lib_n<2>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
+      case 3: return launch_rollout_lib_n<3>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
+      case 4: return launch_rollout_lib_n<4>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
+      case 5: return launch_rollout_lib_n<5>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
+      case 6: return launch_rollout_lib_n<6>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
+      case 7: return launch_rollout_lib_n<7>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
+      case 8: return launch_rollout_lib_n<8>(h, lib, coefs, z0, z0ps, P, S, T, dt, Zs, Spad, Zref, st, dts);
       default: return set_error(h, GLASDI_ERR_INVALID, "rollout: latent dimension must be 1..8");
     }
   }

@@ -217,7 +217,7 @@ int glasdi_mlp_forward_train(glasdi_handle* h, int n_linear, const int* widths, 
   int rc = check_mlp_args(h, n_linear, widths, W_dev, b_dev, true, act_id, rows);
   if (rc) return rc;
   if (!X || !Y_out || (n_linear > 1 && (!pre_out || !post_out))) return set_error(h, GLASDI_ERR_INVALID, "mlp forward: null pointer");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const float* in = X;
   size_t off = 0;
@@ -242,7 +242,7 @@ int glasdi_mlp_backward(glasdi_handle* h, int n_linear, const int* widths, const
   int rc = check_mlp_args(h, n_linear, widths, W_dev, nullptr, false, act_id, rows);
   if (rc) return rc;
   if (!X || !dY || (n_linear > 1 && (!pre || !post))) return set_error(h, GLASDI_ERR_INVALID, "mlp backward: null pointer");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   // scratch: two ping-pong gradient buffers of rows x (widest hidden layer)
   int maxw = 1;
@@ -283,7 +283,7 @@ int glasdi_mse_loss_grad(glasdi_handle* h, const float* A, const float* B, int64
                          void* stream) {
   if (!h) return GLASDI_ERR_INVALID;
   if (!A || !B || !loss_out || n < 1) return set_error(h, GLASDI_ERR_INVALID, "mse: bad arguments");
-  GL_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard device_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   double* partial = nullptr;
   GL_CUDA(h, cudaMallocFromPoolAsync((void**)&partial, tmlp::kMseBlocks * sizeof(double), h->pool, st));

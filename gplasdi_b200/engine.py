@@ -174,6 +174,23 @@ class Engine:
                                                 float(dt), out.data_ptr(), _stream_ptr()))
         return out
 
+    def rollout_grid(self, coefs, z0, t_grid) -> torch.Tensor:
+        """`rollout` on an arbitrary time grid (what scipy's odeint accepts in the reference's SINDy.simulate):
+        t_grid fp64 [T] on the host -> Z fp64 [P,S,T,n], Z[..., k, :] = z(t_grid[k])."""
+        coefs = self._dev(coefs, torch.float64)
+        z0 = self._dev(z0, torch.float32)
+        t = np.ascontiguousarray(np.asarray(t_grid, dtype=np.float64))
+        P, S, nc = coefs.shape
+        n = z0.shape[-1]
+        if nc != n * self.library_terms(n):
+            raise ValueError(f"coefficient rows of {nc} values do not match the selected library ({self.library_terms(n)} x {n})")
+        per_sample = 1 if z0.dim() == 3 else 0
+        out = torch.empty((P, S, len(t), n), dtype=torch.float64, device=self.tdev)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.glasdi_rollout_grid(self.h, coefs.data_ptr(), z0.data_ptr(), per_sample, P, S, n, len(t),
+                                                     t.ctypes.data_as(C.POINTER(C.c_double)), out.data_ptr(), _stream_ptr()))
+        return out
+
     # ---- fused greedy step ---------------------------------------------------------------------
     def greedy_step(self, coefs, z0, T: int, dt: float, out=None):
         """-> (max_std fp32 [P], argmax int64 [1] (-1 if none), maxval fp32 [1]); CUDA tensors."""

@@ -187,23 +187,37 @@ class BayesianGLaSDI:
         ae = self.autoencoder
         self.load_checkpoint()
 
+        import time
+        import torch.distributed as dist
+        from .latent_dynamics.sindy import _uniform_dt
+        tm = {}
+        t0 = time.perf_counter()
         Z0 = np.stack(initial_condition_latent(ps.test_space, self.physics, ae))
+        tm["initial_condition_latent_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
         gp_dictionnary = fit_gps(ps.train_space, self.best_coefs)
+        tm["fit_gps_host_s"] = time.perf_counter() - t0             # scikit-learn hyper-parameter fit: host, out of scope
         eng = _engine_for(ae)
         # posterior moments and the (p, s, k)-ordered legacy-stream draws on the device: [n_test, n_samples, n_coef] fp64
+        t0 = time.perf_counter()
         coef_samples = sample_coefs_all_device(gp_dictionnary, ps.test_space, self.n_samples, eng)
+        torch.cuda.synchronize()
+        tm["gp_posterior_and_draws_s"] = time.perf_counter() - t0
 
-        import torch.distributed as dist
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank(group) if world > 1 else 0
         bounds = sharding.shard_bounds(n_test, world)
         lo, hi = bounds[rank], bounds[rank + 1]
 
-        dt = float(self.physics.t_grid[1] - self.physics.t_grid[0]) if len(self.physics.t_grid) > 1 else 0.0
+        dt = _uniform_dt(self.physics.t_grid)      # a non-uniform grid raises here instead of rolling out wrongly
+        t0 = time.perf_counter()
         ms, key = sharding.sharded_greedy_step(eng, coef_samples[lo:hi], Z0[lo:hi], len(self.physics.t_grid), dt,
                                                lo, group)
+        key_host = int(key.item())
+        tm["greedy_step_and_allreduce_s"] = time.perf_counter() - t0
+        self.last_timings = tm
         self.last_max_std = ms.cpu().numpy()
-        _, m_index = sharding.unpack_maxloc(int(key.item()))
+        _, m_index = sharding.unpack_maxloc(key_host)
         if m_index < 0:
             raise RuntimeError("no test parameter has a positive standard deviation")
         new_sample = ps.test_space[m_index, :].reshape(1, -1)

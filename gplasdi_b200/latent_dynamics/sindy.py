@@ -23,16 +23,24 @@ from ..engine import default_engine
 from .. import _lib
 
 
-def _uniform_dt(t_grid) -> float:
+def _is_uniform(t_grid) -> bool:
     t = np.asarray(t_grid, dtype=np.float64)
     if t.ndim != 1 or t.size < 1:
         raise ValueError("t_grid must be a 1-d array")
-    if t.size == 1:
-        return 0.0
+    if t.size <= 2:
+        return True
     d = np.diff(t)
-    if not np.allclose(d, d[0], rtol=1e-9, atol=1e-14):
-        raise ValueError("the CUDA rollout needs a uniform time grid (the reference's physics grids are uniform)")
-    return float(d[0])
+    return bool(np.allclose(d, d[0], rtol=1e-9, atol=1e-14))
+
+
+def _uniform_dt(t_grid) -> float:
+    """Step of a uniform grid (the fused greedy step and the exact affine propagator need one; `simulate` / `sample` take
+    any grid through glasdi_rollout_grid)."""
+    t = np.asarray(t_grid, dtype=np.float64)
+    if not _is_uniform(t):
+        raise ValueError("this call needs a uniform time grid (the reference's physics grids are uniform); "
+                         "SINDy.simulate / sample accept arbitrary grids")
+    return 0.0 if t.size == 1 else float(t[1] - t[0])
 
 
 def lib_size(n_z: int, poly_order: int) -> int:
@@ -156,8 +164,10 @@ class SINDy(LatentDynamics):
         """One trajectory; returns np.ndarray fp64 [nt, dim] like scipy odeint does in the reference."""
         c = np.asarray(coefs, dtype=np.float64).reshape(1, 1, self.ncoefs)
         z = np.asarray(z0, dtype=np.float32).reshape(1, self.dim)
-        dt = _uniform_dt(t_grid)
-        Z = self.engine.rollout(c, z, len(t_grid), dt)
+        if _is_uniform(t_grid):
+            Z = self.engine.rollout(c, z, len(t_grid), _uniform_dt(t_grid))
+        else:                                # odeint takes any grid (sindy.py:115): step-adaptive RK4 kernel
+            Z = self.engine.rollout_grid(c, z, t_grid)
         return Z[0, 0].cpu().numpy()
 
     def sample(self, coefs_sample, z0_sample, t_grid):
@@ -166,8 +176,10 @@ class SINDy(LatentDynamics):
         z = np.asarray(z0_sample, dtype=np.float32)
         assert len(c) == len(z)
         N = c.shape[0]
-        dt = _uniform_dt(t_grid)
-        Z = self.engine.rollout(c.reshape(N, 1, self.ncoefs), z.reshape(N, self.dim), len(t_grid), dt)
+        if _is_uniform(t_grid):
+            Z = self.engine.rollout(c.reshape(N, 1, self.ncoefs), z.reshape(N, self.dim), len(t_grid), _uniform_dt(t_grid))
+        else:
+            Z = self.engine.rollout_grid(c.reshape(N, 1, self.ncoefs), z.reshape(N, self.dim), t_grid)
         return Z[:, 0].cpu().numpy()
 
     def rollout_ensemble(self, coef_samples, Z0, t_grid):

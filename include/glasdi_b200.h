@@ -180,6 +180,13 @@ int glasdi_set_decoder(glasdi_handle* h, int n_linear, const int* widths,
 int glasdi_rollout(glasdi_handle* h, const double* coefs, const float* z0, int z0_per_sample,
                    int P, int S, int n, int T, double dt, double* Z_out, void* stream);
 
+/* The same rollout on an ARBITRARY increasing (or decreasing) time grid, as scipy's odeint accepts it in SINDy.simulate
+ * (sindy.py:104-117): t_grid HOST fp64 [T], Z_out[.., k, :] = z(t_grid[k]), z(t_grid[0]) = z0.  Every library, the affine one
+ * included, is integrated by fp64 RK4 whose sub-step count is re-chosen at every output step from the Jacobian bound
+ * (h L <= 1/16); synchronises `stream` once (the grid is copied from a host temporary). */
+int glasdi_rollout_grid(glasdi_handle* h, const double* coefs, const float* z0, int z0_per_sample,
+                        int P, int S, int n, int T, const double* t_grid_host, double* Z_out, void* stream);
+
 /* fused greedy step ---------------------------------------------------------------------------
  * Replaces: gplasdi.py:262-268 = the simulate double loop + get_fom_max_std(ae, Zis).
  * Rollout (fp64) -> MLP decode -> population std over the S samples (ddof = 0) per (t, dof)

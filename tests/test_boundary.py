@@ -95,8 +95,12 @@ def test_sindy_constructor_contract():
         SINDy(5, 101, {"sindy": {"fd_type": "weno"}})
     with pytest.raises(AssertionError):
         SINDy(5, 7, {"sindy": {"fd_type": "sbp48"}})      # shorter than the boundary closure
+    # a non-uniform grid is accepted by simulate (glasdi_rollout_grid, tested on the GPU); the calls that need ONE step
+    # (the fused greedy step, the exact propagator) still refuse it
+    from gplasdi_b200.latent_dynamics.sindy import _uniform_dt, _is_uniform
+    assert not _is_uniform(np.array([0.0, 0.1, 0.3])) and _is_uniform(np.linspace(0.0, 1.0, 11))
     with pytest.raises(ValueError):
-        ld.simulate(np.zeros(30), np.zeros(5), np.array([0.0, 0.1, 0.3]))   # non-uniform grid
+        _uniform_dt(np.array([0.0, 0.1, 0.3]))
 
 
 def _build_c_host(tmp_path):

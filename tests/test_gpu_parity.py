@@ -93,6 +93,29 @@ def test_library_rollout_matches_reference_simulate_sindy(engine, golden_dir, n,
     assert engine.get_option(_lib.OPT_SINDY_LIBRARY) == _lib.LIB_POLY1      # restored
 
 
+def test_rollout_on_a_non_uniform_time_grid_matches_odeint(engine):
+    """SINDy.simulate / sample accept any time grid, as scipy's odeint does in the reference (sindy.py:104-117): the
+    step-adaptive RK4 kernel behind glasdi_rollout_grid against the oracle's odeint on a stretched, irregular grid."""
+    from gplasdi_b200.latent_dynamics.sindy import SINDy
+    wl, Ws, bs = setup_wl(engine, "tiny")
+    inp = synth.make_inputs(wl)
+    rs = np.random.RandomState(2)
+    t_grid = np.concatenate([[0.0], np.cumsum(rs.uniform(0.002, 0.08, size=40))])
+    ld = SINDy(wl.n_z, len(t_grid), {"sindy": {"fd_type": "sbp12"}}, engine=engine)
+    coefs = inp["coefs"][:3, 0]; z0 = inp["z0"][:3]
+    Z = ld.sample(coefs, z0, t_grid)
+    Z1 = ld.simulate(coefs[1], z0[1], t_grid)
+    for k in range(3):
+        ref = orc.simulate(coefs[k], z0[k].astype(np.float64), t_grid)
+        assert np.max(np.abs(Z[k] - ref)) <= TRAJ_RTOL * np.max(np.abs(ref))
+    assert np.array_equal(Z1, Z[1])
+    # a uniform grid handed to the grid entry point agrees with the exact propagator
+    tu = np.arange(wl.T) * wl.dt
+    Zg = engine.rollout_grid(inp["coefs"][:2], inp["z0"][:2], tu).cpu().numpy()
+    Ze = engine.rollout(inp["coefs"][:2], inp["z0"][:2], wl.T, wl.dt).cpu().numpy()
+    assert np.max(np.abs(Zg - Ze)) <= 1e-6 * np.max(np.abs(Ze))
+
+
 def test_library_greedy_step_matches_oracle(engine):
     """The fused greedy step on a quadratic + sine library: rollout_lib_kernel feeds the same decode / variance kernels.
     Oracle: odeint on the legacy right-hand side + the reference's decode / std / first-strict-maximum."""
