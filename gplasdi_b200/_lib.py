@@ -28,6 +28,7 @@ INT_EXPM, INT_RK4 = 0, 1
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 SIGNATURES = {
     "glasdi_abi_version": (_i, []),
+    "glasdi_source_hash": (C.c_char_p, []),
     "glasdi_library_terms": (_i, [_i, _i]),
     "glasdi_create": (_i, [C.POINTER(_vp), _i]),
     "glasdi_destroy": (_i, [_vp]),
@@ -76,12 +77,27 @@ def load(build_if_missing: bool = True):
         if not build_if_missing:
             raise RuntimeError(f"{path} is missing: run `python -m gplasdi_b200.build` (no CPU fallback exists)")
         _build.build()
+    # a library older than the sources beside it is rebuilt when a compiler is there and refused otherwise -- decided from
+    # the hash file the build writes next to the library, BEFORE the library is opened (dlopen would keep a stale mapping)
+    if os.path.isdir(_build.CSRC) and os.environ.get("GLASDI_LIBDIR") is None:
+        built_from = _build.built_hash()
+        if built_from != _build.source_hash():
+            import shutil
+            if not build_if_missing or shutil.which(_build._nvcc()) is None:
+                raise RuntimeError(f"{path} was built from other sources (hash {built_from[:12]}, sources "
+                                   f"{_build.source_hash()[:12]}): run `python -m gplasdi_b200.build`")
+            _build.build(force=True)       # file times cannot be trusted once the hashes disagree
+    lib = _open(path)
+    _LIB = lib
+    return lib
+
+
+def _open(path):
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    _LIB = lib
     return lib
 
 

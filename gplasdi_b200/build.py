@@ -21,8 +21,26 @@ def _nvcc() -> str:
     return "nvcc"
 
 
+def source_hash() -> str:
+    """sha1 over the CUDA sources and the public header: compiled into the library (`glasdi_source_hash`) so that a
+    library older than the sources is detected whatever the file times say (a snapshot copy resets them)."""
+    import hashlib
+    h = hashlib.sha1()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(HERE, "..", "include", "glasdi_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
+def built_hash() -> str:
+    side = os.path.join(LIBDIR, "source_hash.txt")
+    return open(side).read().strip() if os.path.exists(side) else "none"
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or built_hash() != source_hash():
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "glasdi_b200.h")]
@@ -35,6 +53,8 @@ def _stale(src: str, obj: str) -> bool:
         return True
     t = os.path.getmtime(obj)
     deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    if src == "api.cu":                                   # carries the hash of ALL sources
+        deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu")]
     deps.append(os.path.join(HERE, "..", "include", "glasdi_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -45,6 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
+    shash = source_hash()
     objs = []
     procs = []
     for src in SOURCES:
@@ -52,7 +73,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         if not force and not _stale(src, obj):
             continue
-        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("GLASDI_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
+        extra = [f'-DGLASDI_SOURCE_HASH="{shash}"'] if src == "api.cu" else []
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, *os.environ.get("GLASDI_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False
@@ -68,6 +90,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed; see gplasdi_b200/lib/build.log")
     cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    with open(os.path.join(LIBDIR, "source_hash.txt"), "w") as f:      # what _lib.load compares before it opens the library
+        f.write(shash + "\n")
     return LIB
 
 

@@ -129,6 +129,11 @@ extern "C" {
 
 int glasdi_abi_version(void) { return GLASDI_ABI_VERSION; }
 
+#ifndef GLASDI_SOURCE_HASH
+#define GLASDI_SOURCE_HASH "unknown"
+#endif
+const char* glasdi_source_hash(void) { return GLASDI_SOURCE_HASH; }
+
 int glasdi_create(glasdi_handle** out, int device) {
   if (!out) return GLASDI_ERR_INVALID;
   *out = nullptr;

@@ -132,6 +132,9 @@ enum glasdi_library {
 int glasdi_library_terms(int library, int n);
 
 int glasdi_abi_version(void);
+/* sha1 of the CUDA sources + this header the library was built from (gplasdi_b200/build.py::source_hash); the Python
+ * loader compares it with the sources beside it and rebuilds, or refuses, a stale library */
+const char* glasdi_source_hash(void);
 
 /* lifetime ------------------------------------------------------------------------------------ */
 int glasdi_create(glasdi_handle** out, int device);
