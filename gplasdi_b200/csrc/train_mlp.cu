@@ -66,12 +66,17 @@ __global__ void __launch_bounds__(TT) gemm_kernel(const float* __restrict__ A, i
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tx = tid & 15, ty = tid >> 4;
+  // split-K (gridDim.z > 1, only without an epilogue): slice z of the contraction goes to its own partial result
+  // C + z * M * ldc; splitk_reduce_kernel adds the slices in a fixed order
+  const int kper = ((K + gridDim.z - 1) / gridDim.z + BK - 1) / BK * BK;
+  const int kbeg = blockIdx.z * kper, kend = min(K, kbeg + kper);
+  C += (size_t)blockIdx.z * M * ldc;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
     // 64 x 16 elements of each operand, four per thread; the fast index of the global layout runs over the threads
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -80,7 +85,7 @@ __global__ void __launch_bounds__(TT) gemm_kernel(const float* __restrict__ A, i
       if (TA) { mm = idx & (BM - 1); kk = idx >> 6; } else { kk = idx & (BK - 1); mm = idx >> 4; }
       const int m = m0 + mm, k = k0 + kk;
       float v = 0.f;
-      if (m < M && k < K) {
+      if (m < M && k < kend) {
         const size_t o = TA ? (size_t)k * lda + m : (size_t)m * lda + k;
         v = A[o];
         if (GA) v *= act_grad(act, preA[o]);
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(TT) gemm_kernel(const float* __restrict__ A, i
       if (TB) { kk = idx & (BK - 1); nn = idx >> 4; } else { nn = idx & (BN - 1); kk = idx >> 6; }
       const int n = n0 + nn, k = k0 + kk;
       float v = 0.f;
-      if (n < N && k < K) v = TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
+      if (n < N && k < kend) v = TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
       Bs[kk][nn] = v;
     }
     __syncthreads();
@@ -182,10 +187,21 @@ __global__ void mse_final_kernel(const double* __restrict__ partial, int nb, lon
   *loss = (float)(t / (double)n);
 }
 
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t n,
+                                                           float* __restrict__ C) {
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    float t = 0.f;
+    for (int s = 0; s < splits; ++s) t += part[(size_t)s * n + i];
+    C[i] = t;
+  }
+}
+
+// splits > 1: C is a [splits][M][ldc] scratch, reduced by the caller (products whose contraction is the row count: dW)
 template <bool TA, bool TB, bool GA, bool FWD>
 static void launch_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
-                        const float* preA, int act, const float* bias, float* pre_out, int apply_act, cudaStream_t st) {
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+                        const float* preA, int act, const float* bias, float* pre_out, int apply_act, cudaStream_t st,
+                        int splits = 1) {
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
   gemm_kernel<TA, TB, GA, FWD><<<grid, TT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, preA, act, bias, pre_out, apply_act);
 }
 
@@ -263,8 +279,20 @@ int glasdi_mlp_backward(glasdi_handle* h, int n_linear, const int* widths, const
     const float* pre_l = last ? nullptr : pre + offs[l];       // its pre-activation (hidden layers)
     if (!dW_out[l] || !db_out[l]) return set_error(h, GLASDI_ERR_INVALID, "mlp backward: null gradient pointer");
     // dW[o, i] = sum_r dA[r, o] in[r, i];  db[o] = sum_r dA[r, o];  dA = g * act'(pre)
-    if (last) tmlp::launch_gemm<true, false, false, false>(g, wo, in, wi, dW_out[l], wi, wo, wi, (int)rows, nullptr, act_id, nullptr, nullptr, 0, st);
-    else tmlp::launch_gemm<true, false, true, false>(g, wo, in, wi, dW_out[l], wi, wo, wi, (int)rows, pre_l, act_id, nullptr, nullptr, 0, st);
+    // the contraction runs over the rows (thousands) while dW has a handful of tiles: split it over enough CTAs for two
+    // waves, partial products in a scratch, fixed-order reduction (no atomics)
+    const int tiles = ((wo + tmlp::BM - 1) / tmlp::BM) * ((wi + tmlp::BN - 1) / tmlp::BN);
+    int splits = std::max(1, std::min({64, (2 * h->num_sms + tiles - 1) / tiles, (int)((rows + 4 * tmlp::BK - 1) / (4 * tmlp::BK))}));
+    float* part = dW_out[l];
+    if (splits > 1) GL_CUDA(h, cudaMallocFromPoolAsync((void**)&part, (size_t)splits * wo * wi * sizeof(float), h->pool, st));
+    if (last) tmlp::launch_gemm<true, false, false, false>(g, wo, in, wi, part, wi, wo, wi, (int)rows, nullptr, act_id, nullptr, nullptr, 0, st, splits);
+    else tmlp::launch_gemm<true, false, true, false>(g, wo, in, wi, part, wi, wo, wi, (int)rows, pre_l, act_id, nullptr, nullptr, 0, st, splits);
+    if (splits > 1) {
+      const size_t nel = (size_t)wo * wi;
+      tmlp::splitk_reduce_kernel<<<(unsigned)std::min<size_t>((nel + 255) / 256, 1024), 256, 0, st>>>(part, splits, nel, dW_out[l]);
+      cudaFreeAsync(part, st);
+      h->launches++;
+    }
     tmlp::bias_grad_kernel<<<(wo + 31) / 32, 256, 0, st>>>(g, pre_l, (int)rows, wo, act_id, db_out[l]);
     h->launches += 2;
     float* gin = l == 0 ? dX_out : gbuf[l & 1];
