@@ -917,7 +917,10 @@ static void launch_fd_hw(const float* Z, int B, int T, int n, int fd_id, float i
   const bool aligned = ((reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(dZ)) & 15) == 0;
   if (n == 5 && aligned) {
     const long long total = (long long)B * T * n;
-    constexpr int Q = HW == 1 ? 2 : 1;      // quads per thread (measured: two help the narrow stencil, 79 -> 86 % of the HBM rate)
+    // quads per thread (measured: two help the narrow stencil, 79 -> 86 % of the HBM rate; for the wider ones more quads
+    // per thread -- fewer halo loads per output -- were SLOWER: sbp24 0.071 -> 0.078 ms at Q = 2, sbp36 / sbp48 0.090 / 0.100
+    // -> 0.164 / 0.170 ms at Q = 4 with 56-float windows in registers, round 2)
+    constexpr int Q = HW == 1 ? 2 : 1;
     const long long per_block = (long long)kFdThreads * Q * 4;
     const unsigned int blocks = (unsigned int)((total + per_block - 1) / per_block);
     fd_dzdt_vec_kernel<HW, 5, Q><<<blocks, kFdThreads, 0, st>>>(Z, total, T, fd_id, inv_dt, dZ);
