@@ -293,6 +293,25 @@ __device__ __forceinline__ float act_apply_t(int act_rt, float x) {
   }
 }
 
+// ---- screening-pass activations: bare MUFU forms, activation resolved at compile time (ACT < 0: runtime switch) ----
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// bare MUFU forms, activation resolved at compile time: 3-6 instructions per value (the runtime switch + __expf / __logf
+// range handling of act_fast cost ~25 in xact_kernel's epilogue: 40 instructions per value, profiles/r02_xact_*)
+template <int ACT>
+__device__ __forceinline__ float act_mufu(float a, int act_rt) {   // ACT < 0: runtime switch (the rarely used activations)
+  constexpr float kL2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  if constexpr (ACT == GLASDI_ACT_SIGMOID) return mufu_rcp(1.0f + mufu_ex2(-kL2e * a));
+  else if constexpr (ACT == GLASDI_ACT_TANH) return fmaf(2.0f, mufu_rcp(1.0f + mufu_ex2(-2.0f * kL2e * a)), -1.0f);
+  else if constexpr (ACT == GLASDI_ACT_SOFTPLUS) return fmaf(kLn2, mufu_lg2(1.0f + mufu_ex2(-kL2e * fabsf(a))), fmaxf(a, 0.0f));
+  else if constexpr (ACT == GLASDI_ACT_SILU) return a * mufu_rcp(1.0f + mufu_ex2(-kL2e * a));
+  else if constexpr (ACT == GLASDI_ACT_RELU) return fmaxf(a, 0.0f);
+  else if constexpr (ACT == GLASDI_ACT_IDENTITY) return a;
+  else if constexpr (ACT < 0) return act_apply(act_rt, a);
+  else return act_apply(ACT, a);
+}
+
 // packed fp32 pairs (Blackwell FFMA2 / FADD2): one instruction for two lanes of the epilogue sums
 __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
   unsigned long long r;

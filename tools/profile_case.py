@@ -26,3 +26,5 @@ for _ in range(reps):
     print("stage ms (rollout, decode, launches):", eng.stage_times(), "idx", int(am),
           "screen (refine ms, candidates, max dev):", eng.screen_stats() if mode >= 1 else None, flush=True)
 eng.check_numeric()
+if mode == 2:
+    print("quad ms:", getattr(eng, "last_quad_ms", None))
