@@ -181,3 +181,12 @@ def test_trainer_export_load_round_trip_with_reference_keys(tmp_path):
     for k in s1:
         assert torch.equal(s1[k]["exp_avg"], s2[k]["exp_avg"]) and torch.equal(s1[k]["exp_avg_sq"], s2[k]["exp_avg_sq"])
         assert float(s1[k]["step"]) == float(s2[k]["step"]) == 2.0
+
+
+def test_library_carries_the_hash_of_its_sources():
+    """The loader refuses (or rebuilds) a library built from other sources: the sha1 of csrc/ + the header is compiled into
+    the library and written beside it (gplasdi_b200/build.py::source_hash)."""
+    from gplasdi_b200 import _lib, build
+    lib = _lib.load()
+    assert lib.glasdi_source_hash().decode() == build.source_hash() == build.built_hash()
+    assert not build.needs_build()
