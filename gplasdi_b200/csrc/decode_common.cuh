@@ -312,9 +312,9 @@ __device__ __forceinline__ void pm_stage(uint8_t* base, const FrontMlp& f, int n
 // one n8 tile j of a layer for the warp's 16 samples: acc = bias + A W^T, three split MMAs per k block.  The number of k
 // blocks is a template argument behind a warp-uniform switch: a predicated-off HMMA still takes its issue slot (the first
 // version spent 55 % of its HMMA slots on them, profiles/r02_gram_generic_mma_*).
-template <int NKB>
-__device__ __forceinline__ void pm_tile_n(const PmLayer& Ly, int j, int g, int t, const uint32_t (&Ah)[kPmMaxKb][4],
-                                          const uint32_t (&Al)[kPmMaxKb][4], float (&acc)[4]) {
+template <int NKB, int KBM>
+__device__ __forceinline__ void pm_tile_n(const PmLayer& Ly, int j, int g, int t, const uint32_t (&Ah)[KBM][4],
+                                          const uint32_t (&Al)[KBM][4], float (&acc)[4]) {
   const float2 bb = *reinterpret_cast<const float2*>(Ly.bias + 8 * j + 2 * t);
   acc[0] = bb.x; acc[1] = bb.y; acc[2] = bb.x; acc[3] = bb.y;
   const __half* rh = Ly.wh + (size_t)(8 * j + g) * Ly.ld + 2 * t;
@@ -328,23 +328,30 @@ __device__ __forceinline__ void pm_tile_n(const PmLayer& Ly, int j, int g, int t
     mma16816(acc, Ah[kb], bl0, bl1);
   }
 }
-__device__ __forceinline__ void pm_tile(const PmLayer& Ly, int j, int g, int t, const uint32_t (&Ah)[kPmMaxKb][4],
-                                        const uint32_t (&Al)[kPmMaxKb][4], float (&acc)[4]) {
-  switch (Ly.nkb) {
-    case 1: pm_tile_n<1>(Ly, j, g, t, Ah, Al, acc); break;
-    case 2: pm_tile_n<2>(Ly, j, g, t, Ah, Al, acc); break;
-    case 3: pm_tile_n<3>(Ly, j, g, t, Ah, Al, acc); break;
-    default: pm_tile_n<4>(Ly, j, g, t, Ah, Al, acc); break;
+// KBM = k16 blocks the caller's fragment arrays hold (2 when every layer input is <= 32 wide: half the registers)
+template <int KBM>
+__device__ __forceinline__ void pm_tile(const PmLayer& Ly, int j, int g, int t, const uint32_t (&Ah)[KBM][4],
+                                        const uint32_t (&Al)[KBM][4], float (&acc)[4]) {
+  if constexpr (KBM <= 2) {
+    if (Ly.nkb == 1) pm_tile_n<1, KBM>(Ly, j, g, t, Ah, Al, acc);
+    else pm_tile_n<2, KBM>(Ly, j, g, t, Ah, Al, acc);
+  } else {
+    switch (Ly.nkb) {
+      case 1: pm_tile_n<1, KBM>(Ly, j, g, t, Ah, Al, acc); break;
+      case 2: pm_tile_n<2, KBM>(Ly, j, g, t, Ah, Al, acc); break;
+      case 3: pm_tile_n<3, KBM>(Ly, j, g, t, Ah, Al, acc); break;
+      default: pm_tile_n<4, KBM>(Ly, j, g, t, Ah, Al, acc); break;
+    }
   }
 }
 // layers 0 .. n_layers-1 (none of them the written-out one): A fragments of layer 0 in, A fragments of layer n_layers out
-template <typename ActF>
-__device__ __forceinline__ void pm_chain(const PmLayer* Ly, int n_layers, int g, int t, uint32_t (&Ah)[kPmMaxKb][4],
-                                         uint32_t (&Al)[kPmMaxKb][4], ActF act) {
+template <int KBM, typename ActF>
+__device__ __forceinline__ void pm_chain(const PmLayer* Ly, int n_layers, int g, int t, uint32_t (&Ah)[KBM][4],
+                                         uint32_t (&Al)[KBM][4], ActF act) {
   for (int l = 0; l < n_layers; ++l) {
-    uint32_t Nh[kPmMaxKb][4], Nl[kPmMaxKb][4];
+    uint32_t Nh[KBM][4], Nl[KBM][4];
 #pragma unroll
-    for (int jp = 0; jp < kPmMaxKb; ++jp) {
+    for (int jp = 0; jp < KBM; ++jp) {
       if (2 * jp < Ly[l].nt) {
         float a0[4], a1[4] = {0.f, 0.f, 0.f, 0.f};
         pm_tile(Ly[l], 2 * jp, g, t, Ah, Al, a0);
@@ -361,16 +368,17 @@ __device__ __forceinline__ void pm_chain(const PmLayer* Ly, int n_layers, int g,
       }
     }
 #pragma unroll
-    for (int kb = 0; kb < kPmMaxKb; ++kb)
+    for (int kb = 0; kb < KBM; ++kb)
 #pragma unroll
       for (int q = 0; q < 4; ++q) { Ah[kb][q] = Nh[kb][q]; Al[kb][q] = Nl[kb][q]; }
   }
 }
 // A fragments of layer 0 from the latent states of rows g and g + 8: this lane's components 2t, 2t + 1 (0 beyond n <= 8)
-__device__ __forceinline__ void pm_latent_frag(float zlo0, float zlo1, float zhi0, float zhi1, uint32_t (&Ah)[kPmMaxKb][4],
-                                               uint32_t (&Al)[kPmMaxKb][4]) {
+template <int KBM>
+__device__ __forceinline__ void pm_latent_frag(float zlo0, float zlo1, float zhi0, float zhi1, uint32_t (&Ah)[KBM][4],
+                                               uint32_t (&Al)[KBM][4]) {
 #pragma unroll
-  for (int kb = 0; kb < kPmMaxKb; ++kb)
+  for (int kb = 0; kb < KBM; ++kb)
 #pragma unroll
     for (int q = 0; q < 4; ++q) { Ah[kb][q] = 0u; Al[kb][q] = 0u; }
   split_h2(zlo0, zlo1, Ah[0][0], Al[0][0]);

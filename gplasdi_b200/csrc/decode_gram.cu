@@ -23,6 +23,8 @@
 // SCREENING pass only -- refine.cu re-evaluates every near-maximum (t, dof) exactly and checks the deviation.
 #include "decode_gram.cuh"
 
+#include <type_traits>
+
 #include <algorithm>
 #include <cmath>
 
@@ -460,7 +462,11 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         // bare MUFU forms (6 instead of ~12 instructions per softplus; the pilot goes through the same function)
         auto act = [&](float x) { return act_mufu<ACT>(x, act_rt); };
         const int k0 = 2 * t, k1 = 2 * t + 1;
-        uint32_t Ah[kPmMaxKb][4], Al[kPmMaxKb][4];
+        bool narrow32 = true;                                // every layer input <= 32 wide: two k16 blocks of fragments
+        for (int l = 0; l < nf; ++l) narrow32 = narrow32 && P.front.widths[l] <= 32;
+        auto run = [&](auto kbm_tag) {
+        constexpr int KBM = decltype(kbm_tag)::value;
+        uint32_t Ah[KBM][4], Al[KBM][4];
         for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
           const float* __restrict__ zb = P.Zs + (size_t)item * NZ * P.Spad;
           if (pw == 0) {
@@ -512,6 +518,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kGProdThreads) : "memory");     // pilot is rewritten next item
         }
+        };
+        if (narrow32) run(std::integral_constant<int, 2>{});
+        else run(std::integral_constant<int, kPmMaxKb>{});
       } else {
       if (regs_path) {
         narrow_layers_stage(xbuf, P.front, n_pre, ptid, kGProdThreads);
