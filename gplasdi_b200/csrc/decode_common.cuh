@@ -312,7 +312,7 @@ __device__ __forceinline__ void pm_stage(uint8_t* base, const FrontMlp& f, int n
 // one n8 tile j of a layer for the warp's 16 samples: acc = bias + A W^T, three split MMAs per k block.  The number of k
 // blocks is a template argument behind a warp-uniform switch: a predicated-off HMMA still takes its issue slot (the first
 // version spent 55 % of its HMMA slots on them, profiles/r02_gram_generic_mma_*).
-template <int NKB, int KBM>
+template <int NKB, int KBM, bool WLO = true>
 __device__ __forceinline__ void pm_tile_n(const PmLayer& Ly, int j, int g, int t, const uint32_t (&Ah)[KBM][4],
                                           const uint32_t (&Al)[KBM][4], float (&acc)[4]) {
   const float2 bb = *reinterpret_cast<const float2*>(Ly.bias + 8 * j + 2 * t);
@@ -322,25 +322,28 @@ __device__ __forceinline__ void pm_tile_n(const PmLayer& Ly, int j, int g, int t
 #pragma unroll
   for (int kb = 0; kb < NKB; ++kb) {
     const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(rh + 16 * kb), bh1 = *reinterpret_cast<const uint32_t*>(rh + 16 * kb + 8);
-    const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(rl + 16 * kb), bl1 = *reinterpret_cast<const uint32_t*>(rl + 16 * kb + 8);
     mma16816(acc, Ah[kb], bh0, bh1);
     mma16816(acc, Al[kb], bh0, bh1);
-    mma16816(acc, Ah[kb], bl0, bl1);
+    if constexpr (WLO) {           // the weights' fp16 remainder: dropped where the layer's OUTPUT is rounded to fp16 anyway and
+                                   // the rounding is common to the samples and the pilot (the screening's Gram operand)
+      const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(rl + 16 * kb), bl1 = *reinterpret_cast<const uint32_t*>(rl + 16 * kb + 8);
+      mma16816(acc, Ah[kb], bl0, bl1);
+    }
   }
 }
 // KBM = k16 blocks the caller's fragment arrays hold (2 when every layer input is <= 32 wide: half the registers)
-template <int KBM>
+template <int KBM, bool WLO = true>
 __device__ __forceinline__ void pm_tile(const PmLayer& Ly, int j, int g, int t, const uint32_t (&Ah)[KBM][4],
                                         const uint32_t (&Al)[KBM][4], float (&acc)[4]) {
   if constexpr (KBM <= 2) {
-    if (Ly.nkb == 1) pm_tile_n<1, KBM>(Ly, j, g, t, Ah, Al, acc);
-    else pm_tile_n<2, KBM>(Ly, j, g, t, Ah, Al, acc);
+    if (Ly.nkb == 1) pm_tile_n<1, KBM, WLO>(Ly, j, g, t, Ah, Al, acc);
+    else pm_tile_n<2, KBM, WLO>(Ly, j, g, t, Ah, Al, acc);
   } else {
     switch (Ly.nkb) {
-      case 1: pm_tile_n<1, KBM>(Ly, j, g, t, Ah, Al, acc); break;
-      case 2: pm_tile_n<2, KBM>(Ly, j, g, t, Ah, Al, acc); break;
-      case 3: pm_tile_n<3, KBM>(Ly, j, g, t, Ah, Al, acc); break;
-      default: pm_tile_n<4, KBM>(Ly, j, g, t, Ah, Al, acc); break;
+      case 1: pm_tile_n<1, KBM, WLO>(Ly, j, g, t, Ah, Al, acc); break;
+      case 2: pm_tile_n<2, KBM, WLO>(Ly, j, g, t, Ah, Al, acc); break;
+      case 3: pm_tile_n<3, KBM, WLO>(Ly, j, g, t, Ah, Al, acc); break;
+      default: pm_tile_n<4, KBM, WLO>(Ly, j, g, t, Ah, Al, acc); break;
     }
   }
 }

@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             pm_chain(Ly, nf - 1, g, t, Ah, Al, act);
             for (int j = 0; j < P.nkg; ++j) {
               float acc[4] = {0.f, 0.f, 0.f, 0.f};
-              if (j < ntl) pm_tile(Ly[nf - 1], j, g, t, Ah, Al, acc);
+              if (j < ntl) pm_tile<KBM, false>(Ly[nf - 1], j, g, t, Ah, Al, acc);
               if (g == 0) {
                 sPilot[8 * j + k0] = (8 * j + k0 < P.K) ? act(acc[0]) * hscale : 0.f;
                 sPilot[8 * j + k1] = (8 * j + k1 < P.K) ? act(acc[1]) * hscale : 0.f;
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             mbar_wait_relaxed(&B->h_empty[buf], ((h_it / kRing) & 1u) ^ 1u);
             for (int j = j_begin; j < j_end; ++j) {
               float acc[4] = {0.f, 0.f, 0.f, 0.f};
-              if (j < ntl) pm_tile(Ly[nf - 1], j, g, t, Ah, Al, acc);
+              if (j < ntl) pm_tile<KBM, false>(Ly[nf - 1], j, g, t, Ah, Al, acc);
               const float2 pv = *reinterpret_cast<const float2*>(sPilot + 8 * j + k0);
               const int k = 8 * j + k0;
               float v0 = fmaf(act(acc[0]), hscale, -pv.x), v1 = fmaf(act(acc[1]), hscale, -pv.y);
