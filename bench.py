@@ -171,7 +171,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # Blocks of test parameters the OTHER named shapes (BASELINE.json configs[2..4]) are timed on: a fixed GLOBAL block, split
 # over the ranks like the real grid would be (strong scaling), sized for >= 1 s of timed device work at N = 1.
-NAMED_BLOCKS = {"burgers2d": (None, 10), "vlasov1d1v": (64, 3), "rising_bubble": (48, 2)}     # (params or None = whole grid, steps)
+NAMED_BLOCKS = {"burgers2d": (None, 30), "vlasov1d1v": (64, 4), "rising_bubble": (48, 2)}     # (params or None = whole grid, steps)
 
 
 def issued_tensor_flop(eng_widths, P, S, T, mode_gram: bool, passes: int):
@@ -504,7 +504,10 @@ def time_named_shape(eng, nm, blk, nsteps, world, rank, dev, sampler, barrier, m
     wide_passes = 3 if mode_id == _lib.MODE_DIRECT else 1
     a, b = issued_tensor_flop(wl.widths, Pb, wl.S, wl.T, mode_id == _lib.MODE_SCREENED_GRAM, wide_passes)
     K = wl.widths[-2]
-    path = ("gram_kernel (front MLP producers + tcgen05 Gram MMAs) + quad_kernel + select/refine" if K <= 111 else
+    path = ("gram_kernel (front MLP as a warp-level mma.sync chain with split fp16 operands + tcgen05 Gram MMAs) + quad_kernel + "
+            "select/refine; bound by the producers (legacy HMMA + MUFU), not by the tcgen05 pipe: `frac` (issued tcgen05 FLOP) is "
+            "small by construction, `frac_algorithmic` exceeds what a decode-every-sample kernel could reach because the "
+            "covariance form needs K/D-times fewer FLOP" if K <= 111 else
             f"wide_pre_kernel (narrow front layers in registers) + xact_kernel / xvar_kernel ({wide_passes} fp16 pass(es) of the "
             "last front layer and of the last layer + variance epilogue on tcgen05, decode_wide.cu) + select + wide_cand_kernel "
             "(exact CUDA-core re-evaluation of the candidates' rows)")
