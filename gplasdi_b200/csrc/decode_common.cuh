@@ -285,7 +285,15 @@ __host__ inline size_t pm_smem_bytes(const int* widths, int nf) {
 // Writes the image of layers 0 .. nf-1 at `base` (every thread of the calling group, stride nthreads; the caller
 // synchronises): per layer [hi | lo] fp16 weights [out_pad][in_pad + 8] + fp32 biases [out_pad].  `last_exact8`: the
 // last layer's outputs are padded to 8 (its tiles are written out), the others to 16 (they feed the next layer's k blocks).
-struct PmLayer { const __half* wh; const __half* wl; const float* bias; int nkb, op, ld, nt; };   // nt: n8 tiles with real units
+// Layer descriptor: 32-bit SHARED-space addresses (explicit ld.shared: generic loads of the weight image were long-scoreboard
+// stalls, 19 % of the samples of the first version) -- the callers keep the descriptor array itself in shared memory too.
+struct PmLayer { uint32_t wh, wl, bias; int nkb, op, ld, nt; };   // nt: n8 tiles with real units; ld in halfs
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ void pm_stage(uint8_t* base, const FrontMlp& f, int nf, int tid, int nthreads, PmLayer* out) {
   size_t off = 0;
   for (int l = 0; l < nf; ++l) {
@@ -304,48 +312,70 @@ __device__ __forceinline__ void pm_stage(uint8_t* base, const FrontMlp& f, int n
     off = (off + 15) / 16 * 16;
     float* b = reinterpret_cast<float*>(base + off);
     for (int o = tid; o < op; o += nthreads) b[o] = o < wo ? f.b[l][o] : 0.f;
-    out[l] = PmLayer{w, w + (size_t)op * ld, b, ip / 16, op, ld, (wo + 7) / 8};
+    if (tid == 0)
+      out[l] = PmLayer{smem_u32(w), smem_u32(w + (size_t)op * ld), smem_u32(b), ip / 16, op, ld, (wo + 7) / 8};
     off += (size_t)op * sizeof(float);
     off = (off + 15) / 16 * 16;
   }
 }
-// one n8 tile j of a layer for the warp's 16 samples: acc = bias + A W^T, three split MMAs per k block.  The number of k
-// blocks is a template argument behind a warp-uniform switch: a predicated-off HMMA still takes its issue slot (the first
-// version spent 55 % of its HMMA slots on them, profiles/r02_gram_generic_mma_*).
-template <int NKB, int KBM, bool WLO = true>
-__device__ __forceinline__ void pm_tile_n(const PmLayer& Ly, int j, int g, int t, const uint32_t (&Ah)[KBM][4],
-                                          const uint32_t (&Al)[KBM][4], float (&acc)[4]) {
-  const float2 bb = *reinterpret_cast<const float2*>(Ly.bias + 8 * j + 2 * t);
-  acc[0] = bb.x; acc[1] = bb.y; acc[2] = bb.x; acc[3] = bb.y;
-  const __half* rh = Ly.wh + (size_t)(8 * j + g) * Ly.ld + 2 * t;
-  const __half* rl = Ly.wl + (size_t)(8 * j + g) * Ly.ld + 2 * t;
+// n8 tiles j0 (and j1 if TWO) of a layer for the warp's 16 samples: acc = bias + A W^T, three split MMAs per k block (two
+// without the weights' fp16 remainder, WLO = false: where the layer's OUTPUT is rounded to fp16 anyway and the rounding is
+// common to the samples and the pilot).  The two tiles' accumulation chains are independent and issued interleaved; the
+// number of k blocks is a template argument behind a warp-uniform switch (a predicated-off HMMA still takes its issue slot).
+template <int NKB, int KBM, bool WLO, bool TWO>
+__device__ __forceinline__ void pm_tiles_n(const PmLayer& Ly, int j0, int j1, int g, int t, const uint32_t (&Ah)[KBM][4],
+                                           const uint32_t (&Al)[KBM][4], float (&a0)[4], float (&a1)[4]) {
+  const uint32_t row = (uint32_t)(g * Ly.ld + 2 * t) * 2u, tile = (uint32_t)(8 * Ly.ld) * 2u;
+  const uint32_t h0 = Ly.wh + row + (uint32_t)j0 * tile, l0 = Ly.wl + row + (uint32_t)j0 * tile;
+  const uint32_t h1 = Ly.wh + row + (uint32_t)j1 * tile, l1 = Ly.wl + row + (uint32_t)j1 * tile;
+  {
+    const float2 b0 = lds_f2(Ly.bias + (uint32_t)(8 * j0 + 2 * t) * 4u);
+    a0[0] = b0.x; a0[1] = b0.y; a0[2] = b0.x; a0[3] = b0.y;
+    if constexpr (TWO) {
+      const float2 b1 = lds_f2(Ly.bias + (uint32_t)(8 * j1 + 2 * t) * 4u);
+      a1[0] = b1.x; a1[1] = b1.y; a1[2] = b1.x; a1[3] = b1.y;
+    }
+  }
 #pragma unroll
   for (int kb = 0; kb < NKB; ++kb) {
-    const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(rh + 16 * kb), bh1 = *reinterpret_cast<const uint32_t*>(rh + 16 * kb + 8);
-    mma16816(acc, Ah[kb], bh0, bh1);
-    mma16816(acc, Al[kb], bh0, bh1);
-    if constexpr (WLO) {           // the weights' fp16 remainder: dropped where the layer's OUTPUT is rounded to fp16 anyway and
-                                   // the rounding is common to the samples and the pilot (the screening's Gram operand)
-      const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(rl + 16 * kb), bl1 = *reinterpret_cast<const uint32_t*>(rl + 16 * kb + 8);
-      mma16816(acc, Ah[kb], bl0, bl1);
+    const uint32_t x0 = lds_u32(h0 + 32u * kb), x1 = lds_u32(h0 + 32u * kb + 16u);
+    uint32_t y0 = 0, y1 = 0;
+    if constexpr (TWO) { y0 = lds_u32(h1 + 32u * kb); y1 = lds_u32(h1 + 32u * kb + 16u); }
+    mma16816(a0, Ah[kb], x0, x1);
+    if constexpr (TWO) mma16816(a1, Ah[kb], y0, y1);
+    mma16816(a0, Al[kb], x0, x1);
+    if constexpr (TWO) mma16816(a1, Al[kb], y0, y1);
+    if constexpr (WLO) {
+      const uint32_t u0 = lds_u32(l0 + 32u * kb), u1 = lds_u32(l0 + 32u * kb + 16u);
+      mma16816(a0, Ah[kb], u0, u1);
+      if constexpr (TWO) {
+        const uint32_t v0 = lds_u32(l1 + 32u * kb), v1 = lds_u32(l1 + 32u * kb + 16u);
+        mma16816(a1, Ah[kb], v0, v1);
+      }
     }
   }
 }
 // KBM = k16 blocks the caller's fragment arrays hold (2 when every layer input is <= 32 wide: half the registers)
+template <int KBM, bool WLO, bool TWO>
+__device__ __forceinline__ void pm_tiles(const PmLayer& Ly, int j0, int j1, int g, int t, const uint32_t (&Ah)[KBM][4],
+                                         const uint32_t (&Al)[KBM][4], float (&a0)[4], float (&a1)[4]) {
+  if constexpr (KBM <= 2) {
+    if (Ly.nkb == 1) pm_tiles_n<1, KBM, WLO, TWO>(Ly, j0, j1, g, t, Ah, Al, a0, a1);
+    else pm_tiles_n<2, KBM, WLO, TWO>(Ly, j0, j1, g, t, Ah, Al, a0, a1);
+  } else {
+    switch (Ly.nkb) {
+      case 1: pm_tiles_n<1, KBM, WLO, TWO>(Ly, j0, j1, g, t, Ah, Al, a0, a1); break;
+      case 2: pm_tiles_n<2, KBM, WLO, TWO>(Ly, j0, j1, g, t, Ah, Al, a0, a1); break;
+      case 3: pm_tiles_n<3, KBM, WLO, TWO>(Ly, j0, j1, g, t, Ah, Al, a0, a1); break;
+      default: pm_tiles_n<4, KBM, WLO, TWO>(Ly, j0, j1, g, t, Ah, Al, a0, a1); break;
+    }
+  }
+}
 template <int KBM, bool WLO = true>
 __device__ __forceinline__ void pm_tile(const PmLayer& Ly, int j, int g, int t, const uint32_t (&Ah)[KBM][4],
                                         const uint32_t (&Al)[KBM][4], float (&acc)[4]) {
-  if constexpr (KBM <= 2) {
-    if (Ly.nkb == 1) pm_tile_n<1, KBM, WLO>(Ly, j, g, t, Ah, Al, acc);
-    else pm_tile_n<2, KBM, WLO>(Ly, j, g, t, Ah, Al, acc);
-  } else {
-    switch (Ly.nkb) {
-      case 1: pm_tile_n<1, KBM, WLO>(Ly, j, g, t, Ah, Al, acc); break;
-      case 2: pm_tile_n<2, KBM, WLO>(Ly, j, g, t, Ah, Al, acc); break;
-      case 3: pm_tile_n<3, KBM, WLO>(Ly, j, g, t, Ah, Al, acc); break;
-      default: pm_tile_n<4, KBM, WLO>(Ly, j, g, t, Ah, Al, acc); break;
-    }
-  }
+  float dummy[4];
+  pm_tiles<KBM, WLO, false>(Ly, j, j, g, t, Ah, Al, acc, dummy);
 }
 // layers 0 .. n_layers-1 (none of them the written-out one): A fragments of layer 0 in, A fragments of layer n_layers out
 template <int KBM, typename ActF>
@@ -357,8 +387,8 @@ __device__ __forceinline__ void pm_chain(const PmLayer* Ly, int n_layers, int g,
     for (int jp = 0; jp < KBM; ++jp) {
       if (2 * jp < Ly[l].nt) {
         float a0[4], a1[4] = {0.f, 0.f, 0.f, 0.f};
-        pm_tile(Ly[l], 2 * jp, g, t, Ah, Al, a0);
-        if (2 * jp + 1 < Ly[l].nt) pm_tile(Ly[l], 2 * jp + 1, g, t, Ah, Al, a1);     // else pure padding: next layer's weights are 0
+        if (2 * jp + 1 < Ly[l].nt) pm_tiles<KBM, true, true>(Ly[l], 2 * jp, 2 * jp + 1, g, t, Ah, Al, a0, a1);
+        else pm_tiles<KBM, true, false>(Ly[l], 2 * jp, 2 * jp, g, t, Ah, Al, a0, a1);    // tile 2 jp + 1 is pure padding
 #pragma unroll
         for (int q = 0; q < 4; ++q) { a0[q] = act(a0[q]); a1[q] = act(a1[q]); }
         split_h2(a0[0], a0[1], Nh[jp][0], Nl[jp][0]);      // row g,     k = 16 jp + 2t, + 1

@@ -447,7 +447,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
       }
       if (mma_path) {
         const int nf = P.front.n_front;
-        PmLayer Ly[kMaxLinear];
+        __shared__ PmLayer sLy[kMaxLinear];
+        PmLayer* Ly = sLy;
         pm_stage(smem + L.xb, P.front, nf, ptid, kGProdThreads, Ly);
         asm volatile("bar.sync 2, %0;" ::"n"(kGProdThreads) : "memory");
         const int pw = ptid >> 5;                            // producer warp 0..15
@@ -474,12 +475,17 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             const float zp0 = k0 < NZ ? __ldg(zb + (size_t)k0 * P.Spad) : 0.f, zp1 = k1 < NZ ? __ldg(zb + (size_t)k1 * P.Spad) : 0.f;
             pm_latent_frag(zp0, zp1, zp0, zp1, Ah, Al);
             pm_chain(Ly, nf - 1, g, t, Ah, Al, act);
-            for (int j = 0; j < P.nkg; ++j) {
-              float acc[4] = {0.f, 0.f, 0.f, 0.f};
-              if (j < ntl) pm_tile<KBM, false>(Ly[nf - 1], j, g, t, Ah, Al, acc);
+            for (int j = 0; j < P.nkg; j += 2) {
+              float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+              if (j + 1 < ntl) pm_tiles<KBM, false, true>(Ly[nf - 1], j, j + 1, g, t, Ah, Al, acc, acc1);
+              else if (j < ntl) pm_tiles<KBM, false, false>(Ly[nf - 1], j, j, g, t, Ah, Al, acc, acc1);
               if (g == 0) {
                 sPilot[8 * j + k0] = (8 * j + k0 < P.K) ? act(acc[0]) * hscale : 0.f;
                 sPilot[8 * j + k1] = (8 * j + k1 < P.K) ? act(acc[1]) * hscale : 0.f;
+                if (j + 1 < P.nkg) {
+                  sPilot[8 * j + 8 + k0] = (8 * j + 8 + k0 < P.K) ? act(acc1[0]) * hscale : 0.f;
+                  sPilot[8 * j + 8 + k1] = (8 * j + 8 + k1 < P.K) ? act(acc1[1]) * hscale : 0.f;
+                }
               }
             }
           }
@@ -496,9 +502,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
             const uint32_t buf = h_it % kRing;
             uint8_t* Hb = sH + buf * kBufBytes;
             mbar_wait_relaxed(&B->h_empty[buf], ((h_it / kRing) & 1u) ^ 1u);
-            for (int j = j_begin; j < j_end; ++j) {
-              float acc[4] = {0.f, 0.f, 0.f, 0.f};
-              if (j < ntl) pm_tile<KBM, false>(Ly[nf - 1], j, g, t, Ah, Al, acc);
+            auto emit = [&](int j, const float (&acc)[4]) {
               const float2 pv = *reinterpret_cast<const float2*>(sPilot + 8 * j + k0);
               const int k = 8 * j + k0;
               float v0 = fmaf(act(acc[0]), hscale, -pv.x), v1 = fmaf(act(acc[1]), hscale, -pv.y);
@@ -510,6 +514,13 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
               if (P.check_overflow) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3))));
               *reinterpret_cast<uint32_t*>(Hb + h_offset(j, col_lo) + 4 * t) = h2_as_u32(__floats2half2_rn(v0, v1));
               *reinterpret_cast<uint32_t*>(Hb + h_offset(j, col_hi) + 4 * t) = h2_as_u32(__floats2half2_rn(v2, v3));
+            };
+            for (int j = j_begin; j < j_end; j += 2) {
+              float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+              if (j + 1 < ntl) pm_tiles<KBM, false, true>(Ly[nf - 1], j, j + 1, g, t, Ah, Al, acc, acc1);
+              else if (j < ntl) pm_tiles<KBM, false, false>(Ly[nf - 1], j, j, g, t, Ah, Al, acc, acc1);
+              emit(j, acc);
+              if (j + 1 < j_end) emit(j + 1, acc1);
             }
             fence_proxy_async_smem();
             __syncwarp();

@@ -609,7 +609,7 @@ template <int ACT>      // compile-time activation (bare MUFU forms); < 0: runti
 __global__ void __launch_bounds__(kPmThreads, 1) wide_pre_mma_kernel(const __grid_constant__ PreParams P) {
   extern __shared__ __align__(16) uint8_t pmsm[];
   const int nf = P.f.n_front;
-  dv::PmLayer Ly[kMaxLinear];
+  __shared__ dv::PmLayer Ly[kMaxLinear];
   dv::pm_stage(pmsm, P.f, nf, threadIdx.x, blockDim.x, Ly);
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -641,11 +641,9 @@ __global__ void __launch_bounds__(kPmThreads, 1) wide_pre_mma_kernel(const __gri
     dv::pm_chain(Ly, nf - 1, g, t, Ah, Al, act);
     // the layer that feeds xact_kernel: (act(.) 2^eX) as fp16 into the B' tiles [kg][256 columns][8]
     const dv::PmLayer& LL = Ly[nf - 1];
-    for (int j = 0; j < nkg; ++j) {
+    auto emit = [&](int j, bool real, const float (&acc)[4]) {
       uint32_t o_lo = 0u, o_hi = 0u;
-      if (8 * j < LL.op) {
-        float acc[4];
-        dv::pm_tile(LL, j, g, t, Ah, Al, acc);
+      if (real) {
         const int k = 8 * j + 2 * t;
         const float v0 = (k < P.K1 && s_lo < P.S) ? act(acc[0]) * P.scale : 0.f;
         const float v1 = (k + 1 < P.K1 && s_lo < P.S) ? act(acc[1]) * P.scale : 0.f;
@@ -659,6 +657,14 @@ __global__ void __launch_bounds__(kPmThreads, 1) wide_pre_mma_kernel(const __gri
       uint32_t* dst = reinterpret_cast<uint32_t*>(xt + ((size_t)j * 256 + col0 + g) * 8 + 2 * t);
       dst[0] = o_lo;
       dst[8 * 8 / 2] = o_hi;                               // column + 8: 8 columns x 16 bytes further
+    };
+    const int ntl = LL.op / 8;
+    for (int j = 0; j < nkg; j += 2) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j + 1 < ntl) dv::pm_tiles<dv::kPmMaxKb, true, true>(LL, j, j + 1, g, t, Ah, Al, acc, acc1);
+      else if (j < ntl) dv::pm_tiles<dv::kPmMaxKb, true, false>(LL, j, j, g, t, Ah, Al, acc, acc1);
+      emit(j, j < ntl, acc);
+      if (j + 1 < nkg) emit(j + 1, j + 1 < ntl, acc1);
     }
   }
   if (!(amax <= 65000.f) || nanacc != 0.f) atomicOr(P.flags + 0, 1);
