@@ -171,7 +171,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # Blocks of test parameters the OTHER named shapes (BASELINE.json configs[2..4]) are timed on: a fixed GLOBAL block, split
 # over the ranks like the real grid would be (strong scaling), sized for >= 1 s of timed device work at N = 1.
-NAMED_BLOCKS = {"burgers2d": (None, 30), "vlasov1d1v": (64, 4), "rising_bubble": (48, 2)}     # (params or None = whole grid, steps)
+NAMED_BLOCKS = {"burgers2d": (None, 45), "vlasov1d1v": (64, 4), "rising_bubble": (48, 2)}     # (params or None = whole grid, steps)
 
 
 def issued_tensor_flop(eng_widths, P, S, T, mode_gram: bool, passes: int):
