@@ -470,22 +470,19 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_kernel(const __grid_constan
         uint32_t Ah[KBM][4], Al[KBM][4];
         for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
           const float* __restrict__ zb = P.Zs + (size_t)item * NZ * P.Spad;
-          if (pw == 0) {
-            // pilot table: the chain on 16 copies of sample 0; row 0 (lanes 0..3) holds units 8 j + 2 t, + 1
+          {
+            // pilot table: the chain on 16 copies of sample 0; row 0 (lanes 0..3) holds units 8 j + 2 t, + 1.  EVERY warp
+            // runs the narrow chain and takes one of the last layer's tiles (one warp doing all of them kept the other
+            // fifteen at the barrier below for a whole chunk time: 13 % of the stall samples)
             const float zp0 = k0 < NZ ? __ldg(zb + (size_t)k0 * P.Spad) : 0.f, zp1 = k1 < NZ ? __ldg(zb + (size_t)k1 * P.Spad) : 0.f;
             pm_latent_frag(zp0, zp1, zp0, zp1, Ah, Al);
             pm_chain(Ly, nf - 1, g, t, Ah, Al, act);
-            for (int j = 0; j < P.nkg; j += 2) {
-              float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-              if (j + 1 < ntl) pm_tiles<KBM, false, true>(Ly[nf - 1], j, j + 1, g, t, Ah, Al, acc, acc1);
-              else if (j < ntl) pm_tiles<KBM, false, false>(Ly[nf - 1], j, j, g, t, Ah, Al, acc, acc1);
+            for (int j = pw; j < P.nkg; j += kGProdWarps) {
+              float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4];
+              if (j < ntl) pm_tiles<KBM, false, false>(Ly[nf - 1], j, j, g, t, Ah, Al, acc, acc1);
               if (g == 0) {
                 sPilot[8 * j + k0] = (8 * j + k0 < P.K) ? act(acc[0]) * hscale : 0.f;
                 sPilot[8 * j + k1] = (8 * j + k1 < P.K) ? act(acc[1]) * hscale : 0.f;
-                if (j + 1 < P.nkg) {
-                  sPilot[8 * j + 8 + k0] = (8 * j + 8 + k0 < P.K) ? act(acc1[0]) * hscale : 0.f;
-                  sPilot[8 * j + 8 + k1] = (8 * j + 8 + k1 < P.K) ? act(acc1[1]) * hscale : 0.f;
-                }
               }
             }
           }
