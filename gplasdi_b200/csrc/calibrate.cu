@@ -160,6 +160,20 @@ __host__ __device__ int gelsy_factor(double (*G)[NA], GelsyWork& W, double rcond
   }
   // effective rank (xGELSY): grow the leading triangle while smax * rcond <= smin (incremental estimates)
   int rank = 0;
+  // Shortcut for the well-conditioned series of a trained model: the estimates satisfy smin_est >= sigma_min and
+  // smax_est <= sigma_max <= |R|_F, and sigma_min(R) >= |det R| ((n - 1) / |R|_F^2)^((n - 1) / 2); when that lower bound
+  // already clears rcond |R|_F, xLAIC1 would accept every column (the leading triangles are better conditioned still).
+  if (nr == NA) {
+    double det = 1.0, fro2 = 0.0;
+    for (int i = 0; i < NA; ++i) {
+      det *= G[i][i];
+      for (int k = i; k < NA; ++k) fro2 += G[i][k] * G[i][k];
+    }
+    double lb = det;
+    const double f = (double)(NA - 1) / fro2;
+    for (int i = 0; i < NA - 1; ++i) lb *= sqrt(f);
+    if (lb >= rcond * sqrt(fro2)) { W.rank = NA; return NA; }
+  }
   if (nr > 0) {
     double xmin[NA], xmax[NA], col[NA];
     xmin[0] = 1.0; xmax[0] = 1.0;
