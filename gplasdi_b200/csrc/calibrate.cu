@@ -439,8 +439,12 @@ __global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __r
   const float* __restrict__ z = Z + (size_t)b * T * N;
   if (use_smem) {
     // one coalesced sweep: T*N/32 independent loads per lane in flight, HBM sees the series exactly once
+    // asynchronous 4-byte copies (a series is T N floats at a 4-byte aligned offset: no 16-byte bulk copies): all
+    // T N / 32 copies of a lane are in flight at once instead of one load -> store round trip after the other
     float* mine = s_series + (size_t)wib * T * N;
-    for (int f = lane; f < T * N; f += 32) mine[f] = __ldg(z + f);
+    for (int f = lane; f < T * N; f += 32)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(mine + f)), "l"(z + f) : "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     z = mine;
   }
@@ -591,7 +595,9 @@ __global__ void __launch_bounds__(kBwdThreads) sindy_fit_bwd_kernel(const float*
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const float* __restrict__ z = Z + (size_t)b * T * N;
-  for (int f = tid; f < T * N; f += kBwdThreads) sZ[f] = __ldg(z + f);
+  for (int f = tid; f < T * N; f += kBwdThreads)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sZ + f)), "l"(z + f) : "memory");
+  asm volatile("cp.async.wait_all;" ::: "memory");
   if (tid < NR) sRf[tid / N][tid % N] = __ldg(coefs + (size_t)b * NR + tid);
   __syncthreads();
   const float gs = g_sindy ? __ldg(g_sindy + b) : 0.f;
@@ -826,7 +832,9 @@ __global__ void __launch_bounds__(kBwdThreads) sindy_fit_cta_kernel(const float*
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const float* __restrict__ zg = Z + (size_t)b * T * N;
-  for (int f = tid; f < T * N; f += kBwdThreads) s_fit[f] = __ldg(zg + f);
+  for (int f = tid; f < T * N; f += kBwdThreads)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_fit + f)), "l"(zg + f) : "memory");
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   const float* z = s_fit;
 
