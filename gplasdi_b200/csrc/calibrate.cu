@@ -415,13 +415,13 @@ constexpr int kFitThreads = 128;             // 4 warps = 4 training series per 
 // registers.  A shuffle butterfly sums over lanes; the tiny Cholesky factorisation / substitutions run as
 // rolled loops on a 528-byte per-warp shared-memory scratch (lane 0 factorises, lanes 0..n-1 solve one
 // right-hand side each), which keeps the kernel's code small enough to live in the instruction cache.
-template <int N, int HW>
+template <int N, int HW, bool SMEM>
 __global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __restrict__ Z, int B, int T, int fd_id,
                                                                 float inv_dt, int norm_order,
                                                                 float* __restrict__ coefs_out,
                                                                 float* __restrict__ loss_sindy_out,
                                                                 float* __restrict__ loss_coef_out,
-                                                                int32_t* __restrict__ info_out, int use_smem) {
+                                                                int32_t* __restrict__ info_out) {
   constexpr int NA = N + 1;                    // library size [1 | z]
   constexpr int NG = NA * (NA + 1) / 2;        // upper triangle of the Gram matrix, row-major
   constexpr int NR = NA * N;                   // right-hand side
@@ -437,7 +437,8 @@ __global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __r
   const int b = blockIdx.x * (kFitThreads / 32) + wib;
   if (b >= B) return;                          // whole warp leaves together (no block barriers below)
   const float* __restrict__ z = Z + (size_t)b * T * N;
-  if (use_smem) {
+  uint32_t zs = 0;                             // SMEM: shared-space address of the warp's copy (explicit ld.shared below)
+  if constexpr (SMEM) {
     // one coalesced sweep: T*N/32 independent loads per lane in flight, HBM sees the series exactly once
     // asynchronous 4-byte copies (a series is T N floats at a 4-byte aligned offset: no 16-byte bulk copies): all
     // T N / 32 copies of a lane are in flight at once instead of one load -> store round trip after the other
@@ -446,8 +447,18 @@ __global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __r
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(mine + f)), "l"(z + f) : "memory");
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    z = mine;
+    zs = smem_u32(mine);
   }
+  // a generic pointer that may be global or shared compiles to generic loads (15 % long-scoreboard stalls in the first ncu)
+  auto ldz = [&](int idx) -> float {
+    if constexpr (SMEM) {
+      float v;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(zs + 4u * (uint32_t)idx));
+      return v;
+    } else {
+      return __ldg(z + idx);
+    }
+  };
 
   double acc[NS];
 #pragma unroll
@@ -457,8 +468,8 @@ __global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __r
     x[0] = 1.f;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      x[1 + i] = z[t * N + i];
-      d[i] = inv_dt * sbp_row<HW>(sc, t, T, [&](int row) { return z[row * N + i]; });
+      x[1 + i] = ldz(t * N + i);
+      d[i] = inv_dt * sbp_row<HW>(sc, t, T, [&](int row) { return ldz(row * N + i); });
     }
     double xd[NA], dd[N];
 #pragma unroll
@@ -522,10 +533,10 @@ __global__ void __launch_bounds__(kFitThreads) sindy_fit_kernel(const float* __r
   for (int t = lane; t < T; t += 32) {
     float zr[N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) zr[j] = z[t * N + j];
+    for (int j = 0; j < N; ++j) zr[j] = ldz(t * N + j);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const float d = inv_dt * sbp_row<HW>(sc, t, T, [&](int row) { return z[row * N + i]; });
+      const float d = inv_dt * sbp_row<HW>(sc, t, T, [&](int row) { return ldz(row * N + i); });
       float pred = Rf[0][i];
 #pragma unroll
       for (int j = 0; j < N; ++j) pred = fmaf(zr[j], Rf[1 + j][i], pred);
@@ -987,10 +998,15 @@ static void launch_fit_nh(const float* Z, int B, int T, int fd_id, float inv_dt,
   const int use_smem = smem <= 100 * 1024;            // 2 CTAs per SM keep their series resident (reading through
                                                       // L1/L2 instead, for more resident warps, measured 10 % slower)
   if (!use_smem) smem = 0;
-  if (smem > 40 * 1024)
-    cudaFuncSetAttribute(sindy_fit_kernel<N, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  sindy_fit_kernel<N, HW><<<(B + per_cta - 1) / per_cta, kFitThreads, smem, st>>>(Z, B, T, fd_id, inv_dt, norm_order,
-                                                                                  coefs, ls, lc, info, use_smem);
+  if (use_smem) {
+    if (smem > 40 * 1024)
+      cudaFuncSetAttribute(sindy_fit_kernel<N, HW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sindy_fit_kernel<N, HW, true><<<(B + per_cta - 1) / per_cta, kFitThreads, smem, st>>>(Z, B, T, fd_id, inv_dt, norm_order,
+                                                                                          coefs, ls, lc, info);
+  } else {
+    sindy_fit_kernel<N, HW, false><<<(B + per_cta - 1) / per_cta, kFitThreads, 0, st>>>(Z, B, T, fd_id, inv_dt, norm_order,
+                                                                                        coefs, ls, lc, info);
+  }
 }
 
 template <int N>
